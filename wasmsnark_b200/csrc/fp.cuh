@@ -1,0 +1,284 @@
+// fp.cuh -- N x 32-bit-limb Montgomery prime field, values canonical in [0, p).
+//
+// Replaces the reference's generated WASM field module
+//   f1m_add/sub/neg      /root/reference/src/build_f1m.js:67-113
+//   f1m_mul              /root/reference/src/build_f1m.js:235-436   (R = 2^(32N), :37-39)
+//   f1m_square           /root/reference/src/build_f1m.js:439-737
+//   f1m_toMontgomery     /root/reference/src/build_f1m.js:749-756   (mul by R^2)
+//   f1m_fromMontgomery   /root/reference/src/build_f1m.js:758-770   (mul by 1)
+//   f1m_inverse          /root/reference/src/build_f1m.js:772-783
+// Results are byte-identical to the reference's because every routine returns the
+// canonical representative (the reference ends each op with a conditional subtract,
+// build_f1m.js:426-435), whatever the internal schedule.
+//
+// Device path: whole number held in registers, each row of the product is one PTX
+// mad.lo.cc / madc.hi.cc carry chain (fp_asm.cuh) that ptxas lowers to one IMAD.WIDE.U32
+// per limb product.  Host path (g++ / nvcc host pass): portable CIOS on uint64_t, used
+// only by the CPU unit tests of the group-law code.
+#pragma once
+#include <cstdint>
+#include "hd.cuh"
+#include "field_consts.cuh"
+#include "fp_asm.cuh"
+
+namespace ws {
+
+template <class P>
+struct Fp {
+    static constexpr int N = P::N;
+    uint32_t v[N];
+
+    HD static Fp zero() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = 0;
+        return r;
+    }
+    HD static Fp one() {   // Montgomery form of 1  (f1m_one)
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = P::one(i);
+        return r;
+    }
+    HD static Fp r2() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = P::r2(i);
+        return r;
+    }
+    HD static Fp modulus() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = P::mod(i);
+        return r;
+    }
+    HD bool is_zero() const {
+        uint32_t t = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) t |= v[i];
+        return t == 0;
+    }
+    HD bool operator==(const Fp& o) const {
+        uint32_t t = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) t |= v[i] ^ o.v[i];
+        return t == 0;
+    }
+    HD bool operator!=(const Fp& o) const { return !(*this == o); }
+};
+
+// ---------------------------------------------------------------- add / sub / neg
+template <class P>
+HD Fp<P> add(const Fp<P>& a, const Fp<P>& b) {
+    constexpr int N = P::N;
+    Fp<P> s, t;
+#ifdef __CUDA_ARCH__
+    const Fp<P> m = Fp<P>::modulus();
+    if constexpr (N == 8) {
+        add_n8(s.v, a.v, b.v);
+        uint32_t bw = sub_n8(t.v, s.v, m.v);
+#pragma unroll
+        for (int i = 0; i < N; i++) s.v[i] = bw ? s.v[i] : t.v[i];
+    } else {
+        add_n24(s.v, a.v, b.v);
+        uint32_t bw = sub_n24(t.v, s.v, m.v);
+#pragma unroll
+        for (int i = 0; i < N; i++) s.v[i] = bw ? s.v[i] : t.v[i];
+    }
+#else
+    uint64_t c = 0;
+    for (int i = 0; i < N; i++) {
+        c += (uint64_t)a.v[i] + b.v[i];
+        s.v[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    int64_t bw = 0;
+    for (int i = 0; i < N; i++) {
+        int64_t d = (int64_t)s.v[i] - P::mod(i) + bw;
+        t.v[i] = (uint32_t)d;
+        bw = d >> 32;
+    }
+    if (!bw) s = t;
+#endif
+    return s;
+}
+
+template <class P>
+HD Fp<P> sub(const Fp<P>& a, const Fp<P>& b) {
+    constexpr int N = P::N;
+    Fp<P> d;
+#ifdef __CUDA_ARCH__
+    const Fp<P> m = Fp<P>::modulus();
+    if constexpr (N == 8) {
+        uint32_t bw = sub_n8(d.v, a.v, b.v);
+        addmask_n8(d.v, m.v, bw);
+    } else {
+        uint32_t bw = sub_n24(d.v, a.v, b.v);
+        addmask_n24(d.v, m.v, bw);
+    }
+#else
+    int64_t bw = 0;
+    for (int i = 0; i < N; i++) {
+        int64_t t = (int64_t)a.v[i] - b.v[i] + bw;
+        d.v[i] = (uint32_t)t;
+        bw = t >> 32;
+    }
+    if (bw) {
+        uint64_t c = 0;
+        for (int i = 0; i < N; i++) {
+            c += (uint64_t)d.v[i] + P::mod(i);
+            d.v[i] = (uint32_t)c;
+            c >>= 32;
+        }
+    }
+#endif
+    return d;
+}
+
+template <class P>
+HD Fp<P> neg(const Fp<P>& a) {
+    // f1m_neg: 0 -> 0, else p - a   (build_f1m.js:103-113)
+    if (a.is_zero()) return a;
+    return sub(Fp<P>::zero(), a);
+}
+
+template <class P>
+HD Fp<P> dbl(const Fp<P>& a) { return add(a, a); }
+
+// ---------------------------------------------------------------- Montgomery product
+template <class P>
+HD Fp<P> mul(const Fp<P>& A, const Fp<P>& B) {
+    constexpr int N = P::N;
+    Fp<P> res;
+#ifdef __CUDA_ARCH__
+    // Two accumulators: e aligned on limb 0, o aligned on limb 1 (see tools/gen_fp_asm.py).
+    // After each row the running value is divided by 2^32, which swaps their roles.
+    uint32_t e[N], o[N];
+    const Fp<P> M = Fp<P>::modulus();
+    const uint32_t* a = A.v;
+    const uint32_t* b = B.v;
+    const uint32_t* p = M.v;
+#define WS_ROW0(NN)                                   \
+    mul_n##NN(e, a, b[0]);                            \
+    mul_n##NN(o, a + 1, b[0]);                        \
+    {                                                 \
+        uint32_t m = e[0] * P::NP0;                   \
+        cmad_n##NN(o, p + 1, m);                      \
+        o[N - 1] += cmad_n##NN(e, p, m);              \
+    }
+#define WS_ROW(NN, E, O, bi)                          \
+    {                                                 \
+        shift_mad_n##NN(E, O, a + 1, bi);             \
+        O[N - 1] += cmad_n##NN(E, a, bi);             \
+        uint32_t m = E[0] * P::NP0;                   \
+        cmad_n##NN(O, p + 1, m);                      \
+        O[N - 1] += cmad_n##NN(E, p, m);              \
+    }
+    if constexpr (N == 8) {
+        WS_ROW0(8)
+#pragma unroll
+        for (int i = 1; i < N; i += 2) {
+            WS_ROW(8, o, e, b[i])
+            if (i + 1 < N) WS_ROW(8, e, o, b[i + 1])
+        }
+        merge_n8(e, o);
+        uint32_t bw = sub_n8(res.v, e, p);
+#pragma unroll
+        for (int i = 0; i < N; i++) res.v[i] = bw ? e[i] : res.v[i];
+    } else {
+        WS_ROW0(24)
+#pragma unroll
+        for (int i = 1; i < N; i += 2) {
+            WS_ROW(24, o, e, b[i])
+            if (i + 1 < N) WS_ROW(24, e, o, b[i + 1])
+        }
+        merge_n24(e, o);
+        uint32_t bw = sub_n24(res.v, e, p);
+#pragma unroll
+        for (int i = 0; i < N; i++) res.v[i] = bw ? e[i] : res.v[i];
+    }
+#undef WS_ROW0
+#undef WS_ROW
+#else
+    // portable CIOS (host unit tests only)
+    uint32_t t[N + 2];
+    for (int i = 0; i < N + 2; i++) t[i] = 0;
+    for (int i = 0; i < N; i++) {
+        uint64_t c = 0;
+        for (int j = 0; j < N; j++) {
+            c += (uint64_t)A.v[j] * B.v[i] + t[j];
+            t[j] = (uint32_t)c;
+            c >>= 32;
+        }
+        c += t[N];
+        t[N] = (uint32_t)c;
+        t[N + 1] = (uint32_t)(c >> 32);
+        uint32_t m = t[0] * P::NP0;
+        c = ((uint64_t)m * P::mod(0) + t[0]) >> 32;
+        for (int j = 1; j < N; j++) {
+            c += (uint64_t)m * P::mod(j) + t[j];
+            t[j - 1] = (uint32_t)c;
+            c >>= 32;
+        }
+        c += t[N];
+        t[N - 1] = (uint32_t)c;
+        t[N] = t[N + 1] + (uint32_t)(c >> 32);
+    }
+    int64_t bw = 0;
+    uint32_t d[N];
+    for (int i = 0; i < N; i++) {
+        int64_t x = (int64_t)t[i] - P::mod(i) + bw;
+        d[i] = (uint32_t)x;
+        bw = x >> 32;
+    }
+    bool ge = t[N] != 0 || bw == 0;
+    for (int i = 0; i < N; i++) res.v[i] = ge ? d[i] : t[i];
+#endif
+    return res;
+}
+
+template <class P>
+HD Fp<P> sqr(const Fp<P>& a) { return mul(a, a); }
+
+template <class P>
+HD Fp<P> to_mont(const Fp<P>& a) { return mul(a, Fp<P>::r2()); }
+
+template <class P>
+HD Fp<P> from_mont(const Fp<P>& a) {
+    Fp<P> one = Fp<P>::zero();
+    one.v[0] = 1;
+    return mul(a, one);
+}
+
+// a^(p-2): the reference inverts with int_inverseMod (build_f1m.js:772-783); the inverse of
+// a non-zero residue is unique, so Fermat gives the same canonical bytes.  inverse(0) = 0.
+template <class P>
+HD Fp<P> inv(const Fp<P>& a) {
+    constexpr int N = P::N;
+    Fp<P> r = Fp<P>::one();
+    bool started = false;
+    for (int i = N - 1; i >= 0; i--) {
+        uint32_t w = P::pm2(i);
+        for (int b = 31; b >= 0; b--) {
+            if (started) r = sqr(r);
+            if ((w >> b) & 1) {
+                r = started ? mul(r, a) : a;
+                started = true;
+            }
+        }
+    }
+    return r;
+}
+
+template <class P>
+HD Fp<P> select(bool c, const Fp<P>& a, const Fp<P>& b) {   // c ? a : b
+    Fp<P> r;
+#pragma unroll
+    for (int i = 0; i < P::N; i++) r.v[i] = c ? a.v[i] : b.v[i];
+    return r;
+}
+
+using Fq = Fp<BN128_Fq>;
+using Fr = Fp<BN128_Fr>;
+
+}  // namespace ws
