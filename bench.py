@@ -1,0 +1,282 @@
+#!/usr/bin/env python3
+"""bench.py -- BASELINE.json metric on B200: BN128 G1 multi-scalar multiplication, n = 2^20
+scalar-point pairs (configs[1]); `python bench.py --gpus N --steps K --warmup W`.
+
+One step = one pass of the hot path over one batch of synthetic input: sum s_i * P_i for
+2^20 uniformly random RAW 256-bit scalars and 2^20 affine Montgomery G1 points.
+  value   pairs/s with inputs resident in HBM when the timed region starts (device-pointer ABI)
+  e2e     pairs/s through the host-buffer C ABI call (ws_bn128_g1_multiexp): pinned host
+          buffers, H2D of scalars+points and D2H of the 96-byte result inside the timed region
+  roofline  dominant kernel k_msm_accumulate: 96 algorithmic bytes per pair
+            / its CUDA-event duration, against the measured HBM copy peak
+  cpu_baseline  the reference's own g1m_multiexp2 (w = 7; compiled from its WASM image,
+            oracle/_ref) on a bounded sample, over the host cores, as src/bn128.js:353-383 splits
+`--impl reference` runs only that CPU arm and prints the same line shape.
+N > 1 (torchrun): contiguous point ranges per rank (the reference's split), one 128-byte
+all_gather of partial sums over NCCL, tiny on-device combine; strong scaling of one 2^20 job.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+LOG2N = int(os.environ.get("WS_BENCH_LOG2N", "20"))
+N_PAIRS = 1 << LOG2N
+ALG_BYTES_PER_PAIR = 96          # 32 B scalar + 64 B affine point
+KERNELS_PER_MSM = 14             # digits, 2x3 scan, scatter, filltasks, accumulate, combine, segreduce, bitsum, final
+
+
+def make_inputs(n, seed=0xB201):
+    import numpy as np
+    from oracle import bn128 as O
+    import util
+    aff, P0, D = util.arith_points(O.Fq, O.G1_GEN, n, 0xB202)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    scalars = rng.bytes(32 * n)
+    return scalars, util.g1_points_bytes(aff), P0, D
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            pass
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        out = self.p.communicate()[0]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_arm(scalars, points, sample_pairs, threads):
+    """The reference's g1m_multiexp2 over `threads` workers on the first `sample_pairs` pairs."""
+    import util
+    t0 = time.perf_counter()
+    util.ref_g1_multiexp_threads(scalars[:32 * sample_pairs], points[:64 * sample_pairs], nthreads=threads)
+    dt = time.perf_counter() - t0
+    return sample_pairs / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref_wasm
+    if not ref_wasm.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (reference not mounted at build time)"}))
+        return
+    cores = os.cpu_count() or 1
+    sample = min(N_PAIRS, 4096 * cores)
+    scalars, points, _, _ = make_inputs(sample)
+    vals = []
+    for k in range(args.warmup + args.steps):
+        v, dt = cpu_reference_arm(scalars, points, sample, cores)
+        if k >= args.warmup:
+            vals.append((v, dt))
+    v = sum(x for x, _ in vals) / len(vals)
+    ms = 1000.0 * sum(d for _, d in vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": "BN128 G1-MSM scalar-point pairs/sec (n=2^%d)" % LOG2N, "value": v, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs (256-bit Montgomery)", "data": "synthetic",
+        "config": {"workload": "BN128 G1 MSM, 2^%d random 256-bit scalar x affine point pairs" % LOG2N, "sample_pairs": sample},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "reference",
+                         "sample": "first %d pairs, %d threads x g1m_multiexp2(w=7) of the reference's WASM image compiled natively (oracle/_ref), partials combined with g1m_add" % (sample, cores)},
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from wasmsnark_b200 import build_bn128
+    import util
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W = max(3, args.warmup)
+
+    scalars, points, P0, D = make_inputs(N_PAIRS)
+    # contiguous range of this rank (src/bn128.js:353-361: floor(n/W) each, last takes the rest)
+    per = N_PAIRS // world
+    lo = rank * per
+    cnt = per if rank < world - 1 else N_PAIRS - per * (world - 1)
+    h_s = torch.frombuffer(bytearray(scalars[32 * lo:32 * (lo + cnt)]), dtype=torch.uint8).pin_memory()
+    h_p = torch.frombuffer(bytearray(points[64 * lo:64 * (lo + cnt)]), dtype=torch.uint8).pin_memory()
+    d_s, d_p = h_s.cuda(), h_p.cuda()
+    d_out = torch.zeros(256, dtype=torch.uint8, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    bn = build_bn128(local)
+    lib, h = bn.lib, bn.ctx.h
+    stream = torch.cuda.current_stream()
+    st = ctypes.c_void_p(stream.cuda_stream)
+
+    gathered = torch.zeros(world * 96, dtype=torch.uint8, device="cuda") if world > 1 else None
+
+    def step_dev():
+        bn.ctx.check(lib.ws_bn128_g1_multiexp_dev(h, d_s.data_ptr(), d_p.data_ptr(), cnt, d_out.data_ptr(), 0, st))
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, d_out[:96])
+            bn.ctx.check(lib.ws_bn128_g1_sum_dev(h, gathered.data_ptr(), world, d_out.data_ptr(), st))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- correctness of what is being timed (closed form of sum s_i (P0 + i D))
+    step_dev()
+    torch.cuda.synchronize()
+    if rank == 0:
+        import numpy as np
+        sc = [int.from_bytes(scalars[32 * i:32 * i + 32], "little") for i in range(N_PAIRS)]
+        want = util.closed_form_sum(sc, P0, D)
+        got = util.g1_result_tuple(bytes(d_out[:96].cpu().numpy()))
+        if got != want:
+            raise SystemExit("PARITY FAILURE: MSM result differs from the oracle")
+
+    # ---- device-resident timing
+    lib.ws_set_profiling(h, 1)
+    for _ in range(W):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    evs = []
+    stage_ms = {}
+    for _ in range(args.steps):
+        flush.fill_(1)                      # L2 flush (256 MiB), outside the timed events
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step_dev()
+        e1.record(stream)
+        evs.append((e0, e1))
+        torch.cuda.synchronize()
+        for nm, ms in bn.ctx.timings():
+            stage_ms[nm] = stage_ms.get(nm, 0.0) + ms
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    lib.ws_set_profiling(h, 0)
+
+    # ---- end to end through the host-buffer ABI (pinned host memory; H2D + D2H inside)
+    out_host = torch.zeros(96, dtype=torch.uint8).pin_memory()
+
+    def step_e2e():
+        bn.ctx.check(lib.ws_bn128_g1_multiexp(h, h_s.data_ptr(), h_p.data_ptr(), cnt, out_host.data_ptr()))
+        if world > 1:
+            d_out[:96].copy_(out_host, non_blocking=True)
+            dist.all_gather_into_tensor(gathered, d_out[:96])
+            bn.ctx.check(lib.ws_bn128_g1_sum_dev(h, gathered.data_ptr(), world, d_out.data_ptr(), st))
+            out_host.copy_(d_out[:96])
+    for _ in range(W):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        value = N_PAIRS / (ms_per_step * 1e-3)
+        acc_ms = stage_ms.get("accumulate", 0.0) / args.steps
+        peak, which = peaks()
+        achieved = (ALG_BYTES_PER_PAIR * cnt) / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else None
+        line = {
+            "metric": "BN128 G1-MSM scalar-point pairs/sec (n=2^%d)" % LOG2N, "value": value, "unit": "pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs (256-bit Montgomery)", "data": "synthetic",
+            "config": {"workload": "BN128 G1 MSM, 2^%d uniformly random raw 256-bit scalars x affine Montgomery points (BASELINE configs[1])" % LOG2N,
+                       "pairs": N_PAIRS, "parallelism": "point-range shard x%d + all_gather of 96-B partials" % world if world > 1 else "single GPU",
+                       "l2": "flushed between timed steps (256 MiB fill, outside the event pair)", "bit_exact_vs_oracle": True},
+            "clocks": clocks,
+            "e2e": {"value": N_PAIRS / (e2e_s / args.steps), "unit": "pairs/s", "h2d_bytes_per_step": 96 * cnt, "d2h_bytes_per_step": 96,
+                    "ms_per_step": 1000.0 * e2e_s / args.steps, "timer": "host perf_counter around the blocking C-ABI calls, max over ranks"},
+            "gpu_launches": KERNELS_PER_MSM * args.steps * 1,
+            "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate<G1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if achieved else None, "traffic": None, "peak_source": which,
+                         "kernel_ms": acc_ms, "note": "integer-multiply bound: 8M+2S Montgomery products per pair per window"},
+            "stages_ms": {k: v / args.steps for k, v in stage_ms.items()},
+        }
+        if not args.no_cpu_baseline:
+            from oracle import ref_wasm
+            if ref_wasm.available():
+                cores = os.cpu_count() or 1
+                sample = min(N_PAIRS, 2048 * cores)
+                v1, _ = cpu_reference_arm(scalars, points, min(sample, 4096), 1)
+                v, dt = cpu_reference_arm(scalars, points, sample, cores)
+                line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "reference", "single_thread_value": v1,
+                                        "sample": "first %d pairs (%.1f s), reference g1m_multiexp2(w=7) from its WASM image compiled natively, %d threads as src/bn128.js:353-383 splits; single-thread on %d pairs" % (sample, dt, cores, min(sample, 4096))}
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": "pairs/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+        print(json.dumps(line))
+    bn.terminate()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,111 @@
+/* wasmsnark_b200.h -- C ABI of libwasmsnark_b200.so: the B200 (sm_100a) replacement for the
+ * data-parallel proving path of iden3/wasmsnark.
+ *
+ * Every entry point below states the reference interface it replaces (paths relative to the
+ * reference checkout).  In the reference these are WebAssembly exports taking i32 offsets into
+ * one linear memory, driven by the JS host src/bn128.js; here they take plain host (or,
+ * for the *_dev variants, device) pointers and sizes.  All buffers use the reference's byte
+ * layouts unchanged: field elements are 8 (BN128) or 24 (MNT6753) 32-bit little-endian limbs;
+ * key points / coefficients are in Montgomery form (R = 2^256 resp. 2^768), witness scalars
+ * are plain and are consumed as raw 256-bit integers (never reduced).
+ *
+ * Return value: 0 on success, a negative WS_E_* code otherwise (ws_last_error() gives text).
+ * The library never falls back to a CPU implementation: without a usable CUDA device
+ * ws_create fails with WS_E_CUDA.
+ *
+ * Threading: a ws_ctx owns one CUDA device, one stream set and one workspace; calls on the
+ * same ctx must be serialised by the caller (the reference likewise has one in-flight command
+ * per worker, src/bn128.js:272-300).  Different ctx objects are independent.
+ */
+#ifndef WASMSNARK_B200_H
+#define WASMSNARK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ws_ctx ws_ctx;
+
+enum {
+    WS_OK = 0,
+    WS_E_ARG = -1,     /* null pointer, bad length, bad header, misaligned device pointer */
+    WS_E_SIZE = -2,    /* FFT size not a power of two or > 2^28 (reference traps: src/build_fft.js:137-154) */
+    WS_E_CUDA = -3,    /* CUDA runtime error (no device, out of memory, launch failure) */
+    WS_E_FIELD = -4    /* unknown field id */
+};
+
+/* field ids for the batch field operations */
+enum {
+    WS_BN128_FQ = 0,   /* f1m_*  : src/bn128/build_bn128.js:33 (q, :19)  */
+    WS_BN128_FR = 1,   /* frm_*  : src/bn128/build_bn128.js:34 (r, :20)  */
+    WS_MNT6753_FQ = 2  /* f1m_* of the MNT6753 image: src/mnt6753/build_mnt6753.js:19 */
+};
+
+/* ---- context -------------------------------------------------------------------------------
+ * Replaces buildBn128() (src/bn128.js:173-265): instead of 8 workers with a 320 MB WASM memory
+ * each, one CUDA context on `device` with a growable HBM workspace.                           */
+int ws_create(int device, ws_ctx** out);
+void ws_destroy(ws_ctx* ctx);                       /* Bn128.terminate(), src/bn128.js:562-566 */
+const char* ws_last_error(const ws_ctx* ctx);
+const char* ws_version(void);
+
+/* ---- field arithmetic (config C1 / C5) -----------------------------------------------------
+ * out[i] = x[i] (op) y[i] for n elements; x, y, out are n*32 bytes (n*96 for MNT6753).
+ * Replaces f1m_mul / frm_mul        src/build_f1m.js:235-436
+ *          f1m_add, f1m_sub         src/build_f1m.js:67-101
+ *          f1m_square               src/build_f1m.js:439-737      (y ignored)
+ *          f1m_toMontgomery / fromMontgomery  src/build_f1m.js:749-770   (y ignored)
+ *          f1m_inverse              src/build_f1m.js:772-783      (y ignored)
+ * and the batch forms fft_toMontgomeryN / fromMontgomeryN / mulN  src/build_fft.js:418-547.  */
+enum { WS_OP_MUL = 0, WS_OP_ADD = 1, WS_OP_SUB = 2, WS_OP_SQUARE = 3, WS_OP_TOMONT = 4, WS_OP_FROMMONT = 5, WS_OP_INVERSE = 6 };
+int ws_fp_batch(ws_ctx* ctx, int field, int op, const uint8_t* x, const uint8_t* y, uint8_t* out, size_t n);
+
+/* Fq2 (BN128, u^2 = -1) batch multiply: replaces f2m_mul src/build_f2m.js:127-163; 64-byte elements. */
+int ws_bn128_fq2_mul_batch(ws_ctx* ctx, const uint8_t* x, const uint8_t* y, uint8_t* out, size_t n);
+
+/* ---- multi-scalar multiplication (config C2) -------------------------------------------------
+ * Replaces Bn128.g1_multiexp(scalars, points)  src/bn128.js:353-383
+ *          -> worker G1_MULTIEXP               src/bn128.js:102-113
+ *          -> g1m_multiexp2(ps, pp, n, 7, pr)  src/build_multiexp.js:651-744
+ * scalars: n*32 bytes raw LE; points: n*64 bytes affine Montgomery (x == 0 means infinity,
+ * src/build_multiexp.js:335-349).  out: 96 bytes X|Y|Z Montgomery.  The reference returns an
+ * un-normalised Jacobian triple (callers must g1_affine it, src/bn128.js:706); this library
+ * returns the normalised representative of the same point: (x, y, 1), or (0, 1, 0) for infinity,
+ * i.e. exactly what g1m_affine of the reference's result gives (build_curve_jacobian_a0.js:424-457). */
+int ws_bn128_g1_multiexp(ws_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t out[96]);
+
+/* Replaces Bn128.g2_multiexp  src/bn128.js:385-415 -> G2_MULTIEXP :114-125 -> g2m_multiexp
+ * src/build_multiexp.js:498-580.  points: n*128 bytes (x.c0|x.c1|y.c0|y.c1); out: 192 bytes.   */
+int ws_bn128_g2_multiexp(ws_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t out[192]);
+
+/* Device-resident variants: d_scalars / d_points / d_out are device pointers (16-byte aligned)
+ * on the ctx's device, work is enqueued on `stream` (a cudaStream_t, may be NULL = ctx stream)
+ * and the call returns without synchronising.  d_out receives the same 96 / 192 bytes.
+ * window_bits = 0 picks the window size from n.                                                */
+int ws_bn128_g1_multiexp_dev(ws_ctx* ctx, const void* d_scalars, const void* d_points, size_t n, void* d_out, int window_bits, void* stream);
+int ws_bn128_g2_multiexp_dev(ws_ctx* ctx, const void* d_scalars, const void* d_points, size_t n, void* d_out, int window_bits, void* stream);
+
+/* Multi-GPU combine: d_parts holds `count` partial sums in the 96-byte (G1) / 192-byte (G2) result
+ * format above (e.g. all-gathered over NCCL from the ranks that each took a contiguous point range,
+ * as the reference's workers do, src/bn128.js:353-372); d_out receives their normalised sum.
+ * Replaces the serial g1m_add loop over worker results, src/bn128.js:376-380 / :408-412.          */
+int ws_bn128_g1_sum_dev(ws_ctx* ctx, const void* d_parts, int count, void* d_out, void* stream);
+int ws_bn128_g2_sum_dev(ws_ctx* ctx, const void* d_parts, int count, void* d_out, void* stream);
+
+/* Stage timing on/off (CUDA events recorded between the pipeline's kernels on the launch stream). */
+int ws_set_profiling(ws_ctx* ctx, int on);
+/* Tuning/test hook: force the per-task entry cap of the MSM accumulate kernel (0 = automatic). */
+int ws_set_msm_task_cap(ws_ctx* ctx, unsigned cap);
+
+/* Elapsed device time (ms, CUDA events on the launch stream) of the kernels enqueued by the last
+ * *_dev / host call on this ctx, split per pipeline stage; names[i] are static strings.
+ * Returns the number of stages written (<= cap).  Synchronises the ctx stream.                  */
+int ws_last_timings(ws_ctx* ctx, const char** names, float* ms, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WASMSNARK_B200_H */

@@ -1,0 +1,55 @@
+// host_msm.cpp -- sequential CPU emulation of the MSM pipeline's index logic
+// (msm_core.cuh bodies run thread by thread; the cooperative steps -- scan, warp combine,
+// block bit-sums -- are replaced by their serial definitions).  Test scaffolding only.
+#include <cstring>
+#include <vector>
+#include "../../wasmsnark_b200/csrc/msm_core.cuh"
+using namespace ws;
+
+template <class C>
+static void run(const uint8_t* scalars, const uint8_t* points, uint32_t n, int c, uint32_t T, uint8_t* out_affine) {
+    MsmPlan p = msm_make_plan(n, c, T);
+    const Affine<C>* pts = (const Affine<C>*)points;
+    std::vector<int16_t> digits((size_t)p.nwin * n);
+    std::vector<uint32_t> counts(p.nbuckets, 0), bstart(p.nbuckets + 1), tstart(p.nbuckets + 1);
+    for (uint32_t i = 0; i < n; i++) msm_digits_body(p, i, (const uint32_t*)scalars + (size_t)i * 8, pts[i].is_inf(), digits.data(), counts.data());
+    bstart[0] = 0; tstart[0] = 0;
+    for (uint32_t b = 0; b < p.nbuckets; b++) {
+        bstart[b + 1] = bstart[b] + counts[b];
+        tstart[b + 1] = tstart[b] + msm_ntasks(p, counts[b]);
+    }
+    std::vector<uint32_t> entries(bstart[p.nbuckets] + 1), task_bucket(p.max_tasks), heavy(p.nbuckets);
+    uint32_t nheavy = 0;
+    for (uint32_t i = 0; i < n; i++) msm_scatter_body(p, i, digits.data(), bstart.data(), counts.data(), entries.data());
+    for (uint32_t b = 0; b < p.nbuckets; b++) msm_filltasks_body(p, b, bstart.data(), tstart.data(), task_bucket.data(), heavy.data(), &nheavy);
+    uint32_t ntasks = tstart[p.nbuckets];
+    std::vector<XYZZ<C>> partials(ntasks + 1);
+    for (uint32_t t = 0; t < ntasks; t++) partials[t] = msm_accumulate_body<C>(p, t, bstart.data(), tstart.data(), task_bucket.data(), entries.data(), pts);
+    for (uint32_t h = 0; h < nheavy; h++) {   // combine (serial stand-in for the warp tree)
+        uint32_t b = heavy[h];
+        XYZZ<C> acc = partials[tstart[b]];
+        for (uint32_t t = tstart[b] + 1; t < tstart[b + 1]; t++) acc = padd<C>(acc, partials[t]);
+        partials[tstart[b]] = acc;
+    }
+    std::vector<XYZZ<C>> segA((size_t)p.nwin * p.S), segT((size_t)p.nwin * p.S), bits((size_t)p.nwin * (p.logS + 1)), R(p.nwin);
+    for (int w = 0; w < p.nwin; w++)
+        for (uint32_t s = 0; s < p.S; s++) msm_segreduce_body<C>(p, w, s, tstart.data(), partials.data(), segA.data(), segT.data());
+    for (int w = 0; w < p.nwin; w++) {        // bit sums (serial stand-in for the block reduction)
+        XYZZ<C>* bw = &bits[(size_t)w * (p.logS + 1)];
+        for (int k = 0; k <= p.logS; k++) bw[k] = XYZZ<C>::inf();
+        for (uint32_t s = 0; s < p.S; s++) {
+            bw[0] = padd<C>(bw[0], segA[(size_t)w * p.S + s]);
+            for (int k = 0; k < p.logS; k++)
+                if ((s >> k) & 1) bw[1 + k] = padd<C>(bw[1 + k], segT[(size_t)w * p.S + s]);
+        }
+    }
+    for (int w = 0; w < p.nwin; w++) R[w] = msm_window_value<C>(p, w, bits.data());
+    XYZZ<C> res = msm_horner_windows<C>(p, R.data());
+    Jac<C> a = to_affine<C>(res);
+    memcpy(out_affine, &a, sizeof(a));
+}
+
+extern "C" {
+void h_msm_g1(const uint8_t* scalars, const uint8_t* points, uint32_t n, int c, uint32_t T, uint8_t* out) { run<G1Curve>(scalars, points, n, c, T, out); }
+void h_msm_g2(const uint8_t* scalars, const uint8_t* points, uint32_t n, int c, uint32_t T, uint8_t* out) { run<G2Curve>(scalars, points, n, c, T, out); }
+}

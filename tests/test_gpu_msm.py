@@ -1,0 +1,112 @@
+"""C2 multi-scalar multiplication parity on the GPU, through the C ABI.
+
+ * small sets vs the definitional oracle sum (G1 and G2), every window size that changes the
+   carry-window shape, forced task splits (warp combine path);
+ * adversarial set: duplicates, P / -P, infinity (x = 0) entries, scalars {0,1,r-1,r,2^256-1,..};
+ * 2^14 prefix vs the reference's own g1m_multiexp2 (w = 7), after g1m_affine as
+   test/bn128_prover.js:31-46 compares;
+ * full size n = 2^20 (BASELINE.json configs[1]): raw 256-bit scalars and scalars < r, checked
+   with the closed form of sum s_i (P0 + i D) and, when oracle/_ref is present, against the
+   reference algorithm run over the host cores.
+"""
+import ctypes
+import random
+
+import pytest
+
+from oracle import bn128 as O
+from oracle import ref_wasm
+import util
+from util import RR, b32
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def bn():
+    from wasmsnark_b200 import build_bn128
+    b = build_bn128(0)
+    yield b
+    b.terminate()
+
+
+def dev_multiexp(bn, g, scalars_b, points_b, n, c=0, T=0):
+    """call the *_dev entry with explicit window bits (torch only allocates device memory)."""
+    import torch
+    psize, osize = (64, 96) if g == 1 else (128, 192)
+    ds = torch.frombuffer(bytearray(scalars_b), dtype=torch.uint8).cuda()
+    dp = torch.frombuffer(bytearray(points_b), dtype=torch.uint8).cuda()
+    dout = torch.zeros(256, dtype=torch.uint8, device="cuda")
+    fn = bn.lib.ws_bn128_g1_multiexp_dev if g == 1 else bn.lib.ws_bn128_g2_multiexp_dev
+    bn.lib.ws_set_msm_task_cap(bn.ctx.h, T)
+    st = torch.cuda.current_stream().cuda_stream
+    bn.ctx.check(fn(bn.ctx.h, ds.data_ptr(), dp.data_ptr(), n, dout.data_ptr(), c, ctypes.c_void_p(st)))
+    torch.cuda.synchronize()
+    bn.lib.ws_set_msm_task_cap(bn.ctx.h, 0)
+    return bytes(dout[:osize].cpu().numpy())
+
+
+def small_cases(F, gen, rnd, n):
+    from test_host_math import gen_points
+    from test_host_msm import adversarial
+    pts = gen_points(F, gen, rnd, n)
+    cases = [
+        ([rnd.getrandbits(256) for _ in range(n)], pts),
+        ([rnd.randrange(RR) for _ in range(n)], pts),
+        adversarial(F, gen, rnd, n),
+        ([5] * n, [pts[0]] * n),
+        ([0] * 4, pts[:4]),
+        ([(1 << 256) - 1], pts[:1]),
+        ([], []),
+    ]
+    return cases
+
+
+@pytest.mark.parametrize("g", [1, 2])
+def test_small_sets_vs_oracle(bn, g):
+    rnd = random.Random(100 + g)
+    F = O.Fq if g == 1 else O.Fq2
+    gen = O.G1_GEN if g == 1 else O.G2_GEN
+    enc = util.g1_affine_m if g == 1 else util.g2_affine_m
+    dec = util.g1_result_tuple if g == 1 else util.g2_result_tuple
+    for sc, ps in small_cases(F, gen, rnd, 40 if g == 1 else 20):
+        want = O.pt_affine(F, O.multiexp_naive(F, sc, ps))
+        sb = b"".join(b32(s) for s in sc)
+        pb = b"".join(enc(P) for P in ps)
+        host = bn.g1_multiexp(sb, pb) if g == 1 else bn.g2_multiexp(sb, pb)
+        assert dec(host) == want
+        if not sc:
+            continue
+        for c, T in ((16, 0), (13, 4), (7, 3), (4, 0), (2, 2), (11, 1)):
+            assert dec(dev_multiexp(bn, g, sb, pb, len(sc), c, T)) == want, (c, T, len(sc))
+
+
+@pytest.mark.skipif(not ref_wasm.available(), reason="oracle/_ref not built")
+def test_2p14_vs_reference_multiexp2(bn):
+    n = 1 << 14
+    aff, P0, D = util.arith_points(O.Fq, O.G1_GEN, n, 0xB202)
+    rnd = random.Random(0xB201)
+    sc = [rnd.getrandbits(256) for _ in range(n)]
+    for k in range(0, n, 97):          # sprinkle zeros / ones / small values like a real witness
+        sc[k] = (0, 1, rnd.getrandbits(32))[k % 3]
+    sb = b"".join(b32(s) for s in sc)
+    pb = bytearray(util.g1_points_bytes(aff))
+    for k in range(5, n, 251):         # some infinity entries (x = 0)
+        pb[64 * k:64 * k + 64] = bytes(64)
+    pb = bytes(pb)
+    want = util.ref_g1_multiexp_threads(sb, pb, nthreads=8)
+    assert bn.g1_multiexp(sb, pb) == want
+
+
+@pytest.mark.parametrize("reduced", [False, True])
+def test_full_size_2p20(bn, reduced):
+    n = 1 << 20
+    aff, P0, D = util.arith_points(O.Fq, O.G1_GEN, n, 0xB202)
+    rnd = random.Random(0xB201 + reduced)
+    sc = [rnd.randrange(RR) if reduced else rnd.getrandbits(256) for _ in range(n)]
+    sb = b"".join(b32(s) for s in sc)
+    pb = util.g1_points_bytes(aff)
+    got = bn.g1_multiexp(sb, pb)
+    assert util.g1_result_tuple(got) == util.closed_form_sum(sc, P0, D)
+    if ref_wasm.available() and not reduced:
+        assert got == util.ref_g1_multiexp_threads(sb, pb)

@@ -1,0 +1,83 @@
+"""Host-side mirror of the reference's `Bn128` class (/root/reference/src/bn128.js:267-720)
+over the CUDA library.  Same method names, argument meaning and result layouts, so code and
+tests written against the reference read the same here:
+
+    bn128 = build_bn128()                      # index.js:20-22 `buildBn128()`
+    r = bn128.g1_multiexp(scalars, points)     # src/bn128.js:353-383 -> 96 bytes X|Y|Z Montgomery
+    r = bn128.g2_multiexp(scalars, points)     # src/bn128.js:385-415 -> 192 bytes
+
+Differences, by design: calls are synchronous (the reference returns Promises resolved by its
+worker pool), and multiexp results come back already normalised to (x, y, 1) / (0, 1, 0) --
+the representative g1_affine() of the reference's result would give.
+"""
+import ctypes
+
+from . import _lib
+from ._lib import Context, as_ptr
+
+
+class Bn128:
+    # src/bn128.js:176-177
+    q = 21888242871839275222246405745257275088696311157297823662689037894645226208583
+    r = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    n8 = 32
+
+    def __init__(self, device=0):
+        self.ctx = Context(device)
+        self.lib = self.ctx.lib
+
+    # -- Bn128.terminate(), src/bn128.js:562-566
+    def terminate(self):
+        self.ctx.close()
+
+    def _multiexp(self, fn, scalars, points, psize, osize):
+        if len(scalars) % 32:
+            raise ValueError("scalars must be n*32 bytes")
+        n = len(scalars) // 32
+        if len(points) < n * psize:
+            raise ValueError("points buffer too short for %d scalars" % n)
+        out = ctypes.create_string_buffer(osize)
+        self.ctx.check(fn(self.ctx.h, as_ptr(scalars), as_ptr(points), n, ctypes.cast(out, ctypes.c_void_p)))
+        return out.raw
+
+    def g1_multiexp(self, scalars, points):
+        """src/bn128.js:353-383: scalars n*32 B raw LE, points n*64 B affine Montgomery."""
+        return self._multiexp(self.lib.ws_bn128_g1_multiexp, scalars, points, 64, 96)
+
+    def g2_multiexp(self, scalars, points):
+        """src/bn128.js:385-415: points n*128 B."""
+        return self._multiexp(self.lib.ws_bn128_g2_multiexp, scalars, points, 128, 192)
+
+    # -- field batches (WASM exports f1m_*/frm_*; batch forms fft_mulN etc.)
+    def fp_batch(self, field, op, x, y=None):
+        esz = 96 if field == _lib.FIELD_MNT6753_FQ else 32
+        n = len(x) // esz
+        out = ctypes.create_string_buffer(max(1, n * esz))
+        self.ctx.check(self.lib.ws_fp_batch(self.ctx.h, field, op, as_ptr(x), as_ptr(y), ctypes.cast(out, ctypes.c_void_p), n))
+        return out.raw[:n * esz]
+
+    def fq2_mul_batch(self, x, y):
+        n = len(x) // 64
+        out = ctypes.create_string_buffer(max(1, n * 64))
+        self.ctx.check(self.lib.ws_bn128_fq2_mul_batch(self.ctx.h, as_ptr(x), as_ptr(y), ctypes.cast(out, ctypes.c_void_p), n))
+        return out.raw[:n * 64]
+
+    # -- bin2int / bin2g1 / bin2g2, src/bn128.js:319-351
+    @staticmethod
+    def bin2int(b):
+        return str(int.from_bytes(b[:32], "little"))
+
+    @classmethod
+    def bin2g1(cls, b):
+        return [cls.bin2int(b[0:32]), cls.bin2int(b[32:64]), cls.bin2int(b[64:96])]
+
+    @classmethod
+    def bin2g2(cls, b):
+        return [[cls.bin2int(b[0:32]), cls.bin2int(b[32:64])],
+                [cls.bin2int(b[64:96]), cls.bin2int(b[96:128])],
+                [cls.bin2int(b[128:160]), cls.bin2int(b[160:192])]]
+
+
+def build_bn128(device=0):
+    """index.js:20-22 / src/bn128.js:173-265 `buildBn128()`."""
+    return Bn128(device)

@@ -1,0 +1,75 @@
+// ctx.cuh -- the library context: device, stream, growable HBM arenas, stage timer.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+
+#include "../../include/wasmsnark_b200.h"
+
+namespace ws {
+
+// CUDA-event stamps between pipeline stages, on the stream the kernels are launched on.
+struct StageTimer {
+    static constexpr int MAX = 48;
+    cudaEvent_t ev[MAX];
+    const char* name[MAX];
+    int n = 0;
+    bool enabled = false;
+    cudaStream_t last_stream = nullptr;
+    void begin(cudaStream_t st) {
+        n = 0;
+        last_stream = st;
+        mark("begin", st);
+    }
+    void mark(const char* nm, cudaStream_t st) {
+        if (!enabled || n >= MAX) return;
+        name[n] = nm;
+        cudaEventRecord(ev[n], st);
+        n++;
+    }
+};
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct Arena {
+    void* ptr = nullptr;
+    size_t size = 0;
+};
+
+}  // namespace ws
+
+struct ws_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    ws::Arena arenas[8];
+    ws::StageTimer timer;
+    std::string err;
+    unsigned force_T = 0;
+
+    // Arena `slot` grown to at least `bytes` (contents are scratch: not preserved on growth).
+    void* arena(int slot, size_t bytes) {
+        ws::Arena& a = arenas[slot];
+        if (a.size >= bytes && a.ptr) return a.ptr;
+        if (a.ptr) {
+            cudaStreamSynchronize(stream);
+            cudaFree(a.ptr);
+            a.ptr = nullptr;
+            a.size = 0;
+        }
+        size_t want = bytes + bytes / 8 + 4096;
+        if (cudaMalloc(&a.ptr, want) != cudaSuccess) {
+            a.ptr = nullptr;
+            return nullptr;
+        }
+        a.size = want;
+        return a.ptr;
+    }
+    int fail(int code, const char* msg) {
+        err = msg;
+        return code;
+    }
+    int fail_cuda(const char* where) {
+        cudaError_t e = cudaGetLastError();
+        err = std::string(where) + ": " + cudaGetErrorString(e);
+        return WS_E_CUDA;
+    }
+};

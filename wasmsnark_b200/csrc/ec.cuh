@@ -62,9 +62,10 @@ struct Jac {
 template <class C>
 HD XYZZ<C> pneg(const XYZZ<C>& p) { return XYZZ<C>{p.x, neg(p.y), p.zz, p.zzz}; }
 
-// 2*(x, y) for an affine, finite point   [mdbl-2008-s-1]
+// 2*(x, y) for an affine, finite point   [mdbl-2008-s-1].  Out of line: it is the rare
+// P == Q branch of the mixed addition and would only bloat the accumulate kernel.
 template <class C>
-HD XYZZ<C> dbl_affine(const Affine<C>& p) {
+HD_NOINLINE XYZZ<C> dbl_affine(const Affine<C>& p) {
     using F = typename C::F;
     F U = dbl(p.y);
     F V = sqr(U);
@@ -160,6 +161,25 @@ HD XYZZ<C> from_jac(const Jac<C>& p) {
     return XYZZ<C>{p.x, p.y, zz, mul(zz, p.z)};
 }
 
+// Out-of-line forms for the latency-bound tail kernels (segment reduce, bit sums, Horner):
+// one copy of the group law per curve instead of one per call site keeps the kernels small.
+template <class C>
+HD_NOINLINE void padd_to(XYZZ<C>* r, const XYZZ<C>* a, const XYZZ<C>* b) { *r = padd<C>(*a, *b); }
+template <class C>
+HD_NOINLINE void pdbl_to(XYZZ<C>* r, const XYZZ<C>* a) { *r = pdbl<C>(*a); }
+template <class C>
+HD XYZZ<C> padd_call(const XYZZ<C>& a, const XYZZ<C>& b) {
+    XYZZ<C> r;
+    padd_to<C>(&r, &a, &b);
+    return r;
+}
+template <class C>
+HD XYZZ<C> pdbl_call(const XYZZ<C>& a) {
+    XYZZ<C> r;
+    pdbl_to<C>(&r, &a);
+    return r;
+}
+
 // k * P, MSB first double-and-add over a little-endian byte string, as
 // g?m_timesScalar (/root/reference/src/build_timesscalar.js:20-77).
 template <class C>
@@ -168,8 +188,8 @@ HD XYZZ<C> times_scalar(const XYZZ<C>& p, const uint8_t* k, int len) {
     for (int i = len - 1; i >= 0; i--) {
         uint32_t byte = k[i];
         for (int b = 7; b >= 0; b--) {
-            r = pdbl<C>(r);
-            if ((byte >> b) & 1) r = padd<C>(r, p);
+            r = pdbl_call<C>(r);
+            if ((byte >> b) & 1) r = padd_call<C>(r, p);
         }
     }
     return r;

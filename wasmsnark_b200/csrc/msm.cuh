@@ -1,0 +1,384 @@
+// msm.cuh -- CUDA kernels and launch sequence of the MSM pipeline (see msm_core.cuh for the
+// algorithm and the reference citations).  sm_100a; integer pipe bound, no tensor cores.
+#pragma once
+#include <cuda_runtime.h>
+#include "ctx.cuh"
+#include "msm_core.cuh"
+
+namespace ws {
+
+// ------------------------------------------------------------------ small utilities
+template <class T>
+__device__ __forceinline__ T shfl_down_struct(const T& v, int off) {
+    static_assert(sizeof(T) % 4 == 0, "word-sized structs only");
+    T r;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&v);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 4); i++) dst[i] = __shfl_down_sync(0xFFFFFFFFu, src[i], off);
+    return r;
+}
+
+// 16-byte vector copy of a POD struct from global memory (structs are 32-byte multiples and
+// the arrays are 256-byte aligned device allocations).
+template <class T>
+__device__ __forceinline__ T ldg_struct(const T* p) {
+    static_assert(sizeof(T) % 16 == 0, "");
+    T r;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = __ldg(s + i);
+    return r;
+}
+template <class T>
+__device__ __forceinline__ void stg_struct(T* p, const T& v) {
+    static_assert(sizeof(T) % 16 == 0, "");
+    const uint4* s = reinterpret_cast<const uint4*>(&v);
+    uint4* d = reinterpret_cast<uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
+}
+
+// ------------------------------------------------------------------ exclusive scan (u32)
+// mode 0: value = in[i];  mode 1: value = ceil(in[i] / T).   out has n + 1 entries.
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t scan_value(uint32_t v, int mode, uint32_t T) { return mode ? (v + T - 1) / T : v; }
+
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                              uint32_t* __restrict__ tile_sums, uint32_t n, int mode, uint32_t T) {
+    __shared__ uint32_t warp_tot[SCAN_THREADS / 32];
+    uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        uint32_t x = (base + k < n) ? scan_value(in[base + k], mode, T) : 0u;
+        v[k] = sum;           // exclusive within the thread
+        sum += x;
+    }
+    // inclusive warp scan of the thread sums
+    uint32_t inc = sum;
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, off);
+        if (lane >= off) inc += t;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t t = lane < SCAN_THREADS / 32 ? warp_tot[lane] : 0u;
+        uint32_t ti = t;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t u = __shfl_up_sync(0xFFFFFFFFu, ti, off);
+            if (lane >= off) ti += u;
+        }
+        if (lane < SCAN_THREADS / 32) warp_tot[lane] = ti - t;   // exclusive warp offsets
+        if (lane == SCAN_THREADS / 32 - 1) tile_sums[blockIdx.x] = ti;
+    }
+    __syncthreads();
+    uint32_t off0 = warp_tot[wid] + (inc - sum);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++)
+        if (base + k < n) out[base + k] = off0 + v[k];
+}
+
+// single block: exclusive scan of the tile sums in place; total -> out[n]
+static __global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* __restrict__ tile_sums, uint32_t ntiles, uint32_t* __restrict__ out, uint32_t n) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < ntiles; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t x = i < ntiles ? tile_sums[i] : 0u;
+        uint32_t inc = x;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, off);
+            if (lane >= off) inc += t;
+        }
+        if (lane == 31) warp_tot[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t t = warp_tot[lane], ti = t;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t u = __shfl_up_sync(0xFFFFFFFFu, ti, off);
+                if (lane >= off) ti += u;
+            }
+            warp_tot[lane] = ti - t;
+        }
+        __syncthreads();
+        uint32_t carry = carry_s;
+        uint32_t excl = carry + warp_tot[wid] + inc - x;
+        if (i < ntiles) tile_sums[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = excl + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = carry_s;
+}
+
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t* __restrict__ out, const uint32_t* __restrict__ tile_sums, uint32_t n) {
+    uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t add = tile_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++)
+        if (base + k < n) out[base + k] += add;
+}
+
+// out[0..n] = exclusive scan; tile_sums: scratch of ceil(n / SCAN_TILE) words
+inline void launch_scan(const uint32_t* in, uint32_t* out, uint32_t* tile_sums, uint32_t n, int mode, uint32_t T, cudaStream_t st) {
+    uint32_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_tiles<<<ntiles, SCAN_THREADS, 0, st>>>(in, out, tile_sums, n, mode, T);
+    k_scan_sums<<<1, 1024, 0, st>>>(tile_sums, ntiles, out, n);
+    k_scan_add<<<ntiles, SCAN_THREADS, 0, st>>>(out, tile_sums, n);
+}
+
+// ------------------------------------------------------------------ MSM kernels
+template <class C>
+static __global__ void __launch_bounds__(256) k_msm_digits(MsmPlan p, const uint32_t* __restrict__ scalars, const Affine<C>* __restrict__ points,
+                                                    int16_t* __restrict__ digits, uint32_t* __restrict__ counts) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const uint4* sp = reinterpret_cast<const uint4*>(scalars) + (size_t)i * 2;
+    uint4 a = __ldg(sp), b = __ldg(sp + 1);
+    uint32_t s8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    typename C::F x = ldg_struct(&points[i].x);
+    msm_digits_body(p, i, s8, x.is_zero(), digits, counts);
+}
+
+static __global__ void __launch_bounds__(256) k_msm_scatter(MsmPlan p, const int16_t* __restrict__ digits, const uint32_t* __restrict__ bstart,
+                                                     uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    msm_scatter_body(p, i, digits, bstart, cursor, entries);
+}
+
+static __global__ void __launch_bounds__(256) k_msm_filltasks(MsmPlan p, const uint32_t* __restrict__ bstart, const uint32_t* __restrict__ tstart,
+                                                       uint32_t* __restrict__ task_bucket, uint32_t* __restrict__ heavy_list, uint32_t* heavy_count) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.nbuckets) return;
+    msm_filltasks_body(p, b, bstart, tstart, task_bucket, heavy_list, heavy_count);
+}
+
+// The dominant kernel: one thread per task, points gathered with 128-bit loads, XYZZ
+// accumulator in registers.
+template <class C, int THREADS, int MINB>
+static __global__ void __launch_bounds__(THREADS, MINB) k_msm_accumulate(MsmPlan p, const uint32_t* __restrict__ bstart, const uint32_t* __restrict__ tstart,
+                                                                  const uint32_t* __restrict__ task_bucket, const uint32_t* __restrict__ entries,
+                                                                  const Affine<C>* __restrict__ points, XYZZ<C>* __restrict__ partials) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t ntasks = tstart[p.nbuckets];
+    if (t >= ntasks) return;
+    uint32_t b = task_bucket[t];
+    uint32_t j = t - tstart[b];
+    uint32_t lo = bstart[b] + j * p.T;
+    uint32_t hi = bstart[b + 1];
+    if (hi > lo + p.T) hi = lo + p.T;
+    XYZZ<C> acc = XYZZ<C>::inf();
+    for (uint32_t k = lo; k < hi; k++) {
+        uint32_t e = __ldg(entries + k);
+        Affine<C> q = ldg_struct(points + (e & 0x7FFFFFFFu));
+        if (e >> 31) q.y = neg(q.y);
+        acc = pmadd<C>(acc, q);
+    }
+    stg_struct(partials + t, acc);
+}
+
+// Buckets split over several tasks: one warp per bucket, lanes stride over the partial sums,
+// then a shuffle tree.  The sum lands in the bucket's first partial slot.
+template <class C>
+static __global__ void __launch_bounds__(128) k_msm_combine(MsmPlan p, const uint32_t* __restrict__ tstart, const uint32_t* __restrict__ heavy_list,
+                                                     const uint32_t* __restrict__ heavy_count, XYZZ<C>* partials) {
+    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    int lane = threadIdx.x & 31;
+    uint32_t nh = *heavy_count;
+    for (uint32_t h = warp; h < nh; h += nwarps) {
+        uint32_t b = heavy_list[h];
+        uint32_t t0 = tstart[b], t1 = tstart[b + 1];
+        XYZZ<C> acc = XYZZ<C>::inf();
+        for (uint32_t t = t0 + lane; t < t1; t += 32) acc = padd_call<C>(acc, partials[t]);
+#pragma unroll 1
+        for (int off = 16; off > 0; off >>= 1) {
+            XYZZ<C> o = shfl_down_struct(acc, off);
+            acc = padd_call<C>(acc, o);
+        }
+        if (lane == 0) partials[t0] = acc;
+    }
+}
+
+template <class C>
+static __global__ void __launch_bounds__(128) k_msm_segreduce(MsmPlan p, const uint32_t* __restrict__ tstart, const XYZZ<C>* __restrict__ partials,
+                                                       XYZZ<C>* __restrict__ segA, XYZZ<C>* __restrict__ segT) {
+    uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint32_t)p.nwin * p.S) return;
+    msm_segreduce_body<C>(p, idx / p.S, idx % p.S, tstart, partials, segA, segT);
+}
+
+// grid (nwin, logS + 1): plane 0 sums the A's, plane 1+k sums the T's of segments with bit k set
+template <class C>
+static __global__ void __launch_bounds__(256) k_msm_bitsum(MsmPlan p, const XYZZ<C>* __restrict__ segA, const XYZZ<C>* __restrict__ segT, XYZZ<C>* __restrict__ bits) {
+    __shared__ XYZZ<C> wsum[8];
+    uint32_t w = blockIdx.x;
+    int k = blockIdx.y;
+    XYZZ<C> acc = XYZZ<C>::inf();
+    for (uint32_t s = threadIdx.x; s < p.S; s += blockDim.x) {
+        if (k == 0) {
+            acc = padd_call<C>(acc, segA[(size_t)w * p.S + s]);
+        } else if ((s >> (k - 1)) & 1) {
+            acc = padd_call<C>(acc, segT[(size_t)w * p.S + s]);
+        }
+    }
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll 1
+    for (int off = 16; off > 0; off >>= 1) {
+        XYZZ<C> o = shfl_down_struct(acc, off);
+        acc = padd_call<C>(acc, o);
+    }
+    if (lane == 0) wsum[wid] = acc;
+    __syncthreads();
+    if (wid == 0) {
+        acc = lane < (int)(blockDim.x >> 5) ? wsum[lane] : XYZZ<C>::inf();
+#pragma unroll 1
+        for (int off = 4; off > 0; off >>= 1) {
+            XYZZ<C> o = shfl_down_struct(acc, off);
+            acc = padd_call<C>(acc, o);
+        }
+        if (lane == 0) bits[(size_t)w * (p.logS + 1) + k] = acc;
+    }
+}
+
+// one block: thread w builds its window value, thread 0 runs the Horner over windows.
+// out_xyzz: the sum (device consumers); out_jac: (x, y, 1) / (0, 1, 0), Montgomery.
+template <class C>
+static __global__ void __launch_bounds__(160) k_msm_final(MsmPlan p, const XYZZ<C>* __restrict__ bits, XYZZ<C>* R, XYZZ<C>* out_xyzz, Jac<C>* out_jac) {
+    int w = threadIdx.x;
+    if (w < p.nwin) R[w] = msm_window_value<C>(p, w, bits);
+    __syncthreads();
+    if (w == 0) {
+        XYZZ<C> res = msm_horner_windows<C>(p, R);
+        if (out_xyzz) *out_xyzz = res;
+        if (out_jac) *out_jac = to_affine<C>(res);
+    }
+}
+
+// Sum of `count` points given as normalised / Jacobian triples; result normalised.
+template <class C>
+__global__ void __launch_bounds__(32) k_sum_points(const Jac<C>* __restrict__ in, int count, Jac<C>* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    XYZZ<C> acc = XYZZ<C>::inf();
+    for (int i = 0; i < count; i++) acc = padd_call<C>(acc, from_jac<C>(in[i]));
+    *out = to_affine<C>(acc);
+}
+
+// ------------------------------------------------------------------ workspace + launch
+struct MsmWorkspace {
+    int16_t* digits;
+    uint32_t *counts, *cursor, *bstart, *tstart, *tile_sums, *entries, *task_bucket, *heavy_list, *heavy_count;
+    void *partials, *segA, *segT, *bits, *R;
+};
+
+// Carves the workspace out of one device buffer; returns bytes needed (base may be null to size).
+template <class C>
+inline size_t msm_carve(const MsmPlan& p, uint8_t* base, MsmWorkspace* ws) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        uint8_t* ptr = base ? base + off : nullptr;
+        off += align256(bytes);
+        return ptr;
+    };
+    size_t entries = (size_t)p.nwin * p.n;
+    uint8_t* d = take(entries * sizeof(int16_t));
+    uint8_t* cn = take((size_t)p.nbuckets * 4);
+    uint8_t* cu = take((size_t)p.nbuckets * 4);
+    uint8_t* bs = take(((size_t)p.nbuckets + 1) * 4);
+    uint8_t* ts = take(((size_t)p.nbuckets + 1) * 4);
+    uint8_t* tl = take(((size_t)p.nbuckets / SCAN_TILE + 2) * 4);
+    uint8_t* en = take((entries + 1) * 4);
+    uint8_t* tb = take((size_t)p.max_tasks * 4);
+    uint8_t* hl = take((size_t)p.nbuckets * 4);
+    uint8_t* hc = take(256);
+    uint8_t* pa = take((size_t)p.max_tasks * sizeof(XYZZ<C>));
+    uint8_t* sa = take((size_t)p.nwin * p.S * sizeof(XYZZ<C>));
+    uint8_t* sT = take((size_t)p.nwin * p.S * sizeof(XYZZ<C>));
+    uint8_t* bi = take((size_t)p.nwin * (p.logS + 1) * sizeof(XYZZ<C>));
+    uint8_t* rr = take((size_t)p.nwin * sizeof(XYZZ<C>));
+    if (ws) {
+        ws->digits = (int16_t*)d;
+        ws->counts = (uint32_t*)cn;
+        ws->cursor = (uint32_t*)cu;
+        ws->bstart = (uint32_t*)bs;
+        ws->tstart = (uint32_t*)ts;
+        ws->tile_sums = (uint32_t*)tl;
+        ws->entries = (uint32_t*)en;
+        ws->task_bucket = (uint32_t*)tb;
+        ws->heavy_list = (uint32_t*)hl;
+        ws->heavy_count = (uint32_t*)hc;
+        ws->partials = pa;
+        ws->segA = sa;
+        ws->segT = sT;
+        ws->bits = bi;
+        ws->R = rr;
+    }
+    return off;
+}
+
+// Window size / task cap for n pairs on a 148-SM part.
+inline void msm_choose(uint32_t n, int* c, uint32_t* T) {
+    int lg = 0;
+    while ((1ull << (lg + 1)) <= n) lg++;
+    int cc = lg - 4;
+    if (cc < 4) cc = 4;
+    if (cc > 16) cc = 16;
+    *c = cc;
+    int nwin = (257 + cc - 1) / cc;
+    uint64_t entries = (uint64_t)nwin * n;
+    uint64_t want_tasks = 148ull * 512ull * 4ull;     // a few waves of resident threads
+    uint64_t t = entries / want_tasks;
+    if (t < 8) t = 8;
+    if (t > 64) t = 64;
+    *T = (uint32_t)t;
+}
+
+template <class C>
+inline cudaError_t msm_launch(const MsmPlan& p, const MsmWorkspace& w, const uint32_t* d_scalars, const Affine<C>* d_points,
+                              XYZZ<C>* d_out_xyzz, Jac<C>* d_out_jac, cudaStream_t st, StageTimer* tm = nullptr) {
+    using X = XYZZ<C>;
+    auto mark = [&](const char* nm) { if (tm) tm->mark(nm, st); };
+    cudaMemsetAsync(w.counts, 0, (size_t)p.nbuckets * 4, st);
+    cudaMemsetAsync(w.heavy_count, 0, 4, st);
+    if (p.n) k_msm_digits<C><<<(p.n + 255) / 256, 256, 0, st>>>(p, d_scalars, d_points, w.digits, w.counts);
+    mark("digits");
+    launch_scan(w.counts, w.bstart, w.tile_sums, p.nbuckets, 0, 1, st);
+    launch_scan(w.counts, w.tstart, w.tile_sums, p.nbuckets, 1, p.T, st);
+    cudaMemcpyAsync(w.cursor, w.counts, (size_t)p.nbuckets * 4, cudaMemcpyDeviceToDevice, st);
+    mark("scan");
+    if (p.n) k_msm_scatter<<<(p.n + 255) / 256, 256, 0, st>>>(p, w.digits, w.bstart, w.cursor, w.entries);
+    k_msm_filltasks<<<(p.nbuckets + 255) / 256, 256, 0, st>>>(p, w.bstart, w.tstart, w.task_bucket, w.heavy_list, w.heavy_count);
+    mark("scatter");
+    constexpr int AT = sizeof(typename C::F) > 32 ? 128 : 256;
+    constexpr int AB = sizeof(typename C::F) > 32 ? 1 : 2;
+    k_msm_accumulate<C, AT, AB><<<(p.max_tasks + AT - 1) / AT, AT, 0, st>>>(p, w.bstart, w.tstart, w.task_bucket, w.entries, d_points, (X*)w.partials);
+    mark("accumulate");
+    k_msm_combine<C><<<148 * 4, 128, 0, st>>>(p, w.tstart, w.heavy_list, w.heavy_count, (X*)w.partials);
+    mark("combine");
+    uint32_t nseg = (uint32_t)p.nwin * p.S;
+    k_msm_segreduce<C><<<(nseg + 127) / 128, 128, 0, st>>>(p, w.tstart, (const X*)w.partials, (X*)w.segA, (X*)w.segT);
+    mark("segreduce");
+    k_msm_bitsum<C><<<dim3(p.nwin, p.logS + 1), 256, 0, st>>>(p, (const X*)w.segA, (const X*)w.segT, (X*)w.bits);
+    mark("bitsum");
+    k_msm_final<C><<<1, 160, 0, st>>>(p, (const X*)w.bits, (X*)w.R, d_out_xyzz, d_out_jac);
+    mark("final");
+    return cudaGetLastError();
+}
+
+}  // namespace ws

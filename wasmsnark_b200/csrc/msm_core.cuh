@@ -1,0 +1,210 @@
+// msm_core.cuh -- per-thread bodies of the multi-scalar-multiplication pipeline.
+//
+// Replaces g1m_multiexp2 / g2m_multiexp of the reference
+//   /root/reference/src/build_multiexp.js:498-580 (multiexp), :651-744 (multiexp2),
+//   called with w = 7 from /root/reference/src/bn128.js:109,121
+// with a bucket (Pippenger) method.  What is kept from the reference, because it decides the
+// result: scalars are RAW 256-bit little-endian integers, never reduced mod r
+// (build_multiexp.js:30-155 slices all 256 bits); an affine key point whose x coordinate is
+// zero is the point at infinity (:335-349); the sum is a group element, compared after
+// g?m_affine.  What is free and changed: window size, bucketing, summation order.
+//
+// Pipeline (one launch each, all on one stream, no host round trip):
+//   digits     signed c-bit digits of every scalar (carry into a possible extra window),
+//              bucket histogram with global atomics
+//   scan       exclusive scan of the histogram -> bucket offsets; second scan of
+//              ceil(len/T) -> task offsets
+//   scatter    counting sort of (point index, sign) into bucket order
+//   accumulate one thread per task (<= T entries of one bucket): gather affine points,
+//              8M+2S mixed additions into an XYZZ register accumulator
+//   combine    buckets split over several tasks: one warp per bucket, shuffle tree
+//   segreduce  per segment of L consecutive buckets: running-sum pair (A, T)
+//   bitsum     per window: sum of A's and the log2(S) bit-plane sums of the T's
+//   final      per window Horner over bit planes, then Horner over windows, affine
+//
+// The bodies below are HD so that tests/host/host_msm.cpp can run the identical index
+// logic sequentially on a CPU (no GPU in the build container); the cooperative steps
+// (scan, warp combine, block bit-sum) have their parallel versions in msm.cuh.
+#pragma once
+#include "ec.cuh"
+
+namespace ws {
+
+struct MsmPlan {
+    uint32_t n;        // number of (scalar, point) pairs
+    int c;             // window bits, 2..16
+    int nwin;          // windows incl. the carry window: ceil(257 / c)
+    uint32_t B;        // buckets per window = 2^(c-1); bucket b holds digit magnitude b+1
+    uint32_t T;        // max entries per accumulate task
+    uint32_t L;        // buckets per reduce segment (power of two, <= B)
+    uint32_t S;        // segments per window = B / L
+    int logS;
+    uint32_t nbuckets; // nwin * B
+    uint32_t max_tasks;
+};
+
+HD MsmPlan msm_make_plan(uint32_t n, int c, uint32_t T) {
+    MsmPlan p;
+    p.n = n;
+    p.c = c;
+    p.nwin = (257 + c - 1) / c;
+    p.B = 1u << (c - 1);
+    p.T = T;
+    p.L = p.B < 8 ? p.B : 8;
+    p.S = p.B / p.L;
+    p.logS = 0;
+    while ((1u << p.logS) < p.S) p.logS++;
+    p.nbuckets = (uint32_t)p.nwin * p.B;
+    uint64_t entries = (uint64_t)p.nwin * n;
+    p.max_tasks = (uint32_t)(entries / T) + p.nbuckets + 1;
+    return p;
+}
+
+HD uint32_t atomic_add_u32(uint32_t* p, uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return atomicAdd(p, v);
+#else
+    uint32_t o = *p;
+    *p = o + v;
+    return o;
+#endif
+}
+
+// ---- digits: thread i ------------------------------------------------------------------
+// scalar8: the 8 u32 limbs (raw, LE) of scalar i.  is_inf: point i is infinity (x == 0).
+// digits[w * n + i] = signed digit in [-2^(c-1), 2^(c-1)), counts[w * B + |d| - 1]++.
+HD void msm_digits_body(const MsmPlan& p, uint32_t i, const uint32_t* scalar8, bool is_inf,
+                        int16_t* digits, uint32_t* counts) {
+    uint32_t s[9];
+#pragma unroll
+    for (int k = 0; k < 8; k++) s[k] = is_inf ? 0u : scalar8[k];
+    s[8] = 0;
+    const uint32_t mask = (1u << p.c) - 1u;
+    const uint32_t half = 1u << (p.c - 1);
+    uint32_t carry = 0;
+    for (int w = 0; w < p.nwin; w++) {
+        int bit = w * p.c;
+        uint32_t raw = 0;
+        if (bit < 256) {
+            int limb = bit >> 5, sh = bit & 31;
+            uint64_t two = (uint64_t)s[limb] | ((uint64_t)s[limb + 1] << 32);
+            raw = (uint32_t)(two >> sh) & mask;
+        }
+        uint32_t d = raw + carry;            // 0 .. 2^c
+        int32_t sd;
+        if (d >= half && w != p.nwin - 1) {   // the top window keeps its sign: nothing above it takes a carry
+            sd = (int32_t)d - (int32_t)(mask + 1u);   // -2^(c-1) .. 0
+            carry = 1;
+        } else {
+            sd = (int32_t)d;
+            carry = 0;
+        }
+        digits[(size_t)w * p.n + i] = (int16_t)sd;
+        if (sd != 0) {
+            uint32_t mag = sd < 0 ? (uint32_t)(-sd) : (uint32_t)sd;
+            atomic_add_u32(&counts[(size_t)w * p.B + (mag - 1)], 1u);
+        }
+    }
+}
+
+// ---- scatter: thread i -----------------------------------------------------------------
+// cursor[] starts as a copy of the histogram and is counted down; entries[] receives
+// (i | sign << 31) grouped by bucket (order inside a bucket is irrelevant to the sum).
+HD void msm_scatter_body(const MsmPlan& p, uint32_t i, const int16_t* digits, const uint32_t* bstart,
+                         uint32_t* cursor, uint32_t* entries) {
+    for (int w = 0; w < p.nwin; w++) {
+        int32_t sd = digits[(size_t)w * p.n + i];
+        if (sd == 0) continue;
+        uint32_t neg = sd < 0;
+        uint32_t mag = neg ? (uint32_t)(-sd) : (uint32_t)sd;
+        size_t b = (size_t)w * p.B + (mag - 1);
+        uint32_t k = atomic_add_u32(&cursor[b], 0xFFFFFFFFu) - 1u;   // counts down to 0
+        entries[bstart[b] + k] = i | (neg << 31);
+    }
+}
+
+// ---- task table: thread b (one per bucket) ----------------------------------------------
+HD uint32_t msm_ntasks(const MsmPlan& p, uint32_t len) { return (len + p.T - 1) / p.T; }
+
+HD void msm_filltasks_body(const MsmPlan& p, uint32_t b, const uint32_t* bstart, const uint32_t* tstart,
+                           uint32_t* task_bucket, uint32_t* heavy_list, uint32_t* heavy_count) {
+    uint32_t t0 = tstart[b], t1 = tstart[b + 1];
+    for (uint32_t t = t0; t < t1; t++) task_bucket[t] = b;
+    if (t1 - t0 > 1) heavy_list[atomic_add_u32(heavy_count, 1u)] = b;
+}
+
+// ---- accumulate: thread t (one per task) ------------------------------------------------
+template <class C>
+HD XYZZ<C> msm_accumulate_body(const MsmPlan& p, uint32_t t, const uint32_t* bstart, const uint32_t* tstart,
+                               const uint32_t* task_bucket, const uint32_t* entries, const Affine<C>* points) {
+    uint32_t b = task_bucket[t];
+    uint32_t j = t - tstart[b];
+    uint32_t lo = bstart[b] + j * p.T;
+    uint32_t hi = bstart[b + 1];
+    if (hi > lo + p.T) hi = lo + p.T;
+    XYZZ<C> acc = XYZZ<C>::inf();
+    for (uint32_t k = lo; k < hi; k++) {
+        uint32_t e = entries[k];
+        Affine<C> q = points[e & 0x7FFFFFFFu];
+        if (e >> 31) q.y = neg(q.y);
+        acc = pmadd<C>(acc, q);
+    }
+    return acc;
+}
+
+// ---- bucket value seen by the reduce phase ------------------------------------------------
+template <class C>
+HD XYZZ<C> msm_bucket_value(const uint32_t* tstart, const XYZZ<C>* partials, size_t b) {
+    uint32_t t0 = tstart[b];
+    if (tstart[b + 1] == t0) return XYZZ<C>::inf();
+    return partials[t0];
+}
+
+// ---- segreduce: thread (w, s) ------------------------------------------------------------
+// Over buckets b = s*L .. s*L+L-1 of window w (weights b+1):
+//   T = sum S_b ;  A = sum (b - s*L + 1) * S_b      (running-sum trick, 2 adds per bucket)
+template <class C>
+HD void msm_segreduce_body(const MsmPlan& p, uint32_t w, uint32_t s, const uint32_t* tstart,
+                           const XYZZ<C>* partials, XYZZ<C>* segA, XYZZ<C>* segT) {
+    XYZZ<C> run = XYZZ<C>::inf(), acc = XYZZ<C>::inf();
+    size_t base = (size_t)w * p.B + (size_t)s * p.L;
+    bool any = false;
+    for (int k = (int)p.L - 1; k >= 0; k--) {
+        XYZZ<C> v = msm_bucket_value<C>(tstart, partials, base + k);
+        if (!v.is_inf()) {
+            run = padd_call<C>(run, v);
+            any = true;
+        }
+        if (any) acc = padd_call<C>(acc, run);
+    }
+    segA[(size_t)w * p.S + s] = acc;
+    segT[(size_t)w * p.S + s] = run;
+}
+
+// ---- final: window value from the bit-plane sums, then Horner over windows ------------------
+// bits[w * (logS + 1) + 0] = sum_s A_s ; bits[w * (logS+1) + 1 + k] = sum_{s : bit k of s} T_s
+//   R_w = A + L * sum_k 2^k * bit_k
+template <class C>
+HD XYZZ<C> msm_window_value(const MsmPlan& p, uint32_t w, const XYZZ<C>* bits) {
+    const XYZZ<C>* bw = bits + (size_t)w * (p.logS + 1);
+    XYZZ<C> acc = XYZZ<C>::inf();
+    for (int k = p.logS - 1; k >= 0; k--) {
+        acc = pdbl_call<C>(acc);
+        acc = padd_call<C>(acc, bw[1 + k]);
+    }
+    for (uint32_t l = p.L; l > 1; l >>= 1) acc = pdbl_call<C>(acc);
+    return padd_call<C>(acc, bw[0]);
+}
+
+template <class C>
+HD XYZZ<C> msm_horner_windows(const MsmPlan& p, const XYZZ<C>* R) {
+    XYZZ<C> res = R[p.nwin - 1];
+    for (int w = p.nwin - 2; w >= 0; w--) {
+        if (!res.is_inf())
+            for (int k = 0; k < p.c; k++) res = pdbl_call<C>(res);
+        res = padd_call<C>(res, R[w]);
+    }
+    return res;
+}
+
+}  // namespace ws

@@ -1,0 +1,21 @@
+// msm_g1.cu -- BN128 G1 instantiation of the MSM pipeline + its C ABI entry points.
+#include "msm_impl.cuh"
+using namespace ws;
+
+extern "C" {
+WS_API int ws_bn128_g1_multiexp(ws_ctx* c, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t out[96]) {
+    return multiexp_host<G1Curve>(c, scalars, points, n, out);
+}
+WS_API int ws_bn128_g1_multiexp_dev(ws_ctx* c, const void* ds, const void* dp, size_t n, void* dout, int wb, void* stream) {
+    if (!c || !dout || (n && (!ds || !dp))) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
+    cudaSetDevice(c->device);
+    return multiexp_dev<G1Curve>(c, ds, dp, n, dout, wb, stream ? (cudaStream_t)stream : c->stream);
+}
+WS_API int ws_bn128_g1_sum_dev(ws_ctx* c, const void* d_parts, int count, void* d_out, void* stream) {
+    if (!c || !d_parts || !d_out || count < 0) return c ? c->fail(WS_E_ARG, "bad argument") : WS_E_ARG;
+    cudaSetDevice(c->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    k_sum_points<G1Curve><<<1, 32, 0, st>>>((const Jac<G1Curve>*)d_parts, count, (Jac<G1Curve>*)d_out);
+    return cudaGetLastError() == cudaSuccess ? WS_OK : c->fail_cuda("sum_points");
+}
+}

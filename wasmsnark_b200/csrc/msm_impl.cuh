@@ -1,0 +1,58 @@
+// msm_impl.cuh -- host-side driver of the MSM pipeline, instantiated per curve in
+// msm_g1.cu / msm_g2.cu (separate translation units so they compile in parallel).
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/wasmsnark_b200.h"
+#include "ctx.cuh"
+#include "msm.cuh"
+
+#define WS_API __attribute__((visibility("default")))
+
+namespace ws {
+
+template <class C>
+inline int multiexp_dev(ws_ctx* c, const void* d_scalars, const void* d_points, size_t n, void* d_out, int window_bits, cudaStream_t st) {
+    if (n > 0x7FFFFFFFull) return c->fail(WS_E_ARG, "n too large");
+    if (((uintptr_t)d_scalars | (uintptr_t)d_points | (uintptr_t)d_out) & 15) return c->fail(WS_E_ARG, "device pointers must be 16-byte aligned");
+    int cb;
+    uint32_t T;
+    msm_choose((uint32_t)n, &cb, &T);
+    if (window_bits) {
+        if (window_bits < 2 || window_bits > 16) return c->fail(WS_E_ARG, "window_bits must be in 2..16");
+        cb = window_bits;
+    }
+    if (c->force_T) T = c->force_T;
+    MsmPlan p = msm_make_plan((uint32_t)n, cb, T);
+    size_t need = msm_carve<C>(p, nullptr, nullptr);
+    uint8_t* base = (uint8_t*)c->arena(1, need);
+    if (!base) return c->fail_cuda("msm workspace");
+    MsmWorkspace w;
+    msm_carve<C>(p, base, &w);
+    c->timer.begin(st);
+    cudaError_t e = msm_launch<C>(p, w, (const uint32_t*)d_scalars, (const Affine<C>*)d_points, nullptr, (Jac<C>*)d_out, st, &c->timer);
+    if (e != cudaSuccess) return c->fail_cuda("msm launch");
+    return WS_OK;
+}
+
+template <class C>
+inline int multiexp_host(ws_ctx* c, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t* out) {
+    if (!c || !out || (n && (!scalars || !points))) return c ? c->fail(WS_E_ARG, "null buffer") : WS_E_ARG;
+    cudaSetDevice(c->device);
+    constexpr size_t PS = sizeof(Affine<C>), OS = sizeof(Jac<C>);
+    uint8_t* d = (uint8_t*)c->arena(0, align256(n * 32) + align256(n * PS) + 256);
+    if (!d) return c->fail_cuda("input workspace");
+    uint8_t *ds = d, *dp = d + align256(n * 32), *dout = dp + align256(n * PS);
+    if (n) {
+        cudaMemcpyAsync(ds, scalars, n * 32, cudaMemcpyHostToDevice, c->stream);
+        cudaMemcpyAsync(dp, points, n * PS, cudaMemcpyHostToDevice, c->stream);
+    }
+    int rc = multiexp_dev<C>(c, ds, dp, n, dout, 0, c->stream);
+    if (rc) return rc;
+    cudaMemcpyAsync(out, dout, OS, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) return c->fail_cuda("multiexp");
+    return WS_OK;
+}
+
+
+
+}  // namespace ws
