@@ -34,13 +34,23 @@ ALG_BYTES_PER_PAIR = 96          # 32 B scalar + 64 B affine point (SURVEY.md 8d
 KERNELS_PER_MSM = 14             # digits, 2x3 scan, scatter, filltasks, accumulate, combine, segreduce, bitsum, final
 
 
-def make_inputs(n, seed=0xB201):
+SCALARS = os.environ.get("WS_BENCH_SCALARS", "fr")      # "fr": uniform in [0, r) ; "raw256": uniform 256-bit
+
+
+def make_inputs(n, seed=0xB201, dist=None):
     import numpy as np
     from oracle import bn128 as O
     import util
+    dist = dist or SCALARS
     aff, P0, D = util.arith_points(O.Fq, O.G1_GEN, n, 0xB202)
     rng = np.random.Generator(np.random.PCG64(seed))
-    scalars = rng.bytes(32 * n)
+    if dist == "raw256":
+        scalars = rng.bytes(32 * n)
+    else:
+        # uniform field elements: 320 random bits reduced mod r (bias < 2^-64), 32-byte LE
+        raw = rng.bytes(40 * n)
+        r = O.R_ORDER
+        scalars = b"".join((int.from_bytes(raw[40 * i:40 * i + 40], "little") % r).to_bytes(32, "little") for i in range(n))
     return scalars, util.g1_points_bytes(aff), P0, D
 
 
@@ -162,8 +172,10 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     bn = build_bn128(local)
     lib, h = bn.lib, bn.ctx.h
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()            # a real (non-legacy) stream: the library launches on it
+    torch.cuda.set_stream(stream)
     st = ctypes.c_void_p(stream.cuda_stream)
+    assert stream.cuda_stream != 0
 
     gathered = torch.zeros(world * 96, dtype=torch.uint8, device="cuda") if world > 1 else None
 
@@ -185,7 +197,7 @@ def main():
         import numpy as np
         sc = [int.from_bytes(scalars[32 * i:32 * i + 32], "little") for i in range(N_PAIRS)]
         want = util.closed_form_sum(sc, P0, D)
-        got = util.g1_result_tuple(bytes(d_out[:96].cpu().numpy()))
+        got = util.g1_result_tuple(bn.g1_affine(bytes(d_out[:96].cpu().numpy())))
         if got != want:
             raise SystemExit("PARITY FAILURE: MSM result differs from the oracle")
 
@@ -249,7 +261,7 @@ def main():
             "metric": "BN128 G1-MSM scalar-point pairs/sec (n=2^%d)" % LOG2N, "value": value, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs (256-bit Montgomery)", "data": "synthetic",
-            "config": {"workload": "BN128 G1 MSM, 2^%d uniformly random raw 256-bit scalars x affine Montgomery points (BASELINE configs[1])" % LOG2N,
+            "config": {"workload": "BN128 G1 MSM, 2^%d scalar-point pairs (BASELINE configs[1]): scalars %s, affine Montgomery points" % (LOG2N, "uniform in [0, r)" if SCALARS == "fr" else "uniform raw 256-bit"),
                        "pairs": N_PAIRS, "parallelism": "point-range shard x%d + all_gather of 96-B partials" % world if world > 1 else "single GPU",
                        "l2": "flushed between timed steps (256 MiB fill, outside the event pair)", "bit_exact_vs_oracle": True},
             "clocks": clocks,

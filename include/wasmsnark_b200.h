@@ -71,15 +71,22 @@ int ws_bn128_fq2_mul_batch(ws_ctx* ctx, const uint8_t* x, const uint8_t* y, uint
  *          -> worker G1_MULTIEXP               src/bn128.js:102-113
  *          -> g1m_multiexp2(ps, pp, n, 7, pr)  src/build_multiexp.js:651-744
  * scalars: n*32 bytes raw LE; points: n*64 bytes affine Montgomery (x == 0 means infinity,
- * src/build_multiexp.js:335-349).  out: 96 bytes X|Y|Z Montgomery.  The reference returns an
- * un-normalised Jacobian triple (callers must g1_affine it, src/bn128.js:706); this library
- * returns the normalised representative of the same point: (x, y, 1), or (0, 1, 0) for infinity,
- * i.e. exactly what g1m_affine of the reference's result gives (build_curve_jacobian_a0.js:424-457). */
+ * src/build_multiexp.js:335-349).  out: 96 bytes X|Y|Z Montgomery, an UN-NORMALISED Jacobian triple as
+ * in the reference (callers normalise with g1_affine, src/bn128.js:706); which representative of
+ * the point comes back is unspecified there and here -- compare after ws_bn128_g1_affine, the way
+ * the reference's own test does (test/bn128_prover.js:31-46).                                     */
 int ws_bn128_g1_multiexp(ws_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t out[96]);
 
 /* Replaces Bn128.g2_multiexp  src/bn128.js:385-415 -> G2_MULTIEXP :114-125 -> g2m_multiexp
  * src/build_multiexp.js:498-580.  points: n*128 bytes (x.c0|x.c1|y.c0|y.c1); out: 192 bytes.   */
 int ws_bn128_g2_multiexp(ws_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t out[192]);
+
+/* Replaces Bn128.g1_affine / g2_affine (src/bn128.js:417-427 -> g?m_affine,
+ * src/build_curve_jacobian_a0.js:424-457) and, with from_montgomery != 0, the following
+ * g?_fromMontgomery (src/bn128.js:429-439): `count` Jacobian triples in, (x, y, 1) out, infinity
+ * becomes (0, 1, 0).  96-byte (G1) / 192-byte (G2) records.                                      */
+int ws_bn128_g1_affine(ws_ctx* ctx, const uint8_t* in, uint8_t* out, size_t count, int from_montgomery);
+int ws_bn128_g2_affine(ws_ctx* ctx, const uint8_t* in, uint8_t* out, size_t count, int from_montgomery);
 
 /* Device-resident variants: d_scalars / d_points / d_out are device pointers (16-byte aligned)
  * on the ctx's device, work is enqueued on `stream` (a cudaStream_t, may be NULL = ctx stream)

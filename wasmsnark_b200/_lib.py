@@ -42,6 +42,8 @@ SIGNATURES = {
     "ws_bn128_g2_multiexp": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "ws_bn128_g1_multiexp_dev": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp]),
     "ws_bn128_g2_multiexp_dev": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp]),
+    "ws_bn128_g1_affine": (_i, [_vp, _vp, _vp, _sz, _i]),
+    "ws_bn128_g2_affine": (_i, [_vp, _vp, _vp, _sz, _i]),
     "ws_bn128_g1_sum_dev": (_i, [_vp, _vp, _i, _vp, _vp]),
     "ws_bn128_g2_sum_dev": (_i, [_vp, _vp, _i, _vp, _vp]),
 }

@@ -6,9 +6,9 @@ tests written against the reference read the same here:
     r = bn128.g1_multiexp(scalars, points)     # src/bn128.js:353-383 -> 96 bytes X|Y|Z Montgomery
     r = bn128.g2_multiexp(scalars, points)     # src/bn128.js:385-415 -> 192 bytes
 
-Differences, by design: calls are synchronous (the reference returns Promises resolved by its
-worker pool), and multiexp results come back already normalised to (x, y, 1) / (0, 1, 0) --
-the representative g1_affine() of the reference's result would give.
+Difference, by design: calls are synchronous (the reference returns Promises resolved by its
+worker pool).  Like the reference, multiexp returns an un-normalised Jacobian triple; use
+g1_affine / g2_affine before comparing.
 """
 import ctypes
 
@@ -47,6 +47,27 @@ class Bn128:
     def g2_multiexp(self, scalars, points):
         """src/bn128.js:385-415: points n*128 B."""
         return self._multiexp(self.lib.ws_bn128_g2_multiexp, scalars, points, 128, 192)
+
+    def _affine(self, fn, p, size, from_montgomery):
+        n = len(p) // size
+        out = ctypes.create_string_buffer(max(1, n * size))
+        self.ctx.check(fn(self.ctx.h, as_ptr(p), ctypes.cast(out, ctypes.c_void_p), n, from_montgomery))
+        return out.raw[:n * size]
+
+    def g1_affine(self, p):
+        """src/bn128.js:417-421 (accepts one or several 96-byte triples)."""
+        return self._affine(self.lib.ws_bn128_g1_affine, p, 96, 0)
+
+    def g2_affine(self, p):
+        """src/bn128.js:423-427."""
+        return self._affine(self.lib.ws_bn128_g2_affine, p, 192, 0)
+
+    def g1_affine_std(self, p):
+        """g1_affine followed by g1_fromMontgomery (src/bn128.js:706-712)."""
+        return self._affine(self.lib.ws_bn128_g1_affine, p, 96, 1)
+
+    def g2_affine_std(self, p):
+        return self._affine(self.lib.ws_bn128_g2_affine, p, 192, 1)
 
     # -- field batches (WASM exports f1m_*/frm_*; batch forms fft_mulN etc.)
     def fp_batch(self, field, op, x, y=None):

@@ -161,6 +161,35 @@ HD XYZZ<C> from_jac(const Jac<C>& p) {
     return XYZZ<C>{p.x, p.y, zz, mul(zz, p.z)};
 }
 
+// XYZZ -> Jacobian triple of the same point: (X*ZZ, Y*ZZZ, ZZ)  (Z := ZZ, so Z^2 = ZZ^2, Z^3 = ZZ^3 = ZZZ^2)
+template <class C>
+HD Jac<C> to_jac(const XYZZ<C>& p) {
+    using F = typename C::F;
+    if (p.is_inf()) return Jac<C>{F::zero(), F::one(), F::zero()};
+    return Jac<C>{mul(p.x, p.zz), mul(p.y, p.zzz), p.zz};
+}
+
+// Jacobian doubling for a = 0 [dbl-2009-l], the same formula as the reference's g?m_double
+// (build_curve_jacobian_a0.js:174-235): 2M + 5S in three dependency levels of three independent
+// products each, which is what the single-thread Horner tail wants.
+template <class C>
+HD Jac<C> jdbl_a0(const Jac<C>& p) {
+    using F = typename C::F;
+    if (p.z.is_zero()) return p;
+    F A = sqr(p.x);
+    F B = sqr(p.y);
+    F G = mul(p.y, p.z);
+    F Cc = sqr(B);
+    F D = sqr(add(p.x, B));
+    F E = add(dbl(A), A);
+    F Fv = sqr(E);
+    D = dbl(sub(sub(D, A), Cc));
+    F X3 = sub(Fv, dbl(D));
+    F C8 = dbl(dbl(dbl(Cc)));
+    F Y3 = sub(mul(sub(D, X3), E), C8);
+    return Jac<C>{X3, Y3, dbl(G)};
+}
+
 // Out-of-line forms for the latency-bound tail kernels (segment reduce, bit sums, Horner):
 // one copy of the group law per curve instead of one per call site keeps the kernels small.
 template <class C>

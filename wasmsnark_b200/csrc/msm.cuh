@@ -193,26 +193,47 @@ static __global__ void __launch_bounds__(THREADS, MINB) k_msm_accumulate(MsmPlan
     stg_struct(partials + t, acc);
 }
 
-// Buckets split over several tasks: one warp per bucket, lanes stride over the partial sums,
-// then a shuffle tree.  The sum lands in the bucket's first partial slot.
+// Buckets split over several tasks: one 256-thread block per such bucket.  Threads stride over
+// the bucket's partial sums, then shuffle tree per warp and one more over the 8 warp sums, so a
+// bucket that swallowed a large share of the input (all-equal scalars, the carry window of raw
+// 256-bit scalars, the 1-valued signals of a witness) costs m/256 + 8 additions of depth instead
+// of m.  The sum lands in the bucket's first partial slot.
 template <class C>
-static __global__ void __launch_bounds__(128) k_msm_combine(MsmPlan p, const uint32_t* __restrict__ tstart, const uint32_t* __restrict__ heavy_list,
-                                                     const uint32_t* __restrict__ heavy_count, XYZZ<C>* partials) {
-    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    int lane = threadIdx.x & 31;
+static __global__ void __launch_bounds__(256) k_msm_combine(MsmPlan p, const uint32_t* __restrict__ tstart, const uint32_t* __restrict__ heavy_list,
+                                                            const uint32_t* __restrict__ heavy_count, XYZZ<C>* partials) {
+    __shared__ XYZZ<C> wsum[8];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t nh = *heavy_count;
-    for (uint32_t h = warp; h < nh; h += nwarps) {
+    for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
         uint32_t b = heavy_list[h];
         uint32_t t0 = tstart[b], t1 = tstart[b + 1];
+        uint32_t m = t1 - t0;
+        bool small = m <= 32;                      // one warp is enough
         XYZZ<C> acc = XYZZ<C>::inf();
-        for (uint32_t t = t0 + lane; t < t1; t += 32) acc = padd_call<C>(acc, partials[t]);
+        if (!small || wid == 0) {
+            for (uint32_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) acc = padd_call<C>(acc, partials[t]);
 #pragma unroll 1
-        for (int off = 16; off > 0; off >>= 1) {
-            XYZZ<C> o = shfl_down_struct(acc, off);
-            acc = padd_call<C>(acc, o);
+            for (int off = 16; off > 0; off >>= 1) {
+                XYZZ<C> o = shfl_down_struct(acc, off);
+                acc = padd_call<C>(acc, o);
+            }
         }
-        if (lane == 0) partials[t0] = acc;
+        if (small) {
+            if (threadIdx.x == 0) partials[t0] = acc;
+            continue;                              // block-uniform branch
+        }
+        if (lane == 0) wsum[wid] = acc;
+        __syncthreads();
+        if (wid == 0) {
+            acc = lane < 8 ? wsum[lane] : XYZZ<C>::inf();
+#pragma unroll 1
+            for (int off = 4; off > 0; off >>= 1) {
+                XYZZ<C> o = shfl_down_struct(acc, off);
+                acc = padd_call<C>(acc, o);
+            }
+            if (lane == 0) partials[t0] = acc;
+        }
+        __syncthreads();
     }
 }
 
@@ -258,7 +279,8 @@ static __global__ void __launch_bounds__(256) k_msm_bitsum(MsmPlan p, const XYZZ
 }
 
 // one block: thread w builds its window value, thread 0 runs the Horner over windows.
-// out_xyzz: the sum (device consumers); out_jac: (x, y, 1) / (0, 1, 0), Montgomery.
+// out_xyzz: the sum (device consumers); out_jac: an un-normalised Jacobian triple X|Y|Z of the sum,
+// Montgomery -- the reference's g1m_multiexp result format (callers normalise with g1_affine).
 template <class C>
 static __global__ void __launch_bounds__(160) k_msm_final(MsmPlan p, const XYZZ<C>* __restrict__ bits, XYZZ<C>* R, XYZZ<C>* out_xyzz, Jac<C>* out_jac) {
     int w = threadIdx.x;
@@ -267,17 +289,31 @@ static __global__ void __launch_bounds__(160) k_msm_final(MsmPlan p, const XYZZ<
     if (w == 0) {
         XYZZ<C> res = msm_horner_windows<C>(p, R);
         if (out_xyzz) *out_xyzz = res;
-        if (out_jac) *out_jac = to_affine<C>(res);
+        if (out_jac) *out_jac = to_jac<C>(res);
     }
 }
 
-// Sum of `count` points given as normalised / Jacobian triples; result normalised.
+// Sum of `count` points given as Jacobian triples; result an (un-normalised) Jacobian triple.
 template <class C>
-__global__ void __launch_bounds__(32) k_sum_points(const Jac<C>* __restrict__ in, int count, Jac<C>* out) {
+static __global__ void __launch_bounds__(32) k_sum_points(const Jac<C>* __restrict__ in, int count, Jac<C>* out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     XYZZ<C> acc = XYZZ<C>::inf();
     for (int i = 0; i < count; i++) acc = padd_call<C>(acc, from_jac<C>(in[i]));
-    *out = to_affine<C>(acc);
+    *out = to_jac<C>(acc);
+}
+
+// g?m_affine (+ optional g?m_fromMontgomery) over an array of Jacobian triples, one thread each.
+template <class C>
+static __global__ void __launch_bounds__(64) k_affine_points(const Jac<C>* __restrict__ in, Jac<C>* __restrict__ out, int count, int from_montgomery) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Jac<C> a = to_affine<C>(from_jac<C>(in[i]));
+    if (from_montgomery) {
+        a.x = from_mont(a.x);
+        a.y = from_mont(a.y);
+        a.z = from_mont(a.z);
+    }
+    out[i] = a;
 }
 
 // ------------------------------------------------------------------ workspace + launch
@@ -369,7 +405,7 @@ inline cudaError_t msm_launch(const MsmPlan& p, const MsmWorkspace& w, const uin
     constexpr int AB = sizeof(typename C::F) > 32 ? 1 : 2;
     k_msm_accumulate<C, AT, AB><<<(p.max_tasks + AT - 1) / AT, AT, 0, st>>>(p, w.bstart, w.tstart, w.task_bucket, w.entries, d_points, (X*)w.partials);
     mark("accumulate");
-    k_msm_combine<C><<<148 * 4, 128, 0, st>>>(p, w.tstart, w.heavy_list, w.heavy_count, (X*)w.partials);
+    k_msm_combine<C><<<148 * 8, 256, 0, st>>>(p, w.tstart, w.heavy_list, w.heavy_count, (X*)w.partials);
     mark("combine");
     uint32_t nseg = (uint32_t)p.nwin * p.S;
     k_msm_segreduce<C><<<(nseg + 127) / 128, 128, 0, st>>>(p, w.tstart, (const X*)w.partials, (X*)w.segA, (X*)w.segT);

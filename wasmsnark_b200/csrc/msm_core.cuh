@@ -200,8 +200,15 @@ template <class C>
 HD XYZZ<C> msm_horner_windows(const MsmPlan& p, const XYZZ<C>* R) {
     XYZZ<C> res = R[p.nwin - 1];
     for (int w = p.nwin - 2; w >= 0; w--) {
-        if (!res.is_inf())
-            for (int k = 0; k < p.c; k++) res = pdbl_call<C>(res);
+        if (!res.is_inf()) {
+            if (C::A_ZERO) {
+                Jac<C> j = to_jac<C>(res);
+                for (int k = 0; k < p.c; k++) j = jdbl_a0<C>(j);
+                res = from_jac<C>(j);
+            } else {
+                for (int k = 0; k < p.c; k++) res = pdbl_call<C>(res);
+            }
+        }
         res = padd_call<C>(res, R[w]);
     }
     return res;

@@ -18,4 +18,17 @@ WS_API int ws_bn128_g1_sum_dev(ws_ctx* c, const void* d_parts, int count, void* 
     k_sum_points<G1Curve><<<1, 32, 0, st>>>((const Jac<G1Curve>*)d_parts, count, (Jac<G1Curve>*)d_out);
     return cudaGetLastError() == cudaSuccess ? WS_OK : c->fail_cuda("sum_points");
 }
+WS_API int ws_bn128_g1_affine(ws_ctx* c, const uint8_t* in, uint8_t* out, size_t count, int from_montgomery) {
+    if (!c || !in || !out) return c ? c->fail(WS_E_ARG, "null buffer") : WS_E_ARG;
+    if (count == 0) return WS_OK;
+    cudaSetDevice(c->device);
+    uint8_t* d = (uint8_t*)c->arena(0, 2 * align256(count * 96));
+    if (!d) return c->fail_cuda("workspace");
+    uint8_t* dout = d + align256(count * 96);
+    cudaMemcpyAsync(d, in, count * 96, cudaMemcpyHostToDevice, c->stream);
+    k_affine_points<G1Curve><<<(unsigned)((count + 63) / 64), 64, 0, c->stream>>>((const Jac<G1Curve>*)d, (Jac<G1Curve>*)dout, (int)count, from_montgomery);
+    cudaMemcpyAsync(out, dout, count * 96, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) return c->fail_cuda("affine");
+    return WS_OK;
+}
 }
