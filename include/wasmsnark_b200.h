@@ -106,6 +106,8 @@ int ws_bn128_g2_sum_dev(ws_ctx* ctx, const void* d_parts, int count, void* d_out
 int ws_set_profiling(ws_ctx* ctx, int on);
 /* Tuning/test hook: force the per-task entry cap of the MSM accumulate kernel (0 = automatic). */
 int ws_set_msm_task_cap(ws_ctx* ctx, unsigned cap);
+/* Tuning/test hook: buckets per segment in the bucket-reduction step (power of two, default 32). */
+int ws_set_msm_seg_len(ws_ctx* ctx, unsigned len);
 
 /* Elapsed device time (ms, CUDA events on the launch stream) of the kernels enqueued by the last
  * *_dev / host call on this ctx, split per pipeline stage; names[i] are static strings.

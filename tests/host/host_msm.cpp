@@ -18,15 +18,17 @@ static void run(const uint8_t* scalars, const uint8_t* points, uint32_t n, int c
         bstart[b + 1] = bstart[b] + counts[b];
         tstart[b + 1] = tstart[b] + msm_ntasks(p, counts[b]);
     }
-    std::vector<uint32_t> entries(bstart[p.nbuckets] + 1), task_bucket(p.max_tasks), heavy(p.nbuckets);
-    uint32_t nheavy = 0;
+    std::vector<uint32_t> entries(bstart[p.nbuckets] + 1), task_bucket(p.max_tasks), heavy(2 * (size_t)p.nbuckets), len_hist(p.T + 2, 0), len_cursor(p.T + 2, 0), order(p.max_tasks);
+    uint32_t nheavy[2] = {0, 0};
     for (uint32_t i = 0; i < n; i++) msm_scatter_body(p, i, digits.data(), bstart.data(), counts.data(), entries.data());
-    for (uint32_t b = 0; b < p.nbuckets; b++) msm_filltasks_body(p, b, bstart.data(), tstart.data(), task_bucket.data(), heavy.data(), &nheavy);
+    for (uint32_t b = 0; b < p.nbuckets; b++) msm_filltasks_body(p, b, bstart.data(), tstart.data(), task_bucket.data(), len_hist.data(), heavy.data(), nheavy);
     uint32_t ntasks = tstart[p.nbuckets];
+    msm_task_offsets_body(p, len_hist.data(), len_cursor.data());
+    for (uint32_t t = 0; t < ntasks; t++) msm_task_order_body(p, t, bstart.data(), tstart.data(), task_bucket.data(), len_cursor.data(), order.data());
     std::vector<XYZZ<C>> partials(ntasks + 1);
-    for (uint32_t t = 0; t < ntasks; t++) partials[t] = msm_accumulate_body<C>(p, t, bstart.data(), tstart.data(), task_bucket.data(), entries.data(), pts);
-    for (uint32_t h = 0; h < nheavy; h++) {   // combine (serial stand-in for the warp tree)
-        uint32_t b = heavy[h];
+    for (uint32_t i = 0; i < ntasks; i++) partials[order[i]] = msm_accumulate_body<C>(p, order[i], bstart.data(), tstart.data(), task_bucket.data(), entries.data(), pts);
+    for (uint32_t h = 0; h < nheavy[0] + nheavy[1]; h++) {   // combine (serial stand-in for the warp / block trees)
+        uint32_t b = h < nheavy[0] ? heavy[h] : heavy[p.nbuckets + (h - nheavy[0])];
         XYZZ<C> acc = partials[tstart[b]];
         for (uint32_t t = tstart[b] + 1; t < tstart[b + 1]; t++) acc = padd<C>(acc, partials[t]);
         partials[tstart[b]] = acc;

@@ -113,4 +113,11 @@ WS_API int ws_set_msm_task_cap(ws_ctx* c, unsigned T) {
     return WS_OK;
 }
 
+// test / tuning hook: buckets per reduce segment (power of two)
+WS_API int ws_set_msm_seg_len(ws_ctx* c, unsigned L) {
+    if (!c || (L & (L - 1))) return WS_E_ARG;   // 0 = automatic
+    c->seg_len = L;
+    return WS_OK;
+}
+
 }  // extern "C"

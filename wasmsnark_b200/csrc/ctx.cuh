@@ -44,6 +44,7 @@ struct ws_ctx {
     ws::StageTimer timer;
     std::string err;
     unsigned force_T = 0;
+    unsigned seg_len = 0;    // 0 = automatic
 
     // Arena `slot` grown to at least `bytes` (contents are scratch: not preserved on growth).
     void* arena(int slot, size_t bytes) {

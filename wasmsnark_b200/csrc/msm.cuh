@@ -162,22 +162,69 @@ static __global__ void __launch_bounds__(256) k_msm_scatter(MsmPlan p, const int
     msm_scatter_body(p, i, digits, bstart, cursor, entries);
 }
 
+// Task-length histogram / placement go through a per-block shared-memory histogram so that the
+// few hot lengths cost one global atomic per block instead of one per task.
+constexpr uint32_t LEN_SH = 1026;   // shared histogram capacity (task caps above it use global atomics)
+
 static __global__ void __launch_bounds__(256) k_msm_filltasks(MsmPlan p, const uint32_t* __restrict__ bstart, const uint32_t* __restrict__ tstart,
-                                                       uint32_t* __restrict__ task_bucket, uint32_t* __restrict__ heavy_list, uint32_t* heavy_count) {
+                                                              uint32_t* __restrict__ task_bucket, uint32_t* len_hist, uint32_t* __restrict__ heavy, uint32_t* heavy_count) {
+    __shared__ uint32_t sh[LEN_SH];
+    const bool use_sh = p.T + 2 <= LEN_SH;
+    if (use_sh) {
+        for (uint32_t l = threadIdx.x; l < p.T + 2; l += blockDim.x) sh[l] = 0;
+        __syncthreads();
+    }
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= p.nbuckets) return;
-    msm_filltasks_body(p, b, bstart, tstart, task_bucket, heavy_list, heavy_count);
+    if (b < p.nbuckets) msm_filltasks_body(p, b, bstart, tstart, task_bucket, use_sh ? sh : len_hist, heavy, heavy_count);
+    if (use_sh) {
+        __syncthreads();
+        for (uint32_t l = threadIdx.x; l < p.T + 2; l += blockDim.x)
+            if (sh[l]) atomicAdd(&len_hist[l], sh[l]);
+    }
+}
+
+static __global__ void k_msm_task_offsets(MsmPlan p, const uint32_t* __restrict__ len_hist, uint32_t* __restrict__ len_cursor) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) msm_task_offsets_body(p, len_hist, len_cursor);
+}
+
+static __global__ void __launch_bounds__(256) k_msm_task_order(MsmPlan p, const uint32_t* __restrict__ bstart, const uint32_t* __restrict__ tstart,
+                                                               const uint32_t* __restrict__ task_bucket, uint32_t* len_cursor, uint32_t* __restrict__ order) {
+    __shared__ uint32_t sh[LEN_SH];
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t ntasks = tstart[p.nbuckets];
+    if (p.T + 2 > LEN_SH) {
+        if (t < ntasks) msm_task_order_body(p, t, bstart, tstart, task_bucket, len_cursor, order);
+        return;
+    }
+    for (uint32_t l = threadIdx.x; l < p.T + 2; l += blockDim.x) sh[l] = 0;
+    __syncthreads();
+    uint32_t len = 0, pos = 0;
+    if (t < ntasks) {
+        uint32_t b = task_bucket[t];
+        uint32_t rem = bstart[b + 1] - bstart[b] - (t - tstart[b]) * p.T;
+        len = rem < p.T ? rem : p.T;
+        pos = atomicAdd(&sh[len], 1u);
+    }
+    __syncthreads();
+    for (uint32_t l = threadIdx.x; l < p.T + 2; l += blockDim.x) {
+        uint32_t c = sh[l];
+        if (c) sh[l] = atomicAdd(&len_cursor[l], c);
+    }
+    __syncthreads();
+    if (t < ntasks) order[sh[len] + pos] = t;
 }
 
 // The dominant kernel: one thread per task, points gathered with 128-bit loads, XYZZ
 // accumulator in registers.
 template <class C, int THREADS, int MINB>
 static __global__ void __launch_bounds__(THREADS, MINB) k_msm_accumulate(MsmPlan p, const uint32_t* __restrict__ bstart, const uint32_t* __restrict__ tstart,
-                                                                  const uint32_t* __restrict__ task_bucket, const uint32_t* __restrict__ entries,
+                                                                  const uint32_t* __restrict__ task_bucket, const uint32_t* __restrict__ order,
+                                                                  const uint32_t* __restrict__ entries,
                                                                   const Affine<C>* __restrict__ points, XYZZ<C>* __restrict__ partials) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t ntasks = tstart[p.nbuckets];
-    if (t >= ntasks) return;
+    if (i >= ntasks) return;
+    uint32_t t = order[i];          // tasks sorted by length, longest first: lanes stay in step
     uint32_t b = task_bucket[t];
     uint32_t j = t - tstart[b];
     uint32_t lo = bstart[b] + j * p.T;
@@ -193,34 +240,41 @@ static __global__ void __launch_bounds__(THREADS, MINB) k_msm_accumulate(MsmPlan
     stg_struct(partials + t, acc);
 }
 
-// Buckets split over several tasks: one 256-thread block per such bucket.  Threads stride over
-// the bucket's partial sums, then shuffle tree per warp and one more over the 8 warp sums, so a
-// bucket that swallowed a large share of the input (all-equal scalars, the carry window of raw
-// 256-bit scalars, the 1-valued signals of a witness) costs m/256 + 8 additions of depth instead
-// of m.  The sum lands in the bucket's first partial slot.
+// Buckets split over several tasks.  2..16 partial sums: one thread per bucket adds them up
+// serially (full lane efficiency; the common case when the task cap is below the bucket size).
+// The sum lands in the bucket's first partial slot.
 template <class C>
-static __global__ void __launch_bounds__(256) k_msm_combine(MsmPlan p, const uint32_t* __restrict__ tstart, const uint32_t* __restrict__ heavy_list,
-                                                            const uint32_t* __restrict__ heavy_count, XYZZ<C>* partials) {
+static __global__ void __launch_bounds__(128) k_msm_combine_small(MsmPlan p, const uint32_t* __restrict__ tstart, const uint32_t* __restrict__ heavy,
+                                                                  const uint32_t* __restrict__ heavy_count, XYZZ<C>* partials) {
+    uint32_t nh = heavy_count[0];
+    for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < nh; h += gridDim.x * blockDim.x) {
+        uint32_t b = heavy[h];
+        uint32_t t0 = tstart[b], t1 = tstart[b + 1];
+        XYZZ<C> acc = partials[t0];
+        for (uint32_t t = t0 + 1; t < t1; t++) acc = padd_call<C>(acc, partials[t]);
+        partials[t0] = acc;
+    }
+}
+
+// More than 16 partial sums (a bucket that swallowed a large share of the input: all-equal scalars,
+// the carry window of raw 256-bit scalars, the 1-valued signals of a witness): one 256-thread block
+// per bucket, threads stride over the partials, shuffle tree per warp, then over the 8 warp sums --
+// m/256 + 8 additions of depth instead of m.
+template <class C>
+static __global__ void __launch_bounds__(256) k_msm_combine_big(MsmPlan p, const uint32_t* __restrict__ tstart, const uint32_t* __restrict__ heavy,
+                                                                const uint32_t* __restrict__ heavy_count, XYZZ<C>* partials) {
     __shared__ XYZZ<C> wsum[8];
     int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t nh = *heavy_count;
+    uint32_t nh = heavy_count[1];
     for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
-        uint32_t b = heavy_list[h];
+        uint32_t b = heavy[p.nbuckets + h];
         uint32_t t0 = tstart[b], t1 = tstart[b + 1];
-        uint32_t m = t1 - t0;
-        bool small = m <= 32;                      // one warp is enough
         XYZZ<C> acc = XYZZ<C>::inf();
-        if (!small || wid == 0) {
-            for (uint32_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) acc = padd_call<C>(acc, partials[t]);
+        for (uint32_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) acc = padd_call<C>(acc, partials[t]);
 #pragma unroll 1
-            for (int off = 16; off > 0; off >>= 1) {
-                XYZZ<C> o = shfl_down_struct(acc, off);
-                acc = padd_call<C>(acc, o);
-            }
-        }
-        if (small) {
-            if (threadIdx.x == 0) partials[t0] = acc;
-            continue;                              // block-uniform branch
+        for (int off = 16; off > 0; off >>= 1) {
+            XYZZ<C> o = shfl_down_struct(acc, off);
+            acc = padd_call<C>(acc, o);
         }
         if (lane == 0) wsum[wid] = acc;
         __syncthreads();
@@ -319,7 +373,7 @@ static __global__ void __launch_bounds__(64) k_affine_points(const Jac<C>* __res
 // ------------------------------------------------------------------ workspace + launch
 struct MsmWorkspace {
     int16_t* digits;
-    uint32_t *counts, *cursor, *bstart, *tstart, *tile_sums, *entries, *task_bucket, *heavy_list, *heavy_count;
+    uint32_t *counts, *cursor, *bstart, *tstart, *tile_sums, *entries, *task_bucket, *order, *heavy, *small_ctrs;   // small_ctrs: [0..1] heavy counts, [8..] len_hist, [8+T+2..] len_cursor
     void *partials, *segA, *segT, *bits, *R;
 };
 
@@ -341,8 +395,9 @@ inline size_t msm_carve(const MsmPlan& p, uint8_t* base, MsmWorkspace* ws) {
     uint8_t* tl = take(((size_t)p.nbuckets / SCAN_TILE + 2) * 4);
     uint8_t* en = take((entries + 1) * 4);
     uint8_t* tb = take((size_t)p.max_tasks * 4);
-    uint8_t* hl = take((size_t)p.nbuckets * 4);
-    uint8_t* hc = take(256);
+    uint8_t* od = take((size_t)p.max_tasks * 4);
+    uint8_t* hl = take((size_t)p.nbuckets * 8);
+    uint8_t* hc = take((8 + 2 * ((size_t)p.T + 2)) * 4);
     uint8_t* pa = take((size_t)p.max_tasks * sizeof(XYZZ<C>));
     uint8_t* sa = take((size_t)p.nwin * p.S * sizeof(XYZZ<C>));
     uint8_t* sT = take((size_t)p.nwin * p.S * sizeof(XYZZ<C>));
@@ -357,8 +412,9 @@ inline size_t msm_carve(const MsmPlan& p, uint8_t* base, MsmWorkspace* ws) {
         ws->tile_sums = (uint32_t*)tl;
         ws->entries = (uint32_t*)en;
         ws->task_bucket = (uint32_t*)tb;
-        ws->heavy_list = (uint32_t*)hl;
-        ws->heavy_count = (uint32_t*)hc;
+        ws->order = (uint32_t*)od;
+        ws->heavy = (uint32_t*)hl;
+        ws->small_ctrs = (uint32_t*)hc;
         ws->partials = pa;
         ws->segA = sa;
         ws->segT = sT;
@@ -391,7 +447,10 @@ inline cudaError_t msm_launch(const MsmPlan& p, const MsmWorkspace& w, const uin
     using X = XYZZ<C>;
     auto mark = [&](const char* nm) { if (tm) tm->mark(nm, st); };
     cudaMemsetAsync(w.counts, 0, (size_t)p.nbuckets * 4, st);
-    cudaMemsetAsync(w.heavy_count, 0, 4, st);
+    uint32_t* heavy_count = w.small_ctrs;
+    uint32_t* len_hist = w.small_ctrs + 8;
+    uint32_t* len_cursor = len_hist + p.T + 2;
+    cudaMemsetAsync(w.small_ctrs, 0, (8 + 2 * ((size_t)p.T + 2)) * 4, st);
     if (p.n) k_msm_digits<C><<<(p.n + 255) / 256, 256, 0, st>>>(p, d_scalars, d_points, w.digits, w.counts);
     mark("digits");
     launch_scan(w.counts, w.bstart, w.tile_sums, p.nbuckets, 0, 1, st);
@@ -399,13 +458,17 @@ inline cudaError_t msm_launch(const MsmPlan& p, const MsmWorkspace& w, const uin
     cudaMemcpyAsync(w.cursor, w.counts, (size_t)p.nbuckets * 4, cudaMemcpyDeviceToDevice, st);
     mark("scan");
     if (p.n) k_msm_scatter<<<(p.n + 255) / 256, 256, 0, st>>>(p, w.digits, w.bstart, w.cursor, w.entries);
-    k_msm_filltasks<<<(p.nbuckets + 255) / 256, 256, 0, st>>>(p, w.bstart, w.tstart, w.task_bucket, w.heavy_list, w.heavy_count);
     mark("scatter");
+    k_msm_filltasks<<<(p.nbuckets + 255) / 256, 256, 0, st>>>(p, w.bstart, w.tstart, w.task_bucket, len_hist, w.heavy, heavy_count);
+    k_msm_task_offsets<<<1, 32, 0, st>>>(p, len_hist, len_cursor);
+    k_msm_task_order<<<(p.max_tasks + 255) / 256, 256, 0, st>>>(p, w.bstart, w.tstart, w.task_bucket, len_cursor, w.order);
+    mark("tasks");
     constexpr int AT = sizeof(typename C::F) > 32 ? 128 : 256;
     constexpr int AB = sizeof(typename C::F) > 32 ? 1 : 2;
-    k_msm_accumulate<C, AT, AB><<<(p.max_tasks + AT - 1) / AT, AT, 0, st>>>(p, w.bstart, w.tstart, w.task_bucket, w.entries, d_points, (X*)w.partials);
+    k_msm_accumulate<C, AT, AB><<<(p.max_tasks + AT - 1) / AT, AT, 0, st>>>(p, w.bstart, w.tstart, w.task_bucket, w.order, w.entries, d_points, (X*)w.partials);
     mark("accumulate");
-    k_msm_combine<C><<<148 * 8, 256, 0, st>>>(p, w.tstart, w.heavy_list, w.heavy_count, (X*)w.partials);
+    k_msm_combine_small<C><<<148 * 8, 128, 0, st>>>(p, w.tstart, w.heavy, heavy_count, (X*)w.partials);
+    k_msm_combine_big<C><<<148, 256, 0, st>>>(p, w.tstart, w.heavy, heavy_count, (X*)w.partials);
     mark("combine");
     uint32_t nseg = (uint32_t)p.nwin * p.S;
     k_msm_segreduce<C><<<(nseg + 127) / 128, 128, 0, st>>>(p, w.tstart, (const X*)w.partials, (X*)w.segA, (X*)w.segT);

@@ -43,14 +43,18 @@ struct MsmPlan {
     uint32_t max_tasks;
 };
 
-HD MsmPlan msm_make_plan(uint32_t n, int c, uint32_t T) {
+HD MsmPlan msm_make_plan(uint32_t n, int c, uint32_t T, uint32_t L = 0) {
     MsmPlan p;
     p.n = n;
     p.c = c;
     p.nwin = (257 + c - 1) / c;
     p.B = 1u << (c - 1);
     p.T = T;
-    p.L = p.B < 8 ? p.B : 8;
+    if (L == 0) {   // enough segments to occupy the part (~64K threads), at most 16 buckets each
+        L = 16;
+        while (L > 2 && (uint64_t)p.nwin * (p.B / L) < 65536) L >>= 1;
+    }
+    p.L = p.B < L ? p.B : L;
     p.S = p.B / p.L;
     p.logS = 0;
     while ((1u << p.logS) < p.S) p.logS++;
@@ -126,11 +130,41 @@ HD void msm_scatter_body(const MsmPlan& p, uint32_t i, const int16_t* digits, co
 // ---- task table: thread b (one per bucket) ----------------------------------------------
 HD uint32_t msm_ntasks(const MsmPlan& p, uint32_t len) { return (len + p.T - 1) / p.T; }
 
+// Writes the bucket's task descriptors, counts task lengths (for the length sort that keeps the
+// lanes of a warp in step) and files multi-task buckets for the combine step:
+//   heavy[0 .. ) buckets with 2..32 tasks (one warp each), heavy[nbuckets .. ) buckets with more
+//   (one block each); heavy_count[0], heavy_count[1] are the two list lengths.
 HD void msm_filltasks_body(const MsmPlan& p, uint32_t b, const uint32_t* bstart, const uint32_t* tstart,
-                           uint32_t* task_bucket, uint32_t* heavy_list, uint32_t* heavy_count) {
+                           uint32_t* task_bucket, uint32_t* len_hist, uint32_t* heavy, uint32_t* heavy_count) {
     uint32_t t0 = tstart[b], t1 = tstart[b + 1];
-    for (uint32_t t = t0; t < t1; t++) task_bucket[t] = b;
-    if (t1 - t0 > 1) heavy_list[atomic_add_u32(heavy_count, 1u)] = b;
+    uint32_t blen = bstart[b + 1] - bstart[b];
+    for (uint32_t t = t0; t < t1; t++) {
+        task_bucket[t] = b;
+        uint32_t rem = blen - (t - t0) * p.T;
+        atomic_add_u32(&len_hist[rem < p.T ? rem : p.T], 1u);
+    }
+    uint32_t m = t1 - t0;
+    if (m > 16) heavy[p.nbuckets + atomic_add_u32(heavy_count + 1, 1u)] = b;
+    else if (m > 1) heavy[atomic_add_u32(heavy_count, 1u)] = b;
+}
+
+// Start offsets of each task length in the execution order: longest first.  One thread.
+HD void msm_task_offsets_body(const MsmPlan& p, const uint32_t* len_hist, uint32_t* len_cursor) {
+    uint32_t run = 0;
+    for (uint32_t l = p.T; l >= 1; l--) {
+        len_cursor[l] = run;
+        run += len_hist[l];
+    }
+    len_cursor[0] = run;
+}
+
+// thread t: place task t in the execution order
+HD void msm_task_order_body(const MsmPlan& p, uint32_t t, const uint32_t* bstart, const uint32_t* tstart,
+                            const uint32_t* task_bucket, uint32_t* len_cursor, uint32_t* order) {
+    uint32_t b = task_bucket[t];
+    uint32_t rem = bstart[b + 1] - bstart[b] - (t - tstart[b]) * p.T;
+    uint32_t len = rem < p.T ? rem : p.T;
+    order[atomic_add_u32(&len_cursor[len], 1u)] = t;
 }
 
 // ---- accumulate: thread t (one per task) ------------------------------------------------

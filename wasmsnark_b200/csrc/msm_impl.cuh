@@ -22,7 +22,7 @@ inline int multiexp_dev(ws_ctx* c, const void* d_scalars, const void* d_points, 
         cb = window_bits;
     }
     if (c->force_T) T = c->force_T;
-    MsmPlan p = msm_make_plan((uint32_t)n, cb, T);
+    MsmPlan p = msm_make_plan((uint32_t)n, cb, T, c->seg_len);
     size_t need = msm_carve<C>(p, nullptr, nullptr);
     uint8_t* base = (uint8_t*)c->arena(1, need);
     if (!base) return c->fail_cuda("msm workspace");
