@@ -28,6 +28,7 @@ extern "C" {
 #endif
 
 typedef struct ws_ctx ws_ctx;
+typedef struct ws_pkey ws_pkey;   /* a proving key resident in HBM (see ws_bn128_pkey_load) */
 
 enum {
     WS_OK = 0,
@@ -101,6 +102,48 @@ int ws_bn128_g2_multiexp_dev(ws_ctx* ctx, const void* d_scalars, const void* d_p
  * Replaces the serial g1m_add loop over worker results, src/bn128.js:376-380 / :408-412.          */
 int ws_bn128_g1_sum_dev(ws_ctx* ctx, const void* d_parts, int count, void* d_out, void* stream);
 int ws_bn128_g2_sum_dev(ws_ctx* ctx, const void* d_parts, int count, void* d_out, void* stream);
+
+/* ---- NTT over Fr (config C3) -------------------------------------------------------------------
+ * Replaces fft_fft(px, n, odd) / fft_ifft(px, n, odd)   src/build_fft.js:159-221 (+ __rawfft :223-372,
+ * __finalInverse :550-648): in place on n 32-byte Montgomery Fr elements, natural order in and out.
+ * odd != 0 evaluates on the odd 2n-th roots of unity (twiddle starts at w_2m).  n must be a power of
+ * two <= 2^28, else WS_E_SIZE (the reference traps, src/build_fft.js:137-154).                     */
+int ws_bn128_fr_fft(ws_ctx* ctx, uint8_t* px, size_t n, int odd);
+int ws_bn128_fr_ifft(ws_ctx* ctx, uint8_t* px, size_t n, int odd);
+/* device-resident form: d_px on the ctx's device, enqueued on `stream`, no synchronisation */
+int ws_bn128_fr_fft_dev(ws_ctx* ctx, void* d_px, size_t n, int odd, int inverse, void* stream);
+
+/* ---- H polynomial (worker command CALC_H) ----------------------------------------------------------
+ * Replaces Bn128.calcH(signals, polsA, polsB, nSignals, domainSize)  src/bn128.js:569-578 -> :126-166.
+ * signals: nSignals*32 bytes plain LE; polsA / polsB: the key's sections (per signal: u32 ncoefs, then
+ * {u32 idx, 32-byte Montgomery coef} x ncoefs; tools/buildpkey.js:79-89); out: domainSize*32 bytes,
+ * the coefficients n..2n-1 of A*B, out of Montgomery form.                                          */
+int ws_bn128_calc_h(ws_ctx* ctx, const uint8_t* signals, const uint8_t* polsA, size_t lenA, const uint8_t* polsB, size_t lenB,
+                    uint32_t n_signals, uint32_t domain_size, uint8_t* out);
+
+/* ---- Groth16 prover (config C4) -------------------------------------------------------------------
+ * Replaces Bn128.groth16GenProof(signals, pkey)  src/bn128.js:580-720 (public surface main_bn128.js:27-41).
+ * witness: nVars*32 bytes plain LE (tools/buildwitness.js:36-69); pkey: proving_key.bin
+ * (tools/buildpkey.js:130-183).  r, s: 32 raw bytes each; NULL draws them from the OS CSPRNG like
+ * the reference (src/bn128.js:642-664); all-zero r and s is the reference's debug mode (:666-668)
+ * pinned by example/bn128/proof_good0.json.
+ * Outputs are what the reference formats into decimal strings (src/bn128.js:714-718): affine and out of
+ * Montgomery form -- pi_a, pi_c: x|y|z (96 bytes), pi_b: x.c0|x.c1|y.c0|y.c1|z.c0|z.c1 (192 bytes);
+ * z is 1 (or the point is (0,1,0) at infinity).                                                      */
+int ws_bn128_groth16_prove(ws_ctx* ctx, const uint8_t* witness, size_t witness_len, const uint8_t* pkey, size_t pkey_len,
+                           const uint8_t* r, const uint8_t* s, uint8_t pi_a[96], uint8_t pi_b[192], uint8_t pi_c[96]);
+
+/* Resident proving key: parses and uploads proving_key.bin once (sections to HBM, the two polynomial
+ * sections regrouped per row); the reference re-slices and re-posts the key on every proof
+ * (src/bn128.js:592-604).  The handle belongs to `ctx`.                                              */
+int ws_bn128_pkey_load(ws_ctx* ctx, const uint8_t* pkey, size_t pkey_len, ws_pkey** out);
+void ws_bn128_pkey_free(ws_pkey* key);
+int ws_bn128_pkey_info(const ws_pkey* key, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size);
+int ws_bn128_groth16_prove_key(ws_ctx* ctx, const ws_pkey* key, const uint8_t* witness, size_t witness_len,
+                               const uint8_t* r, const uint8_t* s, uint8_t pi_a[96], uint8_t pi_b[192], uint8_t pi_c[96]);
+/* d_witness: nVars*32 bytes on the device; d_rs: r|s, 64 bytes on the device; d_out: 384 bytes
+ * (pi_a | pi_b | pi_c) on the device; enqueued on `stream`, no synchronisation.                      */
+int ws_bn128_groth16_prove_dev(ws_ctx* ctx, const ws_pkey* key, const void* d_witness, const void* d_rs, void* d_out, void* stream);
 
 /* Stage timing on/off (CUDA events recorded between the pipeline's kernels on the launch stream). */
 int ws_set_profiling(ws_ctx* ctx, int on);

@@ -27,5 +27,21 @@ def main():
         subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-w", "-o", so, c])
 
 
+def copy_example():
+    """The reference's example key / witness / golden proof (35 MB of DATA, not sources) into the
+    git-ignored oracle/_ref/example_bn128/, so that the C4 parity test can run on the GPU box,
+    where /root/reference does not exist."""
+    import shutil
+    src = os.path.join(REF, "example", "bn128")
+    dst = os.path.join(OUT, "example_bn128")
+    if not os.path.isdir(src):
+        return
+    os.makedirs(dst, exist_ok=True)
+    for f in ("proving_key.bin", "witness.bin", "proof_good0.json"):
+        if not os.path.exists(os.path.join(dst, f)):
+            shutil.copyfile(os.path.join(src, f), os.path.join(dst, f))
+
+
 if __name__ == "__main__":
+    copy_example()
     main()

@@ -5,4 +5,4 @@ libwasmsnark_b200.so (include/wasmsnark_b200.h).  All arithmetic runs in hand-wr
 kernels; there is no CPU implementation in this package.
 """
 from ._lib import load_library, LibraryNotBuilt  # noqa: F401
-from .bn128 import Bn128, build_bn128  # noqa: F401
+from .bn128 import Bn128, ProvingKey, build_bn128, groth16GenProof, genZKSnarkProof  # noqa: F401

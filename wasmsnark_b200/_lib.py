@@ -45,6 +45,16 @@ SIGNATURES = {
     "ws_bn128_g2_multiexp_dev": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp]),
     "ws_bn128_g1_affine": (_i, [_vp, _vp, _vp, _sz, _i]),
     "ws_bn128_g2_affine": (_i, [_vp, _vp, _vp, _sz, _i]),
+    "ws_bn128_fr_fft": (_i, [_vp, _vp, _sz, _i]),
+    "ws_bn128_fr_ifft": (_i, [_vp, _vp, _sz, _i]),
+    "ws_bn128_fr_fft_dev": (_i, [_vp, _vp, _sz, _i, _i, _vp]),
+    "ws_bn128_calc_h": (_i, [_vp, _vp, _vp, _sz, _vp, _sz, ctypes.c_uint32, ctypes.c_uint32, _vp]),
+    "ws_bn128_groth16_prove": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "ws_bn128_pkey_load": (_i, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),
+    "ws_bn128_pkey_free": (None, [_vp]),
+    "ws_bn128_pkey_info": (_i, [_vp, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]),
+    "ws_bn128_groth16_prove_key": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "ws_bn128_groth16_prove_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "ws_bn128_g1_sum_dev": (_i, [_vp, _vp, _i, _vp, _vp]),
     "ws_bn128_g2_sum_dev": (_i, [_vp, _vp, _i, _vp, _vp]),
 }

@@ -69,6 +69,48 @@ class Bn128:
     def g2_affine_std(self, p):
         return self._affine(self.lib.ws_bn128_g2_affine, p, 192, 1)
 
+    # -- NTT (WASM exports fft_fft / fft_ifft, src/build_fft.js:159-221); returns the transformed buffer
+    def fft(self, px, odd=0):
+        buf = ctypes.create_string_buffer(bytes(px), len(px))
+        self.ctx.check(self.lib.ws_bn128_fr_fft(self.ctx.h, ctypes.cast(buf, ctypes.c_void_p), len(px) // 32, odd))
+        return buf.raw
+
+    def ifft(self, px, odd=0):
+        buf = ctypes.create_string_buffer(bytes(px), len(px))
+        self.ctx.check(self.lib.ws_bn128_fr_ifft(self.ctx.h, ctypes.cast(buf, ctypes.c_void_p), len(px) // 32, odd))
+        return buf.raw
+
+    def calcH(self, signals, polsA, polsB, nSignals, domainSize):
+        """src/bn128.js:569-578 -> worker CALC_H (:126-166): domainSize*32 bytes, non-Montgomery."""
+        out = ctypes.create_string_buffer(domainSize * 32)
+        self.ctx.check(self.lib.ws_bn128_calc_h(self.ctx.h, as_ptr(signals), as_ptr(polsA), len(polsA), as_ptr(polsB), len(polsB),
+                                                nSignals, domainSize, ctypes.cast(out, ctypes.c_void_p)))
+        return out.raw
+
+    # -- proving key kept in HBM across proofs (the reference re-posts it to its workers every time)
+    def load_proving_key(self, pkey):
+        h = ctypes.c_void_p()
+        self.ctx.check(self.lib.ws_bn128_pkey_load(self.ctx.h, as_ptr(pkey), len(pkey), ctypes.byref(h)))
+        return ProvingKey(self, h)
+
+    def groth16GenProof(self, signals, pkey, r=None, s=None, raw=False):
+        """src/bn128.js:580-720.  `pkey` is proving_key.bin bytes or a ProvingKey from
+        load_proving_key().  r, s: 32-byte strings injected for tests (None => CSPRNG like the
+        reference; the values used are kept in self._pr / self._ps like src/bn128.js:663-664 when
+        injected).  Returns {pi_a, pi_b, pi_c} as decimal strings (src/bn128.js:714-718)."""
+        pa = ctypes.create_string_buffer(96)
+        pb = ctypes.create_string_buffer(192)
+        pc = ctypes.create_string_buffer(96)
+        outs = [ctypes.cast(x, ctypes.c_void_p) for x in (pa, pb, pc)]
+        self._pr, self._ps = r, s
+        if isinstance(pkey, ProvingKey):
+            self.ctx.check(self.lib.ws_bn128_groth16_prove_key(self.ctx.h, pkey.h, as_ptr(signals), len(signals), as_ptr(r), as_ptr(s), *outs))
+        else:
+            self.ctx.check(self.lib.ws_bn128_groth16_prove(self.ctx.h, as_ptr(signals), len(signals), as_ptr(pkey), len(pkey), as_ptr(r), as_ptr(s), *outs))
+        if raw:
+            return pa.raw, pb.raw, pc.raw
+        return {"pi_a": self.bin2g1(pa.raw), "pi_b": self.bin2g2(pb.raw), "pi_c": self.bin2g1(pc.raw)}
+
     # -- field batches (WASM exports f1m_*/frm_*; batch forms fft_mulN etc.)
     def fp_batch(self, field, op, x, y=None):
         esz = 96 if field == _lib.FIELD_MNT6753_FQ else 32
@@ -97,6 +139,42 @@ class Bn128:
         return [[cls.bin2int(b[0:32]), cls.bin2int(b[32:64])],
                 [cls.bin2int(b[64:96]), cls.bin2int(b[96:128])],
                 [cls.bin2int(b[128:160]), cls.bin2int(b[160:192])]]
+
+
+class ProvingKey:
+    """Handle on a proving key resident in HBM (ws_bn128_pkey_load)."""
+
+    def __init__(self, bn, h):
+        self.bn, self.h = bn, h
+        a, b, c = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+        bn.lib.ws_bn128_pkey_info(h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        self.nVars, self.nPublic, self.domainSize = a.value, b.value, c.value
+
+    def free(self):
+        if self.h:
+            self.bn.lib.ws_bn128_pkey_free(self.h)
+            self.h = None
+
+
+def groth16GenProof(witness, provingKey, cb=None, device=0):
+    """main_bn128.js:27-41 `window.groth16GenProof(witness, provingKey, cb)` (README name
+    genZKSnarkProof): cb(err, proof) if given, else returns the proof."""
+    try:
+        bn = build_bn128(device)
+        try:
+            proof = bn.groth16GenProof(witness, provingKey)
+        finally:
+            bn.terminate()
+    except Exception as e:      # noqa: BLE001 -- the reference forwards any rejection to cb(err)
+        if cb:
+            return cb(e, None)
+        raise
+    if cb:
+        return cb(None, proof)
+    return proof
+
+
+genZKSnarkProof = groth16GenProof
 
 
 def build_bn128(device=0):

@@ -41,6 +41,7 @@ WS_API void ws_destroy(ws_ctx* c) {
     for (int i = 0; i < StageTimer::MAX; i++) cudaEventDestroy(c->timer.ev[i]);
     for (auto& a : c->arenas)
         if (a.ptr) cudaFree(a.ptr);
+    if (c->tw_table) cudaFree(c->tw_table);
     cudaStreamDestroy(c->stream);
     delete c;
 }

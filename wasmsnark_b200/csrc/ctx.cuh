@@ -44,6 +44,8 @@ struct ws_ctx {
     ws::StageTimer timer;
     std::string err;
     unsigned force_T = 0;
+    void* tw_table = nullptr;     // ntt.cuh TwiddleTable storage (Fr*), owned here
+    int tw_logM = 0;
     unsigned seg_len = 0;    // 0 = automatic
 
     // Arena `slot` grown to at least `bytes` (contents are scratch: not preserved on growth).
@@ -51,7 +53,7 @@ struct ws_ctx {
         ws::Arena& a = arenas[slot];
         if (a.size >= bytes && a.ptr) return a.ptr;
         if (a.ptr) {
-            cudaStreamSynchronize(stream);
+            cudaDeviceSynchronize();      // work on any stream may still use the old block
             cudaFree(a.ptr);
             a.ptr = nullptr;
             a.size = 0;

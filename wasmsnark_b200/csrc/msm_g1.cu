@@ -2,6 +2,12 @@
 #include "msm_impl.cuh"
 using namespace ws;
 
+namespace ws {
+int msm_g1_run(ws_ctx* c, const void* ds, const void* dp, size_t n, void* d_out_jac, void* d_out_xyzz, cudaStream_t st) {
+    return multiexp_dev<G1Curve>(c, ds, dp, n, d_out_jac, 0, st, d_out_xyzz, false);
+}
+}  // namespace ws
+
 extern "C" {
 WS_API int ws_bn128_g1_multiexp(ws_ctx* c, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t out[96]) {
     return multiexp_host<G1Curve>(c, scalars, points, n, out);

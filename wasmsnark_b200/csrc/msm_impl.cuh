@@ -5,15 +5,17 @@
 #include "../../include/wasmsnark_b200.h"
 #include "ctx.cuh"
 #include "msm.cuh"
+#include "msm_api.cuh"
 
 #define WS_API __attribute__((visibility("default")))
 
 namespace ws {
 
+// d_out: Jacobian triple (may be null); d_out_xyzz: XYZZ sum for device consumers (may be null)
 template <class C>
-inline int multiexp_dev(ws_ctx* c, const void* d_scalars, const void* d_points, size_t n, void* d_out, int window_bits, cudaStream_t st) {
+inline int multiexp_dev(ws_ctx* c, const void* d_scalars, const void* d_points, size_t n, void* d_out, int window_bits, cudaStream_t st, void* d_out_xyzz = nullptr, bool own_timer = true) {
     if (n > 0x7FFFFFFFull) return c->fail(WS_E_ARG, "n too large");
-    if (((uintptr_t)d_scalars | (uintptr_t)d_points | (uintptr_t)d_out) & 15) return c->fail(WS_E_ARG, "device pointers must be 16-byte aligned");
+    if (((uintptr_t)d_scalars | (uintptr_t)d_points | (uintptr_t)d_out | (uintptr_t)d_out_xyzz) & 15) return c->fail(WS_E_ARG, "device pointers must be 16-byte aligned");
     int cb;
     uint32_t T;
     msm_choose((uint32_t)n, &cb, &T);
@@ -28,8 +30,8 @@ inline int multiexp_dev(ws_ctx* c, const void* d_scalars, const void* d_points, 
     if (!base) return c->fail_cuda("msm workspace");
     MsmWorkspace w;
     msm_carve<C>(p, base, &w);
-    c->timer.begin(st);
-    cudaError_t e = msm_launch<C>(p, w, (const uint32_t*)d_scalars, (const Affine<C>*)d_points, nullptr, (Jac<C>*)d_out, st, &c->timer);
+    if (own_timer) c->timer.begin(st);
+    cudaError_t e = msm_launch<C>(p, w, (const uint32_t*)d_scalars, (const Affine<C>*)d_points, (XYZZ<C>*)d_out_xyzz, (Jac<C>*)d_out, st, own_timer ? &c->timer : nullptr);
     if (e != cudaSuccess) return c->fail_cuda("msm launch");
     return WS_OK;
 }
@@ -52,6 +54,7 @@ inline int multiexp_host(ws_ctx* c, const uint8_t* scalars, const uint8_t* point
     if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) return c->fail_cuda("multiexp");
     return WS_OK;
 }
+
 
 
 

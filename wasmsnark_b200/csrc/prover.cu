@@ -1,0 +1,546 @@
+// prover.cu -- NTT entry points, the H-polynomial pipeline (worker command CALC_H) and the
+// Groth16 prover (Bn128.groth16GenProof) on the GPU, behind the C ABI.
+//
+// Reference call stack replaced here (paths under /root/reference):
+//   Bn128.groth16GenProof(signals, pkey)            src/bn128.js:580-720
+//     header + section slicing                      src/bn128.js:581-604   (layout: tools/buildpkey.js:130-183)
+//     calcH -> worker CALC_H                        src/bn128.js:569-578, :126-166
+//        fft_toMontgomeryN                          src/build_fft.js:418-458
+//        pol_zero, pol_constructLC                  src/build_pol.js:26-143
+//        fft_copyNInterleaved, fft_mulN             src/build_fft.js:374-414, :461-505
+//        fft_ifft / fft_fft(odd)                    src/build_fft.js:159-221
+//        fft_fromMontgomeryN                        src/build_fft.js:507-547
+//     g1_multiexp x4, g2_multiexp x1                src/bn128.js:614-620
+//     final assembly with r, s                      src/bn128.js:642-712
+#include <cuda_runtime.h>
+#include <sys/random.h>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/wasmsnark_b200.h"
+#include "ctx.cuh"
+#include "ec.cuh"
+#include "msm_api.cuh"
+#include "ntt.cuh"
+
+#define WS_API __attribute__((visibility("default")))
+
+using namespace ws;
+
+// ============================================================================ element-wise kernels
+static __global__ void __launch_bounds__(128) k_fr_to_mont(const Fr* __restrict__ in, Fr* __restrict__ out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fr_st(out + i, to_mont(fr_ld(in + i)));
+}
+static __global__ void __launch_bounds__(128) k_fr_from_mont(const Fr* __restrict__ in, Fr* __restrict__ out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fr_st(out + i, from_mont(fr_ld(in + i)));
+}
+
+// pol_constructLC in row form: out[row] = sum over the row's terms of signalM[sig] * coef.
+// The key stores the terms per signal (src/build_pol.js:61-143 walks them signal-major and
+// accumulates into res[idx]); they are regrouped per row once at key load, which turns the
+// scatter-add into a conflict-free gather.  Field addition is commutative, so the sum is the same.
+static __global__ void __launch_bounds__(128) k_csr_lc(const uint32_t* __restrict__ row_start, const uint32_t* __restrict__ sig,
+                                                       const Fr* __restrict__ coef, const Fr* __restrict__ signalsM, Fr* __restrict__ out, uint32_t nrows) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    Fr acc = Fr::zero();
+    uint32_t lo = row_start[r], hi = row_start[r + 1];
+    for (uint32_t k = lo; k < hi; k++) acc = add(acc, mul(fr_ldg(signalsM + sig[k]), fr_ldg(coef + k)));
+    fr_st(out + r, acc);
+}
+
+// P[2i] = a_even[i] * b_even[i]; P[2i+1] = a_odd[i] * b_odd[i]
+// (fft_copyNInterleaved x4 + fft_mulN over the 2n domain, src/bn128.js:146-157)
+static __global__ void __launch_bounds__(128) k_interleave_mul(const Fr* __restrict__ ae, const Fr* __restrict__ be, const Fr* __restrict__ ao,
+                                                               const Fr* __restrict__ bo, Fr* __restrict__ P, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fr_st(P + 2 * (size_t)i, mul(fr_ld(ae + i), fr_ld(be + i)));
+    fr_st(P + 2 * (size_t)i + 1, mul(fr_ld(ao + i), fr_ld(bo + i)));
+}
+
+// ============================================================================ final assembly
+struct FixedPoints {      // alfa1, beta1, delta1 (64 B each), beta2, delta2 (128 B each): pkey bytes 40..488
+    G1Affine alfa1, beta1, delta1;
+    G2Affine beta2, delta2;
+};
+
+struct AssembleArgs {
+    const G1X *A, *B1, *C, *H;
+    const G2X* B2;
+    const FixedPoints* fx;
+    const uint8_t* rs;          // r (32 bytes) then s (32 bytes), raw LE
+    Jac<G1Curve>* pi_a;         // outputs: affine, out of Montgomery form (src/bn128.js:706-712)
+    Jac<G2Curve>* pi_b;
+    Jac<G1Curve>* pi_c;
+};
+
+template <class C>
+__device__ __forceinline__ XYZZ<C> load_fixed(const Affine<C>& p) {   // loadPoint1/2: Z = 1 always (src/bn128.js:441-453)
+    using F = typename C::F;
+    return XYZZ<C>{p.x, p.y, F::one(), F::one()};
+}
+
+template <class C>
+__device__ __forceinline__ Jac<C> affine_std(const XYZZ<C>& p) {   // g?m_affine + g?m_fromMontgomery
+    Jac<C> a = to_affine<C>(p);
+    a.x = from_mont(a.x);
+    a.y = from_mont(a.y);
+    a.z = from_mont(a.z);
+    return a;
+}
+
+// One block, 4 warps; lane 0 of each warp runs one of the independent scalar multiplications.
+static __global__ void __launch_bounds__(128) k_assemble(AssembleArgs g) {
+    __shared__ G1X s_rd1, s_sd1, s_rsd1, s_spia, s_rpib1;
+    __shared__ uint8_t s_rs[64], s_prod[64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 64) s_rs[threadIdx.x] = g.rs[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // int_mul(r, s): exact 512-bit product (src/bn128.js:701, src/build_int.js:285-380)
+        uint32_t r32[8], s32[8], p[16];
+        memcpy(r32, s_rs, 32);
+        memcpy(s32, s_rs + 32, 32);
+        for (int i = 0; i < 16; i++) p[i] = 0;
+        for (int i = 0; i < 8; i++) {
+            uint64_t c = 0;
+            for (int j = 0; j < 8; j++) {
+                c += (uint64_t)r32[i] * s32[j] + p[i + j];
+                p[i + j] = (uint32_t)c;
+                c >>= 32;
+            }
+            p[i + 8] = (uint32_t)c;
+        }
+        memcpy(s_prod, p, 64);
+    }
+    __syncthreads();
+    const uint8_t* r = s_rs;
+    const uint8_t* s = s_rs + 32;
+    if (lane == 0) {
+        if (warp == 0) s_rd1 = times_scalar<G1Curve>(load_fixed<G1Curve>(g.fx->delta1), r, 32);            // r * delta1
+        else if (warp == 1) s_sd1 = times_scalar<G1Curve>(load_fixed<G1Curve>(g.fx->delta1), s, 32);       // s * delta1
+        else if (warp == 2) s_rsd1 = times_scalar<G1Curve>(load_fixed<G1Curve>(g.fx->delta1), s_prod, 64); // (r*s) * delta1
+        else {
+            // pi_b = B2 + beta2 + s * delta2                                   (src/bn128.js:675-678)
+            G2X sd2 = times_scalar<G2Curve>(load_fixed<G2Curve>(g.fx->delta2), s, 32);
+            G2X pib = padd_call<G2Curve>(load_fixed<G2Curve>(g.fx->beta2), *g.B2);
+            pib = padd_call<G2Curve>(sd2, pib);
+            *g.pi_b = affine_std<G2Curve>(pib);
+        }
+    }
+    __syncthreads();
+    if (lane == 0) {
+        if (warp == 0) {
+            // pi_a = A + alfa1 + r * delta1                                    (src/bn128.js:670-673)
+            G1X pia = padd_call<G1Curve>(load_fixed<G1Curve>(g.fx->alfa1), *g.A);
+            pia = padd_call<G1Curve>(s_rd1, pia);
+            s_spia = times_scalar<G1Curve>(pia, s, 32);                         // s * pi_a   (:691)
+            *g.pi_a = affine_std<G1Curve>(pia);
+        } else if (warp == 1) {
+            // pib1 = B1 + beta1 + s * delta1                                   (src/bn128.js:680-683)
+            G1X pib1 = padd_call<G1Curve>(load_fixed<G1Curve>(g.fx->beta1), *g.B1);
+            pib1 = padd_call<G1Curve>(s_sd1, pib1);
+            s_rpib1 = times_scalar<G1Curve>(pib1, r, 32);                       // r * pib1   (:695)
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // pi_c = C + H + s*pi_a + r*pib1 - (r*s)*delta1                        (src/bn128.js:686-704)
+        G1X pic = padd_call<G1Curve>(*g.H, *g.C);
+        pic = padd_call<G1Curve>(s_spia, pic);
+        pic = padd_call<G1Curve>(s_rpib1, pic);
+        pic = padd_call<G1Curve>(pneg<G1Curve>(s_rsd1), pic);
+        *g.pi_c = affine_std<G1Curve>(pic);
+    }
+}
+
+// ============================================================================ proving key
+// Row-grouped form of one polynomial section (u32 ncoefs; {u32 idx; 32-byte coef} x ncoefs per signal;
+// tools/buildpkey.js:79-89).  Returns false if the section runs past `len` or an index is out of range.
+static bool build_csr(const uint8_t* sec, size_t len, uint32_t n_signals, uint32_t domain, std::vector<uint32_t>& row_start,
+                      std::vector<uint32_t>& sig, std::vector<uint8_t>& coef) {
+    row_start.assign((size_t)domain + 1, 0);
+    size_t pos = 0, total = 0;
+    for (uint32_t i = 0; i < n_signals; i++) {
+        if (pos + 4 > len) return false;
+        uint32_t nc;
+        memcpy(&nc, sec + pos, 4);
+        pos += 4;
+        if ((size_t)nc * 36 > len - pos) return false;
+        for (uint32_t k = 0; k < nc; k++) {
+            uint32_t idx;
+            memcpy(&idx, sec + pos, 4);
+            if (idx >= domain) return false;
+            row_start[idx + 1]++;
+            pos += 36;
+        }
+        total += nc;
+    }
+    for (uint32_t r = 0; r < domain; r++) row_start[r + 1] += row_start[r];
+    sig.resize(total + 1);
+    coef.resize((total + 1) * 32);
+    std::vector<uint32_t> cur(row_start.begin(), row_start.end() - 1);
+    pos = 0;
+    for (uint32_t i = 0; i < n_signals; i++) {
+        uint32_t nc;
+        memcpy(&nc, sec + pos, 4);
+        pos += 4;
+        for (uint32_t k = 0; k < nc; k++) {
+            uint32_t idx;
+            memcpy(&idx, sec + pos, 4);
+            uint32_t at = cur[idx]++;
+            sig[at] = i;
+            memcpy(&coef[(size_t)at * 32], sec + pos + 4, 32);
+            pos += 36;
+        }
+    }
+    return true;
+}
+
+struct DevCsr {
+    uint32_t* row_start = nullptr;
+    uint32_t* sig = nullptr;
+    Fr* coef = nullptr;
+    void free_all() {
+        cudaFree(row_start);
+        cudaFree(sig);
+        cudaFree(coef);
+        row_start = sig = nullptr;
+        coef = nullptr;
+    }
+};
+
+static bool upload_csr(const std::vector<uint32_t>& rs, const std::vector<uint32_t>& sg, const std::vector<uint8_t>& cf, DevCsr& d, cudaStream_t st) {
+    if (cudaMalloc(&d.row_start, rs.size() * 4) != cudaSuccess) return false;
+    if (cudaMalloc(&d.sig, sg.size() * 4) != cudaSuccess) return false;
+    if (cudaMalloc(&d.coef, cf.size()) != cudaSuccess) return false;
+    cudaMemcpyAsync(d.row_start, rs.data(), rs.size() * 4, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d.sig, sg.data(), sg.size() * 4, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d.coef, cf.data(), cf.size(), cudaMemcpyHostToDevice, st);
+    return cudaStreamSynchronize(st) == cudaSuccess;
+}
+
+struct ws_pkey {
+    ws_ctx* ctx = nullptr;
+    uint32_t n_vars = 0, n_public = 0, domain = 0;
+    int logn = 0;
+    DevCsr polA, polB;
+    uint8_t* points = nullptr;     // one allocation: A | B1 | B2 | C | H, each 256-byte aligned
+    G1Affine *A = nullptr, *B1 = nullptr, *C = nullptr, *H = nullptr;
+    G2Affine* B2 = nullptr;
+    FixedPoints* fixed = nullptr;
+};
+
+static int log2_exact(uint32_t n) {
+    if (n == 0 || (n & (n - 1))) return -1;
+    int l = 0;
+    while ((1u << l) < n) l++;
+    return l;
+}
+
+static void pkey_release(ws_pkey* k) {
+    if (!k) return;
+    k->polA.free_all();
+    k->polB.free_all();
+    cudaFree(k->points);
+    cudaFree(k->fixed);
+    delete k;
+}
+
+static int pkey_load(ws_ctx* c, const uint8_t* pkey, size_t len, ws_pkey** out) {
+    if (len < 488) return c->fail(WS_E_ARG, "proving key shorter than its header");
+    uint32_t h[10];
+    memcpy(h, pkey, 40);
+    const uint32_t nv = h[0], npub = h[1], dom = h[2];
+    const size_t pA = h[3], pB = h[4], pPA = h[5], pPB1 = h[6], pPB2 = h[7], pPC = h[8], pPH = h[9];
+    int logn = log2_exact(dom);
+    if (logn < 0 || logn > 27) return c->fail(WS_E_SIZE, "domainSize must be a power of two <= 2^27");   // 2n-point transform <= 2^28
+    if (nv == 0 || npub + 1 > nv) return c->fail(WS_E_ARG, "bad nVars / nPublic");
+    const size_t nC = (size_t)nv - npub - 1;
+    if (!(488 <= pA && pA <= pB && pB <= pPA && pPA + (size_t)nv * 64 <= len && pPB1 + (size_t)nv * 64 <= len && pPB2 + (size_t)nv * 128 <= len &&
+          pPC + nC * 64 <= len && pPH + (size_t)dom * 64 <= len))
+        return c->fail(WS_E_ARG, "proving key sections out of bounds");
+    cudaSetDevice(c->device);
+    std::vector<uint32_t> rs, sg;
+    std::vector<uint8_t> cf;
+    ws_pkey* k = new ws_pkey();
+    k->ctx = c;
+    k->n_vars = nv;
+    k->n_public = npub;
+    k->domain = dom;
+    k->logn = logn;
+    // the reference slices polsA as [pPolsA, pPolsA + pPolsB) (src/bn128.js:592); the section proper ends at pPolsB
+    if (!build_csr(pkey + pA, pB - pA, nv, dom, rs, sg, cf) || !upload_csr(rs, sg, cf, k->polA, c->stream)) {
+        pkey_release(k);
+        return c->fail(WS_E_ARG, "polsA section malformed (or out of device memory)");
+    }
+    if (!build_csr(pkey + pB, pPA - pB, nv, dom, rs, sg, cf) || !upload_csr(rs, sg, cf, k->polB, c->stream)) {
+        pkey_release(k);
+        return c->fail(WS_E_ARG, "polsB section malformed (or out of device memory)");
+    }
+    size_t oA = 0, oB1 = oA + align256((size_t)nv * 64), oB2 = oB1 + align256((size_t)nv * 64), oC = oB2 + align256((size_t)nv * 128),
+           oH = oC + align256(nC * 64 + 64), tot = oH + align256((size_t)dom * 64);
+    if (cudaMalloc(&k->points, tot) != cudaSuccess || cudaMalloc(&k->fixed, sizeof(FixedPoints)) != cudaSuccess) {
+        pkey_release(k);
+        return c->fail_cuda("proving key upload");
+    }
+    k->A = (G1Affine*)(k->points + oA);
+    k->B1 = (G1Affine*)(k->points + oB1);
+    k->B2 = (G2Affine*)(k->points + oB2);
+    k->C = (G1Affine*)(k->points + oC);
+    k->H = (G1Affine*)(k->points + oH);
+    cudaMemcpyAsync(k->A, pkey + pPA, (size_t)nv * 64, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(k->B1, pkey + pPB1, (size_t)nv * 64, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(k->B2, pkey + pPB2, (size_t)nv * 128, cudaMemcpyHostToDevice, c->stream);
+    if (nC) cudaMemcpyAsync(k->C, pkey + pPC, nC * 64, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(k->H, pkey + pPH, (size_t)dom * 64, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(k->fixed, pkey + 40, 448, cudaMemcpyHostToDevice, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        pkey_release(k);
+        return c->fail_cuda("proving key upload");
+    }
+    *out = k;
+    return WS_OK;
+}
+
+// ============================================================================ H pipeline + prover (device)
+static bool ensure_twiddles(ws_ctx* c, int logM, cudaStream_t st) {
+    TwiddleTable T;
+    T.tw = (Fr*)c->tw_table;
+    T.logM = c->tw_logM;
+    bool ok = ntt_ensure_table(T, logM, st);
+    c->tw_table = T.tw;
+    c->tw_logM = T.logM;
+    return ok;
+}
+static TwiddleTable twiddles(ws_ctx* c) {
+    TwiddleTable T;
+    T.tw = (Fr*)c->tw_table;
+    T.logM = c->tw_logM;
+    return T;
+}
+
+// h = coefficients n..2n-1 of A*B, out of Montgomery form; everything on `st`.
+// work: (n_signals + 8n) field elements of scratch.
+static int calc_h_dev(ws_ctx* c, const DevCsr& pa, const DevCsr& pb, const Fr* d_signals, uint32_t n_signals, int logn, Fr* d_h, Fr* work, cudaStream_t st) {
+    const uint32_t n = 1u << logn;
+    if (!ensure_twiddles(c, logn + 1, st)) return c->fail_cuda("twiddle table");
+    TwiddleTable T = twiddles(c);
+    Fr* sM = work;
+    Fr* A = sM + n_signals;
+    Fr* B = A + n;
+    Fr* Ao = B + n;
+    Fr* Bo = Ao + n;
+    Fr* P = Bo + n;            // 2n
+    Fr* scratch = P + 2 * (size_t)n;   // 2n
+    c->timer.mark("h:begin", st);
+    k_fr_to_mont<<<(n_signals + 127) / 128, 128, 0, st>>>(d_signals, sM, n_signals);
+    k_csr_lc<<<(n + 127) / 128, 128, 0, st>>>(pa.row_start, pa.sig, pa.coef, sM, A, n);
+    k_csr_lc<<<(n + 127) / 128, 128, 0, st>>>(pb.row_start, pb.sig, pb.coef, sM, B, n);
+    c->timer.mark("h:lc", st);
+    cudaMemcpyAsync(Ao, A, sizeof(Fr) * n, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(Bo, B, sizeof(Fr) * n, cudaMemcpyDeviceToDevice, st);
+    ntt_launch(Ao, scratch, logn, 0, 1, T, st);
+    ntt_launch(Bo, scratch, logn, 0, 1, T, st);
+    ntt_launch(Ao, scratch, logn, 1, 0, T, st);
+    ntt_launch(Bo, scratch, logn, 1, 0, T, st);
+    k_interleave_mul<<<(n + 127) / 128, 128, 0, st>>>(A, B, Ao, Bo, P, n);
+    ntt_launch(P, scratch, logn + 1, 0, 1, T, st);
+    k_fr_from_mont<<<(n + 127) / 128, 128, 0, st>>>(P + n, d_h, n);
+    c->timer.mark("h:ntt", st);
+    return cudaGetLastError() == cudaSuccess ? WS_OK : c->fail_cuda("calc_h");
+}
+
+// d_out: 96 (pi_a) + 192 (pi_b) + 96 (pi_c) bytes, affine, out of Montgomery form.
+static int prove_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_witness, const uint8_t* d_rs, uint8_t* d_out, cudaStream_t st) {
+    const uint32_t nv = k->n_vars, n = k->domain;
+    const size_t work_elems = (size_t)nv + 9 * (size_t)n + 64;
+    uint8_t* base = (uint8_t*)c->arena(2, work_elems * 32 + 8 * 256);
+    if (!base) return c->fail_cuda("prover workspace");
+    Fr* h = (Fr*)base;
+    Fr* work = h + n;
+    uint8_t* res = (uint8_t*)(work + nv + 8 * (size_t)n);
+    G1X* rA = (G1X*)res;
+    G1X* rB1 = rA + 1;
+    G1X* rC = rB1 + 1;
+    G1X* rH = rC + 1;
+    G2X* rB2 = (G2X*)(rH + 1);
+    c->timer.begin(st);
+    int rc = calc_h_dev(c, k->polA, k->polB, (const Fr*)d_witness, nv, k->logn, h, work, st);
+    if (rc) return rc;
+    if ((rc = msm_g1_run(c, h, k->H, n, nullptr, rH, st))) return rc;
+    c->timer.mark("msm:H", st);
+    if ((rc = msm_g1_run(c, d_witness, k->A, nv, nullptr, rA, st))) return rc;
+    c->timer.mark("msm:A", st);
+    if ((rc = msm_g1_run(c, d_witness, k->B1, nv, nullptr, rB1, st))) return rc;
+    c->timer.mark("msm:B1", st);
+    if ((rc = msm_g2_run(c, d_witness, k->B2, nv, nullptr, rB2, st))) return rc;
+    c->timer.mark("msm:B2", st);
+    const size_t nC = (size_t)nv - k->n_public - 1;
+    if ((rc = msm_g1_run(c, d_witness + 32 * ((size_t)k->n_public + 1), k->C, nC, nullptr, rC, st))) return rc;
+    c->timer.mark("msm:C", st);
+    AssembleArgs g;
+    g.A = rA;
+    g.B1 = rB1;
+    g.C = rC;
+    g.H = rH;
+    g.B2 = rB2;
+    g.fx = k->fixed;
+    g.rs = d_rs;
+    g.pi_a = (Jac<G1Curve>*)d_out;
+    g.pi_b = (Jac<G2Curve>*)(d_out + 96);
+    g.pi_c = (Jac<G1Curve>*)(d_out + 288);
+    k_assemble<<<1, 128, 0, st>>>(g);
+    c->timer.mark("assemble", st);
+    return cudaGetLastError() == cudaSuccess ? WS_OK : c->fail_cuda("prove");
+}
+
+static int prove_host(ws_ctx* c, const ws_pkey* k, const uint8_t* witness, size_t wlen, const uint8_t* r, const uint8_t* s, uint8_t* pi_a, uint8_t* pi_b,
+                      uint8_t* pi_c) {
+    if (wlen < (size_t)k->n_vars * 32) return c->fail(WS_E_ARG, "witness shorter than nVars * 32 bytes");
+    cudaSetDevice(c->device);
+    uint8_t rs[64];
+    // r, s: 32 random bytes each (src/bn128.js:642-664) unless injected
+    if (r) memcpy(rs, r, 32);
+    else if (getrandom(rs, 32, 0) != 32) return c->fail(WS_E_ARG, "getrandom failed");
+    if (s) memcpy(rs + 32, s, 32);
+    else if (getrandom(rs + 32, 32, 0) != 32) return c->fail(WS_E_ARG, "getrandom failed");
+    size_t wbytes = (size_t)k->n_vars * 32;
+    uint8_t* d = (uint8_t*)c->arena(3, align256(wbytes) + 1024);
+    if (!d) return c->fail_cuda("witness buffer");
+    uint8_t* d_rs = d + align256(wbytes);
+    uint8_t* d_out = d_rs + 256;
+    cudaMemcpyAsync(d, witness, wbytes, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(d_rs, rs, 64, cudaMemcpyHostToDevice, c->stream);
+    int rc = prove_dev(c, k, d, d_rs, d_out, c->stream);
+    if (rc) return rc;
+    uint8_t outb[384];
+    cudaMemcpyAsync(outb, d_out, 384, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) return c->fail_cuda("prove");
+    memcpy(pi_a, outb, 96);
+    memcpy(pi_b, outb + 96, 192);
+    memcpy(pi_c, outb + 288, 96);
+    return WS_OK;
+}
+
+// ============================================================================ C ABI
+extern "C" {
+
+WS_API int ws_bn128_fr_fft_dev(ws_ctx* c, void* d_px, size_t n, int odd, int inverse, void* stream) {
+    if (!c || !d_px) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
+    int logn = n <= 0xFFFFFFFFull ? log2_exact((uint32_t)n) : -1;
+    if (logn < 0 || logn > 28) return c->fail(WS_E_SIZE, "fft size must be a power of two <= 2^28");
+    cudaSetDevice(c->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    if (!ensure_twiddles(c, logn + 1, st)) return c->fail_cuda("twiddle table");
+    Fr* scratch = (Fr*)c->arena(2, sizeof(Fr) << logn);
+    if (!scratch) return c->fail_cuda("fft scratch");
+    c->timer.begin(st);
+    cudaError_t e = ntt_launch((Fr*)d_px, scratch, logn, odd != 0, inverse != 0, twiddles(c), st);
+    c->timer.mark("ntt", st);
+    return e == cudaSuccess ? WS_OK : c->fail_cuda("ntt");
+}
+
+static int fft_host(ws_ctx* c, uint8_t* px, size_t n, int odd, int inverse) {
+    if (!c || !px) return c ? c->fail(WS_E_ARG, "null buffer") : WS_E_ARG;
+    int logn = n <= 0xFFFFFFFFull ? log2_exact((uint32_t)n) : -1;
+    if (logn < 0 || logn > 28) return c->fail(WS_E_SIZE, "fft size must be a power of two <= 2^28");
+    cudaSetDevice(c->device);
+    uint8_t* d = (uint8_t*)c->arena(3, n * 32);
+    if (!d) return c->fail_cuda("fft buffer");
+    cudaMemcpyAsync(d, px, n * 32, cudaMemcpyHostToDevice, c->stream);
+    int rc = ws_bn128_fr_fft_dev(c, d, n, odd, inverse, c->stream);
+    if (rc) return rc;
+    cudaMemcpyAsync(px, d, n * 32, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) return c->fail_cuda("fft");
+    return WS_OK;
+}
+WS_API int ws_bn128_fr_fft(ws_ctx* c, uint8_t* px, size_t n, int odd) { return fft_host(c, px, n, odd, 0); }
+WS_API int ws_bn128_fr_ifft(ws_ctx* c, uint8_t* px, size_t n, int odd) { return fft_host(c, px, n, odd, 1); }
+
+WS_API int ws_bn128_pkey_load(ws_ctx* c, const uint8_t* pkey, size_t len, ws_pkey** out) {
+    if (!c || !pkey || !out) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
+    *out = nullptr;
+    return pkey_load(c, pkey, len, out);
+}
+WS_API void ws_bn128_pkey_free(ws_pkey* k) {
+    if (!k) return;
+    cudaSetDevice(k->ctx->device);
+    cudaStreamSynchronize(k->ctx->stream);
+    pkey_release(k);
+}
+WS_API int ws_bn128_pkey_info(const ws_pkey* k, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size) {
+    if (!k) return WS_E_ARG;
+    if (n_vars) *n_vars = k->n_vars;
+    if (n_public) *n_public = k->n_public;
+    if (domain_size) *domain_size = k->domain;
+    return WS_OK;
+}
+
+WS_API int ws_bn128_calc_h(ws_ctx* c, const uint8_t* signals, const uint8_t* polsA, size_t lenA, const uint8_t* polsB, size_t lenB, uint32_t n_signals,
+                           uint32_t domain_size, uint8_t* out) {
+    if (!c || !signals || !polsA || !polsB || !out) return c ? c->fail(WS_E_ARG, "null buffer") : WS_E_ARG;
+    int logn = log2_exact(domain_size);
+    if (logn < 0 || logn > 27) return c->fail(WS_E_SIZE, "domainSize must be a power of two <= 2^27");
+    cudaSetDevice(c->device);
+    std::vector<uint32_t> rs, sg;
+    std::vector<uint8_t> cf;
+    DevCsr da, db;
+    int rc = WS_OK;
+    if (!build_csr(polsA, lenA, n_signals, domain_size, rs, sg, cf) || !upload_csr(rs, sg, cf, da, c->stream)) rc = c->fail(WS_E_ARG, "polsA malformed");
+    if (!rc && (!build_csr(polsB, lenB, n_signals, domain_size, rs, sg, cf) || !upload_csr(rs, sg, cf, db, c->stream))) rc = c->fail(WS_E_ARG, "polsB malformed");
+    if (!rc) {
+        size_t n = domain_size;
+        uint8_t* base = (uint8_t*)c->arena(2, ((size_t)2 * n_signals + 9 * n + 64) * 32);
+        if (!base) rc = c->fail_cuda("calc_h workspace");
+        else {
+            Fr* d_sig = (Fr*)base;
+            Fr* h = d_sig + n_signals;
+            Fr* work = h + n;
+            cudaMemcpyAsync(d_sig, signals, (size_t)n_signals * 32, cudaMemcpyHostToDevice, c->stream);
+            c->timer.begin(c->stream);
+            rc = calc_h_dev(c, da, db, d_sig, n_signals, logn, h, work, c->stream);
+            if (!rc) {
+                cudaMemcpyAsync(out, h, n * 32, cudaMemcpyDeviceToHost, c->stream);
+                if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = c->fail_cuda("calc_h");
+            }
+        }
+    }
+    cudaStreamSynchronize(c->stream);
+    da.free_all();
+    db.free_all();
+    return rc;
+}
+
+WS_API int ws_bn128_groth16_prove_key(ws_ctx* c, const ws_pkey* k, const uint8_t* witness, size_t wlen, const uint8_t* r, const uint8_t* s, uint8_t pi_a[96],
+                                      uint8_t pi_b[192], uint8_t pi_c[96]) {
+    if (!c || !k || !witness || !pi_a || !pi_b || !pi_c) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
+    if (k->ctx != c) return c->fail(WS_E_ARG, "proving key belongs to another context");
+    return prove_host(c, k, witness, wlen, r, s, pi_a, pi_b, pi_c);
+}
+
+WS_API int ws_bn128_groth16_prove(ws_ctx* c, const uint8_t* witness, size_t wlen, const uint8_t* pkey, size_t plen, const uint8_t* r, const uint8_t* s,
+                                  uint8_t pi_a[96], uint8_t pi_b[192], uint8_t pi_c[96]) {
+    if (!c || !witness || !pkey || !pi_a || !pi_b || !pi_c) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
+    ws_pkey* k = nullptr;
+    int rc = pkey_load(c, pkey, plen, &k);
+    if (rc) return rc;
+    rc = prove_host(c, k, witness, wlen, r, s, pi_a, pi_b, pi_c);
+    cudaStreamSynchronize(c->stream);
+    pkey_release(k);
+    return rc;
+}
+
+WS_API int ws_bn128_groth16_prove_dev(ws_ctx* c, const ws_pkey* k, const void* d_witness, const void* d_rs, void* d_out, void* stream) {
+    if (!c || !k || !d_witness || !d_rs || !d_out) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
+    if (k->ctx != c) return c->fail(WS_E_ARG, "proving key belongs to another context");
+    if (((uintptr_t)d_witness | (uintptr_t)d_out) & 15) return c->fail(WS_E_ARG, "device pointers must be 16-byte aligned");
+    cudaSetDevice(c->device);
+    return prove_dev(c, k, (const uint8_t*)d_witness, (const uint8_t*)d_rs, (uint8_t*)d_out, stream ? (cudaStream_t)stream : c->stream);
+}
+
+}  // extern "C"
