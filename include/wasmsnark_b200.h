@@ -145,6 +145,18 @@ int ws_bn128_groth16_prove_key(ws_ctx* ctx, const ws_pkey* key, const uint8_t* w
  * (pi_a | pi_b | pi_c) on the device; enqueued on `stream`, no synchronisation.                      */
 int ws_bn128_groth16_prove_dev(ws_ctx* ctx, const ws_pkey* key, const void* d_witness, const void* d_rs, void* d_out, void* stream);
 
+/* ---- multi-GPU prover (one process / one ctx per GPU) --------------------------------------------------
+ * The reference shards every multiexp over its workers by contiguous point ranges and adds the partial
+ * points (src/bn128.js:353-383).  Same split here across ranks: ws_bn128_pkey_load_shard keeps only rank's
+ * ranges of A, B1, B2, C, hExps in HBM (plus the polynomial sections: H is computed on every rank);
+ * ws_bn128_groth16_partials_dev writes the rank's five partial sums (768 bytes: XYZZ records A|B1|C|H|B2);
+ * the caller all-gathers the `world` records (NCCL) and every rank finishes with
+ * ws_bn128_groth16_finish_dev, which adds them and runs the final assembly.                             */
+#define WS_PARTIALS_BYTES 768
+int ws_bn128_pkey_load_shard(ws_ctx* ctx, const uint8_t* pkey, size_t pkey_len, int rank, int world, ws_pkey** out);
+int ws_bn128_groth16_partials_dev(ws_ctx* ctx, const ws_pkey* key, const void* d_witness, void* d_partials, void* stream);
+int ws_bn128_groth16_finish_dev(ws_ctx* ctx, const ws_pkey* key, const void* d_all_partials, int world, const void* d_rs, void* d_out, void* stream);
+
 /* Stage timing on/off (CUDA events recorded between the pipeline's kernels on the launch stream). */
 int ws_set_profiling(ws_ctx* ctx, int on);
 /* Tuning/test hook: force the per-task entry cap of the MSM accumulate kernel (0 = automatic). */

@@ -140,3 +140,34 @@ def test_example_key_golden_proof(bn):
     assert proof == gold["proof_rs"]
     key.free()
     assert bn.groth16GenProof(wit, pk, r=bytes(32), s=bytes(32)) == {kk: good[kk] for kk in ("pi_a", "pi_b", "pi_c")}
+
+
+def test_sharded_partials_emulated_on_one_gpu(bn):
+    """The N > 1 data path without N GPUs: the key loaded as shard 0/3, 1/3, 2/3 on one context, the three
+    768-byte partial records concatenated as an all_gather would, then finish -- must equal the golden proof."""
+    import ctypes
+    import torch
+    from wasmsnark_b200._lib import as_ptr
+    pk = open(os.path.join(GOLD, "synth_small.pkey.bin"), "rb").read()
+    wit = open(os.path.join(GOLD, "synth_small.witness.bin"), "rb").read()
+    g = json.load(open(os.path.join(GOLD, "synth_small.golden.json")))
+    world = 3
+    d_w = torch.frombuffer(bytearray(wit), dtype=torch.uint8).cuda()
+    d_rs = torch.frombuffer(bytearray(bytes.fromhex(g["r"]) + bytes.fromhex(g["s"])), dtype=torch.uint8).cuda()
+    d_all = torch.zeros(768 * world, dtype=torch.uint8, device="cuda")
+    d_out = torch.zeros(384, dtype=torch.uint8, device="cuda")
+    keys = []
+    for r in range(world):
+        k = ctypes.c_void_p()
+        bn.ctx.check(bn.lib.ws_bn128_pkey_load_shard(bn.ctx.h, as_ptr(pk), len(pk), r, world, ctypes.byref(k)))
+        keys.append(k)
+        torch.cuda.synchronize()
+        bn.ctx.check(bn.lib.ws_bn128_groth16_partials_dev(bn.ctx.h, k, d_w.data_ptr(), d_all[768 * r:].data_ptr(), None))
+    bn.ctx.check(bn.lib.ws_bn128_groth16_finish_dev(bn.ctx.h, keys[0], d_all.data_ptr(), world, d_rs.data_ptr(), d_out.data_ptr(), None))
+    bn.ctx.timings()            # synchronises the ctx stream
+    torch.cuda.synchronize()
+    out = bytes(d_out.cpu().numpy())
+    proof = {"pi_a": bn.bin2g1(out[:96]), "pi_b": bn.bin2g2(out[96:288]), "pi_c": bn.bin2g1(out[288:])}
+    assert proof == g["proof_rs"]
+    for k in keys:
+        bn.lib.ws_bn128_pkey_free(k)

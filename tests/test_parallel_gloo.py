@@ -1,0 +1,64 @@
+"""N > 1 host logic on CPU: world_size-2 gloo group.  Each rank takes its contiguous point range
+(shard_range = the reference's worker split, src/bn128.js:353-361), computes its partial sum with the
+oracle standing in for the GPU kernel, the 96-byte partial records are exchanged with the same
+all_gather helper the NCCL path uses, and the combined point must equal the unsharded sum."""
+import os
+import random
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import bn128 as O
+from wasmsnark_b200.parallel import all_gather_records, shard_range
+
+
+def test_shard_range_matches_reference_split():
+    for n in (0, 1, 7, 8, 66232, 1 << 20):
+        for w in (1, 2, 3, 8):
+            ranges = [shard_range(n, r, w) for r in range(w)]
+            assert ranges[0][0] == 0
+            for (lo, cnt), (lo2, _) in zip(ranges, ranges[1:]):
+                assert lo + cnt == lo2
+            assert ranges[-1][0] + ranges[-1][1] == n
+            assert all(cnt == n // w for _, cnt in ranges[:-1])       # floor(n/W) each, last takes the rest
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def _worker(rank, world, port, scalars, points, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, cnt = shard_range(len(scalars), rank, world)
+    part = O.multiexp(O.Fq, scalars[lo:lo + cnt], points[lo:lo + cnt])
+    rec = torch.frombuffer(bytearray(O.g1_to_bytes_m(part)), dtype=torch.uint8)
+    allrec = all_gather_records(rec, world)
+    assert allrec.numel() == 96 * world
+    acc = O.pt_zero(O.Fq)
+    raw = bytes(allrec.numpy())
+    for r in range(world):
+        x, y, z = (O.from_mont(int.from_bytes(raw[96 * r + 32 * k:96 * r + 32 * k + 32], "little")) for k in range(3))
+        acc = O.pt_add(O.Fq, acc, (x, y, z))
+    q.put((rank, O.pt_affine(O.Fq, acc)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_sum_equals_unsharded():
+    rnd = random.Random(9)
+    n = 37
+    base = (O.G1_GEN[0], O.G1_GEN[1], 1)
+    points = [O.pt_times_scalar(O.Fq, base, rnd.randrange(1, O.R_ORDER)) for _ in range(n)]
+    scalars = [rnd.getrandbits(256) for _ in range(n)]
+    want = O.pt_affine(O.Fq, O.multiexp(O.Fq, scalars, points))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + random.randrange(2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, scalars, points, q)) for r in range(2)]
+    [p.start() for p in procs]
+    got = [q.get(timeout=120) for _ in range(2)]
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert sorted(r for r, _ in got) == [0, 1]
+    assert all(res == want for _, res in got)

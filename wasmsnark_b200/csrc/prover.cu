@@ -228,6 +228,12 @@ struct ws_pkey {
     ws_ctx* ctx = nullptr;
     uint32_t n_vars = 0, n_public = 0, domain = 0;
     int logn = 0;
+    // point-range shard held by this key object (rank r of w): contiguous ranges, floor(n/w) each and the
+    // last rank takes the remainder -- the reference's worker split (src/bn128.js:353-361)
+    int rank = 0, world = 1;
+    uint32_t v_lo = 0, v_cnt = 0;     // A / B1 / B2 over the signals
+    uint32_t c_lo = 0, c_cnt = 0;     // C over signals nPublic+1 ..
+    uint32_t h_lo = 0, h_cnt = 0;     // hExps over the domain
     DevCsr polA, polB;
     uint8_t* points = nullptr;     // one allocation: A | B1 | B2 | C | H, each 256-byte aligned
     G1Affine *A = nullptr, *B1 = nullptr, *C = nullptr, *H = nullptr;
@@ -251,7 +257,14 @@ static void pkey_release(ws_pkey* k) {
     delete k;
 }
 
-static int pkey_load(ws_ctx* c, const uint8_t* pkey, size_t len, ws_pkey** out) {
+static void shard_range(uint32_t n, int rank, int world, uint32_t* lo, uint32_t* cnt) {
+    uint32_t per = n / (uint32_t)world;
+    *lo = per * (uint32_t)rank;
+    *cnt = rank < world - 1 ? per : n - per * (uint32_t)(world - 1);
+}
+
+static int pkey_load(ws_ctx* c, const uint8_t* pkey, size_t len, ws_pkey** out, int rank = 0, int world = 1) {
+    if (world < 1 || rank < 0 || rank >= world) return c->fail(WS_E_ARG, "bad rank / world");
     if (len < 488) return c->fail(WS_E_ARG, "proving key shorter than its header");
     uint32_t h[10];
     memcpy(h, pkey, 40);
@@ -273,6 +286,11 @@ static int pkey_load(ws_ctx* c, const uint8_t* pkey, size_t len, ws_pkey** out) 
     k->n_public = npub;
     k->domain = dom;
     k->logn = logn;
+    k->rank = rank;
+    k->world = world;
+    shard_range(nv, rank, world, &k->v_lo, &k->v_cnt);
+    shard_range((uint32_t)nC, rank, world, &k->c_lo, &k->c_cnt);
+    shard_range(dom, rank, world, &k->h_lo, &k->h_cnt);
     // the reference slices polsA as [pPolsA, pPolsA + pPolsB) (src/bn128.js:592); the section proper ends at pPolsB
     if (!build_csr(pkey + pA, pB - pA, nv, dom, rs, sg, cf) || !upload_csr(rs, sg, cf, k->polA, c->stream)) {
         pkey_release(k);
@@ -282,8 +300,9 @@ static int pkey_load(ws_ctx* c, const uint8_t* pkey, size_t len, ws_pkey** out) 
         pkey_release(k);
         return c->fail(WS_E_ARG, "polsB section malformed (or out of device memory)");
     }
-    size_t oA = 0, oB1 = oA + align256((size_t)nv * 64), oB2 = oB1 + align256((size_t)nv * 64), oC = oB2 + align256((size_t)nv * 128),
-           oH = oC + align256(nC * 64 + 64), tot = oH + align256((size_t)dom * 64);
+    const size_t vc = k->v_cnt, cc = k->c_cnt, hc = k->h_cnt;
+    size_t oA = 0, oB1 = oA + align256(vc * 64 + 64), oB2 = oB1 + align256(vc * 64 + 64), oC = oB2 + align256(vc * 128 + 64),
+           oH = oC + align256(cc * 64 + 64), tot = oH + align256(hc * 64 + 64);
     if (cudaMalloc(&k->points, tot) != cudaSuccess || cudaMalloc(&k->fixed, sizeof(FixedPoints)) != cudaSuccess) {
         pkey_release(k);
         return c->fail_cuda("proving key upload");
@@ -293,11 +312,13 @@ static int pkey_load(ws_ctx* c, const uint8_t* pkey, size_t len, ws_pkey** out) 
     k->B2 = (G2Affine*)(k->points + oB2);
     k->C = (G1Affine*)(k->points + oC);
     k->H = (G1Affine*)(k->points + oH);
-    cudaMemcpyAsync(k->A, pkey + pPA, (size_t)nv * 64, cudaMemcpyHostToDevice, c->stream);
-    cudaMemcpyAsync(k->B1, pkey + pPB1, (size_t)nv * 64, cudaMemcpyHostToDevice, c->stream);
-    cudaMemcpyAsync(k->B2, pkey + pPB2, (size_t)nv * 128, cudaMemcpyHostToDevice, c->stream);
-    if (nC) cudaMemcpyAsync(k->C, pkey + pPC, nC * 64, cudaMemcpyHostToDevice, c->stream);
-    cudaMemcpyAsync(k->H, pkey + pPH, (size_t)dom * 64, cudaMemcpyHostToDevice, c->stream);
+    if (vc) {
+        cudaMemcpyAsync(k->A, pkey + pPA + (size_t)k->v_lo * 64, vc * 64, cudaMemcpyHostToDevice, c->stream);
+        cudaMemcpyAsync(k->B1, pkey + pPB1 + (size_t)k->v_lo * 64, vc * 64, cudaMemcpyHostToDevice, c->stream);
+        cudaMemcpyAsync(k->B2, pkey + pPB2 + (size_t)k->v_lo * 128, vc * 128, cudaMemcpyHostToDevice, c->stream);
+    }
+    if (cc) cudaMemcpyAsync(k->C, pkey + pPC + (size_t)k->c_lo * 64, cc * 64, cudaMemcpyHostToDevice, c->stream);
+    if (hc) cudaMemcpyAsync(k->H, pkey + pPH + (size_t)k->h_lo * 64, hc * 64, cudaMemcpyHostToDevice, c->stream);
     cudaMemcpyAsync(k->fixed, pkey + 40, 448, cudaMemcpyHostToDevice, c->stream);
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
         pkey_release(k);
@@ -355,16 +376,17 @@ static int calc_h_dev(ws_ctx* c, const DevCsr& pa, const DevCsr& pb, const Fr* d
     return cudaGetLastError() == cudaSuccess ? WS_OK : c->fail_cuda("calc_h");
 }
 
-// d_out: 96 (pi_a) + 192 (pi_b) + 96 (pi_c) bytes, affine, out of Montgomery form.
-static int prove_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_witness, const uint8_t* d_rs, uint8_t* d_out, cudaStream_t st) {
+// The five partial sums of this key's shard, as XYZZ records: A | B1 | C | H (128 bytes each) | B2 (256).
+constexpr size_t PARTIALS_BYTES = 4 * sizeof(G1X) + sizeof(G2X);   // 768
+
+static int prove_partials_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_witness, uint8_t* d_partials, cudaStream_t st) {
     const uint32_t nv = k->n_vars, n = k->domain;
     const size_t work_elems = (size_t)nv + 9 * (size_t)n + 64;
-    uint8_t* base = (uint8_t*)c->arena(2, work_elems * 32 + 8 * 256);
+    uint8_t* base = (uint8_t*)c->arena(2, work_elems * 32);
     if (!base) return c->fail_cuda("prover workspace");
     Fr* h = (Fr*)base;
     Fr* work = h + n;
-    uint8_t* res = (uint8_t*)(work + nv + 8 * (size_t)n);
-    G1X* rA = (G1X*)res;
+    G1X* rA = (G1X*)d_partials;
     G1X* rB1 = rA + 1;
     G1X* rC = rB1 + 1;
     G1X* rH = rC + 1;
@@ -372,23 +394,50 @@ static int prove_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_witness, cons
     c->timer.begin(st);
     int rc = calc_h_dev(c, k->polA, k->polB, (const Fr*)d_witness, nv, k->logn, h, work, st);
     if (rc) return rc;
-    if ((rc = msm_g1_run(c, h, k->H, n, nullptr, rH, st))) return rc;
+    if ((rc = msm_g1_run(c, h + k->h_lo, k->H, k->h_cnt, nullptr, rH, st))) return rc;
     c->timer.mark("msm:H", st);
-    if ((rc = msm_g1_run(c, d_witness, k->A, nv, nullptr, rA, st))) return rc;
+    const uint8_t* wv = d_witness + 32 * (size_t)k->v_lo;
+    if ((rc = msm_g1_run(c, wv, k->A, k->v_cnt, nullptr, rA, st))) return rc;
     c->timer.mark("msm:A", st);
-    if ((rc = msm_g1_run(c, d_witness, k->B1, nv, nullptr, rB1, st))) return rc;
+    if ((rc = msm_g1_run(c, wv, k->B1, k->v_cnt, nullptr, rB1, st))) return rc;
     c->timer.mark("msm:B1", st);
-    if ((rc = msm_g2_run(c, d_witness, k->B2, nv, nullptr, rB2, st))) return rc;
+    if ((rc = msm_g2_run(c, wv, k->B2, k->v_cnt, nullptr, rB2, st))) return rc;
     c->timer.mark("msm:B2", st);
-    const size_t nC = (size_t)nv - k->n_public - 1;
-    if ((rc = msm_g1_run(c, d_witness + 32 * ((size_t)k->n_public + 1), k->C, nC, nullptr, rC, st))) return rc;
+    if ((rc = msm_g1_run(c, d_witness + 32 * ((size_t)k->n_public + 1 + k->c_lo), k->C, k->c_cnt, nullptr, rC, st))) return rc;
     c->timer.mark("msm:C", st);
+    return cudaGetLastError() == cudaSuccess ? WS_OK : c->fail_cuda("prove");
+}
+
+// Adds up the `world` partial records (the exchange step of the sharded prover: the reference's serial
+// g1m_add over worker results, src/bn128.js:376-380) -- one thread per MSM.
+static __global__ void __launch_bounds__(32) k_sum_partials(const uint8_t* __restrict__ all, int world, uint8_t* __restrict__ out) {
+    int i = threadIdx.x;
+    if (i < 4) {
+        G1X acc = G1X::inf();
+        for (int r = 0; r < world; r++) acc = padd_call<G1Curve>(acc, *((const G1X*)(all + (size_t)r * PARTIALS_BYTES) + i));
+        ((G1X*)out)[i] = acc;
+    } else if (i == 4) {
+        G2X acc = G2X::inf();
+        for (int r = 0; r < world; r++) acc = padd_call<G2Curve>(acc, *(const G2X*)(all + (size_t)r * PARTIALS_BYTES + 4 * sizeof(G1X)));
+        *(G2X*)(out + 4 * sizeof(G1X)) = acc;
+    }
+}
+
+// d_all: world x 768 bytes of partial records; d_out: 96 (pi_a) + 192 (pi_b) + 96 (pi_c) bytes, affine, out of Montgomery form.
+static int prove_finish_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_all, int world, const uint8_t* d_rs, uint8_t* d_out, cudaStream_t st) {
+    uint8_t* sum = (uint8_t*)c->arena(4, 1024);
+    if (!sum) return c->fail_cuda("prover workspace");
+    const uint8_t* src = d_all;
+    if (world > 1) {
+        k_sum_partials<<<1, 32, 0, st>>>(d_all, world, sum);
+        src = sum;
+    }
     AssembleArgs g;
-    g.A = rA;
-    g.B1 = rB1;
-    g.C = rC;
-    g.H = rH;
-    g.B2 = rB2;
+    g.A = (const G1X*)src;
+    g.B1 = g.A + 1;
+    g.C = g.A + 2;
+    g.H = g.A + 3;
+    g.B2 = (const G2X*)(g.A + 4);
     g.fx = k->fixed;
     g.rs = d_rs;
     g.pi_a = (Jac<G1Curve>*)d_out;
@@ -397,6 +446,15 @@ static int prove_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_witness, cons
     k_assemble<<<1, 128, 0, st>>>(g);
     c->timer.mark("assemble", st);
     return cudaGetLastError() == cudaSuccess ? WS_OK : c->fail_cuda("prove");
+}
+
+static int prove_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_witness, const uint8_t* d_rs, uint8_t* d_out, cudaStream_t st) {
+    if (k->world != 1) return c->fail(WS_E_ARG, "sharded key: use the partials / finish entry points");
+    uint8_t* part = (uint8_t*)c->arena(5, 1024);
+    if (!part) return c->fail_cuda("prover workspace");
+    int rc = prove_partials_dev(c, k, d_witness, part, st);
+    if (rc) return rc;
+    return prove_finish_dev(c, k, part, 1, d_rs, d_out, st);
 }
 
 static int prove_host(ws_ctx* c, const ws_pkey* k, const uint8_t* witness, size_t wlen, const uint8_t* r, const uint8_t* s, uint8_t* pi_a, uint8_t* pi_b,
@@ -466,6 +524,24 @@ WS_API int ws_bn128_pkey_load(ws_ctx* c, const uint8_t* pkey, size_t len, ws_pke
     if (!c || !pkey || !out) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
     *out = nullptr;
     return pkey_load(c, pkey, len, out);
+}
+WS_API int ws_bn128_pkey_load_shard(ws_ctx* c, const uint8_t* pkey, size_t len, int rank, int world, ws_pkey** out) {
+    if (!c || !pkey || !out) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
+    *out = nullptr;
+    return pkey_load(c, pkey, len, out, rank, world);
+}
+WS_API int ws_bn128_groth16_partials_dev(ws_ctx* c, const ws_pkey* k, const void* d_witness, void* d_partials, void* stream) {
+    if (!c || !k || !d_witness || !d_partials) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
+    if (k->ctx != c) return c->fail(WS_E_ARG, "proving key belongs to another context");
+    if (((uintptr_t)d_witness | (uintptr_t)d_partials) & 15) return c->fail(WS_E_ARG, "device pointers must be 16-byte aligned");
+    cudaSetDevice(c->device);
+    return prove_partials_dev(c, k, (const uint8_t*)d_witness, (uint8_t*)d_partials, stream ? (cudaStream_t)stream : c->stream);
+}
+WS_API int ws_bn128_groth16_finish_dev(ws_ctx* c, const ws_pkey* k, const void* d_all_partials, int world, const void* d_rs, void* d_out, void* stream) {
+    if (!c || !k || !d_all_partials || !d_rs || !d_out || world < 1) return c ? c->fail(WS_E_ARG, "bad argument") : WS_E_ARG;
+    if (k->ctx != c) return c->fail(WS_E_ARG, "proving key belongs to another context");
+    cudaSetDevice(c->device);
+    return prove_finish_dev(c, k, (const uint8_t*)d_all_partials, world, (const uint8_t*)d_rs, (uint8_t*)d_out, stream ? (cudaStream_t)stream : c->stream);
 }
 WS_API void ws_bn128_pkey_free(ws_pkey* k) {
     if (!k) return;
