@@ -332,6 +332,7 @@ def main():
         d_proof = torch.zeros(384, dtype=torch.uint8, device="cuda")
 
         def step_prove():
+            bn.ctx.check(lib.ws_bn128_groth16_prepare_dev(h, key_h, d_rs.data_ptr(), st))
             bn.ctx.check(lib.ws_bn128_groth16_partials_dev(h, key_h, d_w.data_ptr(), d_part.data_ptr(), st))
             if world > 1:
                 dist.all_gather_into_tensor(d_all, d_part)

@@ -155,6 +155,10 @@ int ws_bn128_groth16_prove_dev(ws_ctx* ctx, const ws_pkey* key, const void* d_wi
 #define WS_PARTIALS_BYTES 768
 int ws_bn128_pkey_load_shard(ws_ctx* ctx, const uint8_t* pkey, size_t pkey_len, int rank, int world, ws_pkey** out);
 int ws_bn128_groth16_partials_dev(ws_ctx* ctx, const ws_pkey* key, const void* d_witness, void* d_partials, void* stream);
+/* optional, before partials: starts the products that depend only on (r, s) and the key's fixed points
+ * (r*delta1, s*delta1, (r*s)*delta1, s*delta2; src/bn128.js:672-702) on a side stream so that they overlap
+ * the multi-scalar multiplications; finish_dev picks the result up (or computes it itself if not prepared). */
+int ws_bn128_groth16_prepare_dev(ws_ctx* ctx, const ws_pkey* key, const void* d_rs, void* stream);
 int ws_bn128_groth16_finish_dev(ws_ctx* ctx, const ws_pkey* key, const void* d_all_partials, int world, const void* d_rs, void* d_out, void* stream);
 
 /* Stage timing on/off (CUDA events recorded between the pipeline's kernels on the launch stream). */

@@ -57,6 +57,7 @@ SIGNATURES = {
     "ws_bn128_groth16_prove_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "ws_bn128_pkey_load_shard": (_i, [_vp, _vp, _sz, _i, _i, ctypes.POINTER(_vp)]),
     "ws_bn128_groth16_partials_dev": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "ws_bn128_groth16_prepare_dev": (_i, [_vp, _vp, _vp, _vp]),
     "ws_bn128_groth16_finish_dev": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "ws_bn128_g1_sum_dev": (_i, [_vp, _vp, _i, _vp, _vp]),
     "ws_bn128_g2_sum_dev": (_i, [_vp, _vp, _i, _vp, _vp]),

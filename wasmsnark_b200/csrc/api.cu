@@ -42,6 +42,13 @@ WS_API void ws_destroy(ws_ctx* c) {
     for (auto& a : c->arenas)
         if (a.ptr) cudaFree(a.ptr);
     if (c->tw_table) cudaFree(c->tw_table);
+    if (c->lanes_ready) {
+        for (int i = 0; i < ws_ctx::NLANES; i++) {
+            cudaStreamDestroy(c->lanes[i]);
+            cudaEventDestroy(c->lane_done[i]);
+        }
+        cudaEventDestroy(c->fork_ev);
+    }
     cudaStreamDestroy(c->stream);
     delete c;
 }

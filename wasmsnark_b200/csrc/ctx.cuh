@@ -40,7 +40,24 @@ struct Arena {
 struct ws_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    ws::Arena arenas[8];
+    ws::Arena arenas[16];
+    // side streams for the prover: independent MSMs and the r/s fixed-base products run concurrently
+    static constexpr int NLANES = 6;
+    cudaStream_t lanes[NLANES] = {};
+    cudaEvent_t lane_done[NLANES] = {};
+    cudaEvent_t fork_ev = nullptr;
+    bool lanes_ready = false;
+    bool pre_pending = false;   // prover: (r, s) products already in flight on lanes[4]
+    bool ensure_lanes() {
+        if (lanes_ready) return true;
+        for (int i = 0; i < NLANES; i++) {
+            if (cudaStreamCreateWithFlags(&lanes[i], cudaStreamNonBlocking) != cudaSuccess) return false;
+            if (cudaEventCreateWithFlags(&lane_done[i], cudaEventDisableTiming) != cudaSuccess) return false;
+        }
+        if (cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming) != cudaSuccess) return false;
+        lanes_ready = true;
+        return true;
+    }
     ws::StageTimer timer;
     std::string err;
     unsigned force_T = 0;

@@ -3,8 +3,8 @@
 using namespace ws;
 
 namespace ws {
-int msm_g2_run(ws_ctx* c, const void* ds, const void* dp, size_t n, void* d_out_jac, void* d_out_xyzz, cudaStream_t st) {
-    return multiexp_dev<G2Curve>(c, ds, dp, n, d_out_jac, 0, st, d_out_xyzz, false);
+int msm_g2_run(ws_ctx* c, const void* ds, const void* dp, size_t n, void* d_out_jac, void* d_out_xyzz, cudaStream_t st, int arena_slot) {
+    return multiexp_dev<G2Curve>(c, ds, dp, n, d_out_jac, 0, st, d_out_xyzz, false, arena_slot);
 }
 }  // namespace ws
 

@@ -13,7 +13,7 @@ namespace ws {
 
 // d_out: Jacobian triple (may be null); d_out_xyzz: XYZZ sum for device consumers (may be null)
 template <class C>
-inline int multiexp_dev(ws_ctx* c, const void* d_scalars, const void* d_points, size_t n, void* d_out, int window_bits, cudaStream_t st, void* d_out_xyzz = nullptr, bool own_timer = true) {
+inline int multiexp_dev(ws_ctx* c, const void* d_scalars, const void* d_points, size_t n, void* d_out, int window_bits, cudaStream_t st, void* d_out_xyzz = nullptr, bool own_timer = true, int arena_slot = 1) {
     if (n > 0x7FFFFFFFull) return c->fail(WS_E_ARG, "n too large");
     if (((uintptr_t)d_scalars | (uintptr_t)d_points | (uintptr_t)d_out | (uintptr_t)d_out_xyzz) & 15) return c->fail(WS_E_ARG, "device pointers must be 16-byte aligned");
     int cb;
@@ -26,7 +26,7 @@ inline int multiexp_dev(ws_ctx* c, const void* d_scalars, const void* d_points, 
     if (c->force_T) T = c->force_T;
     MsmPlan p = msm_make_plan((uint32_t)n, cb, T, c->seg_len);
     size_t need = msm_carve<C>(p, nullptr, nullptr);
-    uint8_t* base = (uint8_t*)c->arena(1, need);
+    uint8_t* base = (uint8_t*)c->arena(arena_slot, need);
     if (!base) return c->fail_cuda("msm workspace");
     MsmWorkspace w;
     msm_carve<C>(p, base, &w);

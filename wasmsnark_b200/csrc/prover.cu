@@ -93,12 +93,18 @@ __device__ __forceinline__ Jac<C> affine_std(const XYZZ<C>& p) {   // g?m_affine
     return a;
 }
 
-// One block, 4 warps; lane 0 of each warp runs one of the independent scalar multiplications.
-static __global__ void __launch_bounds__(128) k_assemble(AssembleArgs g) {
-    __shared__ G1X s_rd1, s_sd1, s_rsd1, s_spia, s_rpib1;
+// The four products that depend only on (r, s) and the key's fixed points: r*delta1, s*delta1,
+// (r*s)*delta1 (512-bit scalar) and s*delta2.  One block, 4 warps, lane 0 of each warp runs one
+// product; launched on a side stream so it overlaps the multi-scalar multiplications.
+struct PreProducts {
+    G1X rd1, sd1, rsd1;
+    G2X sd2;
+};
+
+static __global__ void __launch_bounds__(128) k_assemble_pre(const FixedPoints* __restrict__ fx, const uint8_t* __restrict__ rs, PreProducts* out) {
     __shared__ uint8_t s_rs[64], s_prod[64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x < 64) s_rs[threadIdx.x] = g.rs[threadIdx.x];
+    if (threadIdx.x < 64) s_rs[threadIdx.x] = rs[threadIdx.x];
     __syncthreads();
     if (threadIdx.x == 0) {
         // int_mul(r, s): exact 512-bit product (src/bn128.js:701, src/build_int.js:285-380)
@@ -118,42 +124,50 @@ static __global__ void __launch_bounds__(128) k_assemble(AssembleArgs g) {
         memcpy(s_prod, p, 64);
     }
     __syncthreads();
+    if (lane != 0) return;
+    const uint8_t* r = s_rs;
+    const uint8_t* s = s_rs + 32;
+    if (warp == 0) out->rd1 = times_scalar_w4<G1Curve>(load_fixed<G1Curve>(fx->delta1), r, 32);
+    else if (warp == 1) out->sd1 = times_scalar_w4<G1Curve>(load_fixed<G1Curve>(fx->delta1), s, 32);
+    else if (warp == 2) out->rsd1 = times_scalar_w4<G1Curve>(load_fixed<G1Curve>(fx->delta1), s_prod, 64);
+    else out->sd2 = times_scalar_w4<G2Curve>(load_fixed<G2Curve>(fx->delta2), s, 32);
+}
+
+// After the multi-scalar multiplications: 3 warps.
+//   warp 0: pi_a = A + alfa1 + r*delta1, s*pi_a        (src/bn128.js:670-673, :691)
+//   warp 1: pib1 = B1 + beta1 + s*delta1, r*pib1       (:680-683, :695)
+//   warp 2: pi_b = B2 + beta2 + s*delta2               (:675-678)
+//   then    pi_c = C + H + s*pi_a + r*pib1 - (r*s)*delta1   (:686-704), affine + fromMontgomery (:706-712)
+static __global__ void __launch_bounds__(96) k_assemble_post(AssembleArgs g, const PreProducts* __restrict__ pre) {
+    __shared__ G1X s_spia, s_rpib1;
+    __shared__ uint8_t s_rs[64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 64) s_rs[threadIdx.x] = g.rs[threadIdx.x];
+    __syncthreads();
     const uint8_t* r = s_rs;
     const uint8_t* s = s_rs + 32;
     if (lane == 0) {
-        if (warp == 0) s_rd1 = times_scalar<G1Curve>(load_fixed<G1Curve>(g.fx->delta1), r, 32);            // r * delta1
-        else if (warp == 1) s_sd1 = times_scalar<G1Curve>(load_fixed<G1Curve>(g.fx->delta1), s, 32);       // s * delta1
-        else if (warp == 2) s_rsd1 = times_scalar<G1Curve>(load_fixed<G1Curve>(g.fx->delta1), s_prod, 64); // (r*s) * delta1
-        else {
-            // pi_b = B2 + beta2 + s * delta2                                   (src/bn128.js:675-678)
-            G2X sd2 = times_scalar<G2Curve>(load_fixed<G2Curve>(g.fx->delta2), s, 32);
+        if (warp == 0) {
+            G1X pia = padd_call<G1Curve>(load_fixed<G1Curve>(g.fx->alfa1), *g.A);
+            pia = padd_call<G1Curve>(pre->rd1, pia);
+            s_spia = times_scalar_w4<G1Curve>(pia, s, 32);
+            *g.pi_a = affine_std<G1Curve>(pia);
+        } else if (warp == 1) {
+            G1X pib1 = padd_call<G1Curve>(load_fixed<G1Curve>(g.fx->beta1), *g.B1);
+            pib1 = padd_call<G1Curve>(pre->sd1, pib1);
+            s_rpib1 = times_scalar_w4<G1Curve>(pib1, r, 32);
+        } else {
             G2X pib = padd_call<G2Curve>(load_fixed<G2Curve>(g.fx->beta2), *g.B2);
-            pib = padd_call<G2Curve>(sd2, pib);
+            pib = padd_call<G2Curve>(pre->sd2, pib);
             *g.pi_b = affine_std<G2Curve>(pib);
         }
     }
     __syncthreads();
-    if (lane == 0) {
-        if (warp == 0) {
-            // pi_a = A + alfa1 + r * delta1                                    (src/bn128.js:670-673)
-            G1X pia = padd_call<G1Curve>(load_fixed<G1Curve>(g.fx->alfa1), *g.A);
-            pia = padd_call<G1Curve>(s_rd1, pia);
-            s_spia = times_scalar<G1Curve>(pia, s, 32);                         // s * pi_a   (:691)
-            *g.pi_a = affine_std<G1Curve>(pia);
-        } else if (warp == 1) {
-            // pib1 = B1 + beta1 + s * delta1                                   (src/bn128.js:680-683)
-            G1X pib1 = padd_call<G1Curve>(load_fixed<G1Curve>(g.fx->beta1), *g.B1);
-            pib1 = padd_call<G1Curve>(s_sd1, pib1);
-            s_rpib1 = times_scalar<G1Curve>(pib1, r, 32);                       // r * pib1   (:695)
-        }
-    }
-    __syncthreads();
     if (threadIdx.x == 0) {
-        // pi_c = C + H + s*pi_a + r*pib1 - (r*s)*delta1                        (src/bn128.js:686-704)
         G1X pic = padd_call<G1Curve>(*g.H, *g.C);
         pic = padd_call<G1Curve>(s_spia, pic);
         pic = padd_call<G1Curve>(s_rpib1, pic);
-        pic = padd_call<G1Curve>(pneg<G1Curve>(s_rsd1), pic);
+        pic = padd_call<G1Curve>(pneg<G1Curve>(pre->rsd1), pic);
         *g.pi_c = affine_std<G1Curve>(pic);
     }
 }
@@ -383,7 +397,7 @@ static int prove_partials_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_witn
     const uint32_t nv = k->n_vars, n = k->domain;
     const size_t work_elems = (size_t)nv + 9 * (size_t)n + 64;
     uint8_t* base = (uint8_t*)c->arena(2, work_elems * 32);
-    if (!base) return c->fail_cuda("prover workspace");
+    if (!base || !c->ensure_lanes()) return c->fail_cuda("prover workspace");
     Fr* h = (Fr*)base;
     Fr* work = h + n;
     G1X* rA = (G1X*)d_partials;
@@ -392,20 +406,41 @@ static int prove_partials_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_witn
     G1X* rH = rC + 1;
     G2X* rB2 = (G2X*)(rH + 1);
     c->timer.begin(st);
-    int rc = calc_h_dev(c, k->polA, k->polB, (const Fr*)d_witness, nv, k->logn, h, work, st);
-    if (rc) return rc;
-    if ((rc = msm_g1_run(c, h + k->h_lo, k->H, k->h_cnt, nullptr, rH, st))) return rc;
-    c->timer.mark("msm:H", st);
+    // The four witness MSMs do not depend on H: they go to side streams (own workspace each) and run
+    // while the H pipeline (LC + 5 NTTs) and the H MSM proceed on `st` -- the reference's promise
+    // graph (src/bn128.js:607-622), with streams instead of workers.
+    cudaEventRecord(c->fork_ev, st);
     const uint8_t* wv = d_witness + 32 * (size_t)k->v_lo;
-    if ((rc = msm_g1_run(c, wv, k->A, k->v_cnt, nullptr, rA, st))) return rc;
-    c->timer.mark("msm:A", st);
-    if ((rc = msm_g1_run(c, wv, k->B1, k->v_cnt, nullptr, rB1, st))) return rc;
-    c->timer.mark("msm:B1", st);
-    if ((rc = msm_g2_run(c, wv, k->B2, k->v_cnt, nullptr, rB2, st))) return rc;
-    c->timer.mark("msm:B2", st);
-    if ((rc = msm_g1_run(c, d_witness + 32 * ((size_t)k->n_public + 1 + k->c_lo), k->C, k->c_cnt, nullptr, rC, st))) return rc;
-    c->timer.mark("msm:C", st);
+    int rc = 0;
+    for (int lane = 0; lane < 4 && !rc; lane++) {
+        cudaStream_t ls = c->lanes[lane];
+        cudaStreamWaitEvent(ls, c->fork_ev, 0);
+        if (lane == 0) rc = msm_g2_run(c, wv, k->B2, k->v_cnt, nullptr, rB2, ls, 8 + lane);
+        else if (lane == 1) rc = msm_g1_run(c, wv, k->A, k->v_cnt, nullptr, rA, ls, 8 + lane);
+        else if (lane == 2) rc = msm_g1_run(c, wv, k->B1, k->v_cnt, nullptr, rB1, ls, 8 + lane);
+        else rc = msm_g1_run(c, d_witness + 32 * ((size_t)k->n_public + 1 + k->c_lo), k->C, k->c_cnt, nullptr, rC, ls, 8 + lane);
+        cudaEventRecord(c->lane_done[lane], ls);
+    }
+    if (rc) return rc;
+    if ((rc = calc_h_dev(c, k->polA, k->polB, (const Fr*)d_witness, nv, k->logn, h, work, st))) return rc;
+    if ((rc = msm_g1_run(c, h + k->h_lo, k->H, k->h_cnt, nullptr, rH, st, 1))) return rc;
+    c->timer.mark("msm:H", st);
+    for (int lane = 0; lane < 4; lane++) cudaStreamWaitEvent(st, c->lane_done[lane], 0);
+    c->timer.mark("msm:A,B1,B2,C (side streams)", st);
     return cudaGetLastError() == cudaSuccess ? WS_OK : c->fail_cuda("prove");
+}
+
+// Starts the (r, s)-only products on a side stream; `st` must have d_rs ready at this point.
+static int prove_pre_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_rs, cudaStream_t st) {
+    PreProducts* pre = (PreProducts*)c->arena(6, sizeof(PreProducts));
+    if (!pre || !c->ensure_lanes()) return c->fail_cuda("prover workspace");
+    cudaStream_t ls = c->lanes[4];
+    cudaEventRecord(c->lane_done[5], st);
+    cudaStreamWaitEvent(ls, c->lane_done[5], 0);
+    k_assemble_pre<<<1, 128, 0, ls>>>(k->fixed, d_rs, pre);
+    cudaEventRecord(c->lane_done[4], ls);
+    c->pre_pending = true;
+    return cudaGetLastError() == cudaSuccess ? WS_OK : c->fail_cuda("assemble_pre");
 }
 
 // Adds up the `world` partial records (the exchange step of the sharded prover: the reference's serial
@@ -432,6 +467,12 @@ static int prove_finish_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_all, i
         k_sum_partials<<<1, 32, 0, st>>>(d_all, world, sum);
         src = sum;
     }
+    if (!c->pre_pending) {
+        int rc = prove_pre_dev(c, k, d_rs, st);
+        if (rc) return rc;
+    }
+    cudaStreamWaitEvent(st, c->lane_done[4], 0);
+    c->pre_pending = false;
     AssembleArgs g;
     g.A = (const G1X*)src;
     g.B1 = g.A + 1;
@@ -443,7 +484,7 @@ static int prove_finish_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_all, i
     g.pi_a = (Jac<G1Curve>*)d_out;
     g.pi_b = (Jac<G2Curve>*)(d_out + 96);
     g.pi_c = (Jac<G1Curve>*)(d_out + 288);
-    k_assemble<<<1, 128, 0, st>>>(g);
+    k_assemble_post<<<1, 96, 0, st>>>(g, (const PreProducts*)c->arena(6, sizeof(PreProducts)));
     c->timer.mark("assemble", st);
     return cudaGetLastError() == cudaSuccess ? WS_OK : c->fail_cuda("prove");
 }
@@ -452,8 +493,9 @@ static int prove_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_witness, cons
     if (k->world != 1) return c->fail(WS_E_ARG, "sharded key: use the partials / finish entry points");
     uint8_t* part = (uint8_t*)c->arena(5, 1024);
     if (!part) return c->fail_cuda("prover workspace");
-    int rc = prove_partials_dev(c, k, d_witness, part, st);
+    int rc = prove_pre_dev(c, k, d_rs, st);       // overlaps everything below
     if (rc) return rc;
+    if ((rc = prove_partials_dev(c, k, d_witness, part, st))) return rc;
     return prove_finish_dev(c, k, part, 1, d_rs, d_out, st);
 }
 
@@ -536,6 +578,12 @@ WS_API int ws_bn128_groth16_partials_dev(ws_ctx* c, const ws_pkey* k, const void
     if (((uintptr_t)d_witness | (uintptr_t)d_partials) & 15) return c->fail(WS_E_ARG, "device pointers must be 16-byte aligned");
     cudaSetDevice(c->device);
     return prove_partials_dev(c, k, (const uint8_t*)d_witness, (uint8_t*)d_partials, stream ? (cudaStream_t)stream : c->stream);
+}
+WS_API int ws_bn128_groth16_prepare_dev(ws_ctx* c, const ws_pkey* k, const void* d_rs, void* stream) {
+    if (!c || !k || !d_rs) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
+    if (k->ctx != c) return c->fail(WS_E_ARG, "proving key belongs to another context");
+    cudaSetDevice(c->device);
+    return prove_pre_dev(c, k, (const uint8_t*)d_rs, stream ? (cudaStream_t)stream : c->stream);
 }
 WS_API int ws_bn128_groth16_finish_dev(ws_ctx* c, const ws_pkey* k, const void* d_all_partials, int world, const void* d_rs, void* d_out, void* stream) {
     if (!c || !k || !d_all_partials || !d_rs || !d_out || world < 1) return c ? c->fail(WS_E_ARG, "bad argument") : WS_E_ARG;

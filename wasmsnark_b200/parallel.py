@@ -52,6 +52,7 @@ class ShardedProver:
         import torch
         bn = self.bn
         part = torch.empty(768, dtype=torch.uint8, device=d_witness.device)
+        bn.ctx.check(bn.lib.ws_bn128_groth16_prepare_dev(bn.ctx.h, self.key, d_rs.data_ptr(), stream_ptr))
         bn.ctx.check(bn.lib.ws_bn128_groth16_partials_dev(bn.ctx.h, self.key, d_witness.data_ptr(), part.data_ptr(), stream_ptr))
         allp = all_gather_records(part, self.world, self.group)
         bn.ctx.check(bn.lib.ws_bn128_groth16_finish_dev(bn.ctx.h, self.key, allp.data_ptr(), self.world, d_rs.data_ptr(), d_out.data_ptr(), stream_ptr))
