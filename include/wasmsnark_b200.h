@@ -103,6 +103,21 @@ int ws_bn128_g2_multiexp_dev(ws_ctx* ctx, const void* d_scalars, const void* d_p
 int ws_bn128_g1_sum_dev(ws_ctx* ctx, const void* d_parts, int count, void* d_out, void* stream);
 int ws_bn128_g2_sum_dev(ws_ctx* ctx, const void* d_parts, int count, void* d_out, void* stream);
 
+/* ---- MNT6753 wide-limb path (config C5): 24-limb (768-bit) Montgomery field -------------------------
+ * ws_fp_batch(field = WS_MNT6753_FQ) covers f1m_* of the MNT6753 image.
+ * Fq3 = Fq[u]/(u^3 - 11) product: replaces f3m_mul  src/build_f3m.js:125-189 (non-residue 11,
+ * src/mnt6753/build_mnt6753.js:35-56); elements c0|c1|c2, 288 bytes.                                  */
+int ws_mnt6753_fq3_mul_batch(ws_ctx* ctx, const uint8_t* x, const uint8_t* y, uint8_t* out, size_t n);
+/* G1 multi-scalar multiplication on y^2 = x^3 + 11x + b (curve module src/build_curve_projective.js with
+ * mulByA = 11, src/mnt6753/build_mnt6753.js:90-109).  The reference has NO multiexp for this curve; the
+ * result equals sum_i g1m_timesScalar(P_i, s_i) folded with g1m_add.  scalars: n*96 bytes raw LE; points:
+ * n*192 bytes affine Montgomery x|y (x == 0 => infinity, as in the BN128 path); out: 288 bytes, a
+ * homogeneous projective triple X|Y|Z (x = X/Z, y = Y/Z) as the reference's g1m_* use; infinity = Z 0.  */
+int ws_mnt6753_g1_multiexp(ws_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t out[288]);
+int ws_mnt6753_g1_multiexp_dev(ws_ctx* ctx, const void* d_scalars, const void* d_points, size_t n, void* d_out, int window_bits, void* stream);
+/* g1m_affine (src/build_curve_projective.js:624-652) [+ g1m_fromMontgomery]: projective triples -> (x, y, 1). */
+int ws_mnt6753_g1_affine(ws_ctx* ctx, const uint8_t* in, uint8_t* out, size_t count, int from_montgomery);
+
 /* ---- NTT over Fr (config C3) -------------------------------------------------------------------
  * Replaces fft_fft(px, n, odd) / fft_ifft(px, n, odd)   src/build_fft.js:159-221 (+ __rawfft :223-372,
  * __finalInverse :550-648): in place on n 32-byte Montgomery Fr elements, natural order in and out.

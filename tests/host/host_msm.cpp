@@ -12,7 +12,7 @@ static void run(const uint8_t* scalars, const uint8_t* points, uint32_t n, int c
     const Affine<C>* pts = (const Affine<C>*)points;
     std::vector<int16_t> digits((size_t)p.nwin * n);
     std::vector<uint32_t> counts(p.nbuckets, 0), bstart(p.nbuckets + 1), tstart(p.nbuckets + 1);
-    for (uint32_t i = 0; i < n; i++) msm_digits_body(p, i, (const uint32_t*)scalars + (size_t)i * 8, pts[i].is_inf(), digits.data(), counts.data());
+    for (uint32_t i = 0; i < n; i++) msm_digits_body<8>(p, i, (const uint32_t*)scalars + (size_t)i * 8, pts[i].is_inf(), digits.data(), counts.data());
     bstart[0] = 0; tstart[0] = 0;
     for (uint32_t b = 0; b < p.nbuckets; b++) {
         bstart[b + 1] = bstart[b] + counts[b];

@@ -45,6 +45,10 @@ SIGNATURES = {
     "ws_bn128_g2_multiexp_dev": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp]),
     "ws_bn128_g1_affine": (_i, [_vp, _vp, _vp, _sz, _i]),
     "ws_bn128_g2_affine": (_i, [_vp, _vp, _vp, _sz, _i]),
+    "ws_mnt6753_fq3_mul_batch": (_i, [_vp, _vp, _vp, _vp, _sz]),
+    "ws_mnt6753_g1_multiexp": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "ws_mnt6753_g1_multiexp_dev": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp]),
+    "ws_mnt6753_g1_affine": (_i, [_vp, _vp, _vp, _sz, _i]),
     "ws_bn128_fr_fft": (_i, [_vp, _vp, _sz, _i]),
     "ws_bn128_fr_ifft": (_i, [_vp, _vp, _sz, _i]),
     "ws_bn128_fr_fft_dev": (_i, [_vp, _vp, _sz, _i, _i, _vp]),

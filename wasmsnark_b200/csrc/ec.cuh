@@ -25,12 +25,31 @@ namespace ws {
 struct G1Curve {
     using F = Fq;
     static constexpr bool A_ZERO = true;
+    static constexpr bool PROJECTIVE = false;   // external triple is Jacobian (x = X/Z^2, y = Y/Z^3)
+    static constexpr int SCALAR_LIMBS = 8;
     HD static F mul_a(const F& x) { return F::zero(); }
 };
 struct G2Curve {
     using F = Fq2;
     static constexpr bool A_ZERO = true;
+    static constexpr bool PROJECTIVE = false;
+    static constexpr int SCALAR_LIMBS = 8;
     HD static F mul_a(const F& x) { return F::zero(); }
+};
+
+// MNT6753 G1: y^2 = x^3 + 11 x + b over the 753-bit field (24 limbs); the reference builds it with
+// homogeneous projective coordinates (x = X/Z, y = Y/Z) and mulByA = multiplication by 11
+// (/root/reference/src/mnt6753/build_mnt6753.js:90-109).
+using MntFq = Fp<MNT6753_Fq>;
+struct MntG1Curve {
+    using F = MntFq;
+    static constexpr bool A_ZERO = false;
+    static constexpr bool PROJECTIVE = true;
+    static constexpr int SCALAR_LIMBS = 24;
+    HD static F mul_a(const F& x) {          // 11 x = 8x + 2x + x
+        F x2 = dbl(x), x8 = dbl(dbl(x2));
+        return add(add(x8, x2), x);
+    }
 };
 
 template <class C>
@@ -169,6 +188,17 @@ HD Jac<C> to_jac(const XYZZ<C>& p) {
     return Jac<C>{mul(p.x, p.zz), mul(p.y, p.zzz), p.zz};
 }
 
+// External triple <-> XYZZ for whichever convention the curve's reference module uses.
+template <class C>
+HD Jac<C> to_ext(const XYZZ<C>& p) {
+    using F = typename C::F;
+    if (!C::PROJECTIVE) return to_jac<C>(p);
+    if (p.is_inf()) return Jac<C>{F::zero(), F::one(), F::zero()};
+    return Jac<C>{mul(p.x, p.zzz), mul(p.y, p.zz), mul(p.zz, p.zzz)};     // (X ZZZ : Y ZZ : ZZ ZZZ)
+}
+template <class C>
+HD XYZZ<C> from_ext(const Jac<C>& p);
+
 // Jacobian doubling for a = 0 [dbl-2009-l], the same formula as the reference's g?m_double
 // (build_curve_jacobian_a0.js:174-235): 2M + 5S in three dependency levels of three independent
 // products each, which is what the single-thread Horner tail wants.
@@ -207,6 +237,15 @@ HD XYZZ<C> pdbl_call(const XYZZ<C>& a) {
     XYZZ<C> r;
     pdbl_to<C>(&r, &a);
     return r;
+}
+
+template <class C>
+HD XYZZ<C> from_ext(const Jac<C>& p) {
+    using F = typename C::F;
+    if (!C::PROJECTIVE) return from_jac<C>(p);
+    if (p.z.is_zero()) return XYZZ<C>::inf();
+    F zz = sqr(p.z);
+    return XYZZ<C>{mul(p.x, p.z), mul(p.y, zz), zz, mul(zz, p.z)};       // x = XZ/Z^2, y = YZ^2/Z^3
 }
 
 // k * P, MSB first double-and-add over a little-endian byte string, as

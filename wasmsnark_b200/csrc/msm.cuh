@@ -148,11 +148,19 @@ static __global__ void __launch_bounds__(256) k_msm_digits(MsmPlan p, const uint
                                                     int16_t* __restrict__ digits, uint32_t* __restrict__ counts) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
-    const uint4* sp = reinterpret_cast<const uint4*>(scalars) + (size_t)i * 2;
-    uint4 a = __ldg(sp), b = __ldg(sp + 1);
-    uint32_t s8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    constexpr int SL = C::SCALAR_LIMBS;
+    const uint4* sp = reinterpret_cast<const uint4*>(scalars) + (size_t)i * (SL / 4);
+    uint32_t sl[SL];
+#pragma unroll
+    for (int k = 0; k < SL / 4; k++) {
+        uint4 a = __ldg(sp + k);
+        sl[4 * k] = a.x;
+        sl[4 * k + 1] = a.y;
+        sl[4 * k + 2] = a.z;
+        sl[4 * k + 3] = a.w;
+    }
     typename C::F x = ldg_struct(&points[i].x);
-    msm_digits_body(p, i, s8, x.is_zero(), digits, counts);
+    msm_digits_body<SL>(p, i, sl, x.is_zero(), digits, counts);
 }
 
 static __global__ void __launch_bounds__(256) k_msm_scatter(MsmPlan p, const int16_t* __restrict__ digits, const uint32_t* __restrict__ bstart,
@@ -337,13 +345,12 @@ static __global__ void __launch_bounds__(256) k_msm_bitsum(MsmPlan p, const XYZZ
 // Montgomery -- the reference's g1m_multiexp result format (callers normalise with g1_affine).
 template <class C>
 static __global__ void __launch_bounds__(160) k_msm_final(MsmPlan p, const XYZZ<C>* __restrict__ bits, XYZZ<C>* R, XYZZ<C>* out_xyzz, Jac<C>* out_jac) {
-    int w = threadIdx.x;
-    if (w < p.nwin) R[w] = msm_window_value<C>(p, w, bits);
+    for (int w = threadIdx.x; w < p.nwin; w += blockDim.x) R[w] = msm_window_value<C>(p, w, bits);
     __syncthreads();
-    if (w == 0) {
+    if (threadIdx.x == 0) {
         XYZZ<C> res = msm_horner_windows<C>(p, R);
         if (out_xyzz) *out_xyzz = res;
-        if (out_jac) *out_jac = to_jac<C>(res);
+        if (out_jac) *out_jac = to_ext<C>(res);
     }
 }
 
@@ -352,8 +359,8 @@ template <class C>
 static __global__ void __launch_bounds__(32) k_sum_points(const Jac<C>* __restrict__ in, int count, Jac<C>* out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     XYZZ<C> acc = XYZZ<C>::inf();
-    for (int i = 0; i < count; i++) acc = padd_call<C>(acc, from_jac<C>(in[i]));
-    *out = to_jac<C>(acc);
+    for (int i = 0; i < count; i++) acc = padd_call<C>(acc, from_ext<C>(in[i]));
+    *out = to_ext<C>(acc);
 }
 
 // g?m_affine (+ optional g?m_fromMontgomery) over an array of Jacobian triples, one thread each.
@@ -361,7 +368,7 @@ template <class C>
 static __global__ void __launch_bounds__(64) k_affine_points(const Jac<C>* __restrict__ in, Jac<C>* __restrict__ out, int count, int from_montgomery) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
-    Jac<C> a = to_affine<C>(from_jac<C>(in[i]));
+    Jac<C> a = to_affine<C>(from_ext<C>(in[i]));
     if (from_montgomery) {
         a.x = from_mont(a.x);
         a.y = from_mont(a.y);
@@ -425,14 +432,14 @@ inline size_t msm_carve(const MsmPlan& p, uint8_t* base, MsmWorkspace* ws) {
 }
 
 // Window size / task cap for n pairs on a 148-SM part.
-inline void msm_choose(uint32_t n, int* c, uint32_t* T) {
+inline void msm_choose(uint32_t n, int* c, uint32_t* T, int sbits = 256) {
     int lg = 0;
     while ((1ull << (lg + 1)) <= n) lg++;
     int cc = lg - 4;
     if (cc < 4) cc = 4;
     if (cc > 16) cc = 16;
     *c = cc;
-    int nwin = (257 + cc - 1) / cc;
+    int nwin = (sbits + 1 + cc - 1) / cc;
     uint64_t entries = (uint64_t)nwin * n;
     uint64_t want_tasks = 148ull * 512ull * 4ull;     // a few waves of resident threads
     uint64_t t = entries / want_tasks;

@@ -33,7 +33,8 @@ namespace ws {
 struct MsmPlan {
     uint32_t n;        // number of (scalar, point) pairs
     int c;             // window bits, 2..16
-    int nwin;          // windows incl. the carry window: ceil(257 / c)
+    int sbits;         // scalar width in bits (256 for BN128, 768 for MNT6753)
+    int nwin;          // windows incl. the carry window: ceil((sbits + 1) / c)
     uint32_t B;        // buckets per window = 2^(c-1); bucket b holds digit magnitude b+1
     uint32_t T;        // max entries per accumulate task
     uint32_t L;        // buckets per reduce segment (power of two, <= B)
@@ -43,11 +44,12 @@ struct MsmPlan {
     uint32_t max_tasks;
 };
 
-HD MsmPlan msm_make_plan(uint32_t n, int c, uint32_t T, uint32_t L = 0) {
+HD MsmPlan msm_make_plan(uint32_t n, int c, uint32_t T, uint32_t L = 0, int sbits = 256) {
     MsmPlan p;
     p.n = n;
     p.c = c;
-    p.nwin = (257 + c - 1) / c;
+    p.sbits = sbits;
+    p.nwin = (sbits + 1 + c - 1) / c;
     p.B = 1u << (c - 1);
     p.T = T;
     if (L == 0) {   // enough segments to occupy the part (~64K threads), at most 16 buckets each
@@ -75,21 +77,22 @@ HD uint32_t atomic_add_u32(uint32_t* p, uint32_t v) {
 }
 
 // ---- digits: thread i ------------------------------------------------------------------
-// scalar8: the 8 u32 limbs (raw, LE) of scalar i.  is_inf: point i is infinity (x == 0).
+// scalar_limbs: the SL u32 limbs (raw, LE) of scalar i.  is_inf: point i is infinity (x == 0).
 // digits[w * n + i] = signed digit in [-2^(c-1), 2^(c-1)), counts[w * B + |d| - 1]++.
-HD void msm_digits_body(const MsmPlan& p, uint32_t i, const uint32_t* scalar8, bool is_inf,
+template <int SL>
+HD void msm_digits_body(const MsmPlan& p, uint32_t i, const uint32_t* scalar_limbs, bool is_inf,
                         int16_t* digits, uint32_t* counts) {
-    uint32_t s[9];
+    uint32_t s[SL + 1];
 #pragma unroll
-    for (int k = 0; k < 8; k++) s[k] = is_inf ? 0u : scalar8[k];
-    s[8] = 0;
+    for (int k = 0; k < SL; k++) s[k] = is_inf ? 0u : scalar_limbs[k];
+    s[SL] = 0;
     const uint32_t mask = (1u << p.c) - 1u;
     const uint32_t half = 1u << (p.c - 1);
     uint32_t carry = 0;
     for (int w = 0; w < p.nwin; w++) {
         int bit = w * p.c;
         uint32_t raw = 0;
-        if (bit < 256) {
+        if (bit < 32 * SL) {
             int limb = bit >> 5, sh = bit & 31;
             uint64_t two = (uint64_t)s[limb] | ((uint64_t)s[limb + 1] << 32);
             raw = (uint32_t)(two >> sh) & mask;

@@ -18,13 +18,14 @@ inline int multiexp_dev(ws_ctx* c, const void* d_scalars, const void* d_points, 
     if (((uintptr_t)d_scalars | (uintptr_t)d_points | (uintptr_t)d_out | (uintptr_t)d_out_xyzz) & 15) return c->fail(WS_E_ARG, "device pointers must be 16-byte aligned");
     int cb;
     uint32_t T;
-    msm_choose((uint32_t)n, &cb, &T);
+    constexpr int SBITS = 32 * C::SCALAR_LIMBS;
+    msm_choose((uint32_t)n, &cb, &T, SBITS);
     if (window_bits) {
         if (window_bits < 2 || window_bits > 16) return c->fail(WS_E_ARG, "window_bits must be in 2..16");
         cb = window_bits;
     }
     if (c->force_T) T = c->force_T;
-    MsmPlan p = msm_make_plan((uint32_t)n, cb, T, c->seg_len);
+    MsmPlan p = msm_make_plan((uint32_t)n, cb, T, c->seg_len, SBITS);
     size_t need = msm_carve<C>(p, nullptr, nullptr);
     uint8_t* base = (uint8_t*)c->arena(arena_slot, need);
     if (!base) return c->fail_cuda("msm workspace");
@@ -40,12 +41,12 @@ template <class C>
 inline int multiexp_host(ws_ctx* c, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t* out) {
     if (!c || !out || (n && (!scalars || !points))) return c ? c->fail(WS_E_ARG, "null buffer") : WS_E_ARG;
     cudaSetDevice(c->device);
-    constexpr size_t PS = sizeof(Affine<C>), OS = sizeof(Jac<C>);
-    uint8_t* d = (uint8_t*)c->arena(0, align256(n * 32) + align256(n * PS) + 256);
+    constexpr size_t PS = sizeof(Affine<C>), OS = sizeof(Jac<C>), SS = 4 * C::SCALAR_LIMBS;
+    uint8_t* d = (uint8_t*)c->arena(0, align256(n * SS) + align256(n * PS) + 512);
     if (!d) return c->fail_cuda("input workspace");
-    uint8_t *ds = d, *dp = d + align256(n * 32), *dout = dp + align256(n * PS);
+    uint8_t *ds = d, *dp = d + align256(n * SS), *dout = dp + align256(n * PS);
     if (n) {
-        cudaMemcpyAsync(ds, scalars, n * 32, cudaMemcpyHostToDevice, c->stream);
+        cudaMemcpyAsync(ds, scalars, n * SS, cudaMemcpyHostToDevice, c->stream);
         cudaMemcpyAsync(dp, points, n * PS, cudaMemcpyHostToDevice, c->stream);
     }
     int rc = multiexp_dev<C>(c, ds, dp, n, dout, 0, c->stream);
