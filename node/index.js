@@ -1,0 +1,54 @@
+/* node/index.js -- drop-in for the proving half of wasmsnark's npm surface, on libwasmsnark_b200.so.
+ *
+ *   const { buildBn128 } = require("./node");           // index.js:20-22 of the reference
+ *   const bn128 = await buildBn128();
+ *   const proof = await bn128.groth16GenProof(witness, provingKey);     // src/bn128.js:580-720
+ *
+ * and the browser-global convention of main_bn128.js:27-41:
+ *   groth16GenProof(witness, provingKey, cb)  ->  cb(err, proof) or a Promise; alias genZKSnarkProof (README.md:28).
+ * The returned proof has the reference's shape: decimal strings, pi_a / pi_c = [x, y, "1"],
+ * pi_b = [[x0, x1], [y0, y1], ["1", "0"]] (src/bn128.js:714-718).  Not runnable in the build image (no Node).
+ */
+"use strict";
+const native = require("./wasmsnark_b200.node");
+
+function bin2int(buf, off) {            // src/bn128.js:319-327, with BigInt instead of big-integer
+    const v = new Uint32Array(buf, off, 8);
+    let acc = 0n;
+    for (let i = 7; i >= 0; i--) acc = (acc << 32n) | BigInt(v[i]);
+    return acc.toString();
+}
+const bin2g1 = (b) => [bin2int(b, 0), bin2int(b, 32), bin2int(b, 64)];                                   // :329-335
+const bin2g2 = (b) => [[bin2int(b, 0), bin2int(b, 32)], [bin2int(b, 64), bin2int(b, 96)], [bin2int(b, 128), bin2int(b, 160)]];   // :336-351
+
+class Bn128 {
+    constructor(device) { this.h = native.create(device || 0); }
+    groth16GenProof(signals, pkey, r, s) {
+        return new Promise((resolve, reject) => {
+            native.prove(this.h, signals, pkey, r || null, s || null, (err, p) => {
+                if (err) return reject(err);
+                resolve({ pi_a: bin2g1(p.pi_a), pi_b: bin2g2(p.pi_b), pi_c: bin2g1(p.pi_c) });
+            });
+        });
+    }
+    async g1_multiexp(scalars, points) { return native.g1Multiexp(this.h, scalars, points); }
+    async g2_multiexp(scalars, points) { return native.g2Multiexp(this.h, scalars, points); }
+    g1_affine(p) { return native.g1Affine(this.h, p); }
+    g2_affine(p) { return native.g2Affine(this.h, p); }
+    async calcH(signals, polsA, polsB, nSignals, domainSize) { return native.calcH(this.h, signals, polsA, polsB, nSignals, domainSize); }
+    bin2g1(b) { return bin2g1(b); }
+    bin2g2(b) { return bin2g2(b); }
+    terminate() { native.destroy(this.h); this.h = null; }
+}
+
+async function buildBn128(device) { return new Bn128(device); }
+
+let shared = null;
+function groth16GenProof(witness, provingKey, cb) {
+    if (!shared) shared = new Bn128(0);
+    const p = shared.groth16GenProof(witness, provingKey);
+    if (cb) p.then((proof) => cb(null, proof), (err) => cb(err));
+    else return p;
+}
+
+module.exports = { buildBn128, groth16GenProof, genZKSnarkProof: groth16GenProof };
