@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include "ctx.cuh"
 #include "msm_core.cuh"
+#include "warp_ec.cuh"
 
 namespace ws {
 
@@ -347,10 +348,13 @@ template <class C>
 static __global__ void __launch_bounds__(160) k_msm_final(MsmPlan p, const XYZZ<C>* __restrict__ bits, XYZZ<C>* R, XYZZ<C>* out_xyzz, Jac<C>* out_jac) {
     for (int w = threadIdx.x; w < p.nwin; w += blockDim.x) R[w] = msm_window_value<C>(p, w, bits);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        XYZZ<C> res = msm_horner_windows<C>(p, R);
-        if (out_xyzz) *out_xyzz = res;
-        if (out_jac) *out_jac = to_ext<C>(res);
+    if (threadIdx.x < 32) {      // one full warp: the doublings are 3-lane cooperative (warp_ec.cuh)
+        MsmPlanLite pl{p.nwin, p.c};
+        XYZZ<C> res = msm_horner_windows_warp<C>(pl, R);
+        if (threadIdx.x == 0) {
+            if (out_xyzz) *out_xyzz = res;
+            if (out_jac) *out_jac = to_ext<C>(res);
+        }
     }
 }
 

@@ -23,6 +23,7 @@
 #include "ec.cuh"
 #include "msm_api.cuh"
 #include "ntt.cuh"
+#include "warp_ec.cuh"
 
 #define WS_API __attribute__((visibility("default")))
 
@@ -124,13 +125,16 @@ static __global__ void __launch_bounds__(128) k_assemble_pre(const FixedPoints* 
         memcpy(s_prod, p, 64);
     }
     __syncthreads();
-    if (lane != 0) return;
+    // every lane of a warp carries the same state (warp-cooperative doublings); lane 0 stores
     const uint8_t* r = s_rs;
     const uint8_t* s = s_rs + 32;
-    if (warp == 0) out->rd1 = times_scalar_w4<G1Curve>(load_fixed<G1Curve>(fx->delta1), r, 32);
-    else if (warp == 1) out->sd1 = times_scalar_w4<G1Curve>(load_fixed<G1Curve>(fx->delta1), s, 32);
-    else if (warp == 2) out->rsd1 = times_scalar_w4<G1Curve>(load_fixed<G1Curve>(fx->delta1), s_prod, 64);
-    else out->sd2 = times_scalar_w4<G2Curve>(load_fixed<G2Curve>(fx->delta2), s, 32);
+    if (warp < 3) {
+        G1X v = times_scalar_w4_warp<G1Curve>(load_fixed<G1Curve>(fx->delta1), warp == 0 ? r : (warp == 1 ? s : s_prod), warp == 2 ? 64 : 32);
+        if (lane == 0) (warp == 0 ? out->rd1 : (warp == 1 ? out->sd1 : out->rsd1)) = v;
+    } else {
+        G2X v = times_scalar_w4_warp<G2Curve>(load_fixed<G2Curve>(fx->delta2), s, 32);
+        if (lane == 0) out->sd2 = v;
+    }
 }
 
 // After the multi-scalar multiplications: 3 warps.
@@ -146,21 +150,23 @@ static __global__ void __launch_bounds__(96) k_assemble_post(AssembleArgs g, con
     __syncthreads();
     const uint8_t* r = s_rs;
     const uint8_t* s = s_rs + 32;
-    if (lane == 0) {
-        if (warp == 0) {
-            G1X pia = padd_call<G1Curve>(load_fixed<G1Curve>(g.fx->alfa1), *g.A);
-            pia = padd_call<G1Curve>(pre->rd1, pia);
-            s_spia = times_scalar_w4<G1Curve>(pia, s, 32);
+    if (warp == 0) {
+        G1X pia = padd_call<G1Curve>(load_fixed<G1Curve>(g.fx->alfa1), *g.A);
+        pia = padd_call<G1Curve>(pre->rd1, pia);
+        G1X v = times_scalar_w4_warp<G1Curve>(pia, s, 32);
+        if (lane == 0) {
+            s_spia = v;
             *g.pi_a = affine_std<G1Curve>(pia);
-        } else if (warp == 1) {
-            G1X pib1 = padd_call<G1Curve>(load_fixed<G1Curve>(g.fx->beta1), *g.B1);
-            pib1 = padd_call<G1Curve>(pre->sd1, pib1);
-            s_rpib1 = times_scalar_w4<G1Curve>(pib1, r, 32);
-        } else {
-            G2X pib = padd_call<G2Curve>(load_fixed<G2Curve>(g.fx->beta2), *g.B2);
-            pib = padd_call<G2Curve>(pre->sd2, pib);
-            *g.pi_b = affine_std<G2Curve>(pib);
         }
+    } else if (warp == 1) {
+        G1X pib1 = padd_call<G1Curve>(load_fixed<G1Curve>(g.fx->beta1), *g.B1);
+        pib1 = padd_call<G1Curve>(pre->sd1, pib1);
+        G1X v = times_scalar_w4_warp<G1Curve>(pib1, r, 32);
+        if (lane == 0) s_rpib1 = v;
+    } else if (lane == 0) {
+        G2X pib = padd_call<G2Curve>(load_fixed<G2Curve>(g.fx->beta2), *g.B2);
+        pib = padd_call<G2Curve>(pre->sd2, pib);
+        *g.pi_b = affine_std<G2Curve>(pib);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
