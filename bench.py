@@ -36,7 +36,7 @@ LOG2N = int(os.environ.get("WS_BENCH_LOG2N", "20"))
 N_PAIRS = 1 << LOG2N
 PROVE_LOG2 = int(os.environ.get("WS_BENCH_PROVE_LOG2", "20"))       # constraints (domain size) of the synthetic key
 ALG_BYTES_PER_PAIR = 96          # 32 B scalar + 64 B affine point
-KERNELS_PER_MSM = 17             # digits, 2x3 scan, scatter, 3 task-table, accumulate, 2 combine, segreduce, bitsum, final
+KERNELS_PER_MSM = 18             # digits, 2x3 scan, scatter, 3 task-table, accumulate, 2 combine, segreduce, seg2, bitsum, final
 SCALARS = os.environ.get("WS_BENCH_SCALARS", "fr")      # "fr": uniform in [0, r) ; "raw256": uniform 256-bit
 
 

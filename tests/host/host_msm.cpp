@@ -33,16 +33,22 @@ static void run(const uint8_t* scalars, const uint8_t* points, uint32_t n, int c
         for (uint32_t t = tstart[b] + 1; t < tstart[b + 1]; t++) acc = padd<C>(acc, partials[t]);
         partials[tstart[b]] = acc;
     }
-    std::vector<XYZZ<C>> segA((size_t)p.nwin * p.S), segT((size_t)p.nwin * p.S), bits((size_t)p.nwin * (p.logS + 1)), R(p.nwin);
+    std::vector<XYZZ<C>> segA((size_t)p.nwin * p.S), segT((size_t)p.nwin * p.S), A2s((size_t)p.nwin * p.S2), A2w((size_t)p.nwin * p.S2),
+        T2((size_t)p.nwin * p.S2), bits((size_t)p.nwin * (p.logS2 + 2)), R(p.nwin);
     for (int w = 0; w < p.nwin; w++)
         for (uint32_t s = 0; s < p.S; s++) msm_segreduce_body<C>(p, w, s, tstart.data(), partials.data(), segA.data(), segT.data());
-    for (int w = 0; w < p.nwin; w++) {        // bit sums (serial stand-in for the block reduction)
-        XYZZ<C>* bw = &bits[(size_t)w * (p.logS + 1)];
-        for (int k = 0; k <= p.logS; k++) bw[k] = XYZZ<C>::inf();
-        for (uint32_t s = 0; s < p.S; s++) {
-            bw[0] = padd<C>(bw[0], segA[(size_t)w * p.S + s]);
-            for (int k = 0; k < p.logS; k++)
-                if ((s >> k) & 1) bw[1 + k] = padd<C>(bw[1 + k], segT[(size_t)w * p.S + s]);
+    for (int w = 0; w < p.nwin; w++)
+        for (uint32_t g = 0; g < p.S2; g++)
+            for (int role = 0; role < 2; role++) msm_seg2_body<C>(p, w, g, role, segA.data(), segT.data(), A2s.data(), A2w.data(), T2.data());
+    for (int w = 0; w < p.nwin; w++) {        // plane sums (serial stand-in for the block reduction)
+        XYZZ<C>* bw = &bits[(size_t)w * (p.logS2 + 2)];
+        for (int k = 0; k < p.logS2 + 2; k++) bw[k] = XYZZ<C>::inf();
+        for (uint32_t g = 0; g < p.S2; g++) {
+            size_t o = (size_t)w * p.S2 + g;
+            bw[0] = padd<C>(bw[0], A2s[o]);
+            bw[1] = padd<C>(bw[1], A2w[o]);
+            for (int k = 0; k < p.logS2; k++)
+                if ((g >> k) & 1) bw[2 + k] = padd<C>(bw[2 + k], T2[o]);
         }
     }
     for (int w = 0; w < p.nwin; w++) R[w] = msm_window_value<C>(p, w, bits.data());

@@ -227,6 +227,14 @@ HD_NOINLINE void padd_to(XYZZ<C>* r, const XYZZ<C>* a, const XYZZ<C>* b) { *r = 
 template <class C>
 HD_NOINLINE void pdbl_to(XYZZ<C>* r, const XYZZ<C>* a) { *r = pdbl<C>(*a); }
 template <class C>
+HD_NOINLINE void pmadd_to(XYZZ<C>* r, const XYZZ<C>* a, const Affine<C>* q) { *r = pmadd<C>(*a, *q); }
+template <class C>
+HD XYZZ<C> pmadd_call(const XYZZ<C>& a, const Affine<C>& q) {
+    XYZZ<C> r;
+    pmadd_to<C>(&r, &a, &q);
+    return r;
+}
+template <class C>
 HD XYZZ<C> padd_call(const XYZZ<C>& a, const XYZZ<C>& b) {
     XYZZ<C> r;
     padd_to<C>(&r, &a, &b);

@@ -147,7 +147,7 @@ HD Fp<P> dbl(const Fp<P>& a) { return add(a, a); }
 
 // ---------------------------------------------------------------- Montgomery product
 template <class P>
-HD Fp<P> mul(const Fp<P>& A, const Fp<P>& B) {
+HD Fp<P> mul_inline(const Fp<P>& A, const Fp<P>& B) {
     constexpr int N = P::N;
     Fp<P> res;
 #ifdef __CUDA_ARCH__
@@ -235,6 +235,22 @@ HD Fp<P> mul(const Fp<P>& A, const Fp<P>& B) {
     for (int i = 0; i < N; i++) res.v[i] = ge ? d[i] : t[i];
 #endif
     return res;
+}
+
+// 24-limb products (~1300 instructions) go out of line: one copy per kernel instead of one per call site
+// keeps ptxas time and code size sane; the 8-limb product stays inline (it is the hot path).
+template <class P>
+HD_NOINLINE void mul_to(Fp<P>* r, const Fp<P>* a, const Fp<P>* b) { *r = mul_inline(*a, *b); }
+
+template <class P>
+HD Fp<P> mul(const Fp<P>& a, const Fp<P>& b) {
+    if constexpr (P::N > 8) {
+        Fp<P> r;
+        mul_to<P>(&r, &a, &b);
+        return r;
+    } else {
+        return mul_inline(a, b);
+    }
 }
 
 template <class P>

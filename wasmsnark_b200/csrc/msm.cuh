@@ -244,7 +244,8 @@ static __global__ void __launch_bounds__(THREADS, MINB) k_msm_accumulate(MsmPlan
         uint32_t e = __ldg(entries + k);
         Affine<C> q = ldg_struct(points + (e & 0x7FFFFFFFu));
         if (e >> 31) q.y = neg(q.y);
-        acc = pmadd<C>(acc, q);
+        if constexpr (sizeof(typename C::F) > 64) acc = pmadd_call<C>(acc, q);   // 24-limb fields: keep the kernel small
+        else acc = pmadd<C>(acc, q);
     }
     stg_struct(partials + t, acc);
 }
@@ -308,19 +309,31 @@ static __global__ void __launch_bounds__(128) k_msm_segreduce(MsmPlan p, const u
     msm_segreduce_body<C>(p, idx / p.S, idx % p.S, tstart, partials, segA, segT);
 }
 
-// grid (nwin, logS + 1): plane 0 sums the A's, plane 1+k sums the T's of segments with bit k set
+// second level over the segments: one thread per (window, group, role)
 template <class C>
-static __global__ void __launch_bounds__(256) k_msm_bitsum(MsmPlan p, const XYZZ<C>* __restrict__ segA, const XYZZ<C>* __restrict__ segT, XYZZ<C>* __restrict__ bits) {
+static __global__ void __launch_bounds__(128) k_msm_seg2(MsmPlan p, const XYZZ<C>* __restrict__ segA, const XYZZ<C>* __restrict__ segT,
+                                                         XYZZ<C>* __restrict__ A2s, XYZZ<C>* __restrict__ A2w, XYZZ<C>* __restrict__ T2) {
+    uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t per_role = (uint32_t)p.nwin * p.S2;
+    if (idx >= 2 * per_role) return;
+    int role = idx >= per_role;            // warps are role-uniform when per_role is a multiple of 32
+    uint32_t i = idx - role * per_role;
+    msm_seg2_body<C>(p, i / p.S2, i % p.S2, role, segA, segT, A2s, A2w, T2);
+}
+
+// grid (nwin, logS2 + 2): plane 0 sums A2s, plane 1 sums A2w, plane 2+k sums the T2's of groups with bit k set
+template <class C>
+static __global__ void __launch_bounds__(256) k_msm_bitsum(MsmPlan p, const XYZZ<C>* __restrict__ A2s, const XYZZ<C>* __restrict__ A2w,
+                                                           const XYZZ<C>* __restrict__ T2, XYZZ<C>* __restrict__ bits) {
     __shared__ XYZZ<C> wsum[8];
     uint32_t w = blockIdx.x;
     int k = blockIdx.y;
     XYZZ<C> acc = XYZZ<C>::inf();
-    for (uint32_t s = threadIdx.x; s < p.S; s += blockDim.x) {
-        if (k == 0) {
-            acc = padd_call<C>(acc, segA[(size_t)w * p.S + s]);
-        } else if ((s >> (k - 1)) & 1) {
-            acc = padd_call<C>(acc, segT[(size_t)w * p.S + s]);
-        }
+    for (uint32_t g = threadIdx.x; g < p.S2; g += blockDim.x) {
+        size_t o = (size_t)w * p.S2 + g;
+        if (k == 0) acc = padd_call<C>(acc, A2s[o]);
+        else if (k == 1) acc = padd_call<C>(acc, A2w[o]);
+        else if ((g >> (k - 2)) & 1) acc = padd_call<C>(acc, T2[o]);
     }
     int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll 1
@@ -337,7 +350,7 @@ static __global__ void __launch_bounds__(256) k_msm_bitsum(MsmPlan p, const XYZZ
             XYZZ<C> o = shfl_down_struct(acc, off);
             acc = padd_call<C>(acc, o);
         }
-        if (lane == 0) bits[(size_t)w * (p.logS + 1) + k] = acc;
+        if (lane == 0) bits[(size_t)w * (p.logS2 + 2) + k] = acc;
     }
 }
 
@@ -385,7 +398,7 @@ static __global__ void __launch_bounds__(64) k_affine_points(const Jac<C>* __res
 struct MsmWorkspace {
     int16_t* digits;
     uint32_t *counts, *cursor, *bstart, *tstart, *tile_sums, *entries, *task_bucket, *order, *heavy, *small_ctrs;   // small_ctrs: [0..1] heavy counts, [8..] len_hist, [8+T+2..] len_cursor
-    void *partials, *segA, *segT, *bits, *R;
+    void *partials, *segA, *segT, *A2s, *A2w, *T2, *bits, *R;
 };
 
 // Carves the workspace out of one device buffer; returns bytes needed (base may be null to size).
@@ -412,7 +425,10 @@ inline size_t msm_carve(const MsmPlan& p, uint8_t* base, MsmWorkspace* ws) {
     uint8_t* pa = take((size_t)p.max_tasks * sizeof(XYZZ<C>));
     uint8_t* sa = take((size_t)p.nwin * p.S * sizeof(XYZZ<C>));
     uint8_t* sT = take((size_t)p.nwin * p.S * sizeof(XYZZ<C>));
-    uint8_t* bi = take((size_t)p.nwin * (p.logS + 1) * sizeof(XYZZ<C>));
+    uint8_t* a2s = take((size_t)p.nwin * p.S2 * sizeof(XYZZ<C>));
+    uint8_t* a2w = take((size_t)p.nwin * p.S2 * sizeof(XYZZ<C>));
+    uint8_t* t2 = take((size_t)p.nwin * p.S2 * sizeof(XYZZ<C>));
+    uint8_t* bi = take((size_t)p.nwin * (p.logS2 + 2) * sizeof(XYZZ<C>));
     uint8_t* rr = take((size_t)p.nwin * sizeof(XYZZ<C>));
     if (ws) {
         ws->digits = (int16_t*)d;
@@ -429,6 +445,9 @@ inline size_t msm_carve(const MsmPlan& p, uint8_t* base, MsmWorkspace* ws) {
         ws->partials = pa;
         ws->segA = sa;
         ws->segT = sT;
+        ws->A2s = a2s;
+        ws->A2w = a2w;
+        ws->T2 = t2;
         ws->bits = bi;
         ws->R = rr;
     }
@@ -484,7 +503,9 @@ inline cudaError_t msm_launch(const MsmPlan& p, const MsmWorkspace& w, const uin
     uint32_t nseg = (uint32_t)p.nwin * p.S;
     k_msm_segreduce<C><<<(nseg + 127) / 128, 128, 0, st>>>(p, w.tstart, (const X*)w.partials, (X*)w.segA, (X*)w.segT);
     mark("segreduce");
-    k_msm_bitsum<C><<<dim3(p.nwin, p.logS + 1), 256, 0, st>>>(p, (const X*)w.segA, (const X*)w.segT, (X*)w.bits);
+    uint32_t n2 = 2 * (uint32_t)p.nwin * p.S2;
+    k_msm_seg2<C><<<(n2 + 127) / 128, 128, 0, st>>>(p, (const X*)w.segA, (const X*)w.segT, (X*)w.A2s, (X*)w.A2w, (X*)w.T2);
+    k_msm_bitsum<C><<<dim3(p.nwin, p.logS2 + 2), p.S2 >= 256 ? 256 : (p.S2 >= 64 ? 64 : 32), 0, st>>>(p, (const X*)w.A2s, (const X*)w.A2w, (const X*)w.T2, (X*)w.bits);
     mark("bitsum");
     k_msm_final<C><<<1, 160, 0, st>>>(p, (const X*)w.bits, (X*)w.R, d_out_xyzz, d_out_jac);
     mark("final");

@@ -40,6 +40,9 @@ struct MsmPlan {
     uint32_t L;        // buckets per reduce segment (power of two, <= B)
     uint32_t S;        // segments per window = B / L
     int logS;
+    uint32_t L2;       // level-2 group size over the segments (1 = no second level)
+    uint32_t S2;       // groups per window = S / L2
+    int logS2;
     uint32_t nbuckets; // nwin * B
     uint32_t max_tasks;
 };
@@ -60,6 +63,10 @@ HD MsmPlan msm_make_plan(uint32_t n, int c, uint32_t T, uint32_t L = 0, int sbit
     p.S = p.B / p.L;
     p.logS = 0;
     while ((1u << p.logS) < p.S) p.logS++;
+    p.L2 = p.S >= 256 ? 8 : 1;
+    p.S2 = p.S / p.L2;
+    p.logS2 = 0;
+    while ((1u << p.logS2) < p.S2) p.logS2++;
     p.nbuckets = (uint32_t)p.nwin * p.B;
     uint64_t entries = (uint64_t)p.nwin * n;
     p.max_tasks = (uint32_t)(entries / T) + p.nbuckets + 1;
@@ -218,17 +225,43 @@ HD void msm_segreduce_body(const MsmPlan& p, uint32_t w, uint32_t s, const uint3
     segT[(size_t)w * p.S + s] = run;
 }
 
-// ---- final: window value from the bit-plane sums, then Horner over windows ------------------
-// bits[w * (logS + 1) + 0] = sum_s A_s ; bits[w * (logS+1) + 1 + k] = sum_{s : bit k of s} T_s
-//   R_w = A + L * sum_k 2^k * bit_k
+// ---- level 2 over the segments: thread (w, g, role) -------------------------------------------
+// group g = segments g*L2 .. g*L2+L2-1.  role 0: T2 = sum T_j and A2w = sum j*T_j (running sums);
+// role 1: A2s = sum A_j.  With s = g*L2 + j:
+//   sum_s s*T_s = sum_g (L2 * g * T2_g + A2w_g)
+template <class C>
+HD void msm_seg2_body(const MsmPlan& p, uint32_t w, uint32_t g, int role, const XYZZ<C>* segA, const XYZZ<C>* segT,
+                      XYZZ<C>* A2s, XYZZ<C>* A2w, XYZZ<C>* T2) {
+    size_t base = (size_t)w * p.S + (size_t)g * p.L2;
+    size_t o = (size_t)w * p.S2 + g;
+    if (role == 1) {
+        XYZZ<C> acc = segA[base];
+        for (uint32_t j = 1; j < p.L2; j++) acc = padd_call<C>(acc, segA[base + j]);
+        A2s[o] = acc;
+        return;
+    }
+    XYZZ<C> run = XYZZ<C>::inf(), acc = XYZZ<C>::inf();
+    for (int j = (int)p.L2 - 1; j >= 1; j--) {      // acc = sum_{j>=1} j*T_j ; run = sum_{j>=1} T_j
+        run = padd_call<C>(run, segT[base + j]);
+        acc = padd_call<C>(acc, run);
+    }
+    A2w[o] = acc;
+    T2[o] = padd_call<C>(run, segT[base]);
+}
+
+// ---- final: window value from the plane sums, then Horner over windows -----------------------------
+// bits[w * (logS2 + 2) + 0] = sum_g A2s ; [1] = sum_g A2w ; [2 + k] = sum_{g : bit k of g} T2_g
+//   R_w = P0 + L * (P1 + L2 * sum_k 2^k * plane_k)
 template <class C>
 HD XYZZ<C> msm_window_value(const MsmPlan& p, uint32_t w, const XYZZ<C>* bits) {
-    const XYZZ<C>* bw = bits + (size_t)w * (p.logS + 1);
+    const XYZZ<C>* bw = bits + (size_t)w * (p.logS2 + 2);
     XYZZ<C> acc = XYZZ<C>::inf();
-    for (int k = p.logS - 1; k >= 0; k--) {
+    for (int k = p.logS2 - 1; k >= 0; k--) {
         acc = pdbl_call<C>(acc);
-        acc = padd_call<C>(acc, bw[1 + k]);
+        acc = padd_call<C>(acc, bw[2 + k]);
     }
+    for (uint32_t l = p.L2; l > 1; l >>= 1) acc = pdbl_call<C>(acc);
+    acc = padd_call<C>(acc, bw[1]);
     for (uint32_t l = p.L; l > 1; l >>= 1) acc = pdbl_call<C>(acc);
     return padd_call<C>(acc, bw[0]);
 }
