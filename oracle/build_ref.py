@@ -37,7 +37,7 @@ def copy_example():
     if not os.path.isdir(src):
         return
     os.makedirs(dst, exist_ok=True)
-    for f in ("proving_key.bin", "witness.bin", "proof_good0.json"):
+    for f in ("proving_key.bin", "witness.bin", "proof_good0.json", "proof_good.json", "verification_key.json", "public.json"):
         if not os.path.exists(os.path.join(dst, f)):
             shutil.copyfile(os.path.join(src, f), os.path.join(dst, f))
 

@@ -316,6 +316,62 @@ class RefBn128:
         return format_proof(ba, bb, bc)
 
 
+def groth16_verify(verification_key, inputs, proof, inst=None):
+    """Bn128.groth16Verify (src/bn128.js:722-791) replayed on the reference image: the reference's own
+    acceptance check for proofs with random r, s (test/bn128_prover.js:73-78).  Returns True / False."""
+    own = inst is None
+    m = inst or RefInstance(pages=1000)
+    c = m.call
+    old = m.heap
+    S = 32
+
+    def al(n):
+        h = m.heap
+        while h & 7:                      # setInt requires 8-byte alignment (src/bn128.js:459)
+            h += 1
+        m.heap = h
+        return m.alloc(n)
+
+    def set_f1(p, v):
+        m.put(p, int(v).to_bytes(32, "little"))
+
+    def set_g1(p, e):                     # setG1Affine, src/bn128.js:503-507
+        set_f1(p, e[0]); set_f1(p + S, e[1]); set_f1(p + 2 * S, 1)
+
+    def set_g2(p, e):                     # setG2Affine, src/bn128.js:509-513
+        for k in range(2):
+            set_f1(p + 2 * S * k, e[k][0]); set_f1(p + 2 * S * k + S, e[k][1])
+        set_f1(p + 4 * S, 1); set_f1(p + 5 * S, 0)
+    pA, pB, pIC, pICaux, pICr, pC = al(96), al(192), al(96), al(96), al(32), al(96)
+    pDelta2, pGamma2, pAlfa1, pBeta2 = al(192), al(192), al(96), al(192)
+    set_g1(pA, proof["pi_a"]); c("g1m_toMontgomery", pA, pA)
+    set_g2(pB, proof["pi_b"]); c("g2m_toMontgomery", pB, pB)
+    set_g1(pC, proof["pi_c"]); c("g1m_toMontgomery", pC, pC)
+    set_g2(pDelta2, verification_key["vk_delta_2"]); c("g2m_toMontgomery", pDelta2, pDelta2)
+    set_g2(pGamma2, verification_key["vk_gamma_2"]); c("g2m_toMontgomery", pGamma2, pGamma2)
+    set_g1(pAlfa1, verification_key["vk_alfa_1"]); c("g1m_toMontgomery", pAlfa1, pAlfa1)
+    set_g2(pBeta2, verification_key["vk_beta_2"]); c("g2m_toMontgomery", pBeta2, pBeta2)
+    set_g1(pIC, verification_key["IC"][0]); c("g1m_toMontgomery", pIC, pIC)
+    ok = True
+    for i, v in enumerate(inputs):
+        set_g1(pICaux, verification_key["IC"][i + 1]); c("g1m_toMontgomery", pICaux, pICaux)
+        set_f1(pICr, v)
+        if c("int_gte", pICr, m.const("pr")):
+            ok = False
+            break
+        c("g1m_timesScalar", pICaux, pICr, 32, pICaux)
+        c("g1m_add", pICaux, pIC, pIC)
+    valid = 0
+    if ok:
+        c("g1m_affine", pIC, pIC)
+        c("g1m_neg", pIC, pIC); c("g1m_neg", pC, pC); c("g1m_neg", pAlfa1, pAlfa1)
+        valid = c("bn128_pairingEq4", pA, pB, pIC, pGamma2, pC, pDelta2, pAlfa1, pBeta2, m.const("pOneT"))
+    m.heap = old
+    if own:
+        m.close()
+    return valid == 1
+
+
 def format_proof(ba, bb, bc):
     """bin2g1 / bin2g2 (src/bn128.js:319-351) + the returned object (:714-718)."""
     g = lambda b, i: str(bin2int(b[32 * i:32 * i + 32]))

@@ -171,3 +171,23 @@ def test_sharded_partials_emulated_on_one_gpu(bn):
     assert proof == g["proof_rs"]
     for k in keys:
         bn.lib.ws_bn128_pkey_free(k)
+
+
+@pytest.mark.skipif(not (ref_wasm.available() and os.path.exists(os.path.join(EXAMPLE, "verification_key.json"))), reason="oracle/_ref not staged")
+def test_random_rs_proof_accepted_by_reference_verifier(bn):
+    """The reference's own end-to-end acceptance test (test/bn128_prover.js:51-80): a proof with CSPRNG r, s on
+    test/data/{witness,proving_key}.bin (identical to example/bn128/) is accepted iff
+    groth16Verify(verification_key, public, proof) === true -- here with the reference's verifier run from its
+    compiled WASM image."""
+    pk = open(os.path.join(EXAMPLE, "proving_key.bin"), "rb").read()
+    wit = open(os.path.join(EXAMPLE, "witness.bin"), "rb").read()
+    vk = json.load(open(os.path.join(EXAMPLE, "verification_key.json")))
+    pub = json.load(open(os.path.join(EXAMPLE, "public.json")))
+    key = bn.load_proving_key(pk)
+    p1 = bn.groth16GenProof(wit, key)
+    p2 = bn.groth16GenProof(wit, key)
+    assert p1 != p2
+    assert ref_wasm.groth16_verify(vk, pub, p1) and ref_wasm.groth16_verify(vk, pub, p2)
+    p1["pi_a"][1] = str((int(p1["pi_a"][1]) + 1) % O.Q)
+    assert not ref_wasm.groth16_verify(vk, pub, p1)
+    key.free()

@@ -128,3 +128,19 @@ def test_example_proof_good0():
     proof = O.groth16_gen_proof(wit, pk, 0, 0)
     for k in ("pi_a", "pi_b", "pi_c"):
         assert proof[k] == good[k] == gold[k]
+
+
+@pytest.mark.skipif(not (ref_wasm.available() and os.path.exists(os.path.join(EXAMPLE, "verification_key.json"))), reason="oracle/_ref not staged")
+def test_reference_verifier_on_shipped_proofs():
+    """The reference's own groth16Verify (src/bn128.js:722-791, pairing code of its WASM image) accepts its shipped
+    proofs -- proof_good.json has unknown random r, s -- and rejects a tampered proof / wrong public input."""
+    vk = json.load(open(os.path.join(EXAMPLE, "verification_key.json")))
+    pub = json.load(open(os.path.join(EXAMPLE, "public.json")))
+    for f in ("proof_good.json", "proof_good0.json"):
+        assert ref_wasm.groth16_verify(vk, pub, json.load(open(os.path.join(EXAMPLE, f))))
+    bad = json.load(open(os.path.join(EXAMPLE, "proof_good.json")))
+    bad["pi_c"][0] = str(int(bad["pi_c"][0]) + 1)
+    assert not ref_wasm.groth16_verify(vk, pub, bad)
+    pub2 = list(pub)
+    pub2[3] = str(int(pub2[3]) + 1)
+    assert not ref_wasm.groth16_verify(vk, pub2, json.load(open(os.path.join(EXAMPLE, "proof_good.json"))))
