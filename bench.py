@@ -16,8 +16,10 @@ Same JSON line, key "groth16": the other half of BASELINE's metric -- full Groth
 2^20-constraint key (tools/gen_synth_key.py), device-resident key + witness (value) and through the
 host-buffer call with the resident key (e2e); key "ntt": BASELINE configs[2], 2^22 forward + inverse.
 `--impl reference` runs only the CPU arm and prints the same line shape.
-N > 1 (torchrun, one rank per GPU): contiguous point ranges per rank (the reference's worker split), one
-all_gather of the partial sums over NCCL, tiny on-device combine; strong scaling of one 2^20 job.
+N > 1 (torchrun, one rank per GPU): one MSM of N * 2^20 pairs, contiguous point ranges of 2^20 pairs per rank (the
+reference's worker split), one all_gather of the 96-byte partial sums over NCCL, tiny on-device combine: per-GPU
+work is fixed, so the MSM line is WEAK scaling; the "groth16" object is one fixed 2^20-constraint proof sharded
+over the N GPUs (strong scaling of its latency).
 """
 import argparse
 import ctypes
@@ -40,13 +42,15 @@ KERNELS_PER_MSM = 18             # digits, 2x3 scan, scatter, 3 task-table, accu
 SCALARS = os.environ.get("WS_BENCH_SCALARS", "fr")      # "fr": uniform in [0, r) ; "raw256": uniform 256-bit
 
 
-def make_inputs(n, seed=0xB201, dist=None):
+def make_inputs(n, seed=0xB201, dist=None, offset=0):
+    """n scalar-point pairs: points P0 + (offset + i) * D, i < n (one global arithmetic progression, so that the
+    sum over any set of ranks has a closed form); scalars from PCG64(seed + offset)."""
     import numpy as np
     from oracle import bn128 as O
     import util
     dist = dist or SCALARS
-    aff, P0, D = util.arith_points(O.Fq, O.G1_GEN, n, 0xB202)
-    rng = np.random.Generator(np.random.PCG64(seed))
+    aff, P0, D = util.arith_points(O.Fq, O.G1_GEN, n, 0xB202, offset=offset)
+    rng = np.random.Generator(np.random.PCG64(seed + offset))
     if dist == "raw256":
         scalars = rng.bytes(32 * n)
     else:
@@ -137,7 +141,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": metric_name(), "value": v, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs (256-bit Montgomery)", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (256-bit Montgomery)", "data": "synthetic",
         "config": {"workload": workload_name(), "sample_pairs": sample},
         "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "reference",
                          "sample": "each step = first %d pairs, %d threads x g1m_multiexp2(w=7) of the reference's WASM image compiled natively (oracle/_ref), partials combined with g1m_add" % (sample, cores)},
@@ -198,10 +202,13 @@ def main():
     W = max(3, args.warmup)
     K = args.steps
 
-    scalars, points, P0, D = make_inputs(N_PAIRS)
-    lo, cnt = shard_range(N_PAIRS, rank, world)
-    h_s = torch.frombuffer(bytearray(scalars[32 * lo:32 * (lo + cnt)]), dtype=torch.uint8).pin_memory()
-    h_p = torch.frombuffer(bytearray(points[64 * lo:64 * (lo + cnt)]), dtype=torch.uint8).pin_memory()
+    # weak scaling: the job is one MSM of world * 2^LOG2N pairs; rank r holds the contiguous range [r * 2^LOG2N, (r+1) * 2^LOG2N)
+    TOTAL_PAIRS = N_PAIRS * world
+    lo, cnt = shard_range(TOTAL_PAIRS, rank, world)
+    assert cnt == N_PAIRS
+    scalars, points, P0, D = make_inputs(cnt, offset=lo)
+    h_s = torch.frombuffer(bytearray(scalars), dtype=torch.uint8).pin_memory()
+    h_p = torch.frombuffer(bytearray(points), dtype=torch.uint8).pin_memory()
     stream = torch.cuda.Stream()            # a real (non-legacy) stream: the library launches on it
     torch.cuda.set_stream(stream)
     st = ctypes.c_void_p(stream.cuda_stream)
@@ -226,13 +233,19 @@ def main():
     # ---- correctness of what is being timed (closed form of sum s_i (P0 + i D))
     step_dev()
     torch.cuda.synchronize()
+    from oracle import bn128 as O
+    sc = [int.from_bytes(scalars[32 * i:32 * i + 32], "little") for i in range(cnt)]
+    moments = [sum(sc) % O.R_ORDER, sum((lo + i) * v for i, v in enumerate(sc)) % O.R_ORDER]     # sum s_i, sum i_global * s_i
+    del sc
+    if world > 1:
+        allm = [None] * world
+        dist.all_gather_object(allm, moments)
+        moments = [sum(m[0] for m in allm) % O.R_ORDER, sum(m[1] for m in allm) % O.R_ORDER]
     if rank == 0:
-        sc = [int.from_bytes(scalars[32 * i:32 * i + 32], "little") for i in range(N_PAIRS)]
-        want = util.closed_form_sum(sc, P0, D)
+        want = O.pt_affine(O.Fq, O.pt_add(O.Fq, O.pt_times_scalar(O.Fq, (P0[0], P0[1], 1), moments[0]), O.pt_times_scalar(O.Fq, (D[0], D[1], 1), moments[1])))
         got = util.g1_result_tuple(bn.g1_affine(bytes(d_out[:96].cpu().numpy())))
         if got != want:
             raise SystemExit("PARITY FAILURE: MSM result differs from the oracle")
-        del sc
 
     # ---- device-resident timing (per-stage events on for the roofline numerator's denominator)
     sampler = ClockSampler(local) if rank == 0 else None
@@ -432,7 +445,7 @@ def main():
         extra["groth16"] = {
             "metric": "Groth16 proofs/sec (BN128, 2^%d constraints)" % PROVE_LOG2, "value": 1000.0 / pms, "unit": "proofs/s", "ms_per_proof": pms,
             "config": {"workload": "synthetic proving key nVars = domainSize = 2^%d, nPublic = 58 (tools/gen_synth_key.py), key resident in HBM" % PROVE_LOG2,
-                       "pkey_bytes": len(pk), "witness_bytes": len(wit), "shard": "point ranges x%d, all_gather of 768-byte partial records" % world},
+                       "pkey_bytes": len(pk), "witness_bytes": len(wit), "shard": "point ranges x%d, all_gather of 768-byte partial records" % world, "scaling": "strong (one fixed-size proof over %d GPUs)" % world},
             "e2e": {"value": 1.0 / pe2e, "unit": "proofs/s", "h2d_bytes_per_step": len(wit), "d2h_bytes_per_step": 384, "ms_per_proof": 1000 * pe2e,
                     "note": "witness from pinned host memory each proof; proving key resident (loaded once: %.2f s incl. host-side row regrouping)" % load_s},
             "stages_ms": pstages, "repeatable_bit_exact": same, "algorithmic_bytes": alg_bytes,
@@ -444,23 +457,23 @@ def main():
     if rank == 0:
         serial_ms = total_ms / K
         ms_per_step = pipe_ms / K
-        value = N_PAIRS / (ms_per_step * 1e-3)
+        value = TOTAL_PAIRS / (ms_per_step * 1e-3)
         acc_ms = stage_ms.get("accumulate", 0.0) / K
         peak, which = peaks()
         achieved = (ALG_BYTES_PER_PAIR * cnt) / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else None
         line = {
             "metric": metric_name(), "value": value, "unit": "pairs/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs (256-bit Montgomery)", "data": "synthetic",
-            "config": {"workload": workload_name(), "pairs": N_PAIRS,
-                       "parallelism": "point-range shard x%d + all_gather of 96-B partials" % world if world > 1 else "single GPU",
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (256-bit Montgomery)", "data": "synthetic",
+            "config": {"workload": workload_name(), "pairs": TOTAL_PAIRS, "pairs_per_gpu": N_PAIRS,
+                       "parallelism": "one MSM of %d x 2^%d pairs, contiguous point range per GPU + one all_gather of 96-B partials + on-device combine" % (world, LOG2N) if world > 1 else "single GPU",
                        "in_flight": "2 MSMs (two contexts / streams alternate; K steps inside one CUDA-event pair, max over ranks)",
                        "l2": "inputs rotate over 4 device copies (384 MiB > 126 MB L2); the single-stream latency run flushes L2 between steps",
                        "bit_exact_vs_oracle": True},
-            "latency": {"ms_per_msm_single_stream": serial_ms, "pairs_per_s": N_PAIRS / (serial_ms * 1e-3),
+            "latency": {"ms_per_msm_single_stream": serial_ms, "pairs_per_s": TOTAL_PAIRS / (serial_ms * 1e-3),
                         "note": "one MSM at a time, per-step CUDA events, L2 flushed (256 MiB fill) between steps"},
             "clocks": clocks,
-            "e2e": {"value": N_PAIRS / (e2e_s / K), "unit": "pairs/s", "h2d_bytes_per_step": 96 * cnt, "d2h_bytes_per_step": 96,
+            "e2e": {"value": TOTAL_PAIRS / (e2e_s / K), "unit": "pairs/s", "h2d_bytes_per_step": 96 * cnt, "d2h_bytes_per_step": 96,
                     "ms_per_step": 1000.0 * e2e_s / K, "timer": "host perf_counter around K blocking C-ABI calls (two host threads / contexts when n_gpus = 1), max over ranks"},
             "gpu_launches": KERNELS_PER_MSM * K + (K if world > 1 else 0),
             "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate<G1>", "achieved": achieved, "peak": peak, "unit": "GB/s",

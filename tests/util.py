@@ -51,17 +51,19 @@ def g2_result_tuple(b192):
     return ((v[0], v[1]), (v[2], v[3]), (v[4], v[5]))
 
 
-def arith_points(F, gen, n, seed):
+def arith_points(F, gen, n, seed, offset=0):
     """P_i = P0 + i*D: one affine chord addition per point with a batched
     inversion, so large sets are cheap and sum(s_i P_i) has the closed form
-    (sum s_i) P0 + (sum i s_i) D.  Returns (list of affine (x, y) plain, P0, D)."""
+    (sum s_i) P0 + (sum i s_i) D.  With `offset` the list starts at P0 + offset*D (a rank's slice of one global
+    progression).  Returns (list of affine (x, y) plain, P0, D)."""
     rnd = random.Random(seed)
     base = (gen[0], gen[1], F.one)
     k0, k1 = rnd.randrange(1, RR), rnd.randrange(1, RR)
     P0 = O.pt_affine(F, O.pt_times_scalar(F, base, k0))
     D = O.pt_affine(F, O.pt_times_scalar(F, base, k1))
     assert F is O.Fq, "fast path written for G1"
-    xs, ys = [P0[0]], [P0[1]]
+    start = P0 if offset == 0 else O.pt_affine(F, O.pt_add(F, (P0[0], P0[1], 1), O.pt_times_scalar(F, (D[0], D[1], 1), offset)))
+    xs, ys = [start[0]], [start[1]]
     dx, dy = D[0], D[1]
     # chunks of independent additions: P_{i+m} = P_i + m*D, batch-inverted
     m = 1
