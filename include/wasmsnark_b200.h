@@ -96,6 +96,16 @@ int ws_bn128_g2_affine(ws_ctx* ctx, const uint8_t* in, uint8_t* out, size_t coun
 int ws_bn128_g1_multiexp_dev(ws_ctx* ctx, const void* d_scalars, const void* d_points, size_t n, void* d_out, int window_bits, void* stream);
 int ws_bn128_g2_multiexp_dev(ws_ctx* ctx, const void* d_scalars, const void* d_points, size_t n, void* d_out, int window_bits, void* stream);
 
+/* Window tables for point sets that stay in HBM across many MSMs (what resident proving keys use internally):
+ * build_table writes ws_msm_table_windows(table_c) * n affine points, table[w * n + i] = 2^(table_c * w) * P_i;
+ * multiexp_table then feeds every digit window into one shared bucket set -- wider windows, no doublings.
+ * table_c in 8..22; result format as ws_bn128_g?_multiexp_dev.                                             */
+int ws_msm_table_windows(int table_c);
+int ws_bn128_g1_build_table_dev(ws_ctx* ctx, const void* d_points, size_t n, int table_c, void* d_table, void* stream);
+int ws_bn128_g2_build_table_dev(ws_ctx* ctx, const void* d_points, size_t n, int table_c, void* d_table, void* stream);
+int ws_bn128_g1_multiexp_table_dev(ws_ctx* ctx, const void* d_scalars, const void* d_table, size_t n, int table_c, void* d_out, void* stream);
+int ws_bn128_g2_multiexp_table_dev(ws_ctx* ctx, const void* d_scalars, const void* d_table, size_t n, int table_c, void* d_out, void* stream);
+
 /* Multi-GPU combine: d_parts holds `count` partial sums in the 96-byte (G1) / 192-byte (G2) result
  * format above (e.g. all-gathered over NCCL from the ranks that each took a contiguous point range,
  * as the reference's workers do, src/bn128.js:353-372); d_out receives their normalised sum.
@@ -152,6 +162,10 @@ int ws_bn128_groth16_prove(ws_ctx* ctx, const uint8_t* witness, size_t witness_l
  * sections regrouped per row); the reference re-slices and re-posts the key on every proof
  * (src/bn128.js:592-604).  The handle belongs to `ctx`.                                              */
 int ws_bn128_pkey_load(ws_ctx* ctx, const uint8_t* pkey, size_t pkey_len, ws_pkey** out);
+/* Resident keys additionally get window tables in HBM (2^(c w) * P_i for every point section, c up to 20 bits:
+ * about 13x the key's point bytes): all digit windows of an MSM then share one bucket set and the result needs no
+ * doublings.  on = 0 disables them for keys loaded afterwards (same results, table-free MSM).  Default on.       */
+int ws_set_key_tables(ws_ctx* ctx, int on);
 void ws_bn128_pkey_free(ws_pkey* key);
 int ws_bn128_pkey_info(const ws_pkey* key, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size);
 int ws_bn128_groth16_prove_key(ws_ctx* ctx, const ws_pkey* key, const uint8_t* witness, size_t witness_len,

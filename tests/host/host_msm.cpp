@@ -7,10 +7,25 @@
 using namespace ws;
 
 template <class C>
-static void run(const uint8_t* scalars, const uint8_t* points, uint32_t n, int c, uint32_t T, uint8_t* out_affine) {
-    MsmPlan p = msm_make_plan(n, c, T);
+static void run(const uint8_t* scalars, const uint8_t* points, uint32_t n, int c, uint32_t T, uint8_t* out_affine, int table = 0) {
+    MsmPlan p = msm_make_plan(n, c, T, 0, 256, table);
     const Affine<C>* pts = (const Affine<C>*)points;
-    std::vector<int16_t> digits((size_t)p.nwin * n);
+    std::vector<Affine<C>> tab;
+    if (table) {      // window table T[w * n + i] = 2^(c w) * P_i, affine, x = 0 for infinity (what msm_build_table makes on the device)
+        tab.resize((size_t)p.ndig * n);
+        for (uint32_t i = 0; i < n; i++) {
+            XYZZ<C> cur = XYZZ<C>::from_affine(pts[i]);
+            for (int w = 0; w < p.ndig; w++) {
+                Jac<C> a = to_affine<C>(cur);
+                Affine<C> e{a.x, a.y};
+                if (cur.is_inf()) e = Affine<C>{C::F::zero(), C::F::zero()};
+                tab[(size_t)w * n + i] = e;
+                for (int k = 0; k < c; k++) cur = pdbl<C>(cur);
+            }
+        }
+    }
+    const Affine<C>* gather = table ? tab.data() : pts;
+    std::vector<int32_t> digits((size_t)p.ndig * n);
     std::vector<uint32_t> counts(p.nbuckets, 0), bstart(p.nbuckets + 1), tstart(p.nbuckets + 1);
     for (uint32_t i = 0; i < n; i++) msm_digits_body<8>(p, i, (const uint32_t*)scalars + (size_t)i * 8, pts[i].is_inf(), digits.data(), counts.data());
     bstart[0] = 0; tstart[0] = 0;
@@ -26,7 +41,7 @@ static void run(const uint8_t* scalars, const uint8_t* points, uint32_t n, int c
     msm_task_offsets_body(p, len_hist.data(), len_cursor.data());
     for (uint32_t t = 0; t < ntasks; t++) msm_task_order_body(p, t, bstart.data(), tstart.data(), task_bucket.data(), len_cursor.data(), order.data());
     std::vector<XYZZ<C>> partials(ntasks + 1);
-    for (uint32_t i = 0; i < ntasks; i++) partials[order[i]] = msm_accumulate_body<C>(p, order[i], bstart.data(), tstart.data(), task_bucket.data(), entries.data(), pts);
+    for (uint32_t i = 0; i < ntasks; i++) partials[order[i]] = msm_accumulate_body<C>(p, order[i], bstart.data(), tstart.data(), task_bucket.data(), entries.data(), gather);
     for (uint32_t h = 0; h < nheavy[0] + nheavy[1]; h++) {   // combine (serial stand-in for the warp / block trees)
         uint32_t b = h < nheavy[0] ? heavy[h] : heavy[p.nbuckets + (h - nheavy[0])];
         XYZZ<C> acc = partials[tstart[b]];
@@ -60,4 +75,6 @@ static void run(const uint8_t* scalars, const uint8_t* points, uint32_t n, int c
 extern "C" {
 void h_msm_g1(const uint8_t* scalars, const uint8_t* points, uint32_t n, int c, uint32_t T, uint8_t* out) { run<G1Curve>(scalars, points, n, c, T, out); }
 void h_msm_g2(const uint8_t* scalars, const uint8_t* points, uint32_t n, int c, uint32_t T, uint8_t* out) { run<G2Curve>(scalars, points, n, c, T, out); }
+void h_msm_g1_table(const uint8_t* scalars, const uint8_t* points, uint32_t n, int c, uint32_t T, uint8_t* out) { run<G1Curve>(scalars, points, n, c, T, out, 1); }
+void h_msm_g2_table(const uint8_t* scalars, const uint8_t* points, uint32_t n, int c, uint32_t T, uint8_t* out) { run<G2Curve>(scalars, points, n, c, T, out, 1); }
 }

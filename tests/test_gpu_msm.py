@@ -111,3 +111,50 @@ def test_full_size_2p20(bn, reduced):
     assert util.g1_result_tuple(got) == util.closed_form_sum(sc, P0, D)
     if ref_wasm.available() and not reduced:
         assert got == util.ref_g1_multiexp_threads(sb, pb)
+
+
+@pytest.mark.parametrize("g,table_c", [(1, 16), (1, 20), (1, 9), (2, 12), (2, 17)])
+def test_window_table_msm(bn, g, table_c):
+    """Window-table mode (what resident proving keys use): same sums as the table-free path / the oracle."""
+    import torch
+    rnd = random.Random(300 + g + table_c)
+    if g == 1:
+        n = 5000
+        aff, P0, D = util.arith_points(O.Fq, O.G1_GEN, n, 77)
+        pb = bytearray(util.g1_points_bytes(aff))
+        for k in range(3, n, 97):
+            pb[64 * k:64 * k + 64] = bytes(64)               # infinity entries
+        psize, osize = 64, 96
+    else:
+        from test_host_math import gen_points
+        n = 60
+        pts = gen_points(O.Fq2, O.G2_GEN, rnd, n)
+        pts[7] = O.pt_zero(O.Fq2)
+        pb = bytearray(b"".join(util.g2_affine_m(P) for P in pts))
+        psize, osize = 128, 192
+    sc = [rnd.getrandbits(256) if i % 5 else (0, 1, (1 << 256) - 1, O.R_ORDER, rnd.getrandbits(32))[(i // 5) % 5] for i in range(n)]
+    sb = b"".join(b32(s) for s in sc)
+    want = bn.g1_affine(bn.g1_multiexp(sb, bytes(pb))) if g == 1 else bn.g2_affine(bn.g2_multiexp(sb, bytes(pb)))
+    W = bn.lib.ws_msm_table_windows(table_c)
+    assert W == (257 + table_c - 1) // table_c
+    ds = torch.frombuffer(bytearray(sb), dtype=torch.uint8).cuda()
+    dp = torch.frombuffer(pb, dtype=torch.uint8).cuda()
+    dt = torch.zeros(W * n * psize, dtype=torch.uint8, device="cuda")
+    dout = torch.zeros(256, dtype=torch.uint8, device="cuda")
+    build = bn.lib.ws_bn128_g1_build_table_dev if g == 1 else bn.lib.ws_bn128_g2_build_table_dev
+    run = bn.lib.ws_bn128_g1_multiexp_table_dev if g == 1 else bn.lib.ws_bn128_g2_multiexp_table_dev
+    torch.cuda.synchronize()
+    bn.ctx.check(build(bn.ctx.h, dp.data_ptr(), n, table_c, dt.data_ptr(), None))
+    bn.ctx.check(run(bn.ctx.h, ds.data_ptr(), dt.data_ptr(), n, table_c, dout.data_ptr(), None))
+    bn.ctx.timings()
+    torch.cuda.synchronize()
+    got = bytes(dout[:osize].cpu().numpy())
+    got = bn.g1_affine(got) if g == 1 else bn.g2_affine(got)
+    assert got == want
+    if g == 1:          # the table itself: row w holds 2^(c w) * P_i
+        tab = bytes(dt[:2 * n * 64].cpu().numpy())
+        i = 11
+        x = O.from_mont(int.from_bytes(tab[64 * (n + i):64 * (n + i) + 32], "little"))
+        y = O.from_mont(int.from_bytes(tab[64 * (n + i) + 32:64 * (n + i) + 64], "little"))
+        want_pt = O.pt_affine(O.Fq, O.pt_times_scalar(O.Fq, (aff[i][0], aff[i][1], 1), 1 << table_c))
+        assert (x, y) == (want_pt[0], want_pt[1])

@@ -101,11 +101,16 @@ def test_synth_small_calch_and_proofs(bn):
     assert bn.groth16GenProof(wit, pk, r=bytes(32), s=bytes(32)) == g["proof_r0s0"]
     r, s = bytes.fromhex(g["r"]), bytes.fromhex(g["s"])
     assert bn.groth16GenProof(wit, pk, r=r, s=s) == g["proof_rs"]
-    key = bn.load_proving_key(pk)
+    key = bn.load_proving_key(pk)                        # resident key with window tables (default)
     assert (key.nVars, key.nPublic, key.domainSize) == (300, 5, 256)
-    for _ in range(2):                                   # resident key, repeated proofs
+    for _ in range(2):                                   # repeated proofs
         assert bn.groth16GenProof(wit, key, r=r, s=s) == g["proof_rs"]
     key.free()
+    bn.lib.ws_set_key_tables(bn.ctx.h, 0)                # and without tables
+    key = bn.load_proving_key(pk)
+    assert bn.groth16GenProof(wit, key, r=r, s=s) == g["proof_rs"]
+    key.free()
+    bn.lib.ws_set_key_tables(bn.ctx.h, 1)
 
 
 def test_random_rs_differs_and_bad_keys_rejected(bn):

@@ -68,3 +68,10 @@ def test_pipeline_matches_oracle(host_msm, host_math, g):
             fn(sb, pb, len(sc), c, T, out)
             got = tuple(H.fi(out.raw[k * H.fs:(k + 1) * H.fs]) for k in range(3))
             assert got == want, (c, T, len(sc))
+        # window-table mode (resident keys): one shared bucket set, windows up to 20 bits
+        fnt = host_msm.h_msm_g1_table if g == 1 else host_msm.h_msm_g2_table
+        for c, T in ((20, 64), (16, 3), (9, 2), (17, 64)):
+            out = ctypes.create_string_buffer(3 * H.fs)
+            fnt(sb, pb, len(sc), c, T, out)
+            got = tuple(H.fi(out.raw[k * H.fs:(k + 1) * H.fs]) for k in range(3))
+            assert got == want, ("table", c, T, len(sc))

@@ -15,10 +15,15 @@ from wasmsnark_b200._lib import as_ptr  # noqa: E402
 
 lg = int(sys.argv[1]) if len(sys.argv) > 1 else 18
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+tables = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 pk, wit = gen_synth_key.make(1 << lg, 58, 1 << lg, seed=0xB204)
 bn = build_bn128(0)
 key = ctypes.c_void_p()
+bn.lib.ws_set_key_tables(bn.ctx.h, tables)
+import time
+t0 = time.perf_counter()
 bn.ctx.check(bn.lib.ws_bn128_pkey_load(bn.ctx.h, as_ptr(pk), len(pk), ctypes.byref(key)))
+print('key load %.3f s (tables=%d)' % (time.perf_counter() - t0, tables))
 d_w = torch.frombuffer(bytearray(wit), dtype=torch.uint8).cuda()
 d_rs = torch.frombuffer(bytearray(bytes(range(1, 65))), dtype=torch.uint8).cuda()
 d_out = torch.zeros(384, dtype=torch.uint8, device="cuda")

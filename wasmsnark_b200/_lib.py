@@ -54,6 +54,7 @@ SIGNATURES = {
     "ws_bn128_fr_fft_dev": (_i, [_vp, _vp, _sz, _i, _i, _vp]),
     "ws_bn128_calc_h": (_i, [_vp, _vp, _vp, _sz, _vp, _sz, ctypes.c_uint32, ctypes.c_uint32, _vp]),
     "ws_bn128_groth16_prove": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "ws_set_key_tables": (_i, [_vp, _i]),
     "ws_bn128_pkey_load": (_i, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),
     "ws_bn128_pkey_free": (None, [_vp]),
     "ws_bn128_pkey_info": (_i, [_vp, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]),
@@ -63,6 +64,11 @@ SIGNATURES = {
     "ws_bn128_groth16_partials_dev": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "ws_bn128_groth16_prepare_dev": (_i, [_vp, _vp, _vp, _vp]),
     "ws_bn128_groth16_finish_dev": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "ws_msm_table_windows": (_i, [_i]),
+    "ws_bn128_g1_build_table_dev": (_i, [_vp, _vp, _sz, _i, _vp, _vp]),
+    "ws_bn128_g2_build_table_dev": (_i, [_vp, _vp, _sz, _i, _vp, _vp]),
+    "ws_bn128_g1_multiexp_table_dev": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _vp]),
+    "ws_bn128_g2_multiexp_table_dev": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _vp]),
     "ws_bn128_g1_sum_dev": (_i, [_vp, _vp, _i, _vp, _vp]),
     "ws_bn128_g2_sum_dev": (_i, [_vp, _vp, _i, _vp, _vp]),
 }

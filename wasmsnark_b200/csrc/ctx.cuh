@@ -61,6 +61,7 @@ struct ws_ctx {
     ws::StageTimer timer;
     std::string err;
     unsigned force_T = 0;
+    bool key_tables = true;      // resident proving keys get window tables (prover.cu)
     void* tw_table = nullptr;     // ntt.cuh TwiddleTable storage (Fr*), owned here
     int tw_logM = 0;
     unsigned seg_len = 0;    // 0 = automatic

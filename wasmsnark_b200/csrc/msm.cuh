@@ -146,7 +146,7 @@ inline void launch_scan(const uint32_t* in, uint32_t* out, uint32_t* tile_sums, 
 // ------------------------------------------------------------------ MSM kernels
 template <class C>
 static __global__ void __launch_bounds__(256) k_msm_digits(MsmPlan p, const uint32_t* __restrict__ scalars, const Affine<C>* __restrict__ points,
-                                                    int16_t* __restrict__ digits, uint32_t* __restrict__ counts) {
+                                                    int32_t* __restrict__ digits, uint32_t* __restrict__ counts) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
     constexpr int SL = C::SCALAR_LIMBS;
@@ -164,7 +164,7 @@ static __global__ void __launch_bounds__(256) k_msm_digits(MsmPlan p, const uint
     msm_digits_body<SL>(p, i, sl, x.is_zero(), digits, counts);
 }
 
-static __global__ void __launch_bounds__(256) k_msm_scatter(MsmPlan p, const int16_t* __restrict__ digits, const uint32_t* __restrict__ bstart,
+static __global__ void __launch_bounds__(256) k_msm_scatter(MsmPlan p, const int32_t* __restrict__ digits, const uint32_t* __restrict__ bstart,
                                                      uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
@@ -394,9 +394,53 @@ static __global__ void __launch_bounds__(64) k_affine_points(const Jac<C>* __res
     out[i] = a;
 }
 
+// ------------------------------------------------------------------ window tables (resident keys)
+// table[w * n + i] = 2^(c w) * P_i as an affine point (x = 0: infinity), w < W.  One thread per point:
+// the Jacobian chain P, 2^c P, 2^2c P, ... (dbl-2009-l), then ONE field inversion for all W normalisations
+// (Montgomery's trick over the Z coordinates).  Built once when a proving key is loaded; with it every
+// digit window of an MSM feeds the same bucket set and the result needs no doubling at all.
+constexpr int MSM_TABLE_MAXW = 33;      // c >= 8 on 256-bit scalars
+
+template <class C>
+static __global__ void __launch_bounds__(64) k_msm_build_table(const Affine<C>* __restrict__ points, uint32_t n, int c, int W, Affine<C>* __restrict__ table) {
+    static_assert(C::A_ZERO, "window tables are built with the a = 0 doubling");
+    using F = typename C::F;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<C> p = ldg_struct(points + i);
+    const Affine<C> zero{F::zero(), F::zero()};
+    if (p.is_inf()) {
+        for (int w = 0; w < W; w++) table[(size_t)w * n + i] = zero;
+        return;
+    }
+    Jac<C> J[MSM_TABLE_MAXW];
+    F pref[MSM_TABLE_MAXW];
+    J[0] = Jac<C>{p.x, p.y, F::one()};
+    pref[0] = F::one();
+    int live = 1;                              // windows with a finite point
+    for (int w = 1; w < W; w++) {
+        Jac<C> t = J[w - 1];
+#pragma unroll 1
+        for (int k = 0; k < c; k++) t = jdbl_a0<C>(t);
+        if (t.z.is_zero()) break;              // a point of 2-power order: everything above is infinity
+        J[w] = t;
+        pref[w] = mul(pref[w - 1], t.z);
+        live = w + 1;
+    }
+    F inv_all = inv(pref[live - 1]);
+    for (int w = live - 1; w >= 1; w--) {
+        F zi = mul(inv_all, pref[w - 1]);      // 1 / Z_w
+        inv_all = mul(inv_all, J[w].z);
+        F zi2 = sqr(zi);
+        table[(size_t)w * n + i] = Affine<C>{mul(J[w].x, zi2), mul(J[w].y, mul(zi2, zi))};
+    }
+    table[i] = p;
+    for (int w = live; w < W; w++) table[(size_t)w * n + i] = zero;
+}
+
 // ------------------------------------------------------------------ workspace + launch
 struct MsmWorkspace {
-    int16_t* digits;
+    int32_t* digits;
     uint32_t *counts, *cursor, *bstart, *tstart, *tile_sums, *entries, *task_bucket, *order, *heavy, *small_ctrs;   // small_ctrs: [0..1] heavy counts, [8..] len_hist, [8+T+2..] len_cursor
     void *partials, *segA, *segT, *A2s, *A2w, *T2, *bits, *R;
 };
@@ -410,8 +454,8 @@ inline size_t msm_carve(const MsmPlan& p, uint8_t* base, MsmWorkspace* ws) {
         off += align256(bytes);
         return ptr;
     };
-    size_t entries = (size_t)p.nwin * p.n;
-    uint8_t* d = take(entries * sizeof(int16_t));
+    size_t entries = (size_t)p.ndig * p.n;
+    uint8_t* d = take(entries * sizeof(int32_t));
     uint8_t* cn = take((size_t)p.nbuckets * 4);
     uint8_t* cu = take((size_t)p.nbuckets * 4);
     uint8_t* bs = take(((size_t)p.nbuckets + 1) * 4);
@@ -431,7 +475,7 @@ inline size_t msm_carve(const MsmPlan& p, uint8_t* base, MsmWorkspace* ws) {
     uint8_t* bi = take((size_t)p.nwin * (p.logS2 + 2) * sizeof(XYZZ<C>));
     uint8_t* rr = take((size_t)p.nwin * sizeof(XYZZ<C>));
     if (ws) {
-        ws->digits = (int16_t*)d;
+        ws->digits = (int32_t*)d;
         ws->counts = (uint32_t*)cn;
         ws->cursor = (uint32_t*)cu;
         ws->bstart = (uint32_t*)bs;
@@ -455,12 +499,17 @@ inline size_t msm_carve(const MsmPlan& p, uint8_t* base, MsmWorkspace* ws) {
 }
 
 // Window size / task cap for n pairs on a 148-SM part.
-inline void msm_choose(uint32_t n, int* c, uint32_t* T, int sbits = 256) {
+inline void msm_choose(uint32_t n, int* c, uint32_t* T, int sbits = 256, int table = 0) {
     int lg = 0;
     while ((1ull << (lg + 1)) <= n) lg++;
     int cc = lg - 4;
     if (cc < 4) cc = 4;
     if (cc > 16) cc = 16;
+    if (table) {      // one shared bucket set: the reduce cost is paid once, so wider windows (fewer additions per point) win
+        cc = lg;
+        if (cc < 8) cc = 8;
+        if (cc > 20) cc = 20;
+    }
     *c = cc;
     int nwin = (sbits + 1 + cc - 1) / cc;
     uint64_t entries = (uint64_t)nwin * n;

@@ -32,9 +32,12 @@ namespace ws {
 
 struct MsmPlan {
     uint32_t n;        // number of (scalar, point) pairs
-    int c;             // window bits, 2..16
+    int c;             // window bits, 2..22
     int sbits;         // scalar width in bits (256 for BN128, 768 for MNT6753)
-    int nwin;          // windows incl. the carry window: ceil((sbits + 1) / c)
+    int ndig;          // digit windows incl. the carry window: ceil((sbits + 1) / c)
+    int table;         // 1: the point array is a window table T[w * n + i] = 2^(c w) * P_i (resident keys), all
+                       //    digit windows then share ONE bucket set and no doubling is ever needed
+    int nwin;          // bucket windows: ndig, or 1 with a table
     uint32_t B;        // buckets per window = 2^(c-1); bucket b holds digit magnitude b+1
     uint32_t T;        // max entries per accumulate task
     uint32_t L;        // buckets per reduce segment (power of two, <= B)
@@ -47,12 +50,14 @@ struct MsmPlan {
     uint32_t max_tasks;
 };
 
-HD MsmPlan msm_make_plan(uint32_t n, int c, uint32_t T, uint32_t L = 0, int sbits = 256) {
+HD MsmPlan msm_make_plan(uint32_t n, int c, uint32_t T, uint32_t L = 0, int sbits = 256, int table = 0) {
     MsmPlan p;
     p.n = n;
     p.c = c;
     p.sbits = sbits;
-    p.nwin = (sbits + 1 + c - 1) / c;
+    p.ndig = (sbits + 1 + c - 1) / c;
+    p.table = table;
+    p.nwin = table ? 1 : p.ndig;
     p.B = 1u << (c - 1);
     p.T = T;
     if (L == 0) {   // enough segments to occupy the part (~64K threads), at most 16 buckets each
@@ -68,7 +73,7 @@ HD MsmPlan msm_make_plan(uint32_t n, int c, uint32_t T, uint32_t L = 0, int sbit
     p.logS2 = 0;
     while ((1u << p.logS2) < p.S2) p.logS2++;
     p.nbuckets = (uint32_t)p.nwin * p.B;
-    uint64_t entries = (uint64_t)p.nwin * n;
+    uint64_t entries = (uint64_t)p.ndig * n;
     p.max_tasks = (uint32_t)(entries / T) + p.nbuckets + 1;
     return p;
 }
@@ -85,10 +90,10 @@ HD uint32_t atomic_add_u32(uint32_t* p, uint32_t v) {
 
 // ---- digits: thread i ------------------------------------------------------------------
 // scalar_limbs: the SL u32 limbs (raw, LE) of scalar i.  is_inf: point i is infinity (x == 0).
-// digits[w * n + i] = signed digit in [-2^(c-1), 2^(c-1)), counts[w * B + |d| - 1]++.
+// digits[w * n + i] = signed digit in [-2^(c-1), 2^(c-1)), counts[w' * B + |d| - 1]++  (w' = w, or 0 with a table).
 template <int SL>
 HD void msm_digits_body(const MsmPlan& p, uint32_t i, const uint32_t* scalar_limbs, bool is_inf,
-                        int16_t* digits, uint32_t* counts) {
+                        int32_t* digits, uint32_t* counts) {
     uint32_t s[SL + 1];
 #pragma unroll
     for (int k = 0; k < SL; k++) s[k] = is_inf ? 0u : scalar_limbs[k];
@@ -96,7 +101,7 @@ HD void msm_digits_body(const MsmPlan& p, uint32_t i, const uint32_t* scalar_lim
     const uint32_t mask = (1u << p.c) - 1u;
     const uint32_t half = 1u << (p.c - 1);
     uint32_t carry = 0;
-    for (int w = 0; w < p.nwin; w++) {
+    for (int w = 0; w < p.ndig; w++) {
         int bit = w * p.c;
         uint32_t raw = 0;
         if (bit < 32 * SL) {
@@ -106,34 +111,34 @@ HD void msm_digits_body(const MsmPlan& p, uint32_t i, const uint32_t* scalar_lim
         }
         uint32_t d = raw + carry;            // 0 .. 2^c
         int32_t sd;
-        if (d >= half && w != p.nwin - 1) {   // the top window keeps its sign: nothing above it takes a carry
+        if (d >= half && w != p.ndig - 1) {   // the top window keeps its sign: nothing above it takes a carry
             sd = (int32_t)d - (int32_t)(mask + 1u);   // -2^(c-1) .. 0
             carry = 1;
         } else {
             sd = (int32_t)d;
             carry = 0;
         }
-        digits[(size_t)w * p.n + i] = (int16_t)sd;
+        digits[(size_t)w * p.n + i] = sd;
         if (sd != 0) {
             uint32_t mag = sd < 0 ? (uint32_t)(-sd) : (uint32_t)sd;
-            atomic_add_u32(&counts[(size_t)w * p.B + (mag - 1)], 1u);
+            atomic_add_u32(&counts[(size_t)(p.table ? 0 : w) * p.B + (mag - 1)], 1u);
         }
     }
 }
 
 // ---- scatter: thread i -----------------------------------------------------------------
 // cursor[] starts as a copy of the histogram and is counted down; entries[] receives
-// (i | sign << 31) grouped by bucket (order inside a bucket is irrelevant to the sum).
-HD void msm_scatter_body(const MsmPlan& p, uint32_t i, const int16_t* digits, const uint32_t* bstart,
+// (point index | sign << 31) grouped by bucket (order inside a bucket is irrelevant to the sum).
+HD void msm_scatter_body(const MsmPlan& p, uint32_t i, const int32_t* digits, const uint32_t* bstart,
                          uint32_t* cursor, uint32_t* entries) {
-    for (int w = 0; w < p.nwin; w++) {
+    for (int w = 0; w < p.ndig; w++) {
         int32_t sd = digits[(size_t)w * p.n + i];
         if (sd == 0) continue;
         uint32_t neg = sd < 0;
         uint32_t mag = neg ? (uint32_t)(-sd) : (uint32_t)sd;
-        size_t b = (size_t)w * p.B + (mag - 1);
+        size_t b = (size_t)(p.table ? 0 : w) * p.B + (mag - 1);
         uint32_t k = atomic_add_u32(&cursor[b], 0xFFFFFFFFu) - 1u;   // counts down to 0
-        entries[bstart[b] + k] = i | (neg << 31);
+        entries[bstart[b] + k] = (p.table ? (uint32_t)w * p.n + i : i) | (neg << 31);   // index into the point / table array
     }
 }
 

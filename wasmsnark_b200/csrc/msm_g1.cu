@@ -3,8 +3,18 @@
 using namespace ws;
 
 namespace ws {
-int msm_g1_run(ws_ctx* c, const void* ds, const void* dp, size_t n, void* d_out_jac, void* d_out_xyzz, cudaStream_t st, int arena_slot) {
-    return multiexp_dev<G1Curve>(c, ds, dp, n, d_out_jac, 0, st, d_out_xyzz, false, arena_slot);
+int msm_g1_run(ws_ctx* c, const void* ds, const void* dp, size_t n, void* d_out_jac, void* d_out_xyzz, cudaStream_t st, int arena_slot, int table_c) {
+    return multiexp_dev<G1Curve>(c, ds, dp, n, d_out_jac, 0, st, d_out_xyzz, false, arena_slot, table_c);
+}
+int msm_g1_build_table(ws_ctx* c, const void* d_points, size_t n, int table_c, void* d_table, cudaStream_t st) {
+    return build_table_dev<G1Curve>(c, d_points, n, table_c, d_table, st);
+}
+int msm_table_windows_n(int table_c) { return msm_table_windows(table_c); }
+int msm_table_choose_c(size_t n) {
+    int cc;
+    uint32_t T;
+    msm_choose((uint32_t)n, &cc, &T, 256, 1);
+    return cc;
 }
 }  // namespace ws
 
@@ -37,4 +47,16 @@ WS_API int ws_bn128_g1_affine(ws_ctx* c, const uint8_t* in, uint8_t* out, size_t
     if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) return c->fail_cuda("affine");
     return WS_OK;
 }
+WS_API int ws_bn128_g1_build_table_dev(ws_ctx* c, const void* d_points, size_t n, int table_c, void* d_table, void* stream) {
+    if (!c || !d_points || !d_table) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
+    cudaSetDevice(c->device);
+    return build_table_dev<G1Curve>(c, d_points, n, table_c, d_table, stream ? (cudaStream_t)stream : c->stream);
+}
+WS_API int ws_bn128_g1_multiexp_table_dev(ws_ctx* c, const void* ds, const void* d_table, size_t n, int table_c, void* dout, void* stream) {
+    if (!c || !dout || (n && (!ds || !d_table))) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
+    if (table_c < 8 || table_c > 22) return c->fail(WS_E_ARG, "table window bits must be in 8..22");
+    cudaSetDevice(c->device);
+    return multiexp_dev<G1Curve>(c, ds, d_table, n, dout, 0, stream ? (cudaStream_t)stream : c->stream, nullptr, true, 1, table_c);
+}
+WS_API int ws_msm_table_windows(int table_c) { return table_c >= 8 && table_c <= 22 ? msm_table_windows(table_c) : 0; }
 }

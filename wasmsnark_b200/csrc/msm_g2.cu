@@ -3,8 +3,11 @@
 using namespace ws;
 
 namespace ws {
-int msm_g2_run(ws_ctx* c, const void* ds, const void* dp, size_t n, void* d_out_jac, void* d_out_xyzz, cudaStream_t st, int arena_slot) {
-    return multiexp_dev<G2Curve>(c, ds, dp, n, d_out_jac, 0, st, d_out_xyzz, false, arena_slot);
+int msm_g2_run(ws_ctx* c, const void* ds, const void* dp, size_t n, void* d_out_jac, void* d_out_xyzz, cudaStream_t st, int arena_slot, int table_c) {
+    return multiexp_dev<G2Curve>(c, ds, dp, n, d_out_jac, 0, st, d_out_xyzz, false, arena_slot, table_c);
+}
+int msm_g2_build_table(ws_ctx* c, const void* d_points, size_t n, int table_c, void* d_table, cudaStream_t st) {
+    return build_table_dev<G2Curve>(c, d_points, n, table_c, d_table, st);
 }
 }  // namespace ws
 
@@ -36,5 +39,16 @@ WS_API int ws_bn128_g2_affine(ws_ctx* c, const uint8_t* in, uint8_t* out, size_t
     cudaMemcpyAsync(out, dout, count * 192, cudaMemcpyDeviceToHost, c->stream);
     if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) return c->fail_cuda("affine");
     return WS_OK;
+}
+WS_API int ws_bn128_g2_build_table_dev(ws_ctx* c, const void* d_points, size_t n, int table_c, void* d_table, void* stream) {
+    if (!c || !d_points || !d_table) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
+    cudaSetDevice(c->device);
+    return build_table_dev<G2Curve>(c, d_points, n, table_c, d_table, stream ? (cudaStream_t)stream : c->stream);
+}
+WS_API int ws_bn128_g2_multiexp_table_dev(ws_ctx* c, const void* ds, const void* d_table, size_t n, int table_c, void* dout, void* stream) {
+    if (!c || !dout || (n && (!ds || !d_table))) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
+    if (table_c < 8 || table_c > 22) return c->fail(WS_E_ARG, "table window bits must be in 8..22");
+    cudaSetDevice(c->device);
+    return multiexp_dev<G2Curve>(c, ds, d_table, n, dout, 0, stream ? (cudaStream_t)stream : c->stream, nullptr, true, 1, table_c);
 }
 }

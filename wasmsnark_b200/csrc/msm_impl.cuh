@@ -13,19 +13,21 @@ namespace ws {
 
 // d_out: Jacobian triple (may be null); d_out_xyzz: XYZZ sum for device consumers (may be null)
 template <class C>
-inline int multiexp_dev(ws_ctx* c, const void* d_scalars, const void* d_points, size_t n, void* d_out, int window_bits, cudaStream_t st, void* d_out_xyzz = nullptr, bool own_timer = true, int arena_slot = 1) {
+inline int multiexp_dev(ws_ctx* c, const void* d_scalars, const void* d_points, size_t n, void* d_out, int window_bits, cudaStream_t st, void* d_out_xyzz = nullptr, bool own_timer = true, int arena_slot = 1, int table_c = 0) {
     if (n > 0x7FFFFFFFull) return c->fail(WS_E_ARG, "n too large");
     if (((uintptr_t)d_scalars | (uintptr_t)d_points | (uintptr_t)d_out | (uintptr_t)d_out_xyzz) & 15) return c->fail(WS_E_ARG, "device pointers must be 16-byte aligned");
     int cb;
     uint32_t T;
     constexpr int SBITS = 32 * C::SCALAR_LIMBS;
-    msm_choose((uint32_t)n, &cb, &T, SBITS);
-    if (window_bits) {
+    msm_choose((uint32_t)n, &cb, &T, SBITS, table_c != 0);
+    if (table_c) {            // d_points is a window table built for exactly this window size
+        cb = table_c;
+    } else if (window_bits) {
         if (window_bits < 2 || window_bits > 16) return c->fail(WS_E_ARG, "window_bits must be in 2..16");
         cb = window_bits;
     }
     if (c->force_T) T = c->force_T;
-    MsmPlan p = msm_make_plan((uint32_t)n, cb, T, c->seg_len, SBITS);
+    MsmPlan p = msm_make_plan((uint32_t)n, cb, T, c->seg_len, SBITS, table_c != 0);
     size_t need = msm_carve<C>(p, nullptr, nullptr);
     uint8_t* base = (uint8_t*)c->arena(arena_slot, need);
     if (!base) return c->fail_cuda("msm workspace");
@@ -58,5 +60,20 @@ inline int multiexp_host(ws_ctx* c, const uint8_t* scalars, const uint8_t* point
 
 
 
+
+
+// Builds the window table of `n` points for window size table_c (see k_msm_build_table); d_table must hold
+// msm_table_windows(table_c) * n affine points.
+inline int msm_table_windows(int table_c) { return (257 + table_c - 1) / table_c; }
+
+template <class C>
+inline int build_table_dev(ws_ctx* c, const void* d_points, size_t n, int table_c, void* d_table, cudaStream_t st) {
+    if (table_c < 8 || table_c > 22) return c->fail(WS_E_ARG, "table window bits must be in 8..22");
+    if (n == 0) return WS_OK;
+    int W = msm_table_windows(table_c);
+    if ((uint64_t)W * n >= 0x80000000ull) return c->fail(WS_E_ARG, "table too large for 31-bit point indices");
+    k_msm_build_table<C><<<(unsigned)((n + 63) / 64), 64, 0, st>>>((const Affine<C>*)d_points, (uint32_t)n, table_c, W, (Affine<C>*)d_table);
+    return cudaGetLastError() == cudaSuccess ? WS_OK : c->fail_cuda("build_table");
+}
 
 }  // namespace ws

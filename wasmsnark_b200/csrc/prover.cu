@@ -259,6 +259,9 @@ struct ws_pkey {
     G1Affine *A = nullptr, *B1 = nullptr, *C = nullptr, *H = nullptr;
     G2Affine* B2 = nullptr;
     FixedPoints* fixed = nullptr;
+    // window tables (2^(c w) * P_i, see k_msm_build_table): one per section, built at load; tc_* = window bits, 0 = none
+    void *tA = nullptr, *tB1 = nullptr, *tB2 = nullptr, *tC = nullptr, *tH = nullptr;
+    int tc_v = 0, tc_c = 0, tc_h = 0;
 };
 
 static int log2_exact(uint32_t n) {
@@ -274,6 +277,11 @@ static void pkey_release(ws_pkey* k) {
     k->polB.free_all();
     cudaFree(k->points);
     cudaFree(k->fixed);
+    cudaFree(k->tA);
+    cudaFree(k->tB1);
+    cudaFree(k->tB2);
+    cudaFree(k->tC);
+    cudaFree(k->tH);
     delete k;
 }
 
@@ -281,6 +289,47 @@ static void shard_range(uint32_t n, int rank, int world, uint32_t* lo, uint32_t*
     uint32_t per = n / (uint32_t)world;
     *lo = per * (uint32_t)rank;
     *cnt = rank < world - 1 ? per : n - per * (uint32_t)(world - 1);
+}
+
+// Window tables for the five point sections (HBM is plentiful: 13 x the section size at 2^20).  Failure to
+// allocate is not an error: the section then runs the table-free MSM.
+static void build_key_tables(ws_ctx* c, ws_pkey* k) {
+    auto one = [&](const void* pts, size_t cnt, size_t psize, int* tc, void** tab, bool g2) {
+        *tab = nullptr;
+        if (cnt == 0) return;
+        int cc = *tc ? *tc : msm_table_choose_c(cnt);
+        int W = msm_table_windows_n(cc);
+        if ((uint64_t)W * cnt >= 0x80000000ull) return;
+        void* t = nullptr;
+        if (cudaMalloc(&t, (size_t)W * cnt * psize) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+        int rc = g2 ? msm_g2_build_table(c, pts, cnt, cc, t, c->stream) : msm_g1_build_table(c, pts, cnt, cc, t, c->stream);
+        if (rc || cudaStreamSynchronize(c->stream) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(t);
+            return;
+        }
+        *tc = cc;
+        *tab = t;
+    };
+    one(k->A, k->v_cnt, 64, &k->tc_v, &k->tA, false);
+    if (k->tA) {
+        one(k->B1, k->v_cnt, 64, &k->tc_v, &k->tB1, false);
+        one(k->B2, k->v_cnt, 128, &k->tc_v, &k->tB2, true);
+    }
+    if (!k->tA || !k->tB1 || !k->tB2) {        // all three share tc_v: all or nothing
+        cudaFree(k->tA);
+        cudaFree(k->tB1);
+        cudaFree(k->tB2);
+        k->tA = k->tB1 = k->tB2 = nullptr;
+        k->tc_v = 0;
+    }
+    one(k->C, k->c_cnt, 64, &k->tc_c, &k->tC, false);
+    if (!k->tC) k->tc_c = 0;
+    one(k->H, k->h_cnt, 64, &k->tc_h, &k->tH, false);
+    if (!k->tH) k->tc_h = 0;
 }
 
 static int pkey_load(ws_ctx* c, const uint8_t* pkey, size_t len, ws_pkey** out, int rank = 0, int world = 1) {
@@ -344,6 +393,7 @@ static int pkey_load(ws_ctx* c, const uint8_t* pkey, size_t len, ws_pkey** out, 
         pkey_release(k);
         return c->fail_cuda("proving key upload");
     }
+    if (c->key_tables) build_key_tables(c, k);
     *out = k;
     return WS_OK;
 }
@@ -421,15 +471,15 @@ static int prove_partials_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_witn
     for (int lane = 0; lane < 4 && !rc; lane++) {
         cudaStream_t ls = c->lanes[lane];
         cudaStreamWaitEvent(ls, c->fork_ev, 0);
-        if (lane == 0) rc = msm_g2_run(c, wv, k->B2, k->v_cnt, nullptr, rB2, ls, 8 + lane);
-        else if (lane == 1) rc = msm_g1_run(c, wv, k->A, k->v_cnt, nullptr, rA, ls, 8 + lane);
-        else if (lane == 2) rc = msm_g1_run(c, wv, k->B1, k->v_cnt, nullptr, rB1, ls, 8 + lane);
-        else rc = msm_g1_run(c, d_witness + 32 * ((size_t)k->n_public + 1 + k->c_lo), k->C, k->c_cnt, nullptr, rC, ls, 8 + lane);
+        if (lane == 0) rc = msm_g2_run(c, wv, k->tB2 ? k->tB2 : (const void*)k->B2, k->v_cnt, nullptr, rB2, ls, 8 + lane, k->tc_v);
+        else if (lane == 1) rc = msm_g1_run(c, wv, k->tA ? k->tA : (const void*)k->A, k->v_cnt, nullptr, rA, ls, 8 + lane, k->tc_v);
+        else if (lane == 2) rc = msm_g1_run(c, wv, k->tB1 ? k->tB1 : (const void*)k->B1, k->v_cnt, nullptr, rB1, ls, 8 + lane, k->tc_v);
+        else rc = msm_g1_run(c, d_witness + 32 * ((size_t)k->n_public + 1 + k->c_lo), k->tC ? k->tC : (const void*)k->C, k->c_cnt, nullptr, rC, ls, 8 + lane, k->tc_c);
         cudaEventRecord(c->lane_done[lane], ls);
     }
     if (rc) return rc;
     if ((rc = calc_h_dev(c, k->polA, k->polB, (const Fr*)d_witness, nv, k->logn, h, work, st))) return rc;
-    if ((rc = msm_g1_run(c, h + k->h_lo, k->H, k->h_cnt, nullptr, rH, st, 1))) return rc;
+    if ((rc = msm_g1_run(c, h + k->h_lo, k->tH ? k->tH : (const void*)k->H, k->h_cnt, nullptr, rH, st, 1, k->tc_h))) return rc;
     c->timer.mark("msm:H", st);
     for (int lane = 0; lane < 4; lane++) cudaStreamWaitEvent(st, c->lane_done[lane], 0);
     c->timer.mark("msm:A,B1,B2,C (side streams)", st);
@@ -568,6 +618,11 @@ static int fft_host(ws_ctx* c, uint8_t* px, size_t n, int odd, int inverse) {
 WS_API int ws_bn128_fr_fft(ws_ctx* c, uint8_t* px, size_t n, int odd) { return fft_host(c, px, n, odd, 0); }
 WS_API int ws_bn128_fr_ifft(ws_ctx* c, uint8_t* px, size_t n, int odd) { return fft_host(c, px, n, odd, 1); }
 
+WS_API int ws_set_key_tables(ws_ctx* c, int on) {
+    if (!c) return WS_E_ARG;
+    c->key_tables = on != 0;
+    return WS_OK;
+}
 WS_API int ws_bn128_pkey_load(ws_ctx* c, const uint8_t* pkey, size_t len, ws_pkey** out) {
     if (!c || !pkey || !out) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
     *out = nullptr;
