@@ -102,7 +102,58 @@ struct PreProducts {
     G2X sd2;
 };
 
-static __global__ void __launch_bounds__(128) k_assemble_pre(const FixedPoints* __restrict__ fx, const uint8_t* __restrict__ rs, PreProducts* out) {
+// Fixed-base comb tables of the key's delta1 / delta2: entry [w][k] = k * 2^(4w) * delta (affine), k = 1..15.
+// With them a product k*delta is a sum of one table entry per nibble of k -- no doublings -- and the nibbles
+// are spread over the lanes of a warp, so the (r, s)-only products cost ~10 additions of depth.
+constexpr int D1_WINDOWS = 128;     // 512-bit scalars (r*s)
+constexpr int D2_WINDOWS = 64;      // 256-bit scalars
+struct FixedBaseTables {
+    G1Affine d1[D1_WINDOWS][16];
+    G2Affine d2[D2_WINDOWS][16];
+};
+
+template <class C>
+__device__ __forceinline__ void comb_rows(const Affine<C>& base_pt, int w, Affine<C>* row) {
+    using F = typename C::F;
+    Jac<C> j{base_pt.x, base_pt.y, F::one()};
+    for (int k = 0; k < 4 * w; k++) j = jdbl_a0<C>(j);          // 2^(4w) * delta
+    XYZZ<C> b = from_jac<C>(j), acc = b;
+    row[0] = Affine<C>{F::zero(), F::zero()};
+    for (int k = 1; k < 16; k++) {
+        Jac<C> a = to_affine<C>(acc);
+        row[k] = acc.is_inf() ? Affine<C>{F::zero(), F::zero()} : Affine<C>{a.x, a.y};
+        acc = padd_call<C>(acc, b);
+    }
+}
+
+static __global__ void __launch_bounds__(64) k_build_fixed_tables(const FixedPoints* __restrict__ fx, FixedBaseTables* t) {
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < D1_WINDOWS) comb_rows<G1Curve>(fx->delta1, w, t->d1[w]);
+    else if (w < D1_WINDOWS + D2_WINDOWS) comb_rows<G2Curve>(fx->delta2, w - D1_WINDOWS, t->d2[w - D1_WINDOWS]);
+}
+
+// sum over the nibbles of k (len bytes) of row[w][nibble]: lanes stride over the windows, shuffle tree.
+template <class C, int WINDOWS>
+__device__ __forceinline__ XYZZ<C> comb_product_warp(const Affine<C> (*rows)[16], const uint8_t* k, int len) {
+    const int lane = threadIdx.x & 31;
+    XYZZ<C> acc = XYZZ<C>::inf();
+    for (int w = lane; w < 2 * len && w < WINDOWS; w += 32) {
+        uint32_t nib = (k[w >> 1] >> ((w & 1) * 4)) & 15u;
+        if (nib) {
+            Affine<C> q = rows[w][nib];
+            if (!q.is_inf()) acc = pmadd_call<C>(acc, q);
+        }
+    }
+#pragma unroll 1
+    for (int off = 16; off > 0; off >>= 1) {
+        XYZZ<C> o = shfl_bcast_struct(acc, (lane + off) & 31);     // every lane keeps a full copy of its subtree
+        if (lane < off) acc = padd_call<C>(acc, o);
+    }
+    return acc;       // valid on lane 0
+}
+
+static __global__ void __launch_bounds__(128) k_assemble_pre(const FixedPoints* __restrict__ fx, const FixedBaseTables* __restrict__ tb,
+                                                            const uint8_t* __restrict__ rs, PreProducts* out) {
     __shared__ uint8_t s_rs[64], s_prod[64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < 64) s_rs[threadIdx.x] = rs[threadIdx.x];
@@ -125,9 +176,19 @@ static __global__ void __launch_bounds__(128) k_assemble_pre(const FixedPoints* 
         memcpy(s_prod, p, 64);
     }
     __syncthreads();
-    // every lane of a warp carries the same state (warp-cooperative doublings); lane 0 stores
     const uint8_t* r = s_rs;
     const uint8_t* s = s_rs + 32;
+    if (tb) {         // resident key: fixed-base comb, no doublings
+        if (warp < 3) {
+            G1X v = comb_product_warp<G1Curve, D1_WINDOWS>(tb->d1, warp == 0 ? r : (warp == 1 ? s : s_prod), warp == 2 ? 64 : 32);
+            if (lane == 0) (warp == 0 ? out->rd1 : (warp == 1 ? out->sd1 : out->rsd1)) = v;
+        } else {
+            G2X v = comb_product_warp<G2Curve, D2_WINDOWS>(tb->d2, s, 32);
+            if (lane == 0) out->sd2 = v;
+        }
+        return;
+    }
+    // every lane of a warp carries the same state (warp-cooperative doublings); lane 0 stores
     if (warp < 3) {
         G1X v = times_scalar_w4_warp<G1Curve>(load_fixed<G1Curve>(fx->delta1), warp == 0 ? r : (warp == 1 ? s : s_prod), warp == 2 ? 64 : 32);
         if (lane == 0) (warp == 0 ? out->rd1 : (warp == 1 ? out->sd1 : out->rsd1)) = v;
@@ -259,6 +320,7 @@ struct ws_pkey {
     G1Affine *A = nullptr, *B1 = nullptr, *C = nullptr, *H = nullptr;
     G2Affine* B2 = nullptr;
     FixedPoints* fixed = nullptr;
+    FixedBaseTables* fixed_tables = nullptr;    // comb tables of delta1 / delta2 (built with the window tables)
     // window tables (2^(c w) * P_i, see k_msm_build_table): one per section, built at load; tc_* = window bits, 0 = none
     void *tA = nullptr, *tB1 = nullptr, *tB2 = nullptr, *tC = nullptr, *tH = nullptr;
     int tc_v = 0, tc_c = 0, tc_h = 0;
@@ -277,6 +339,7 @@ static void pkey_release(ws_pkey* k) {
     k->polB.free_all();
     cudaFree(k->points);
     cudaFree(k->fixed);
+    cudaFree(k->fixed_tables);
     cudaFree(k->tA);
     cudaFree(k->tB1);
     cudaFree(k->tB2);
@@ -393,7 +456,20 @@ static int pkey_load(ws_ctx* c, const uint8_t* pkey, size_t len, ws_pkey** out, 
         pkey_release(k);
         return c->fail_cuda("proving key upload");
     }
-    if (c->key_tables) build_key_tables(c, k);
+    if (c->key_tables) {
+        build_key_tables(c, k);
+        if (cudaMalloc(&k->fixed_tables, sizeof(FixedBaseTables)) == cudaSuccess) {
+            k_build_fixed_tables<<<(D1_WINDOWS + D2_WINDOWS + 63) / 64, 64, 0, c->stream>>>(k->fixed, k->fixed_tables);
+            if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+                cudaGetLastError();
+                cudaFree(k->fixed_tables);
+                k->fixed_tables = nullptr;
+            }
+        } else {
+            cudaGetLastError();
+            k->fixed_tables = nullptr;
+        }
+    }
     *out = k;
     return WS_OK;
 }
@@ -493,7 +569,7 @@ static int prove_pre_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_rs, cudaS
     cudaStream_t ls = c->lanes[4];
     cudaEventRecord(c->lane_done[5], st);
     cudaStreamWaitEvent(ls, c->lane_done[5], 0);
-    k_assemble_pre<<<1, 128, 0, ls>>>(k->fixed, d_rs, pre);
+    k_assemble_pre<<<1, 128, 0, ls>>>(k->fixed, k->fixed_tables, d_rs, pre);
     cudaEventRecord(c->lane_done[4], ls);
     c->pre_pending = true;
     return cudaGetLastError() == cudaSuccess ? WS_OK : c->fail_cuda("assemble_pre");
