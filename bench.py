@@ -296,11 +296,13 @@ def main():
     for k in range(2 * W):
         step_pipe(k)
     barrier()
+    launches0 = lib.ws_kernel_launches(h) + bn2.lib.ws_kernel_launches(bn2.ctx.h)
     e0, e1, ej = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record(stream)
     stream2.wait_event(e0)
     for k in range(K):
         step_pipe(k)
+    msm_launches = lib.ws_kernel_launches(h) + bn2.lib.ws_kernel_launches(bn2.ctx.h) - launches0
     ej.record(stream2)
     stream.wait_event(ej)
     e1.record(stream)
@@ -441,8 +443,10 @@ def main():
         e0, e1, ej = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record(stream)
         stream2.wait_event(e0)
+        pl0 = sum(ln.bn.lib.ws_kernel_launches(ln.bn.ctx.h) for ln in lanesP)
         for k in range(K):
             lanesP[k & 1].prove()
+        prove_launches = sum(ln.bn.lib.ws_kernel_launches(ln.bn.ctx.h) for ln in lanesP) - pl0
         ej.record(stream2)
         stream.wait_event(ej)
         e1.record(stream)
@@ -486,7 +490,7 @@ def main():
                     "note": "witness from pinned host memory each proof, two proofs in flight; proving key resident (loaded once per context: %.2f s incl. host-side row regrouping and window tables)" % load_s},
             "stages_ms": pstages, "repeatable_bit_exact": same, "algorithmic_bytes": alg_bytes,
             "hbm_frac": (alg_bytes / (pms * 1e-3) / 1e9) / peaks()[0],
-            "gpu_launches_per_proof": 5 * KERNELS_PER_MSM + 40 + (2 if world > 1 else 1), "keygen_s": gen_s,
+            "gpu_launches_per_proof": int(prove_launches) // K, "keygen_s": gen_s,
         }
         for ln in lanesP:
             ln.bn.lib.ws_bn128_pkey_free(ln.key)
@@ -512,7 +516,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": TOTAL_PAIRS / (e2e_s / K), "unit": "pairs/s", "h2d_bytes_per_step": 96 * cnt, "d2h_bytes_per_step": 96,
                     "ms_per_step": 1000.0 * e2e_s / K, "timer": "host perf_counter around K blocking C-ABI calls (two host threads / contexts when n_gpus = 1), max over ranks"},
-            "gpu_launches": KERNELS_PER_MSM * K + (K if world > 1 else 0),
+            "gpu_launches": int(msm_launches) + (K if world > 1 else 0),
             "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate<G1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if achieved else None, "traffic": None, "peak_source": which,
                          "kernel_ms": acc_ms, "algorithmic_bytes_per_launch": ALG_BYTES_PER_PAIR * cnt,

@@ -190,6 +190,9 @@ int ws_bn128_groth16_partials_dev(ws_ctx* ctx, const ws_pkey* key, const void* d
 int ws_bn128_groth16_prepare_dev(ws_ctx* ctx, const ws_pkey* key, const void* d_rs, void* stream);
 int ws_bn128_groth16_finish_dev(ws_ctx* ctx, const ws_pkey* key, const void* d_all_partials, int world, const void* d_rs, void* d_out, void* stream);
 
+/* Number of this library's CUDA kernels launched on the context so far (MSM, NTT and prover paths). */
+unsigned long long ws_kernel_launches(const ws_ctx* ctx);
+
 /* Stage timing on/off (CUDA events recorded between the pipeline's kernels on the launch stream). */
 int ws_set_profiling(ws_ctx* ctx, int on);
 /* Tuning/test hook: force the per-task entry cap of the MSM accumulate kernel (0 = automatic). */

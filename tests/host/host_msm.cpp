@@ -48,22 +48,23 @@ static void run(const uint8_t* scalars, const uint8_t* points, uint32_t n, int c
         for (uint32_t t = tstart[b] + 1; t < tstart[b + 1]; t++) acc = padd<C>(acc, partials[t]);
         partials[tstart[b]] = acc;
     }
-    std::vector<XYZZ<C>> segA((size_t)p.nwin * p.S), segT((size_t)p.nwin * p.S), A2s((size_t)p.nwin * p.S2), A2w((size_t)p.nwin * p.S2),
-        T2((size_t)p.nwin * p.S2), bits((size_t)p.nwin * (p.logS2 + 2)), R(p.nwin);
+    std::vector<XYZZ<C>> pool(p.pool_elems + 1), bits((size_t)p.nwin * msm_nplanes(p)), R(p.nwin);
     for (int w = 0; w < p.nwin; w++)
-        for (uint32_t s = 0; s < p.S; s++) msm_segreduce_body<C>(p, w, s, tstart.data(), partials.data(), segA.data(), segT.data());
-    for (int w = 0; w < p.nwin; w++)
-        for (uint32_t g = 0; g < p.S2; g++)
-            for (int role = 0; role < 2; role++) msm_seg2_body<C>(p, w, g, role, segA.data(), segT.data(), A2s.data(), A2w.data(), T2.data());
-    for (int w = 0; w < p.nwin; w++) {        // plane sums (serial stand-in for the block reduction)
-        XYZZ<C>* bw = &bits[(size_t)w * (p.logS2 + 2)];
-        for (int k = 0; k < p.logS2 + 2; k++) bw[k] = XYZZ<C>::inf();
-        for (uint32_t g = 0; g < p.S2; g++) {
-            size_t o = (size_t)w * p.S2 + g;
-            bw[0] = padd<C>(bw[0], A2s[o]);
-            bw[1] = padd<C>(bw[1], A2w[o]);
-            for (int k = 0; k < p.logS2; k++)
-                if ((g >> k) & 1) bw[2 + k] = padd<C>(bw[2 + k], T2[o]);
+        for (uint32_t s = 0; s < p.S; s++) msm_segreduce_body<C>(p, w, s, tstart.data(), partials.data(), pool.data());
+    for (int l = 2; l <= p.nlev; l++)
+        for (int w = 0; w < p.nwin; w++)
+            for (uint32_t g = 0; g < p.Sl[l]; g++)
+                for (int role = 0; role < l; role++) msm_level_body<C>(p, l, w, g, role, pool.data());
+    for (int w = 0; w < p.nwin; w++) {        // plane sums over the top level (serial stand-in for the warp reduction)
+        XYZZ<C>* bw = &bits[(size_t)w * msm_nplanes(p)];
+        for (int k = 0; k < msm_nplanes(p); k++) bw[k] = XYZZ<C>::inf();
+        const uint32_t SK = p.Sl[p.nlev];
+        const size_t per = (size_t)SK * p.nwin;
+        for (uint32_t g = 0; g < SK; g++) {
+            size_t o = (size_t)w * SK + g;
+            for (int r = 0; r < p.nlev; r++) bw[r] = padd<C>(bw[r], pool[p.offC[p.nlev] + (size_t)r * per + o]);
+            for (int k = 0; k < p.logSK; k++)
+                if ((g >> k) & 1) bw[p.nlev + k] = padd<C>(bw[p.nlev + k], pool[p.offT[p.nlev] + o]);
         }
     }
     for (int w = 0; w < p.nwin; w++) R[w] = msm_window_value<C>(p, w, bits.data());

@@ -33,6 +33,7 @@ SIGNATURES = {
     "ws_create": (_i, [_i, ctypes.POINTER(_vp)]),
     "ws_destroy": (None, [_vp]),
     "ws_last_error": (ctypes.c_char_p, [_vp]),
+    "ws_kernel_launches": (ctypes.c_ulonglong, [_vp]),
     "ws_set_profiling": (_i, [_vp, _i]),
     "ws_last_timings": (_i, [_vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float), _i]),
     "ws_set_msm_task_cap": (_i, [_vp, ctypes.c_uint]),

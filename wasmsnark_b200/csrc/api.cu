@@ -55,6 +55,8 @@ WS_API void ws_destroy(ws_ctx* c) {
 
 WS_API const char* ws_last_error(const ws_ctx* c) { return c ? c->err.c_str() : "null ctx"; }
 
+WS_API unsigned long long ws_kernel_launches(const ws_ctx* c) { return c ? c->launches : 0; }
+
 WS_API int ws_set_profiling(ws_ctx* c, int on) {
     if (!c) return WS_E_ARG;
     c->timer.enabled = on != 0;

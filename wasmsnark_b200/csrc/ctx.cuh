@@ -60,6 +60,7 @@ struct ws_ctx {
     }
     ws::StageTimer timer;
     std::string err;
+    unsigned long long launches = 0;   // kernels of this library launched so far (ws_kernel_launches)
     unsigned force_T = 0;
     bool key_tables = true;      // resident proving keys get window tables (prover.cu)
     void* tw_table = nullptr;     // ntt.cuh TwiddleTable storage (Fr*), owned here

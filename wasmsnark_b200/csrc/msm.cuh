@@ -303,55 +303,44 @@ static __global__ void __launch_bounds__(256) k_msm_combine_big(MsmPlan p, const
 
 template <class C>
 static __global__ void __launch_bounds__(128) k_msm_segreduce(MsmPlan p, const uint32_t* __restrict__ tstart, const XYZZ<C>* __restrict__ partials,
-                                                       XYZZ<C>* __restrict__ segA, XYZZ<C>* __restrict__ segT) {
+                                                              XYZZ<C>* __restrict__ pool) {
     uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (uint32_t)p.nwin * p.S) return;
-    msm_segreduce_body<C>(p, idx / p.S, idx % p.S, tstart, partials, segA, segT);
+    msm_segreduce_body<C>(p, idx / p.S, idx % p.S, tstart, partials, pool);
 }
 
-// second level over the segments: one thread per (window, group, role)
+// one level of the reduction tree: one thread per (role, window, group); roles are laid out role-major so that
+// warps are role-uniform whenever nwin * Sl[l] is a multiple of 32
 template <class C>
-static __global__ void __launch_bounds__(128) k_msm_seg2(MsmPlan p, const XYZZ<C>* __restrict__ segA, const XYZZ<C>* __restrict__ segT,
-                                                         XYZZ<C>* __restrict__ A2s, XYZZ<C>* __restrict__ A2w, XYZZ<C>* __restrict__ T2) {
+static __global__ void __launch_bounds__(128) k_msm_level(MsmPlan p, int l, XYZZ<C>* pool) {
     uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t per_role = (uint32_t)p.nwin * p.S2;
-    if (idx >= 2 * per_role) return;
-    int role = idx >= per_role;            // warps are role-uniform when per_role is a multiple of 32
+    uint32_t per_role = (uint32_t)p.nwin * p.Sl[l];
+    if (idx >= (uint32_t)l * per_role) return;
+    int role = idx / per_role;
     uint32_t i = idx - role * per_role;
-    msm_seg2_body<C>(p, i / p.S2, i % p.S2, role, segA, segT, A2s, A2w, T2);
+    msm_level_body<C>(p, l, i / p.Sl[l], i % p.Sl[l], role, pool);
 }
 
-// grid (nwin, logS2 + 2): plane 0 sums A2s, plane 1 sums A2w, plane 2+k sums the T2's of groups with bit k set
+// plane sums over the top level (at most 32 groups per window): grid (nwin, nplanes), one warp each.
+// plane r < nlev: sum of carried array r; plane nlev + k: sum of the T's of groups with bit k set.
 template <class C>
-static __global__ void __launch_bounds__(256) k_msm_bitsum(MsmPlan p, const XYZZ<C>* __restrict__ A2s, const XYZZ<C>* __restrict__ A2w,
-                                                           const XYZZ<C>* __restrict__ T2, XYZZ<C>* __restrict__ bits) {
-    __shared__ XYZZ<C> wsum[8];
-    uint32_t w = blockIdx.x;
-    int k = blockIdx.y;
+static __global__ void __launch_bounds__(32) k_msm_bitsum(MsmPlan p, const XYZZ<C>* __restrict__ pool, XYZZ<C>* __restrict__ bits) {
+    const uint32_t w = blockIdx.x;
+    const int k = blockIdx.y, lane = threadIdx.x;
+    const uint32_t SK = p.Sl[p.nlev];
+    const size_t per = (size_t)SK * p.nwin;
     XYZZ<C> acc = XYZZ<C>::inf();
-    for (uint32_t g = threadIdx.x; g < p.S2; g += blockDim.x) {
-        size_t o = (size_t)w * p.S2 + g;
-        if (k == 0) acc = padd_call<C>(acc, A2s[o]);
-        else if (k == 1) acc = padd_call<C>(acc, A2w[o]);
-        else if ((g >> (k - 2)) & 1) acc = padd_call<C>(acc, T2[o]);
+    for (uint32_t g = lane; g < SK; g += 32) {
+        size_t o = (size_t)w * SK + g;
+        if (k < p.nlev) acc = padd_call<C>(acc, pool[p.offC[p.nlev] + (size_t)k * per + o]);
+        else if ((g >> (k - p.nlev)) & 1) acc = padd_call<C>(acc, pool[p.offT[p.nlev] + o]);
     }
-    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll 1
     for (int off = 16; off > 0; off >>= 1) {
         XYZZ<C> o = shfl_down_struct(acc, off);
         acc = padd_call<C>(acc, o);
     }
-    if (lane == 0) wsum[wid] = acc;
-    __syncthreads();
-    if (wid == 0) {
-        acc = lane < (int)(blockDim.x >> 5) ? wsum[lane] : XYZZ<C>::inf();
-#pragma unroll 1
-        for (int off = 4; off > 0; off >>= 1) {
-            XYZZ<C> o = shfl_down_struct(acc, off);
-            acc = padd_call<C>(acc, o);
-        }
-        if (lane == 0) bits[(size_t)w * (p.logS2 + 2) + k] = acc;
-    }
+    if (lane == 0) bits[(size_t)w * msm_nplanes(p) + k] = acc;
 }
 
 // one block: thread w builds its window value, thread 0 runs the Horner over windows.
@@ -442,7 +431,7 @@ static __global__ void __launch_bounds__(64) k_msm_build_table(const Affine<C>* 
 struct MsmWorkspace {
     int32_t* digits;
     uint32_t *counts, *cursor, *bstart, *tstart, *tile_sums, *entries, *task_bucket, *order, *heavy, *small_ctrs;   // small_ctrs: [0..1] heavy counts, [8..] len_hist, [8+T+2..] len_cursor
-    void *partials, *segA, *segT, *A2s, *A2w, *T2, *bits, *R;
+    void *partials, *pool, *bits, *R;
 };
 
 // Carves the workspace out of one device buffer; returns bytes needed (base may be null to size).
@@ -467,12 +456,8 @@ inline size_t msm_carve(const MsmPlan& p, uint8_t* base, MsmWorkspace* ws) {
     uint8_t* hl = take((size_t)p.nbuckets * 8);
     uint8_t* hc = take((8 + 2 * ((size_t)p.T + 2)) * 4);
     uint8_t* pa = take((size_t)p.max_tasks * sizeof(XYZZ<C>));
-    uint8_t* sa = take((size_t)p.nwin * p.S * sizeof(XYZZ<C>));
-    uint8_t* sT = take((size_t)p.nwin * p.S * sizeof(XYZZ<C>));
-    uint8_t* a2s = take((size_t)p.nwin * p.S2 * sizeof(XYZZ<C>));
-    uint8_t* a2w = take((size_t)p.nwin * p.S2 * sizeof(XYZZ<C>));
-    uint8_t* t2 = take((size_t)p.nwin * p.S2 * sizeof(XYZZ<C>));
-    uint8_t* bi = take((size_t)p.nwin * (p.logS2 + 2) * sizeof(XYZZ<C>));
+    uint8_t* po = take(((size_t)p.pool_elems + 1) * sizeof(XYZZ<C>));
+    uint8_t* bi = take((size_t)p.nwin * msm_nplanes(p) * sizeof(XYZZ<C>));
     uint8_t* rr = take((size_t)p.nwin * sizeof(XYZZ<C>));
     if (ws) {
         ws->digits = (int32_t*)d;
@@ -487,11 +472,7 @@ inline size_t msm_carve(const MsmPlan& p, uint8_t* base, MsmWorkspace* ws) {
         ws->heavy = (uint32_t*)hl;
         ws->small_ctrs = (uint32_t*)hc;
         ws->partials = pa;
-        ws->segA = sa;
-        ws->segT = sT;
-        ws->A2s = a2s;
-        ws->A2w = a2w;
-        ws->T2 = t2;
+        ws->pool = po;
         ws->bits = bi;
         ws->R = rr;
     }
@@ -522,7 +503,7 @@ inline void msm_choose(uint32_t n, int* c, uint32_t* T, int sbits = 256, int tab
 
 template <class C>
 inline cudaError_t msm_launch(const MsmPlan& p, const MsmWorkspace& w, const uint32_t* d_scalars, const Affine<C>* d_points,
-                              XYZZ<C>* d_out_xyzz, Jac<C>* d_out_jac, cudaStream_t st, StageTimer* tm = nullptr) {
+                              XYZZ<C>* d_out_xyzz, Jac<C>* d_out_jac, cudaStream_t st, StageTimer* tm = nullptr, unsigned long long* nlaunch = nullptr) {
     using X = XYZZ<C>;
     auto mark = [&](const char* nm) { if (tm) tm->mark(nm, st); };
     cudaMemsetAsync(w.counts, 0, (size_t)p.nbuckets * 4, st);
@@ -550,14 +531,17 @@ inline cudaError_t msm_launch(const MsmPlan& p, const MsmWorkspace& w, const uin
     k_msm_combine_big<C><<<148, 256, 0, st>>>(p, w.tstart, w.heavy, heavy_count, (X*)w.partials);
     mark("combine");
     uint32_t nseg = (uint32_t)p.nwin * p.S;
-    k_msm_segreduce<C><<<(nseg + 127) / 128, 128, 0, st>>>(p, w.tstart, (const X*)w.partials, (X*)w.segA, (X*)w.segT);
+    k_msm_segreduce<C><<<(nseg + 127) / 128, 128, 0, st>>>(p, w.tstart, (const X*)w.partials, (X*)w.pool);
     mark("segreduce");
-    uint32_t n2 = 2 * (uint32_t)p.nwin * p.S2;
-    k_msm_seg2<C><<<(n2 + 127) / 128, 128, 0, st>>>(p, (const X*)w.segA, (const X*)w.segT, (X*)w.A2s, (X*)w.A2w, (X*)w.T2);
-    k_msm_bitsum<C><<<dim3(p.nwin, p.logS2 + 2), p.S2 >= 256 ? 256 : (p.S2 >= 64 ? 64 : 32), 0, st>>>(p, (const X*)w.A2s, (const X*)w.A2w, (const X*)w.T2, (X*)w.bits);
+    for (int l = 2; l <= p.nlev; l++) {
+        uint32_t nt = (uint32_t)l * (uint32_t)p.nwin * p.Sl[l];
+        k_msm_level<C><<<(nt + 127) / 128, 128, 0, st>>>(p, l, (X*)w.pool);
+    }
+    k_msm_bitsum<C><<<dim3(p.nwin, msm_nplanes(p)), 32, 0, st>>>(p, (const X*)w.pool, (X*)w.bits);
     mark("bitsum");
     k_msm_final<C><<<1, 160, 0, st>>>(p, (const X*)w.bits, (X*)w.R, d_out_xyzz, d_out_jac);
     mark("final");
+    if (nlaunch) *nlaunch += (p.n ? 2 : 0) + 6 + 3 + 1 + 2 + 1 + (p.nlev - 1) + 1 + 1;   // digits+scatter, 2 scans, task table, accumulate, combine x2, segreduce, levels, bitsum, final
     return cudaGetLastError();
 }
 

@@ -30,6 +30,8 @@
 
 namespace ws {
 
+constexpr int MSM_MAX_LEVELS = 8;
+
 struct MsmPlan {
     uint32_t n;        // number of (scalar, point) pairs
     int c;             // window bits, 2..22
@@ -43,9 +45,15 @@ struct MsmPlan {
     uint32_t L;        // buckets per reduce segment (power of two, <= B)
     uint32_t S;        // segments per window = B / L
     int logS;
-    uint32_t L2;       // level-2 group size over the segments (1 = no second level)
-    uint32_t S2;       // groups per window = S / L2
-    int logS2;
+    // reduction tree above the segments: level 1 = the S segments; level l >= 2 groups G[l] items of level l-1
+    // into Sl[l] groups per window, until at most 32 remain
+    int nlev;                       // number of levels (>= 1)
+    uint32_t G[MSM_MAX_LEVELS + 1]; // G[1] = L
+    uint32_t Sl[MSM_MAX_LEVELS + 1];// Sl[1] = S
+    uint32_t offT[MSM_MAX_LEVELS + 1];   // element offsets into the level pool: T array of level l
+    uint32_t offC[MSM_MAX_LEVELS + 1];   // carried arrays C[0..l-1] of level l (contiguous, Sl[l] * nwin elements each)
+    uint32_t pool_elems;
+    int logSK;                      // log2 of the top level's group count
     uint32_t nbuckets; // nwin * B
     uint32_t max_tasks;
 };
@@ -68,10 +76,28 @@ HD MsmPlan msm_make_plan(uint32_t n, int c, uint32_t T, uint32_t L = 0, int sbit
     p.S = p.B / p.L;
     p.logS = 0;
     while ((1u << p.logS) < p.S) p.logS++;
-    p.L2 = p.S >= 256 ? 8 : 1;
-    p.S2 = p.S / p.L2;
-    p.logS2 = 0;
-    while ((1u << p.logS2) < p.S2) p.logS2++;
+    p.nlev = 1;
+    p.G[0] = p.Sl[0] = p.offT[0] = p.offC[0] = 0;
+    p.G[1] = p.L;
+    p.Sl[1] = p.S;
+    while (p.Sl[p.nlev] > 32 && p.nlev < MSM_MAX_LEVELS) {
+        uint32_t g = p.Sl[p.nlev] >= 8 ? 8 : p.Sl[p.nlev];
+        p.nlev++;
+        p.G[p.nlev] = g;
+        p.Sl[p.nlev] = p.Sl[p.nlev - 1] / g;
+    }
+    for (int l = p.nlev + 1; l <= MSM_MAX_LEVELS; l++) p.G[l] = p.Sl[l] = p.offT[l] = p.offC[l] = 0;
+    uint32_t off = 0;
+    for (int l = 1; l <= p.nlev; l++) {
+        uint32_t per = p.Sl[l] * (uint32_t)p.nwin;
+        p.offT[l] = off;
+        off += per;
+        p.offC[l] = off;
+        off += per * (uint32_t)l;
+    }
+    p.pool_elems = off;
+    p.logSK = 0;
+    while ((1u << p.logSK) < p.Sl[p.nlev]) p.logSK++;
     p.nbuckets = (uint32_t)p.nwin * p.B;
     uint64_t entries = (uint64_t)p.ndig * n;
     p.max_tasks = (uint32_t)(entries / T) + p.nbuckets + 1;
@@ -214,7 +240,9 @@ HD XYZZ<C> msm_bucket_value(const uint32_t* tstart, const XYZZ<C>* partials, siz
 //   T = sum S_b ;  A = sum (b - s*L + 1) * S_b      (running-sum trick, 2 adds per bucket)
 template <class C>
 HD void msm_segreduce_body(const MsmPlan& p, uint32_t w, uint32_t s, const uint32_t* tstart,
-                           const XYZZ<C>* partials, XYZZ<C>* segA, XYZZ<C>* segT) {
+                           const XYZZ<C>* partials, XYZZ<C>* pool) {
+    XYZZ<C>* segA = pool + p.offC[1];      // carried array 0 of level 1
+    XYZZ<C>* segT = pool + p.offT[1];
     XYZZ<C> run = XYZZ<C>::inf(), acc = XYZZ<C>::inf();
     size_t base = (size_t)w * p.B + (size_t)s * p.L;
     bool any = false;
@@ -230,45 +258,51 @@ HD void msm_segreduce_body(const MsmPlan& p, uint32_t w, uint32_t s, const uint3
     segT[(size_t)w * p.S + s] = run;
 }
 
-// ---- level 2 over the segments: thread (w, g, role) -------------------------------------------
-// group g = segments g*L2 .. g*L2+L2-1.  role 0: T2 = sum T_j and A2w = sum j*T_j (running sums);
-// role 1: A2s = sum A_j.  With s = g*L2 + j:
-//   sum_s s*T_s = sum_g (L2 * g * T2_g + A2w_g)
+// ---- level l >= 2: thread (w, g, role) ----------------------------------------------------------
+// group g = items g*G .. g*G+G-1 of level l-1.
+//   role 0:        T'_g = sum_j T_j ; new carried array C'_{l-1}[g] = sum_j j * T_j   (running sums)
+//   role r, 1..l-1: C'_{r-1}[g] = sum_j C_{r-1}[j]
+// With bucket index b = j_0 + L (j_1 + G_2 (j_2 + ... )):
+//   sum_b (b+1) S_b = sum C_0 + L (sum C_1 + G_2 (sum C_2 + ... + G_K * sum_g g T_g))
 template <class C>
-HD void msm_seg2_body(const MsmPlan& p, uint32_t w, uint32_t g, int role, const XYZZ<C>* segA, const XYZZ<C>* segT,
-                      XYZZ<C>* A2s, XYZZ<C>* A2w, XYZZ<C>* T2) {
-    size_t base = (size_t)w * p.S + (size_t)g * p.L2;
-    size_t o = (size_t)w * p.S2 + g;
-    if (role == 1) {
-        XYZZ<C> acc = segA[base];
-        for (uint32_t j = 1; j < p.L2; j++) acc = padd_call<C>(acc, segA[base + j]);
-        A2s[o] = acc;
+HD void msm_level_body(const MsmPlan& p, int l, uint32_t w, uint32_t g, int role, XYZZ<C>* pool) {
+    const uint32_t G = p.G[l], Sin = p.Sl[l - 1], Sout = p.Sl[l];
+    const size_t in_per = (size_t)Sin * p.nwin, out_per = (size_t)Sout * p.nwin;
+    const size_t ib = (size_t)w * Sin + (size_t)g * G, ob = (size_t)w * Sout + g;
+    if (role > 0) {
+        const XYZZ<C>* in = pool + p.offC[l - 1] + (size_t)(role - 1) * in_per;
+        XYZZ<C> acc = in[ib];
+        for (uint32_t j = 1; j < G; j++) acc = padd_call<C>(acc, in[ib + j]);
+        pool[p.offC[l] + (size_t)(role - 1) * out_per + ob] = acc;
         return;
     }
+    const XYZZ<C>* inT = pool + p.offT[l - 1];
     XYZZ<C> run = XYZZ<C>::inf(), acc = XYZZ<C>::inf();
-    for (int j = (int)p.L2 - 1; j >= 1; j--) {      // acc = sum_{j>=1} j*T_j ; run = sum_{j>=1} T_j
-        run = padd_call<C>(run, segT[base + j]);
+    for (int j = (int)G - 1; j >= 1; j--) {
+        run = padd_call<C>(run, inT[ib + j]);
         acc = padd_call<C>(acc, run);
     }
-    A2w[o] = acc;
-    T2[o] = padd_call<C>(run, segT[base]);
+    pool[p.offC[l] + (size_t)(l - 1) * out_per + ob] = acc;
+    pool[p.offT[l] + ob] = padd_call<C>(run, inT[ib]);
 }
 
-// ---- final: window value from the plane sums, then Horner over windows -----------------------------
-// bits[w * (logS2 + 2) + 0] = sum_g A2s ; [1] = sum_g A2w ; [2 + k] = sum_{g : bit k of g} T2_g
-//   R_w = P0 + L * (P1 + L2 * sum_k 2^k * plane_k)
+// ---- final: window value from the plane sums of the top level, then Horner over windows ---------
+// bits[w * nplanes + r] = sum_g C_r[g] (r < nlev) ; bits[w * nplanes + nlev + k] = sum_{g : bit k of g} T_g
+HD int msm_nplanes(const MsmPlan& p) { return p.nlev + p.logSK; }
+
 template <class C>
 HD XYZZ<C> msm_window_value(const MsmPlan& p, uint32_t w, const XYZZ<C>* bits) {
-    const XYZZ<C>* bw = bits + (size_t)w * (p.logS2 + 2);
+    const XYZZ<C>* bw = bits + (size_t)w * msm_nplanes(p);
     XYZZ<C> acc = XYZZ<C>::inf();
-    for (int k = p.logS2 - 1; k >= 0; k--) {
+    for (int k = p.logSK - 1; k >= 0; k--) {
         acc = pdbl_call<C>(acc);
-        acc = padd_call<C>(acc, bw[2 + k]);
+        acc = padd_call<C>(acc, bw[p.nlev + k]);
     }
-    for (uint32_t l = p.L2; l > 1; l >>= 1) acc = pdbl_call<C>(acc);
-    acc = padd_call<C>(acc, bw[1]);
-    for (uint32_t l = p.L; l > 1; l >>= 1) acc = pdbl_call<C>(acc);
-    return padd_call<C>(acc, bw[0]);
+    for (int l = p.nlev; l >= 1; l--) {
+        for (uint32_t x = p.G[l]; x > 1; x >>= 1) acc = pdbl_call<C>(acc);
+        acc = padd_call<C>(acc, bw[l - 1]);
+    }
+    return acc;
 }
 
 template <class C>

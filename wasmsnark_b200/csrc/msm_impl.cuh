@@ -34,7 +34,7 @@ inline int multiexp_dev(ws_ctx* c, const void* d_scalars, const void* d_points, 
     MsmWorkspace w;
     msm_carve<C>(p, base, &w);
     if (own_timer) c->timer.begin(st);
-    cudaError_t e = msm_launch<C>(p, w, (const uint32_t*)d_scalars, (const Affine<C>*)d_points, (XYZZ<C>*)d_out_xyzz, (Jac<C>*)d_out, st, own_timer ? &c->timer : nullptr);
+    cudaError_t e = msm_launch<C>(p, w, (const uint32_t*)d_scalars, (const Affine<C>*)d_points, (XYZZ<C>*)d_out_xyzz, (Jac<C>*)d_out, st, own_timer ? &c->timer : nullptr, &c->launches);
     if (e != cudaSuccess) return c->fail_cuda("msm launch");
     return WS_OK;
 }
@@ -72,6 +72,7 @@ inline int build_table_dev(ws_ctx* c, const void* d_points, size_t n, int table_
     if (n == 0) return WS_OK;
     int W = msm_table_windows(table_c);
     if ((uint64_t)W * n >= 0x80000000ull) return c->fail(WS_E_ARG, "table too large for 31-bit point indices");
+    c->launches += 1;
     k_msm_build_table<C><<<(unsigned)((n + 63) / 64), 64, 0, st>>>((const Affine<C>*)d_points, (uint32_t)n, table_c, W, (Affine<C>*)d_table);
     return cudaGetLastError() == cudaSuccess ? WS_OK : c->fail_cuda("build_table");
 }

@@ -511,12 +511,13 @@ static int calc_h_dev(ws_ctx* c, const DevCsr& pa, const DevCsr& pb, const Fr* d
     c->timer.mark("h:lc", st);
     cudaMemcpyAsync(Ao, A, sizeof(Fr) * n, cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(Bo, B, sizeof(Fr) * n, cudaMemcpyDeviceToDevice, st);
-    ntt_launch(Ao, scratch, logn, 0, 1, T, st);
-    ntt_launch(Bo, scratch, logn, 0, 1, T, st);
-    ntt_launch(Ao, scratch, logn, 1, 0, T, st);
-    ntt_launch(Bo, scratch, logn, 1, 0, T, st);
+    ntt_launch(Ao, scratch, logn, 0, 1, T, st, &c->launches);
+    ntt_launch(Bo, scratch, logn, 0, 1, T, st, &c->launches);
+    ntt_launch(Ao, scratch, logn, 1, 0, T, st, &c->launches);
+    ntt_launch(Bo, scratch, logn, 1, 0, T, st, &c->launches);
     k_interleave_mul<<<(n + 127) / 128, 128, 0, st>>>(A, B, Ao, Bo, P, n);
-    ntt_launch(P, scratch, logn + 1, 0, 1, T, st);
+    ntt_launch(P, scratch, logn + 1, 0, 1, T, st, &c->launches);
+    c->launches += 5;      // to_mont, 2 x csr_lc, interleave_mul, from_mont
     k_fr_from_mont<<<(n + 127) / 128, 128, 0, st>>>(P + n, d_h, n);
     c->timer.mark("h:ntt", st);
     return cudaGetLastError() == cudaSuccess ? WS_OK : c->fail_cuda("calc_h");
@@ -569,6 +570,7 @@ static int prove_pre_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_rs, cudaS
     cudaStream_t ls = c->lanes[4];
     cudaEventRecord(c->lane_done[5], st);
     cudaStreamWaitEvent(ls, c->lane_done[5], 0);
+    c->launches += 1;
     k_assemble_pre<<<1, 128, 0, ls>>>(k->fixed, k->fixed_tables, d_rs, pre);
     cudaEventRecord(c->lane_done[4], ls);
     c->pre_pending = true;
@@ -616,6 +618,7 @@ static int prove_finish_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_all, i
     g.pi_a = (Jac<G1Curve>*)d_out;
     g.pi_b = (Jac<G2Curve>*)(d_out + 96);
     g.pi_c = (Jac<G1Curve>*)(d_out + 288);
+    c->launches += 1 + (world > 1 ? 1 : 0);
     k_assemble_post<<<1, 96, 0, st>>>(g, (const PreProducts*)c->arena(6, sizeof(PreProducts)));
     c->timer.mark("assemble", st);
     return cudaGetLastError() == cudaSuccess ? WS_OK : c->fail_cuda("prove");
@@ -672,7 +675,7 @@ WS_API int ws_bn128_fr_fft_dev(ws_ctx* c, void* d_px, size_t n, int odd, int inv
     Fr* scratch = (Fr*)c->arena(2, sizeof(Fr) << logn);
     if (!scratch) return c->fail_cuda("fft scratch");
     c->timer.begin(st);
-    cudaError_t e = ntt_launch((Fr*)d_px, scratch, logn, odd != 0, inverse != 0, twiddles(c), st);
+    cudaError_t e = ntt_launch((Fr*)d_px, scratch, logn, odd != 0, inverse != 0, twiddles(c), st, &c->launches);
     c->timer.mark("ntt", st);
     return e == cudaSuccess ? WS_OK : c->fail_cuda("ntt");
 }
