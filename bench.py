@@ -39,6 +39,7 @@ N_PAIRS = 1 << LOG2N
 PROVE_LOG2 = int(os.environ.get("WS_BENCH_PROVE_LOG2", "20"))       # constraints (domain size) of the synthetic key
 ALG_BYTES_PER_PAIR = 96          # 32 B scalar + 64 B affine point
 KERNELS_PER_MSM = 18             # digits, 2x3 scan, scatter, 3 task-table, accumulate, 2 combine, segreduce, seg2, bitsum, final
+NCU_TRAFFIC_BYTES = 650317824   # k_msm_accumulate<G1>, n = 2^20: measured once per round with ncu (profiles/)
 SCALARS = os.environ.get("WS_BENCH_SCALARS", "fr")      # "fr": uniform in [0, r) ; "raw256": uniform 256-bit
 
 
@@ -518,7 +519,8 @@ def main():
                     "ms_per_step": 1000.0 * e2e_s / K, "timer": "host perf_counter around K blocking C-ABI calls (two host threads / contexts when n_gpus = 1), max over ranks"},
             "gpu_launches": int(msm_launches) + (K if world > 1 else 0),
             "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate<G1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if achieved else None, "traffic": None, "peak_source": which,
+                         "frac": achieved / peak if achieved else None, "traffic": NCU_TRAFFIC_BYTES if (LOG2N == 20 and world == 1) else None,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_ncu_accumulate_g1_2p20.txt)", "peak_source": which,
                          "kernel_ms": acc_ms, "algorithmic_bytes_per_launch": ALG_BYTES_PER_PAIR * cnt,
                          "note": "integer-multiply bound (fmaheavy pipe ~80% busy in ncu): 8M+2S Montgomery products per pair per window"},
             "stages_ms": {k: v / K for k, v in stage_ms.items()},
