@@ -107,31 +107,48 @@ def have_ref():
     return ref_wasm.available()
 
 
+class RefWorkerPool:
+    """The reference's worker pool (src/bn128.js:173-265): W instances of its WASM image, created once
+    (buildBn128), each on its own thread; g1_multiexp splits by contiguous ranges and the partial points are
+    added with g1m_add on the main instance (src/bn128.js:353-383)."""
+
+    def __init__(self, nthreads):
+        from concurrent.futures import ThreadPoolExecutor
+        self.W = max(1, nthreads)
+        self.inst = [ref_wasm.RefInstance(pages=5000) for _ in range(self.W)]
+        self.main = ref_wasm.RefInstance(pages=1000)
+        self.p0, self.p1 = self.main.alloc(96), self.main.alloc(96)
+        self.ex = ThreadPoolExecutor(max_workers=self.W)
+
+    def g1_multiexp_affine(self, scalars, points):
+        n = len(scalars) // 32
+        W = max(1, min(self.W, n))
+        per = n // W
+
+        def work(i):
+            cnt = per if i < W - 1 else n - per * (W - 1)
+            return self.inst[i].cmd_g1_multiexp(scalars[i * per * 32:(i * per + cnt) * 32], points[i * per * 64:(i * per + cnt) * 64], cnt)
+        res = list(self.ex.map(work, range(W)))
+        m = self.main
+        m.call("g1m_zero", self.p0)
+        for r in res:
+            m.put(self.p1, r)
+            m.call("g1m_add", self.p0, self.p1, self.p0)
+        m.call("g1m_affine", self.p0, self.p0)
+        return m.get(self.p0, 96)
+
+    def close(self):
+        self.ex.shutdown()
+        for i in self.inst:
+            i.close()
+        self.main.close()
+
+
 def ref_g1_multiexp_threads(scalars, points, nthreads=None):
-    """Reference g1m_multiexp2 (w = 7) over contiguous point ranges, one compiled-WASM instance
-    per thread (src/bn128.js:353-383), combined with g1m_add, then g1m_affine/fromMontgomery."""
+    """One-shot form of RefWorkerPool.g1_multiexp_affine (pool built and torn down inside)."""
     n = len(scalars) // 32
-    W = nthreads or min(os.cpu_count() or 1, 16)
-    W = max(1, min(W, n))
-    per = n // W
-    res = [None] * W
-
-    def work(i):
-        inst = ref_wasm.RefInstance(pages=5000)
-        cnt = per if i < W - 1 else n - per * (W - 1)
-        res[i] = inst.cmd_g1_multiexp(scalars[i * per * 32:(i * per + cnt) * 32], points[i * per * 64:(i * per + cnt) * 64], cnt)
-        inst.close()
-
-    th = [threading.Thread(target=work, args=(i,)) for i in range(W)]
-    [t.start() for t in th]
-    [t.join() for t in th]
-    m = ref_wasm.RefInstance(pages=1000)
-    p0, p1 = m.alloc(96), m.alloc(96)
-    m.call("g1m_zero", p0)
-    for r in res:
-        m.put(p1, r)
-        m.call("g1m_add", p0, p1, p0)
-    m.call("g1m_affine", p0, p0)
-    out = m.get(p0, 96)
-    m.close()
-    return out
+    pool = RefWorkerPool(max(1, min(nthreads or min(os.cpu_count() or 1, 16), n)))
+    try:
+        return pool.g1_multiexp_affine(scalars, points)
+    finally:
+        pool.close()

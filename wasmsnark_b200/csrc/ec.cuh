@@ -271,34 +271,6 @@ HD XYZZ<C> times_scalar(const XYZZ<C>& p, const uint8_t* k, int len) {
     return r;
 }
 
-// k * P with a 4-bit fixed window: 15-entry table, then per nibble 4 doublings (Jacobian dbl-2009-l
-// for a = 0: three levels of independent products, which is what a single thread can overlap) and at
-// most one addition.  Same group element as times_scalar (= g?m_timesScalar); used on the proof's
-// latency-critical tail.
-template <class C>
-HD XYZZ<C> times_scalar_w4(const XYZZ<C>& p, const uint8_t* k, int len) {
-    XYZZ<C> tab[16];
-    tab[0] = XYZZ<C>::inf();
-    tab[1] = p;
-    for (int i = 2; i < 16; i++) tab[i] = (i & 1) ? padd_call<C>(tab[i - 1], p) : pdbl_call<C>(tab[i >> 1]);
-    XYZZ<C> r = XYZZ<C>::inf();
-    for (int i = 2 * len - 1; i >= 0; i--) {
-        uint32_t nib = (k[i >> 1] >> ((i & 1) * 4)) & 15u;
-        if (!r.is_inf()) {
-            if (C::A_ZERO) {
-                Jac<C> j = to_jac<C>(r);
-#pragma unroll 1
-                for (int d = 0; d < 4; d++) j = jdbl_a0<C>(j);
-                r = from_jac<C>(j);
-            } else {
-                for (int d = 0; d < 4; d++) r = pdbl_call<C>(r);
-            }
-        }
-        if (nib) r = padd_call<C>(r, tab[nib]);
-    }
-    return r;
-}
-
 using G1Affine = Affine<G1Curve>;
 using G2Affine = Affine<G2Curve>;
 using G1X = XYZZ<G1Curve>;
