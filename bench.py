@@ -40,6 +40,7 @@ PROVE_LOG2 = int(os.environ.get("WS_BENCH_PROVE_LOG2", "20"))       # constraint
 ALG_BYTES_PER_PAIR = 96          # 32 B scalar + 64 B affine point
 KERNELS_PER_MSM = 18             # digits, 2x3 scan, scatter, 3 task-table, accumulate, 2 combine, segreduce, seg2, bitsum, final
 NCU_TRAFFIC_BYTES = 650317824   # k_msm_accumulate<G1>, n = 2^20: measured once per round with ncu (profiles/)
+NFLIGHT = max(1, int(os.environ.get("WS_BENCH_INFLIGHT", "2")))   # MSMs in flight for the throughput number
 SCALARS = os.environ.get("WS_BENCH_SCALARS", "fr")      # "fr": uniform in [0, r) ; "raw256": uniform 256-bit
 
 
@@ -287,47 +288,56 @@ def main():
     # ---- pipelined throughput: the same K steps, alternating between two contexts (own stream + workspace each,
     #      like two of the reference's workers), so the single-warp tail of one MSM (window Horner) runs under the
     #      next one's bucket accumulation.  Inputs rotate over 4 device copies (384 MiB > L2) instead of a flush.
-    bn2 = build_bn128(local)
-    stream2 = torch.cuda.Stream()
-    st2 = ctypes.c_void_p(stream2.cuda_stream)
+    NF = NFLIGHT
+    bns = [bn] + [build_bn128(local) for _ in range(NF - 1)]
+    streams = [stream] + [torch.cuda.Stream() for _ in range(NF - 1)]
     in_sets = [(d_s, d_p)] + [(d_s.clone(), d_p.clone()) for _ in range(3)]
-    d_out2 = torch.zeros(256, dtype=torch.uint8, device="cuda")
-    gathered2 = torch.zeros(world * 96, dtype=torch.uint8, device="cuda") if world > 1 else None
-    lanes = [(bn, stream, st, d_out, gathered), (bn2, stream2, st2, d_out2, gathered2)]
+    lanes = []
+    for i in range(NF):
+        lanes.append((bns[i], streams[i], ctypes.c_void_p(streams[i].cuda_stream), d_out if i == 0 else torch.zeros(256, dtype=torch.uint8, device="cuda"),
+                      gathered if i == 0 else (torch.zeros(world * 96, dtype=torch.uint8, device="cuda") if world > 1 else None)))
 
     def step_pipe(k):
-        b_, strm, stp, dout, gath = lanes[k & 1]
+        b_, strm, stp, dout, gath = lanes[k % NF]
         ds_, dp_ = in_sets[k & 3]
         with torch.cuda.stream(strm):
             b_.ctx.check(b_.lib.ws_bn128_g1_multiexp_dev(b_.ctx.h, ds_.data_ptr(), dp_.data_ptr(), cnt, dout.data_ptr(), 0, stp))
             if world > 1:
                 dist.all_gather_into_tensor(gath, dout[:96])
                 b_.ctx.check(b_.lib.ws_bn128_g1_sum_dev(b_.ctx.h, gath.data_ptr(), world, dout.data_ptr(), stp))
-    for k in range(2 * W):
+    def all_launches():
+        return sum(b_.lib.ws_kernel_launches(b_.ctx.h) for b_ in bns)
+
+    def fork_join(body):
+        """one CUDA-event pair around `body`, which enqueues work on all the lane streams"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for sx in streams[1:]:
+            sx.wait_event(e0)
+        body()
+        for sx in streams[1:]:
+            ej = torch.cuda.Event()
+            ej.record(sx)
+            stream.wait_event(ej)
+        e1.record(stream)
+        return e0, e1
+    for k in range(NF * W):
         step_pipe(k)
     barrier()
-    launches0 = lib.ws_kernel_launches(h) + bn2.lib.ws_kernel_launches(bn2.ctx.h)
-    e0, e1, ej = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-    e0.record(stream)
-    stream2.wait_event(e0)
-    for k in range(K):
-        step_pipe(k)
-    msm_launches = lib.ws_kernel_launches(h) + bn2.lib.ws_kernel_launches(bn2.ctx.h) - launches0
-    ej.record(stream2)
-    stream.wait_event(ej)
-    e1.record(stream)
+    launches0 = all_launches()
+    e0, e1 = fork_join(lambda: [step_pipe(k) for k in range(K)])
+    msm_launches = all_launches() - launches0
     barrier()
     pipe_ms = e0.elapsed_time(e1)
     t = torch.tensor([pipe_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     pipe_ms = float(t.item())
-    same_result = bool(torch.equal(d_out[:96], d_out2[:96])) or True     # different Jacobian representatives are legal
 
     # ---- end to end through the host-buffer ABI (pinned host memory; H2D + D2H inside): K blocking calls
     #      issued from two host threads, one context each (world == 1), so one call's H2D overlaps the other's compute
-    out_host = torch.zeros(96, dtype=torch.uint8).pin_memory()
-    out_host2 = torch.zeros(96, dtype=torch.uint8).pin_memory()
+    out_hosts = [torch.zeros(96, dtype=torch.uint8).pin_memory() for _ in range(NF)]
+    out_host = out_hosts[0]
 
     def step_e2e(b_=bn, oh=out_host):
         b_.ctx.check(b_.lib.ws_bn128_g1_multiexp(b_.ctx.h, h_s.data_ptr(), h_p.data_ptr(), cnt, oh.data_ptr()))
@@ -337,9 +347,11 @@ def main():
             b_.ctx.check(b_.lib.ws_bn128_g1_sum_dev(b_.ctx.h, gathered.data_ptr(), world, d_out.data_ptr(), st))
             oh.copy_(d_out[:96])
     for _ in range(W):
-        step_e2e()
         if world == 1:
-            step_e2e(bn2, out_host2)
+            for i in range(NF):
+                step_e2e(bns[i], out_hosts[i])
+        else:
+            step_e2e()
     barrier()
     import threading
     t0 = time.perf_counter()
@@ -347,7 +359,7 @@ def main():
         def worker(b_, oh, n_calls):
             for _ in range(n_calls):
                 step_e2e(b_, oh)
-        th = [threading.Thread(target=worker, args=(bn, out_host, (K + 1) // 2)), threading.Thread(target=worker, args=(bn2, out_host2, K // 2))]
+        th = [threading.Thread(target=worker, args=(bns[i], out_hosts[i], K // NF + (1 if i < K % NF else 0))) for i in range(NF)]
         [x.start() for x in th]
         [x.join() for x in th]
     else:
@@ -434,7 +446,8 @@ def main():
                 with torch.cuda.stream(self.stream):
                     self.h_proof.copy_(self.d_proof, non_blocking=True)
 
-        lanesP = [Lane(bn, stream), Lane(bn2, stream2)]
+        NP = min(NF, 2)       # proofs in flight (each lane holds its own resident key + tables)
+        lanesP = [Lane(bns[i], streams[i]) for i in range(NP)]
         load_s = lanesP[0].load_s
         L0 = lanesP[0]
         lib.ws_set_profiling(h, 1)
@@ -447,33 +460,26 @@ def main():
         lat_ms = timed_steps(torch, stream, L0.prove, K, flush, barrier, world, dist) / K
         proof_bytes = bytes(L0.d_proof.cpu().numpy())
         # throughput: the same K proofs, two in flight (alternating lanes), one CUDA-event pair around all of them
-        for k in range(2 * W):
-            lanesP[k & 1].prove()
+        for k in range(NP * W):
+            lanesP[k % NP].prove()
         barrier()
-        e0, e1, ej = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        e0.record(stream)
-        stream2.wait_event(e0)
-        pl0 = sum(ln.bn.lib.ws_kernel_launches(ln.bn.ctx.h) for ln in lanesP)
-        for k in range(K):
-            lanesP[k & 1].prove()
-        prove_launches = sum(ln.bn.lib.ws_kernel_launches(ln.bn.ctx.h) for ln in lanesP) - pl0
-        ej.record(stream2)
-        stream.wait_event(ej)
-        e1.record(stream)
+        pl0 = all_launches()
+        e0, e1 = fork_join(lambda: [lanesP[k % NP].prove() for k in range(K)])
+        prove_launches = all_launches() - pl0
         barrier()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         pms = float(t.item()) / K
         # e2e: witness from pinned host memory -> device and the proof back to the host for every proof, two in flight
-        for k in range(4):
-            lanesP[k & 1].prove_e2e()
+        for k in range(2 * NP):
+            lanesP[k % NP].prove_e2e()
         barrier()
         t0 = time.perf_counter()
         for k in range(K):
-            lanesP[k & 1].prove_e2e()
-        stream.synchronize()
-        stream2.synchronize()
+            lanesP[k % NP].prove_e2e()
+        for sx in streams:
+            sx.synchronize()
         barrier()
         pe2e = (time.perf_counter() - t0) / K
         t = torch.tensor([pe2e], dtype=torch.float64, device="cuda")
@@ -492,7 +498,7 @@ def main():
         alg_bytes = (len(pk) - 40) + len(wit) + 64 * (4 * dom + 2 * dom) + 3 * 32 * 2 * dom
         extra["groth16"] = {
             "metric": "Groth16 proofs/sec (BN128, 2^%d constraints)" % PROVE_LOG2, "value": 1000.0 / pms, "unit": "proofs/s", "ms_per_proof": pms,
-            "in_flight": "2 proofs (two contexts, each with its own resident key + window tables)",
+            "in_flight": "%d proofs (one context each, with its own resident key + window tables)" % NP,
             "latency": {"ms_per_proof_single_stream": lat_ms, "proofs_per_s": 1000.0 / lat_ms},
             "config": {"workload": "synthetic proving key nVars = domainSize = 2^%d, nPublic = 58 (tools/gen_synth_key.py), key resident in HBM" % PROVE_LOG2,
                        "pkey_bytes": len(pk), "witness_bytes": len(wit), "shard": "point ranges x%d, all_gather of 768-byte partial records" % world, "scaling": "strong (one fixed-size proof over %d GPUs)" % world},
@@ -518,14 +524,14 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (256-bit Montgomery)", "data": "synthetic",
             "config": {"workload": workload_name(), "pairs": TOTAL_PAIRS, "pairs_per_gpu": N_PAIRS,
                        "parallelism": "one MSM of %d x 2^%d pairs, contiguous point range per GPU + one all_gather of 96-B partials + on-device combine" % (world, LOG2N) if world > 1 else "single GPU",
-                       "in_flight": "2 MSMs (two contexts / streams alternate; K steps inside one CUDA-event pair, max over ranks)",
+                       "in_flight": "%d MSMs (that many contexts / streams in rotation; K steps inside one CUDA-event pair, max over ranks)" % NF,
                        "l2": "inputs rotate over 4 device copies (384 MiB > 126 MB L2); the single-stream latency run flushes L2 between steps",
                        "bit_exact_vs_oracle": True},
             "latency": {"ms_per_msm_single_stream": serial_ms, "pairs_per_s": TOTAL_PAIRS / (serial_ms * 1e-3),
                         "note": "one MSM at a time, per-step CUDA events, L2 flushed (256 MiB fill) between steps"},
             "clocks": clocks,
             "e2e": {"value": TOTAL_PAIRS / (e2e_s / K), "unit": "pairs/s", "h2d_bytes_per_step": 96 * cnt, "d2h_bytes_per_step": 96,
-                    "ms_per_step": 1000.0 * e2e_s / K, "timer": "host perf_counter around K blocking C-ABI calls (two host threads / contexts when n_gpus = 1), max over ranks"},
+                    "ms_per_step": 1000.0 * e2e_s / K, "timer": "host perf_counter around K blocking C-ABI calls (%d host threads / contexts when n_gpus = 1), max over ranks" % NF},
             "gpu_launches": int(msm_launches) + (K if world > 1 else 0),
             "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate<G1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if achieved else None, "traffic": NCU_TRAFFIC_BYTES if (LOG2N == 20 and world == 1) else None,
@@ -547,8 +553,8 @@ def main():
             else:
                 line["cpu_baseline"] = {"value": None, "unit": "pairs/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
         print(json.dumps(line))
-    bn2.terminate()
-    bn.terminate()
+    for b_ in reversed(bns):
+        b_.terminate()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
