@@ -40,7 +40,7 @@ PROVE_LOG2 = int(os.environ.get("WS_BENCH_PROVE_LOG2", "20"))       # constraint
 ALG_BYTES_PER_PAIR = 96          # 32 B scalar + 64 B affine point
 KERNELS_PER_MSM = 18             # digits, 2x3 scan, scatter, 3 task-table, accumulate, 2 combine, segreduce, seg2, bitsum, final
 NCU_TRAFFIC_BYTES = 650317824   # k_msm_accumulate<G1>, n = 2^20: measured once per round with ncu (profiles/)
-NFLIGHT = max(1, int(os.environ.get("WS_BENCH_INFLIGHT", "2")))   # MSMs in flight for the throughput number
+NFLIGHT = max(1, int(os.environ.get("WS_BENCH_INFLIGHT", "4")))   # MSMs in flight for the throughput number
 SCALARS = os.environ.get("WS_BENCH_SCALARS", "fr")      # "fr": uniform in [0, r) ; "raw256": uniform 256-bit
 
 
@@ -107,6 +107,25 @@ class ClockSampler:
 _POOLS = {}
 
 
+def usable_cores():
+    """Host threads this process can really run at once: the affinity mask, capped by the cgroup CPU quota
+    (os.cpu_count() reports the machine, not the container)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period) + 0.5)))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, int(q / per + 0.5)))
+        except Exception:
+            pass
+    return n
+
+
 def cpu_reference_arm(scalars, points, sample_pairs, threads):
     """The reference's g1m_multiexp2 over `threads` workers on the first `sample_pairs` pairs.  The worker pool
     (one instance of the reference's image per thread) is built once, as buildBn128() does; the timed part is
@@ -139,7 +158,7 @@ def run_reference(args):
     if not ref_wasm.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (reference not mounted at build time)"}))
         return
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     sample = min(N_PAIRS, 8192 * cores)
     scalars, points, _, _ = make_inputs(sample)
     vals = []
@@ -544,7 +563,7 @@ def main():
         if not args.no_cpu_baseline:
             from oracle import ref_wasm
             if ref_wasm.available():
-                cores = os.cpu_count() or 1
+                cores = usable_cores()
                 sample = min(N_PAIRS, 8192 * cores)
                 v1, _ = cpu_reference_arm(scalars, points, min(sample, 4096), 1)
                 v, dt = cpu_reference_arm(scalars, points, sample, cores)

@@ -82,6 +82,19 @@ def test_small_sets_vs_oracle(bn, g):
             assert dec(aff(dev_multiexp(bn, g, sb, pb, len(sc), c, T))) == want, (c, T, len(sc))
 
 
+def test_group_identities_from_reference_suite(bn):
+    """test/bn128.js:84-185 through the MSM entry points: r * G = infinity, 10 * P = P added ten times,
+    P + (-P) = infinity, for G1 and G2."""
+    for g, F, gen, enc, dec, fn, aff in ((1, O.Fq, O.G1_GEN, util.g1_affine_m, util.g1_result_tuple, bn.g1_multiexp, bn.g1_affine),
+                                         (2, O.Fq2, O.G2_GEN, util.g2_affine_m, util.g2_result_tuple, bn.g2_multiexp, bn.g2_affine)):
+        G_ = (gen[0], gen[1], F.one)
+        inf = O.pt_affine(F, O.pt_zero(F))
+        assert dec(aff(fn(b32(RR), enc(G_)))) == inf
+        assert dec(aff(fn(b32(10), enc(G_)))) == dec(aff(fn(b32(1) * 10, enc(G_) * 10)))
+        assert dec(aff(fn(b32(7) + b32(7), enc(G_) + enc(O.pt_neg(F, G_))))) == inf
+        assert dec(aff(fn(b32(RR - 1), enc(G_)))) == O.pt_affine(F, O.pt_neg(F, G_))
+
+
 @pytest.mark.skipif(not ref_wasm.available(), reason="oracle/_ref not built")
 def test_2p14_vs_reference_multiexp2(bn):
     n = 1 << 14

@@ -28,6 +28,7 @@ inline int multiexp_dev(ws_ctx* c, const void* d_scalars, const void* d_points, 
     }
     if (c->force_T) T = c->force_T;
     MsmPlan p = msm_make_plan((uint32_t)n, cb, T, c->seg_len, SBITS, table_c != 0);
+    if ((uint64_t)p.ndig * n >= 0xFFFFFF00ull) return c->fail(WS_E_ARG, "n too large: digit windows x n must fit 32-bit offsets");
     size_t need = msm_carve<C>(p, nullptr, nullptr);
     uint8_t* base = (uint8_t*)c->arena(arena_slot, need);
     if (!base) return c->fail_cuda("msm workspace");
