@@ -556,7 +556,12 @@ def main():
                          "frac": achieved / peak if achieved else None, "traffic": NCU_TRAFFIC_BYTES if (LOG2N == 20 and world == 1) else None,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_ncu_accumulate_g1_2p20.txt)", "peak_source": which,
                          "kernel_ms": acc_ms, "algorithmic_bytes_per_launch": ALG_BYTES_PER_PAIR * cnt,
-                         "note": "integer-multiply bound (fmaheavy pipe ~80% busy in ncu): 8M+2S Montgomery products per pair per window"},
+                         "note": "integer-multiply bound, not HBM bound: 8M+2S Montgomery products (137 IMAD each) per pair per window",
+                         "compute_side": {"montgomery_products_per_s": (10.0 * 16 * cnt) / (acc_ms * 1e-3) if acc_ms > 0 else None,
+                                          "imad_wide_ceiling_products_per_s": 148 * 4 * 8 * 1.965e9 / 137,
+                                          "frac_of_imad_ceiling": ((10.0 * 16 * cnt) / (acc_ms * 1e-3)) / (148 * 4 * 8 * 1.965e9 / 137) if acc_ms > 0 else None,
+                                          "ncu_fmaheavy_pipe_busy_pct": 83.2, "ncu_simt_lanes_per_warp": 31.7,
+                                          "source": "profiles/r1_ncu_accumulate_g1_2p20.txt"}},
             "stages_ms": {k: v / K for k, v in stage_ms.items()},
         }
         line.update(extra)

@@ -199,6 +199,8 @@ int ws_set_profiling(ws_ctx* ctx, int on);
 int ws_set_msm_task_cap(ws_ctx* ctx, unsigned cap);
 /* Tuning/test hook: buckets per segment in the bucket-reduction step (power of two, default 32). */
 int ws_set_msm_seg_len(ws_ctx* ctx, unsigned len);
+/* Tuning/test hook: occupancy variant (launch bounds) of the bucket-accumulation kernel; 0 = default. */
+int ws_set_msm_acc_variant(ws_ctx* ctx, int variant);
 
 /* Elapsed device time (ms, CUDA events on the launch stream) of the kernels enqueued by the last
  * *_dev / host call on this ctx, split per pipeline stage; names[i] are static strings.

@@ -16,7 +16,9 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 wb = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 cap = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 dist = sys.argv[5] if len(sys.argv) > 5 else "fr"
-seg = int(sys.argv[6]) if len(sys.argv) > 6 else 32
+seg = int(sys.argv[6]) if len(sys.argv) > 6 else 0
+variant = int(sys.argv[7]) if len(sys.argv) > 7 else 0
+group = int(sys.argv[8]) if len(sys.argv) > 8 else 1
 n = 1 << log2n
 scalars, points, P0, D = bench.make_inputs(n, dist=dist)
 d_s = torch.frombuffer(bytearray(scalars), dtype=torch.uint8).cuda()
@@ -26,6 +28,7 @@ bn = build_bn128(0)
 bn.lib.ws_set_profiling(bn.ctx.h, 1)
 bn.lib.ws_set_msm_task_cap(bn.ctx.h, cap)
 bn.lib.ws_set_msm_seg_len(bn.ctx.h, seg)
+bn.lib.ws_set_msm_acc_variant(bn.ctx.h, variant)
 tot = {}
 for r in range(reps):
     torch.cuda.synchronize()

@@ -16,10 +16,12 @@ from wasmsnark_b200._lib import as_ptr  # noqa: E402
 lg = int(sys.argv[1]) if len(sys.argv) > 1 else 18
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 tables = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+variant = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 pk, wit = gen_synth_key.make(1 << lg, 58, 1 << lg, seed=0xB204)
 bn = build_bn128(0)
 key = ctypes.c_void_p()
 bn.lib.ws_set_key_tables(bn.ctx.h, tables)
+bn.lib.ws_set_msm_acc_variant(bn.ctx.h, variant)
 import time
 t0 = time.perf_counter()
 bn.ctx.check(bn.lib.ws_bn128_pkey_load(bn.ctx.h, as_ptr(pk), len(pk), ctypes.byref(key)))
@@ -33,4 +35,4 @@ for r in range(reps):
     bn.ctx.check(bn.lib.ws_bn128_groth16_prove_dev(bn.ctx.h, key, d_w.data_ptr(), d_rs.data_ptr(), d_out.data_ptr(), None))
     t = bn.ctx.timings()
     torch.cuda.synchronize()
-print("prove 2^%d:" % lg, " ".join("%s=%.3f" % kv for kv in t), "total=%.3f" % sum(v for _, v in t))
+print("prove 2^%d variant %d:" % (lg, variant), " ".join("%s=%.3f" % kv for kv in t), "total=%.3f" % sum(v for _, v in t))

@@ -38,6 +38,7 @@ SIGNATURES = {
     "ws_last_timings": (_i, [_vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float), _i]),
     "ws_set_msm_task_cap": (_i, [_vp, ctypes.c_uint]),
     "ws_set_msm_seg_len": (_i, [_vp, ctypes.c_uint]),
+    "ws_set_msm_acc_variant": (_i, [_vp, _i]),
     "ws_fp_batch": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz]),
     "ws_bn128_fq2_mul_batch": (_i, [_vp, _vp, _vp, _vp, _sz]),
     "ws_bn128_g1_multiexp": (_i, [_vp, _vp, _vp, _sz, _vp]),

@@ -123,6 +123,12 @@ WS_API int ws_set_msm_task_cap(ws_ctx* c, unsigned T) {
     return WS_OK;
 }
 
+WS_API int ws_set_msm_acc_variant(ws_ctx* c, int v) {
+    if (!c) return WS_E_ARG;
+    c->acc_variant = v;
+    return WS_OK;
+}
+
 // test / tuning hook: buckets per reduce segment (power of two)
 WS_API int ws_set_msm_seg_len(ws_ctx* c, unsigned L) {
     if (!c || (L & (L - 1))) return WS_E_ARG;   // 0 = automatic

@@ -65,6 +65,7 @@ struct ws_ctx {
     bool key_tables = true;      // resident proving keys get window tables (prover.cu)
     void* tw_table = nullptr;     // ntt.cuh TwiddleTable storage (Fr*), owned here
     int tw_logM = 0;
+    int acc_variant = 0;         // tuning hook: launch-bounds variant of the accumulate kernel
     unsigned seg_len = 0;    // 0 = automatic
 
     // Arena `slot` grown to at least `bytes` (contents are scratch: not preserved on growth).

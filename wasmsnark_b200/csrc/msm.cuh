@@ -503,7 +503,7 @@ inline void msm_choose(uint32_t n, int* c, uint32_t* T, int sbits = 256, int tab
 
 template <class C>
 inline cudaError_t msm_launch(const MsmPlan& p, const MsmWorkspace& w, const uint32_t* d_scalars, const Affine<C>* d_points,
-                              XYZZ<C>* d_out_xyzz, Jac<C>* d_out_jac, cudaStream_t st, StageTimer* tm = nullptr, unsigned long long* nlaunch = nullptr) {
+                              XYZZ<C>* d_out_xyzz, Jac<C>* d_out_jac, cudaStream_t st, StageTimer* tm = nullptr, unsigned long long* nlaunch = nullptr, int acc_variant = 0) {
     using X = XYZZ<C>;
     auto mark = [&](const char* nm) { if (tm) tm->mark(nm, st); };
     cudaMemsetAsync(w.counts, 0, (size_t)p.nbuckets * 4, st);
@@ -525,7 +525,19 @@ inline cudaError_t msm_launch(const MsmPlan& p, const MsmWorkspace& w, const uin
     mark("tasks");
     constexpr int AT = sizeof(typename C::F) > 32 ? 128 : 256;
     constexpr int AB = sizeof(typename C::F) > 32 ? 1 : 2;
-    k_msm_accumulate<C, AT, AB><<<(p.max_tasks + AT - 1) / AT, AT, 0, st>>>(p, w.bstart, w.tstart, w.task_bucket, w.order, w.entries, d_points, (X*)w.partials);
+    auto acc_args = [&](auto kern, int threads) {
+        kern<<<(p.max_tasks + threads - 1) / threads, threads, 0, st>>>(p, w.bstart, w.tstart, w.task_bucket, w.order, w.entries, d_points, (X*)w.partials);
+    };
+    bool launched = false;
+    if constexpr (sizeof(typename C::F) == 32) {
+        if (acc_variant == 1) { acc_args(k_msm_accumulate<C, 128, 5>, 128); launched = true; }        // ~100 regs, 20 warps/SM
+        else if (acc_variant == 2) { acc_args(k_msm_accumulate<C, 128, 4>, 128); launched = true; }   // 128 regs, smaller blocks
+        else if (acc_variant == 3) { acc_args(k_msm_accumulate<C, 192, 3>, 192); launched = true; }   // 113 regs, 18 warps/SM
+    } else if constexpr (sizeof(typename C::F) == 64) {
+        if (acc_variant == 1) { acc_args(k_msm_accumulate<C, 64, 3>, 64); launched = true; }          // G2: 168 regs x 3 blocks of 2 warps
+        else if (acc_variant == 2 || acc_variant == 3) { acc_args(k_msm_accumulate<C, 128, 3>, 128); launched = true; }   // G2: 168 regs, 12 warps/SM, spills
+    }
+    if (!launched) acc_args(k_msm_accumulate<C, AT, AB>, AT);
     mark("accumulate");
     k_msm_combine_small<C><<<148 * 8, 128, 0, st>>>(p, w.tstart, w.heavy, heavy_count, (X*)w.partials);
     k_msm_combine_big<C><<<148, 256, 0, st>>>(p, w.tstart, w.heavy, heavy_count, (X*)w.partials);

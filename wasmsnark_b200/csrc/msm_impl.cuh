@@ -35,7 +35,7 @@ inline int multiexp_dev(ws_ctx* c, const void* d_scalars, const void* d_points, 
     MsmWorkspace w;
     msm_carve<C>(p, base, &w);
     if (own_timer) c->timer.begin(st);
-    cudaError_t e = msm_launch<C>(p, w, (const uint32_t*)d_scalars, (const Affine<C>*)d_points, (XYZZ<C>*)d_out_xyzz, (Jac<C>*)d_out, st, own_timer ? &c->timer : nullptr, &c->launches);
+    cudaError_t e = msm_launch<C>(p, w, (const uint32_t*)d_scalars, (const Affine<C>*)d_points, (XYZZ<C>*)d_out_xyzz, (Jac<C>*)d_out, st, own_timer ? &c->timer : nullptr, &c->launches, c->acc_variant);
     if (e != cudaSuccess) return c->fail_cuda("msm launch");
     return WS_OK;
 }
