@@ -5,9 +5,11 @@ Primary line (BASELINE configs[1]): BN128 G1 multi-scalar multiplication, n = 2^
 One step = one pass of the hot path over one batch of synthetic input: sum s_i * P_i for 2^20 uniformly
 random scalars in [0, r) (set WS_BENCH_SCALARS=raw256 for uniform raw 256-bit integers) and 2^20 affine
 Montgomery G1 points.
-  value     pairs/s, inputs resident in HBM when the timed region starts (device-pointer C ABI)
+  value     pairs/s, inputs resident in HBM when the timed region starts (device-pointer C ABI), K steps with
+            WS_BENCH_INFLIGHT (default 4) MSMs in flight on as many contexts/streams, one CUDA-event pair around them;
+            "latency" holds the one-at-a-time figure (per-step events, L2 flushed between steps)
   e2e       pairs/s through the host-buffer C ABI call ws_bn128_g1_multiexp: pinned host buffers, H2D of
-            scalars + points and D2H of the 96-byte result inside the timed region
+            scalars + points and D2H of the 96-byte result inside the timed region (one host thread per context)
   roofline  dominant kernel k_msm_accumulate: 96 algorithmic bytes per pair / its CUDA-event
             duration on the launch stream, against the measured HBM copy peak (MEASURED_PEAKS.json)
   cpu_baseline  the reference's own g1m_multiexp2 (w = 7; its WASM image compiled natively, oracle/_ref) on a
