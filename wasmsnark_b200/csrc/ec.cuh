@@ -240,6 +240,13 @@ HD XYZZ<C> padd_call(const XYZZ<C>& a, const XYZZ<C>& b) {
     padd_to<C>(&r, &a, &b);
     return r;
 }
+// Throughput-bound tail kernel (segment reduction): inline for the 8-limb base field (registers instead of the
+// local-memory round trip of a call), out of line for extension / wide fields to keep the kernel small.
+template <class C>
+HD XYZZ<C> padd_seg(const XYZZ<C>& a, const XYZZ<C>& b) {
+    if constexpr (sizeof(typename C::F) == 32) return padd<C>(a, b);
+    else return padd_call<C>(a, b);
+}
 template <class C>
 HD XYZZ<C> pdbl_call(const XYZZ<C>& a) {
     XYZZ<C> r;

@@ -302,7 +302,7 @@ static __global__ void __launch_bounds__(256) k_msm_combine_big(MsmPlan p, const
 }
 
 template <class C>
-static __global__ void __launch_bounds__(128) k_msm_segreduce(MsmPlan p, const uint32_t* __restrict__ tstart, const XYZZ<C>* __restrict__ partials,
+static __global__ void __launch_bounds__(128, (sizeof(typename C::F) == 32 ? 4 : 1)) k_msm_segreduce(MsmPlan p, const uint32_t* __restrict__ tstart, const XYZZ<C>* __restrict__ partials,
                                                               XYZZ<C>* __restrict__ pool) {
     uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (uint32_t)p.nwin * p.S) return;

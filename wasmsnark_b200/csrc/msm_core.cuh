@@ -249,10 +249,10 @@ HD void msm_segreduce_body(const MsmPlan& p, uint32_t w, uint32_t s, const uint3
     for (int k = (int)p.L - 1; k >= 0; k--) {
         XYZZ<C> v = msm_bucket_value<C>(tstart, partials, base + k);
         if (!v.is_inf()) {
-            run = padd_call<C>(run, v);
+            run = padd_seg<C>(run, v);
             any = true;
         }
-        if (any) acc = padd_call<C>(acc, run);
+        if (any) acc = padd_seg<C>(acc, run);
     }
     segA[(size_t)w * p.S + s] = acc;
     segT[(size_t)w * p.S + s] = run;
