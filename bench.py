@@ -360,32 +360,41 @@ def main():
     out_hosts = [torch.zeros(96, dtype=torch.uint8).pin_memory() for _ in range(NF)]
     out_host = out_hosts[0]
 
-    def step_e2e(b_=bn, oh=out_host):
-        b_.ctx.check(b_.lib.ws_bn128_g1_multiexp(b_.ctx.h, h_s.data_ptr(), h_p.data_ptr(), cnt, oh.data_ptr()))
-        if world > 1:
-            d_out[:96].copy_(oh, non_blocking=True)
-            dist.all_gather_into_tensor(gathered, d_out[:96])
-            b_.ctx.check(b_.lib.ws_bn128_g1_sum_dev(b_.ctx.h, gathered.data_ptr(), world, d_out.data_ptr(), st))
-            oh.copy_(d_out[:96])
-    for _ in range(W):
-        if world == 1:
-            for i in range(NF):
-                step_e2e(bns[i], out_hosts[i])
-        else:
-            step_e2e()
-    barrier()
     import threading
-    t0 = time.perf_counter()
-    if world == 1:
-        def worker(b_, oh, n_calls):
-            for _ in range(n_calls):
-                step_e2e(b_, oh)
-        th = [threading.Thread(target=worker, args=(bns[i], out_hosts[i], K // NF + (1 if i < K % NF else 0))) for i in range(NF)]
+
+    def host_call(b_, oh):
+        b_.ctx.check(b_.lib.ws_bn128_g1_multiexp(b_.ctx.h, h_s.data_ptr(), h_p.data_ptr(), cnt, oh.data_ptr()))
+
+    def exchange(i):
+        """N > 1: the rank's partial (already on the host, as the C ABI returned it) goes back to the device for the
+        single all_gather + on-device combine, and the combined point returns to the host."""
+        b_, strm, stp, dout, gath = lanes[i]
+        with torch.cuda.stream(strm):
+            dout[:96].copy_(out_hosts[i], non_blocking=True)
+            dist.all_gather_into_tensor(gath, dout[:96])
+            b_.ctx.check(b_.lib.ws_bn128_g1_sum_dev(b_.ctx.h, gath.data_ptr(), world, dout.data_ptr(), stp))
+            out_hosts[i].copy_(dout[:96], non_blocking=True)
+
+    def e2e_round(ncalls):
+        """`ncalls` (<= NF) blocking host-buffer calls issued concurrently from as many host threads (one context
+        each), then -- N > 1 only -- the exchanges, in a fixed order on the main thread so that every rank issues
+        the same collective sequence."""
+        th = [threading.Thread(target=host_call, args=(bns[i], out_hosts[i])) for i in range(ncalls)]
         [x.start() for x in th]
         [x.join() for x in th]
-    else:
-        for _ in range(K):
-            step_e2e()
+        if world > 1:
+            for i in range(ncalls):
+                exchange(i)
+            for i in range(ncalls):
+                streams[i].synchronize()
+    for _ in range(W):
+        e2e_round(NF)
+    barrier()
+    t0 = time.perf_counter()
+    done = 0
+    while done < K:
+        e2e_round(min(NF, K - done))
+        done += min(NF, K - done)
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -552,7 +561,7 @@ def main():
                         "note": "one MSM at a time, per-step CUDA events, L2 flushed (256 MiB fill) between steps"},
             "clocks": clocks,
             "e2e": {"value": TOTAL_PAIRS / (e2e_s / K), "unit": "pairs/s", "h2d_bytes_per_step": 96 * cnt, "d2h_bytes_per_step": 96,
-                    "ms_per_step": 1000.0 * e2e_s / K, "timer": "host perf_counter around K blocking C-ABI calls (%d host threads / contexts when n_gpus = 1), max over ranks" % NF},
+                    "ms_per_step": 1000.0 * e2e_s / K, "timer": "host perf_counter around K blocking C-ABI calls issued %d at a time from as many host threads / contexts, max over ranks" % NF},
             "gpu_launches": int(msm_launches) + (K if world > 1 else 0),
             "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate<G1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if achieved else None, "traffic": NCU_TRAFFIC_BYTES if (LOG2N == 20 and world == 1) else None,
