@@ -35,3 +35,23 @@ def test_no_device_fails_loudly():
     from wasmsnark_b200 import _lib
     with pytest.raises(_lib.WsError):
         _lib.Context(0)
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    """The product path never falls back: a missing .so is an error, not a switch to some CPU path."""
+    from wasmsnark_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    with pytest.raises(_lib.LibraryNotBuilt):
+        _lib.load_library("/nonexistent/libwasmsnark_b200.so")
+    monkeypatch.setattr(_lib, "_lib", None)
+    assert _lib.load_library() is not None
+
+
+def test_product_package_does_not_import_oracle():
+    """Only tests/, smoke() and the bench's CPU-baseline legs may touch oracle/."""
+    pkg = os.path.join(ROOT, "wasmsnark_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src.replace("the oracle/", ""), f
