@@ -41,7 +41,7 @@ N_PAIRS = 1 << LOG2N
 PROVE_LOG2 = int(os.environ.get("WS_BENCH_PROVE_LOG2", "20"))       # constraints (domain size) of the synthetic key
 ALG_BYTES_PER_PAIR = 96          # 32 B scalar + 64 B affine point
 KERNELS_PER_MSM = 18             # digits, 2x3 scan, scatter, 3 task-table, accumulate, 2 combine, segreduce, seg2, bitsum, final
-NCU_TRAFFIC_BYTES = 650317824   # k_msm_accumulate<G1>, n = 2^20: measured once per round with ncu (profiles/)
+NCU_TRAFFIC_BYTES = 649606144   # k_msm_accumulate<G1>, n = 2^20: measured once per round with ncu (profiles/)
 NFLIGHT = max(1, int(os.environ.get("WS_BENCH_INFLIGHT", "4")))   # MSMs in flight for the throughput number
 SCALARS = os.environ.get("WS_BENCH_SCALARS", "fr")      # "fr": uniform in [0, r) ; "raw256": uniform 256-bit
 
