@@ -524,6 +524,28 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         pe2e = float(t.item())
+        # the literal drop-in call: groth16GenProof(witness, provingKey) with both as host byte buffers on every call
+        # (src/bn128.js:580); the library fingerprints the key buffer and reuses the uploaded key of the previous call
+        dropin = None
+        if world == 1:
+            pa, pb, pc = (ctypes.create_string_buffer(nb) for nb in (96, 192, 96))
+
+            def dropin_call():
+                bn.ctx.check(lib.ws_bn128_groth16_prove(h, as_ptr(wit), len(wit), as_ptr(pk), len(pk), as_ptr(rs[:32]), as_ptr(rs[32:]), pa, pb, pc))
+            t0 = time.perf_counter()
+            dropin_call()
+            first_s = time.perf_counter() - t0
+            for _ in range(W):
+                dropin_call()
+            t0 = time.perf_counter()
+            for _ in range(K):
+                dropin_call()
+            rep_s = (time.perf_counter() - t0) / K
+            dropin = {"first_call_s": first_s, "repeat_call_ms": 1000 * rep_s, "proofs_per_s": 1.0 / rep_s,
+                      "proof_matches_resident_path": (pa.raw + pb.raw + pc.raw) == proof_bytes,
+                      "note": "blocking ws_bn128_groth16_prove(witness, pkey) with host buffers, one call at a time; first call parses/uploads the key and builds its tables, repeats hash the %d-byte key buffer and reuse it" % len(pk)}
+            lib.ws_set_key_cache(h, 0)
+            lib.ws_set_key_cache(h, 1)
         step_prove = L0.prove
         d_proof = L0.d_proof
         key_h = None
@@ -542,7 +564,7 @@ def main():
                        "pkey_bytes": len(pk), "witness_bytes": len(wit), "shard": "point ranges x%d, all_gather of 768-byte partial records" % world, "scaling": "strong (one fixed-size proof over %d GPUs)" % world},
             "e2e": {"value": 1.0 / pe2e, "unit": "proofs/s", "h2d_bytes_per_step": len(wit), "d2h_bytes_per_step": 384, "ms_per_proof": 1000 * pe2e,
                     "note": "witness from pinned host memory each proof, two proofs in flight; proving key resident (loaded once per context: %.2f s incl. host-side row regrouping and window tables)" % load_s},
-            "stages_ms": pstages, "repeatable_bit_exact": same, "algorithmic_bytes": alg_bytes,
+            "dropin_call": dropin, "stages_ms": pstages, "repeatable_bit_exact": same, "algorithmic_bytes": alg_bytes,
             "hbm_frac": (alg_bytes / (pms * 1e-3) / 1e9) / peaks()[0],
             "gpu_launches_per_proof": int(prove_launches) // K, "keygen_s": gen_s,
         }

@@ -158,6 +158,28 @@ int ws_bn128_calc_h(ws_ctx* ctx, const uint8_t* signals, const uint8_t* polsA, s
 int ws_bn128_groth16_prove(ws_ctx* ctx, const uint8_t* witness, size_t witness_len, const uint8_t* pkey, size_t pkey_len,
                            const uint8_t* r, const uint8_t* s, uint8_t pi_a[96], uint8_t pi_b[192], uint8_t pi_c[96]);
 
+/* ---- Groth16 verifier and pairing, on the HOST (no ws_ctx, no GPU: four pairings are not data-parallel work).
+ * Replaces Bn128.groth16Verify src/bn128.js:722-786 -> bn128_pairingEq4 src/bn128/build_bn128.js:1287-1318, and the
+ * bn128_pairing export (:1320-1346; prepareG1/G2 :265-575, millerLoop :756-836, finalExponentiation :943-1262).
+ * Every field element crosses as a PLAIN (non-Montgomery) 32-byte little-endian integer, i.e. the decimal strings of
+ * verification_key.json / proof.json / public.json; G1 = x|y, G2 = x.c0|x.c1|y.c0|y.c1 (the JSON's [[x0,x1],[y0,y1]]),
+ * all-zero coordinates = point at infinity.
+ * ws_bn128_groth16_verify: ic = IC[0..n_ic-1] (64 B each), n_ic must be n_inputs + 1 (else WS_E_ARG); *valid = 1 iff
+ * e(A,B) e(-vk_x,gamma2) e(-C,delta2) e(-alfa1,beta2) = 1.  An input >= r gives *valid = 0 like the reference (:772);
+ * a coordinate >= q or a point off its curve also gives *valid = 0 (the reference does not check and computes an
+ * unspecified value).
+ * ws_bn128_pairing: out = e(P, Q) as 12 plain Fq values in the reference's ftm order (c0.a0, c0.a1, c0.a2, c1.a0,
+ * c1.a1, c1.a2, each re|im) -- bit-identical to bn128_pairing + ftm_fromMontgomery.  WS_E_ARG for malformed points. */
+int ws_bn128_groth16_verify(const uint8_t vk_alfa_1[64], const uint8_t vk_beta_2[128], const uint8_t vk_gamma_2[128],
+                            const uint8_t vk_delta_2[128], const uint8_t* ic, size_t n_ic, const uint8_t* inputs, size_t n_inputs,
+                            const uint8_t pi_a[64], const uint8_t pi_b[128], const uint8_t pi_c[64], int* valid);
+int ws_bn128_pairing(const uint8_t p[64], const uint8_t q[128], uint8_t out[384]);
+
+/* The stateless call above keeps the parsed / uploaded key of the previous call (one entry per ctx) and reuses it
+ * when the next call's key buffer has the same length and 64-bit content fingerprint (the buffer is hashed on
+ * every call, ~10 GB/s); a different key replaces the entry.  on = 0 disables the cache and drops the entry. */
+int ws_set_key_cache(ws_ctx* ctx, int on);
+
 /* Resident proving key: parses and uploads proving_key.bin once (sections to HBM, the two polynomial
  * sections regrouped per row); the reference re-slices and re-posts the key on every proof
  * (src/bn128.js:592-604).  The handle belongs to `ctx`.                                              */

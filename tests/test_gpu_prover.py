@@ -113,6 +113,37 @@ def test_synth_small_calch_and_proofs(bn):
     bn.lib.ws_set_key_tables(bn.ctx.h, 1)
 
 
+def test_stateless_call_key_cache(bn):
+    """ws_bn128_groth16_prove keeps the previous call's uploaded key, keyed by content: same key -> reused, a key of
+    the same length with different content -> replaced (never a stale proof), cache off -> same bytes."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tools"))
+    import gen_synth_key
+    pk = open(os.path.join(GOLD, "synth_small.pkey.bin"), "rb").read()
+    wit = open(os.path.join(GOLD, "synth_small.witness.bin"), "rb").read()
+    g = json.load(open(os.path.join(GOLD, "synth_small.golden.json")))
+    r, s = bytes.fromhex(g["r"]), bytes.fromhex(g["s"])
+    k = O.parse_pkey(pk)
+    pk2, wit2 = gen_synth_key.make(k["nVars"], k["nPublic"], k["domainSize"], seed=77)      # another key
+    want2 = O.groth16_gen_proof(wit2, pk2, int.from_bytes(r, "little"), int.from_bytes(s, "little"))
+    a = k["pPointsA"]                                                                         # same length, two A points swapped
+    pk3 = pk[:a + 64] + pk[a + 128:a + 192] + pk[a + 64:a + 128] + pk[a + 192:]
+    assert len(pk3) == len(pk) and pk3 != pk
+    want3 = O.groth16_gen_proof(wit, pk3, int.from_bytes(r, "little"), int.from_bytes(s, "little"))
+    assert want3 != g["proof_rs"]
+    for _ in range(2):
+        assert bn.groth16GenProof(wit, pk, r=r, s=s) == g["proof_rs"]
+        assert bn.groth16GenProof(wit, pk, r=r, s=s) == g["proof_rs"]
+        p2 = bn.groth16GenProof(wit2, pk2, r=r, s=s)
+        assert p2 != g["proof_rs"]
+        assert p2 == want2
+        assert bn.groth16GenProof(wit, pk3, r=r, s=s) == want3
+    bn.lib.ws_set_key_cache(bn.ctx.h, 0)
+    assert bn.groth16GenProof(wit2, pk2, r=r, s=s) == p2
+    assert bn.groth16GenProof(wit, pk, r=r, s=s) == g["proof_rs"]
+    bn.lib.ws_set_key_cache(bn.ctx.h, 1)
+
+
 def test_random_rs_differs_and_bad_keys_rejected(bn):
     from wasmsnark_b200._lib import WsError
     pk = open(os.path.join(GOLD, "synth_small.pkey.bin"), "rb").read()
@@ -193,6 +224,8 @@ def test_random_rs_proof_accepted_by_reference_verifier(bn):
     p2 = bn.groth16GenProof(wit, key)
     assert p1 != p2
     assert ref_wasm.groth16_verify(vk, pub, p1) and ref_wasm.groth16_verify(vk, pub, p2)
+    assert bn.groth16Verify(vk, pub, p1) and bn.groth16Verify(vk, pub, p2)        # and by this library's verifier
     p1["pi_a"][1] = str((int(p1["pi_a"][1]) + 1) % O.Q)
     assert not ref_wasm.groth16_verify(vk, pub, p1)
+    assert not bn.groth16Verify(vk, pub, p1)
     key.free()

@@ -57,6 +57,9 @@ SIGNATURES = {
     "ws_bn128_calc_h": (_i, [_vp, _vp, _vp, _sz, _vp, _sz, ctypes.c_uint32, ctypes.c_uint32, _vp]),
     "ws_bn128_groth16_prove": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
     "ws_set_key_tables": (_i, [_vp, _i]),
+    "ws_set_key_cache": (_i, [_vp, _i]),
+    "ws_bn128_groth16_verify": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "ws_bn128_pairing": (_i, [_vp, _vp, _vp]),
     "ws_bn128_pkey_load": (_i, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),
     "ws_bn128_pkey_free": (None, [_vp]),
     "ws_bn128_pkey_info": (_i, [_vp, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]),

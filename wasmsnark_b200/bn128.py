@@ -111,6 +111,10 @@ class Bn128:
             return pa.raw, pb.raw, pc.raw
         return {"pi_a": self.bin2g1(pa.raw), "pi_b": self.bin2g2(pb.raw), "pi_c": self.bin2g1(pc.raw)}
 
+    def groth16Verify(self, verificationKey, input, proof):
+        """src/bn128.js:722-786 (host CPU; see module-level groth16Verify)."""
+        return groth16Verify(verificationKey, input, proof)
+
     # -- field batches (WASM exports f1m_*/frm_*; batch forms fft_mulN etc.)
     def fp_batch(self, field, op, x, y=None):
         esz = 96 if field == _lib.FIELD_MNT6753_FQ else 32
@@ -175,6 +179,58 @@ def groth16GenProof(witness, provingKey, cb=None, device=0):
 
 
 genZKSnarkProof = groth16GenProof
+
+
+def _le32(v):
+    return int(v).to_bytes(32, "little")
+
+
+def _g1_bytes(e):
+    """[x, y, ("1")] decimal strings -> 64 B plain LE (setG1Affine, src/bn128.js:503-507, without the Montgomery step)."""
+    return _le32(e[0]) + _le32(e[1])
+
+
+def _g2_bytes(e):
+    """[[x0, x1], [y0, y1], (["1","0"])] -> 128 B (setG2Affine, src/bn128.js:509-513)."""
+    return _le32(e[0][0]) + _le32(e[0][1]) + _le32(e[1][0]) + _le32(e[1][1])
+
+
+def groth16Verify(verificationKey, input, proof):
+    """Bn128.groth16Verify(verificationKey, input, proof), src/bn128.js:722-786: the objects are the parsed
+    verification_key.json / public.json / proof.json (decimal strings or ints).  Runs on the host
+    (ws_bn128_groth16_verify: four pairings are not GPU work); True / False like the reference.
+    Values that do not fit 256 bits cannot be encoded and give False."""
+    if input is None:
+        input = []
+    elif not isinstance(input, (list, tuple)):
+        input = [input]                                          # src/bn128.js:724-728
+    lib = _lib.load_library()
+    try:
+        ic = b"".join(_g1_bytes(e) for e in verificationKey["IC"])
+        ins = b"".join(_le32(v) for v in input)
+        args = [_g1_bytes(verificationKey["vk_alfa_1"]), _g2_bytes(verificationKey["vk_beta_2"]), _g2_bytes(verificationKey["vk_gamma_2"]),
+                _g2_bytes(verificationKey["vk_delta_2"])]
+        pa, pb, pc = _g1_bytes(proof["pi_a"]), _g2_bytes(proof["pi_b"]), _g1_bytes(proof["pi_c"])
+    except OverflowError:
+        return False
+    if len(verificationKey["IC"]) != len(input) + 1:
+        raise ValueError("verificationKey.IC must hold nPublic + 1 points")
+    valid = ctypes.c_int(0)
+    rc = lib.ws_bn128_groth16_verify(*[as_ptr(a) for a in args], as_ptr(ic), len(verificationKey["IC"]), as_ptr(ins) if input else None,
+                                     len(input), as_ptr(pa), as_ptr(pb), as_ptr(pc), ctypes.byref(valid))
+    if rc != _lib.WS_OK:
+        raise _lib.WsError(rc, "ws_bn128_groth16_verify: bad arguments")
+    return valid.value == 1
+
+
+def pairing(p, q):
+    """bn128_pairing (src/bn128/build_bn128.js:1320-1346) on plain-form points: p = [x, y], q = [[x0, x1], [y0, y1]];
+    returns the 12 Fq coefficients (ints) in the reference's ftm order."""
+    out = ctypes.create_string_buffer(384)
+    rc = _lib.load_library().ws_bn128_pairing(as_ptr(_g1_bytes(p)), as_ptr(_g2_bytes(q)), ctypes.cast(out, ctypes.c_void_p))
+    if rc != _lib.WS_OK:
+        raise _lib.WsError(rc, "ws_bn128_pairing: point not on its curve")
+    return [int.from_bytes(out.raw[32 * i:32 * i + 32], "little") for i in range(12)]
 
 
 def build_bn128(device=0):

@@ -39,6 +39,7 @@ WS_API void ws_destroy(ws_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < StageTimer::MAX; i++) cudaEventDestroy(c->timer.ev[i]);
+    if (c->cached_key && c->cached_key_free) c->cached_key_free(c->cached_key);
     for (auto& a : c->arenas)
         if (a.ptr) cudaFree(a.ptr);
     if (c->tw_table) cudaFree(c->tw_table);

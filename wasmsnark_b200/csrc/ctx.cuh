@@ -62,6 +62,12 @@ struct ws_ctx {
     std::string err;
     unsigned long long launches = 0;   // kernels of this library launched so far (ws_kernel_launches)
     unsigned force_T = 0;
+    // one-entry proving-key cache of the stateless prove call, keyed by a content fingerprint (prover.cu)
+    void* cached_key = nullptr;
+    unsigned long long cached_fp = 0;
+    size_t cached_len = 0;
+    void (*cached_key_free)(void*) = nullptr;
+    bool key_cache = true;
     bool key_tables = true;      // resident proving keys get window tables (prover.cu)
     void* tw_table = nullptr;     // ntt.cuh TwiddleTable storage (Fr*), owned here
     int tw_logM = 0;

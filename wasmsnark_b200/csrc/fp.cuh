@@ -13,8 +13,8 @@
 //
 // Device path: whole number held in registers, each row of the product is one PTX
 // mad.lo.cc / madc.hi.cc carry chain (fp_asm.cuh) that ptxas lowers to one IMAD.WIDE.U32
-// per limb product.  Host path (g++ / nvcc host pass): portable CIOS on uint64_t, used
-// only by the CPU unit tests of the group-law code.
+// per limb product.  Host path (g++ / nvcc host pass): portable CIOS on 64-bit limbs, used by
+// the CPU unit tests of the group-law code and by the host-side Groth16 verifier (pairing.cuh).
 #pragma once
 #include <cstdint>
 #include "hd.cuh"
@@ -200,39 +200,53 @@ HD Fp<P> mul_inline(const Fp<P>& A, const Fp<P>& B) {
 #undef WS_ROW0
 #undef WS_ROW
 #else
-    // portable CIOS (host unit tests only)
-    uint32_t t[N + 2];
-    for (int i = 0; i < N + 2; i++) t[i] = 0;
-    for (int i = 0; i < N; i++) {
-        uint64_t c = 0;
-        for (int j = 0; j < N; j++) {
-            c += (uint64_t)A.v[j] * B.v[i] + t[j];
-            t[j] = (uint32_t)c;
-            c >>= 32;
-        }
-        c += t[N];
-        t[N] = (uint32_t)c;
-        t[N + 1] = (uint32_t)(c >> 32);
-        uint32_t m = t[0] * P::NP0;
-        c = ((uint64_t)m * P::mod(0) + t[0]) >> 32;
-        for (int j = 1; j < N; j++) {
-            c += (uint64_t)m * P::mod(j) + t[j];
-            t[j - 1] = (uint32_t)c;
-            c >>= 32;
-        }
-        c += t[N];
-        t[N - 1] = (uint32_t)c;
-        t[N] = t[N + 1] + (uint32_t)(c >> 32);
+    // portable CIOS on 64-bit limbs (host: unit tests of the group-law code, the Groth16 verifier)
+    constexpr int M = N / 2;
+    static_assert(N % 2 == 0, "even limb count");
+    typedef unsigned __int128 u128;
+    uint64_t a[M], b[M], p[M], t[M + 2];
+    for (int i = 0; i < M; i++) {
+        a[i] = A.v[2 * i] | ((uint64_t)A.v[2 * i + 1] << 32);
+        b[i] = B.v[2 * i] | ((uint64_t)B.v[2 * i + 1] << 32);
+        p[i] = P::mod(2 * i) | ((uint64_t)P::mod(2 * i + 1) << 32);
     }
-    int64_t bw = 0;
-    uint32_t d[N];
-    for (int i = 0; i < N; i++) {
-        int64_t x = (int64_t)t[i] - P::mod(i) + bw;
-        d[i] = (uint32_t)x;
-        bw = x >> 32;
+    uint64_t pinv = (uint64_t)(0u - P::NP0);            // p^-1 mod 2^32, lifted to 2^64 by one Newton step
+    pinv *= 2 - p[0] * pinv;
+    const uint64_t np = 0 - pinv;
+    for (int i = 0; i < M + 2; i++) t[i] = 0;
+    for (int i = 0; i < M; i++) {
+        u128 c = 0;
+        for (int j = 0; j < M; j++) {
+            c += (u128)a[j] * b[i] + t[j];
+            t[j] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[M];
+        t[M] = (uint64_t)c;
+        t[M + 1] = (uint64_t)(c >> 64);
+        uint64_t m = t[0] * np;
+        c = ((u128)m * p[0] + t[0]) >> 64;
+        for (int j = 1; j < M; j++) {
+            c += (u128)m * p[j] + t[j];
+            t[j - 1] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[M];
+        t[M - 1] = (uint64_t)c;
+        t[M] = t[M + 1] + (uint64_t)(c >> 64);
     }
-    bool ge = t[N] != 0 || bw == 0;
-    for (int i = 0; i < N; i++) res.v[i] = ge ? d[i] : t[i];
+    uint64_t d[M], bw = 0;
+    for (int i = 0; i < M; i++) {
+        u128 x = (u128)t[i] - p[i] - bw;
+        d[i] = (uint64_t)x;
+        bw = (uint64_t)(x >> 64) & 1;
+    }
+    bool ge = t[M] != 0 || bw == 0;
+    for (int i = 0; i < M; i++) {
+        uint64_t w = ge ? d[i] : t[i];
+        res.v[2 * i] = (uint32_t)w;
+        res.v[2 * i + 1] = (uint32_t)(w >> 32);
+    }
 #endif
     return res;
 }

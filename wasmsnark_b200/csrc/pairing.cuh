@@ -1,0 +1,237 @@
+// pairing.cuh -- BN128 optimal-ate pairing on the HOST (the Groth16 verifier is four pairings: not data-parallel,
+// SURVEY.md §8f rank 3 keeps it on the CPU).  Built on the same Fp / Fp2 classes as the device code (their portable
+// host paths).
+//
+// Replaces, in the reference's bn128 image:
+//   bn128_prepareG1 / prepareG2 / millerLoop     /root/reference/src/bn128/build_bn128.js:265-836
+//   bn128__frobeniusMap{1,2,3}                   /root/reference/src/bn128/build_bn128.js:838-941
+//   bn128_finalExponentiation                    /root/reference/src/bn128/build_bn128.js:943-1262
+//   bn128_pairing / bn128_pairingEq{1..5}        /root/reference/src/bn128/build_bn128.js:1287-1346
+// The reference precomputes projective line coefficients for the G2 point; here the Miller loop walks the twist
+// point in affine coordinates (one Fq2 inversion per step is cheap on a CPU and keeps the lines three-term).  The
+// Miller values therefore differ from the reference's by factors in proper subfields of Fq12, which the final
+// exponentiation removes: the pairing VALUE (bn128_pairing's output) and every verdict are identical.
+// Final exponent, as the reference: (q^6-1)(q^2+1) then the hard part raised to
+//   q^3 (12z^3+6z^2+4z-1) + q^2 (12z^3+6z^2+6z) + q (12z^3+6z^2+4z) + (12z^3+12z^2+6z+1)     (:1154-1243)
+#pragma once
+#include <cstring>
+#include "ec.cuh"
+#include "fp2.cuh"
+#include "pairing_consts.cuh"
+
+namespace ws {
+namespace pairing {
+
+using F2 = Fq2;
+
+static inline Fq fq_c(const uint32_t v[8]) {
+    Fq r;
+    for (int i = 0; i < 8; i++) r.v[i] = v[i];
+    return r;
+}
+static inline F2 f2_c(const uint32_t c[2][8]) { return F2{fq_c(c[0]), fq_c(c[1])}; }
+static inline F2 conj(const F2& a) { return F2{a.c0, neg(a.c1)}; }
+static inline F2 scale(const F2& a, const Fq& k) { return F2{mul(a.c0, k), mul(a.c1, k)}; }
+// (9 + u)(a0 + a1 u) = 9 a0 - a1 + (9 a1 + a0) u
+static inline F2 mul_xi(const F2& a) {
+    Fq n0 = add(dbl(dbl(dbl(a.c0))), a.c0), n1 = add(dbl(dbl(dbl(a.c1))), a.c1);
+    return F2{sub(n0, a.c1), add(n1, a.c0)};
+}
+
+// ---------------------------------------------------------------- Fq6 = Fq2[v]/(v^3 - xi)
+struct F6 {
+    F2 a0, a1, a2;
+    static F6 zero() { return F6{F2::zero(), F2::zero(), F2::zero()}; }
+    static F6 one() { return F6{F2::one(), F2::zero(), F2::zero()}; }
+    bool operator==(const F6& o) const { return a0 == o.a0 && a1 == o.a1 && a2 == o.a2; }
+};
+static inline F6 add(const F6& x, const F6& y) { return F6{add(x.a0, y.a0), add(x.a1, y.a1), add(x.a2, y.a2)}; }
+static inline F6 sub(const F6& x, const F6& y) { return F6{sub(x.a0, y.a0), sub(x.a1, y.a1), sub(x.a2, y.a2)}; }
+static inline F6 neg(const F6& x) { return F6{neg(x.a0), neg(x.a1), neg(x.a2)}; }
+static inline F6 mul_v(const F6& x) { return F6{mul_xi(x.a2), x.a0, x.a1}; }
+static inline F6 mul(const F6& x, const F6& y) {
+    F2 t0 = mul(x.a0, y.a0), t1 = mul(x.a1, y.a1), t2 = mul(x.a2, y.a2);
+    F2 m12 = sub(sub(mul(add(x.a1, x.a2), add(y.a1, y.a2)), t1), t2);
+    F2 m01 = sub(sub(mul(add(x.a0, x.a1), add(y.a0, y.a1)), t0), t1);
+    F2 m02 = sub(sub(mul(add(x.a0, x.a2), add(y.a0, y.a2)), t0), t2);
+    return F6{add(t0, mul_xi(m12)), add(m01, mul_xi(t2)), add(m02, t1)};
+}
+static inline F6 inv(const F6& x) {
+    F2 A = sub(sqr(x.a0), mul_xi(mul(x.a1, x.a2)));
+    F2 B = sub(mul_xi(sqr(x.a2)), mul(x.a0, x.a1));
+    F2 C = sub(sqr(x.a1), mul(x.a0, x.a2));
+    F2 t = add(mul(x.a0, A), mul_xi(add(mul(x.a2, B), mul(x.a1, C))));
+    F2 ti = inv(t);
+    return F6{mul(A, ti), mul(B, ti), mul(C, ti)};
+}
+
+// ---------------------------------------------------------------- Fq12 = Fq6[w]/(w^2 - v)
+struct F12 {
+    F6 c0, c1;
+    static F12 one() { return F12{F6::one(), F6::zero()}; }
+    bool operator==(const F12& o) const { return c0 == o.c0 && c1 == o.c1; }
+};
+static inline F12 mul(const F12& x, const F12& y) {
+    F6 t0 = mul(x.c0, y.c0), t1 = mul(x.c1, y.c1);
+    F6 m = sub(sub(mul(add(x.c0, x.c1), add(y.c0, y.c1)), t0), t1);
+    return F12{add(t0, mul_v(t1)), m};
+}
+static inline F12 sqr(const F12& x) {
+    // (c0 + c1 w)^2 = c0^2 + v c1^2 + 2 c0 c1 w, with two Fq6 products
+    F6 p = mul(x.c0, x.c1);
+    F6 s = mul(add(x.c0, x.c1), add(x.c0, mul_v(x.c1)));
+    return F12{sub(sub(s, p), mul_v(p)), add(p, p)};
+}
+static inline F12 conj(const F12& x) { return F12{x.c0, neg(x.c1)}; }
+static inline F12 inv(const F12& x) {
+    F6 t = sub(mul(x.c0, x.c0), mul_v(mul(x.c1, x.c1)));
+    F6 ti = inv(t);
+    return F12{mul(x.c0, ti), neg(mul(x.c1, ti))};
+}
+// coefficient of w^i, i = 0..5  (w^2 = v):  c0.a0, c1.a0, c0.a1, c1.a1, c0.a2, c1.a2
+static inline F2& coeff(F12& x, int i) {
+    F6& h = (i & 1) ? x.c1 : x.c0;
+    return (i >> 1) == 0 ? h.a0 : (i >> 1) == 1 ? h.a1 : h.a2;
+}
+// x^(q^k), k = 1..3: (a_i w^i)^(q^k) = frob^k(a_i) * xi^(i (q^k - 1)/6) * w^i
+static inline F12 frobenius(const F12& x, int k) {
+    const uint32_t(*g)[2][8] = k == 1 ? pairing_consts::GAMMA1 : k == 2 ? pairing_consts::GAMMA2 : pairing_consts::GAMMA3;
+    F12 r = x;
+    for (int i = 0; i < 6; i++) {
+        F2 a = coeff(r, i);
+        if (k & 1) a = conj(a);
+        coeff(r, i) = mul(a, f2_c(g[i]));
+    }
+    return r;
+}
+static inline F12 pow_z(const F12& x) {   // x^z, z = 4965661367192848881 (63 bits)
+    F12 r = x;
+    unsigned long long z = pairing_consts::Z;
+    int top = 63;
+    while (!((z >> top) & 1)) top--;
+    for (int b = top - 1; b >= 0; b--) {
+        r = sqr(r);
+        if ((z >> b) & 1) r = mul(r, x);
+    }
+    return r;
+}
+
+// ---------------------------------------------------------------- points
+struct G1A {
+    Fq x, y;
+    bool inf;
+};
+struct G2A {
+    F2 x, y;
+    bool inf;
+};
+static inline bool on_curve(const G1A& p) {   // y^2 = x^3 + 3
+    if (p.inf) return true;
+    Fq three = add(add(Fq::one(), Fq::one()), Fq::one());
+    return sqr(p.y) == add(mul(sqr(p.x), p.x), three);
+}
+static inline bool on_curve(const G2A& p) {   // y^2 = x^3 + 3/xi
+    if (p.inf) return true;
+    return sqr(p.y) == add(mul(sqr(p.x), p.x), f2_c(pairing_consts::TWIST_B));
+}
+
+// line through the (untwisted) point T with twist-slope lam, evaluated at P:  yP - lam xP w + (lam xT - yT) w^3
+static inline F12 line_at(const G2A& T, const F2& lam, const G1A& P) {
+    F12 l{F6::zero(), F6::zero()};
+    l.c0.a0 = F2{P.y, Fq::zero()};
+    l.c1.a0 = neg(scale(lam, P.x));
+    l.c1.a1 = sub(mul(lam, T.x), T.y);
+    return l;
+}
+
+struct MillerState {
+    G1A P;
+    G2A Q, T;
+};
+// d[i] <- 1/d[i] for n <= 8 non-zero values with one field inversion
+static inline void batch_inv(F2* d, int n) {
+    F2 pre[8];
+    F2 acc = F2::one();
+    for (int i = 0; i < n; i++) {
+        pre[i] = acc;
+        acc = mul(acc, d[i]);
+    }
+    acc = inv(acc);
+    for (int i = n - 1; i >= 0; i--) {
+        F2 t = mul(acc, pre[i]);
+        acc = mul(acc, d[i]);
+        d[i] = t;
+    }
+}
+// T <- T + R along the chord/tangent of slope lam, multiplying the line into f
+static inline void step_apply(MillerState& s, const F2& lam, const F2& rx, F12& f) {
+    f = mul(f, line_at(s.T, lam, s.P));
+    F2 x3 = sub(sub(sqr(lam), s.T.x), rx);
+    s.T.y = sub(mul(lam, sub(s.T.x, x3)), s.T.y);
+    s.T.x = x3;
+}
+static inline void steps_double(MillerState** st, int n, F12& f) {
+    F2 den[8];
+    for (int i = 0; i < n; i++) den[i] = dbl(st[i]->T.y);
+    batch_inv(den, n);
+    for (int i = 0; i < n; i++) {
+        F2 x2 = sqr(st[i]->T.x);
+        step_apply(*st[i], mul(add(dbl(x2), x2), den[i]), st[i]->T.x, f);
+    }
+}
+static inline void steps_add(MillerState** st, const G2A* R, int n, F12& f) {
+    F2 den[8];
+    for (int i = 0; i < n; i++) den[i] = sub(R[i].x, st[i]->T.x);
+    batch_inv(den, n);
+    for (int i = 0; i < n; i++) step_apply(*st[i], mul(sub(R[i].y, st[i]->T.y), den[i]), R[i].x, f);
+}
+
+// prod_i f_{6z+2,Q_i}(P_i) * (the two Frobenius lines): one shared squaring and one shared inversion per step
+static inline F12 miller_product(const G1A* P, const G2A* Q, int n) {
+    MillerState all[8];
+    MillerState* st[8];
+    G2A q0[8], q1[8], q2[8];
+    int m = 0;
+    for (int i = 0; i < n && m < 8; i++) {
+        if (P[i].inf || Q[i].inf) continue;                      // e(O, Q) = e(P, O) = 1
+        all[m] = MillerState{P[i], Q[i], Q[i]};
+        st[m] = &all[m];
+        q0[m] = Q[i];
+        q1[m] = G2A{mul(conj(Q[i].x), f2_c(pairing_consts::GAMMA1[2])), mul(conj(Q[i].y), f2_c(pairing_consts::GAMMA1[3])), false};   // pi(Q)
+        q2[m] = G2A{mul(Q[i].x, f2_c(pairing_consts::GAMMA2[2])), neg(mul(Q[i].y, f2_c(pairing_consts::GAMMA2[3]))), false};          // -pi^2(Q)
+        m++;
+    }
+    F12 f = F12::one();
+    if (!m) return f;
+    for (int b = 1; b < pairing_consts::ATE_LOOP_BITS; b++) {
+        f = sqr(f);
+        steps_double(st, m, f);
+        if (pairing_consts::ATE_LOOP[b]) steps_add(st, q0, m, f);
+    }
+    steps_add(st, q1, m, f);
+    steps_add(st, q2, m, f);
+    return f;
+}
+
+static inline F12 final_exponentiation(const F12& f) {
+    // easy part: f^((q^6 - 1)(q^2 + 1)); afterwards the inverse is the conjugate
+    F12 e = mul(conj(f), inv(f));
+    e = mul(frobenius(e, 2), e);
+    // hard part
+    F12 mz = conj(pow_z(e));                    // e^(-z)
+    F12 m2z = sqr(mz);                          // e^(-2z)
+    F12 m6z = mul(sqr(m2z), m2z);               // e^(-6z)
+    F12 p6zz = conj(pow_z(m6z));                // e^(6z^2)
+    F12 p12zzz = pow_z(sqr(p6zz));              // e^(12z^3)
+    F12 k = mul(mul(p12zzz, p6zz), conj(m6z));  // e^(12z^3 + 6z^2 + 6z)
+    F12 l = mul(k, m2z);                        // e^(12z^3 + 6z^2 + 4z)
+    F12 n = mul(mul(k, p6zz), e);               // e^(12z^3 + 12z^2 + 6z + 1)
+    F12 r = mul(frobenius(l, 1), n);
+    r = mul(frobenius(k, 2), r);
+    return mul(frobenius(mul(conj(e), l), 3), r);
+}
+
+static inline F12 pairing(const G1A& P, const G2A& Q) { return final_exponentiation(miller_product(&P, &Q, 1)); }
+
+}  // namespace pairing
+}  // namespace ws
