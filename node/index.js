@@ -21,6 +21,17 @@ function bin2int(buf, off) {            // src/bn128.js:319-327, with BigInt ins
 const bin2g1 = (b) => [bin2int(b, 0), bin2int(b, 32), bin2int(b, 64)];                                   // :329-335
 const bin2g2 = (b) => [[bin2int(b, 0), bin2int(b, 32)], [bin2int(b, 64), bin2int(b, 96)], [bin2int(b, 128), bin2int(b, 160)]];   // :336-351
 
+function int2bin(v) {                   // setInt, src/bn128.js:455-470: decimal string / BigInt -> 32 bytes LE (plain form)
+    let x = BigInt(v);
+    if (x < 0n || x >> 256n) throw new RangeError("field element out of range");
+    const out = new Uint8Array(32);
+    for (let i = 0; i < 32; i++) { out[i] = Number(x & 0xffn); x >>= 8n; }
+    return out;
+}
+const cat = (parts) => { const o = new Uint8Array(parts.reduce((n, p) => n + p.length, 0)); let k = 0; for (const p of parts) { o.set(p, k); k += p.length; } return o; };
+const g1bin = (e) => cat([int2bin(e[0]), int2bin(e[1])]);                                                // setG1Affine :503-507
+const g2bin = (e) => cat([int2bin(e[0][0]), int2bin(e[0][1]), int2bin(e[1][0]), int2bin(e[1][1])]);      // setG2Affine :509-513
+
 class Bn128 {
     constructor(device) { this.h = native.create(device || 0); }
     groth16GenProof(signals, pkey, r, s) {
@@ -36,6 +47,18 @@ class Bn128 {
     g1_affine(p) { return native.g1Affine(this.h, p); }
     g2_affine(p) { return native.g2Affine(this.h, p); }
     async calcH(signals, polsA, polsB, nSignals, domainSize) { return native.calcH(this.h, signals, polsA, polsB, nSignals, domainSize); }
+    async groth16Verify(verificationKey, input, proof) {                // src/bn128.js:722-786
+        if (input === undefined || input === null) input = [];
+        else if (!Array.isArray(input)) input = [input];
+        let vk, ic, ins, pr;
+        try {
+            vk = cat([g1bin(verificationKey.vk_alfa_1), g2bin(verificationKey.vk_beta_2), g2bin(verificationKey.vk_gamma_2), g2bin(verificationKey.vk_delta_2)]);
+            ic = cat(verificationKey.IC.map(g1bin));
+            ins = cat(input.map(int2bin));
+            pr = cat([g1bin(proof.pi_a), g2bin(proof.pi_b), g1bin(proof.pi_c)]);
+        } catch (e) { if (e instanceof RangeError) return false; throw e; }
+        return native.verify(vk.buffer, ic.buffer, ins.buffer, pr.buffer);
+    }
     bin2g1(b) { return bin2g1(b); }
     bin2g2(b) { return bin2g2(b); }
     terminate() { native.destroy(this.h); this.h = null; }

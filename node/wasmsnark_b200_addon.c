@@ -229,6 +229,30 @@ static napi_value CalcH(napi_env env, napi_callback_info info) {
     return ab;
 }
 
+/* verify(vk, ic, inputs, proof): vk = alfa1|beta2|gamma2|delta2 (448 B), ic = (nPublic+1) * 64 B, inputs = nPublic * 32 B,
+ * proof = pi_a|pi_b|pi_c (256 B), all plain little-endian (index.js packs the JSON decimals) -> boolean.
+ * Replaces Bn128.groth16Verify, src/bn128.js:722-786; host code, ~10 ms, so it runs inline. */
+static napi_value Verify(napi_env env, napi_callback_info info) {
+    size_t argc = 4;
+    napi_value argv[4], res;
+    CHECK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+    uint8_t *vk, *ic, *in, *pr;
+    size_t vl, il, nl, pl;
+    if (!get_buffer(env, argv[0], &vk, &vl) || !get_buffer(env, argv[1], &ic, &il) || !get_buffer(env, argv[2], &in, &nl) ||
+        !get_buffer(env, argv[3], &pr, &pl) || vl != 448 || pl != 256 || il % 64 || nl % 32 || il / 64 != nl / 32 + 1) {
+        napi_throw_type_error(env, NULL, "verify(vk448, ic, inputs, proof256)");
+        return NULL;
+    }
+    int valid = 0;
+    int rc = ws_bn128_groth16_verify(vk, vk + 64, vk + 192, vk + 320, ic, il / 64, nl ? in : NULL, nl / 32, pr, pr + 64, pr + 192, &valid);
+    if (rc) {
+        napi_throw_error(env, NULL, "ws_bn128_groth16_verify: bad arguments");
+        return NULL;
+    }
+    CHECK(napi_get_boolean(env, valid == 1, &res));
+    return res;
+}
+
 static napi_value Destroy(napi_env env, napi_callback_info info) {
     /* the external's finalizer destroys the context; nothing to do eagerly */
     (void)env;
@@ -246,6 +270,7 @@ NAPI_MODULE_INIT() {
         {"g1Affine", NULL, G1Affine, NULL, NULL, NULL, napi_default, NULL},
         {"g2Affine", NULL, G2Affine, NULL, NULL, NULL, napi_default, NULL},
         {"calcH", NULL, CalcH, NULL, NULL, NULL, napi_default, NULL},
+        {"verify", NULL, Verify, NULL, NULL, NULL, napi_default, NULL},
     };
     napi_define_properties(env, exports, sizeof props / sizeof props[0], props);
     return exports;
