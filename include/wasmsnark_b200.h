@@ -42,7 +42,9 @@ enum {
 enum {
     WS_BN128_FQ = 0,   /* f1m_*  : src/bn128/build_bn128.js:33 (q, :19)  */
     WS_BN128_FR = 1,   /* frm_*  : src/bn128/build_bn128.js:34 (r, :20)  */
-    WS_MNT6753_FQ = 2  /* f1m_* of the MNT6753 image: src/mnt6753/build_mnt6753.js:19 */
+    WS_MNT6753_FQ = 2, /* f1m_* of the MNT6753 image: src/mnt6753/build_mnt6753.js:19 */
+    WS_BLS12381_FQ = 3, /* f1m_* of the BLS12-381 module: src/bls12381/build_bls12381.js:20,33 (48-byte elements) */
+    WS_BLS12381_FR = 4  /* frm_* of the BLS12-381 module: src/bls12381/build_bls12381.js:21,34 */
 };
 
 /* ---- context -------------------------------------------------------------------------------
@@ -54,7 +56,7 @@ const char* ws_last_error(const ws_ctx* ctx);
 const char* ws_version(void);
 
 /* ---- field arithmetic (config C1 / C5) -----------------------------------------------------
- * out[i] = x[i] (op) y[i] for n elements; x, y, out are n*32 bytes (n*96 for MNT6753).
+ * out[i] = x[i] (op) y[i] for n elements; x, y, out are n*32 bytes (n*96 for MNT6753, n*48 for BLS12-381 Fq).
  * Replaces f1m_mul / frm_mul        src/build_f1m.js:235-436
  *          f1m_add, f1m_sub         src/build_f1m.js:67-101
  *          f1m_square               src/build_f1m.js:439-737      (y ignored)
@@ -127,6 +129,25 @@ int ws_mnt6753_g1_multiexp(ws_ctx* ctx, const uint8_t* scalars, const uint8_t* p
 int ws_mnt6753_g1_multiexp_dev(ws_ctx* ctx, const void* d_scalars, const void* d_points, size_t n, void* d_out, int window_bits, void* stream);
 /* g1m_affine (src/build_curve_projective.js:624-652) [+ g1m_fromMontgomery]: projective triples -> (x, y, 1). */
 int ws_mnt6753_g1_affine(ws_ctx* ctx, const uint8_t* in, uint8_t* out, size_t count, int from_montgomery);
+
+/* ---- BLS12-381: the same kernels instantiated for the reference's bls12381 module --------
+ * src/bls12381/build_bls12381.js:20-43 builds f1m (q, 6 x 64 bit), frm (r), g1m / g2m (a = 0 Jacobian curves,
+ * src/build_curve_jacobian_a0.js), g1m_multiexp / g2m_multiexp (src/build_multiexp.js), fft over frm
+ * (src/build_fft.js) and f2m = f1m[u]/(u^2+1) (src/build_f2m.js).  Conventions as for BN128: 32-byte raw LE scalars,
+ * affine Montgomery points (G1 x|y = 96 bytes, G2 = 192 bytes; x == 0 => infinity), Jacobian results X|Y|Z (G1 144,
+ * G2 288 bytes; compare after *_affine), fft in place on 32-byte Montgomery Fr elements, n a power of two <= 2^28.
+ * ws_fp_batch(field = WS_BLS12381_FQ / WS_BLS12381_FR) covers f1m_* / frm_*.  The reference ships no compiled image
+ * and no host for this module, so these are checked against the big-integer oracle only. */
+int ws_bls12381_fq2_mul_batch(ws_ctx* ctx, const uint8_t* x, const uint8_t* y, uint8_t* out, size_t n);
+int ws_bls12381_g1_multiexp(ws_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t out[144]);
+int ws_bls12381_g1_multiexp_dev(ws_ctx* ctx, const void* d_scalars, const void* d_points, size_t n, void* d_out, int window_bits, void* stream);
+int ws_bls12381_g1_affine(ws_ctx* ctx, const uint8_t* in, uint8_t* out, size_t count, int from_montgomery);
+int ws_bls12381_g2_multiexp(ws_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t out[288]);
+int ws_bls12381_g2_multiexp_dev(ws_ctx* ctx, const void* d_scalars, const void* d_points, size_t n, void* d_out, int window_bits, void* stream);
+int ws_bls12381_g2_affine(ws_ctx* ctx, const uint8_t* in, uint8_t* out, size_t count, int from_montgomery);
+int ws_bls12381_fr_fft(ws_ctx* ctx, uint8_t* px, size_t n, int odd);
+int ws_bls12381_fr_ifft(ws_ctx* ctx, uint8_t* px, size_t n, int odd);
+int ws_bls12381_fr_fft_dev(ws_ctx* ctx, void* d_px, size_t n, int odd, int inverse, void* stream);
 
 /* ---- NTT over Fr (config C3) -------------------------------------------------------------------
  * Replaces fft_fft(px, n, odd) / fft_ifft(px, n, odd)   src/build_fft.js:159-221 (+ __rawfft :223-372,

@@ -9,7 +9,7 @@ template <class T> static T ld(const uint8_t* p) { T t; memcpy(&t, p, sizeof(T))
 template <class T> static void st(uint8_t* p, const T& t) { memcpy(p, &t, sizeof(T)); }
 
 extern "C" {
-// op: 0 add, 1 sub, 2 mul, 3 inv(x), 4 neg(x), 5 to_mont, 6 from_mont ; field: 0 Fq, 1 Fr, 2 MNT6753 Fq
+// op: 0 add, 1 sub, 2 mul, 3 inv(x), 4 neg(x), 5 to_mont, 6 from_mont ; field: 0 Fq, 1 Fr, 2 MNT6753 Fq, 3 BLS12-381 Fq, 4 BLS12-381 Fr
 void h_fp_op(int field, int op, const uint8_t* x, const uint8_t* y, uint8_t* r) {
 #define DO(P)                                                                    \
     {                                                                            \
@@ -25,7 +25,7 @@ void h_fp_op(int field, int op, const uint8_t* x, const uint8_t* y, uint8_t* r) 
         }                                                                        \
         st(r, c);                                                                \
     }
-    if (field == 0) DO(BN128_Fq) else if (field == 1) DO(BN128_Fr) else DO(MNT6753_Fq)
+    if (field == 0) DO(BN128_Fq) else if (field == 1) DO(BN128_Fr) else if (field == 3) DO(BLS12_381_Fq) else if (field == 4) DO(BLS12_381_Fr) else DO(MNT6753_Fq)
 #undef DO
 }
 void h_fq2_op(int op, const uint8_t* x, const uint8_t* y, uint8_t* r) {
@@ -54,4 +54,13 @@ void h_g2_dbl(const uint8_t* a, uint8_t* r) { st(r, pdbl<G2Curve>(ld<G2X>(a))); 
 void h_g2_from_affine(const uint8_t* q, uint8_t* r) { st(r, G2X::from_affine(ld<G2Affine>(q))); }
 void h_g2_to_affine(const uint8_t* a, uint8_t* r) { st(r, to_affine<G2Curve>(ld<G2X>(a))); }
 void h_g2_times_scalar(const uint8_t* a, const uint8_t* k, int len, uint8_t* r) { st(r, times_scalar<G2Curve>(ld<G2X>(a), k, len)); }
+// BLS12-381: k * P + Q on affine Montgomery inputs (96 / 192 B), result as the affine Jacobian triple (x, y, 1) / (0, 1, 0)
+void h_bls_g1_muladd(const uint8_t* p, const uint8_t* k, int len, const uint8_t* q, uint8_t* r) {
+    XYZZ<BlsG1Curve> t = times_scalar<BlsG1Curve>(XYZZ<BlsG1Curve>::from_affine(ld<Affine<BlsG1Curve>>(p)), k, len);
+    st(r, to_affine<BlsG1Curve>(pmadd<BlsG1Curve>(t, ld<Affine<BlsG1Curve>>(q))));
+}
+void h_bls_g2_muladd(const uint8_t* p, const uint8_t* k, int len, const uint8_t* q, uint8_t* r) {
+    XYZZ<BlsG2Curve> t = times_scalar<BlsG2Curve>(XYZZ<BlsG2Curve>::from_affine(ld<Affine<BlsG2Curve>>(p)), k, len);
+    st(r, to_affine<BlsG2Curve>(pmadd<BlsG2Curve>(t, ld<Affine<BlsG2Curve>>(q))));
+}
 }

@@ -7,6 +7,7 @@ chains), and that layer is re-checked on the GPU in tests/test_gpu_field.py.
 import ctypes
 import random
 
+from oracle import bls12381 as BLS
 from oracle import bn128 as O
 
 Q, RR = O.Q, O.R_ORDER
@@ -28,7 +29,7 @@ def edge(p):
 
 def test_fp_ops(host_math):
     rnd = random.Random(1)
-    for field, p, n in ((0, Q, 32), (1, RR, 32), (2, MNT_Q, 96)):
+    for field, p, n in ((0, Q, 32), (1, RR, 32), (2, MNT_Q, 96), (3, BLS.Q, 48), (4, BLS.R_ORDER, 32)):
         Rm = 1 << (8 * n)
         Rinv = pow(Rm, -1, p)
         vals = edge(p) + [rnd.randrange(p) for _ in range(40)]
@@ -158,3 +159,19 @@ def test_g1_group_law(host_math):
 
 def test_g2_group_law(host_math):
     _group_checks(host_math, 2, O.G2_GEN)
+
+
+def test_bls12381_group_law_host(host_math):
+    """k*P + Q on BLS12-381 G1 / G2 with the same ec.cuh templates the kernels instantiate, vs the affine oracle."""
+    rnd = random.Random(9)
+    for F, G, enc, fn, size in ((BLS.Fq, BLS.G1_GEN, BLS.g1_bytes, host_math.h_bls_g1_muladd, 144),
+                                (BLS.Fq2, BLS.G2_GEN, BLS.g2_bytes, host_math.h_bls_g2_muladd, 288)):
+        dec = BLS.g1_from_affine_std if size == 144 else BLS.g2_from_affine_std
+        out = ctypes.create_string_buffer(size)
+        for k, qk in ((1, 1), (2, 3), (rnd.randrange(1 << 256), rnd.randrange(BLS.R_ORDER)), (BLS.R_ORDER, 5), (BLS.R_ORDER - 7, 7), (5, 5)):
+            Qp = BLS.pt_mul(F, G, qk)
+            fn(enc(G), b(k, 32), 32, enc(Qp), out)
+            want = BLS.pt_add(F, BLS.pt_mul(F, G, k), Qp)
+            vals = [i(out.raw[48 * j:48 * j + 48]) for j in range(size // 48)]
+            got_bytes = b"".join(b(BLS.from_mont(v), 48) for v in vals)
+            assert dec(got_bytes) == want, (size, k, qk)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Generates wasmsnark_b200/csrc/fp_asm.cuh: PTX carry-chain primitives for N-limb
-(32-bit limbs) Montgomery arithmetic, N = 8 (BN128, 256 bit) and N = 24 (MNT6753, 768 bit).
+(32-bit limbs) Montgomery arithmetic, N = 8 (BN128 / BLS12-381 Fr, 256 bit), N = 12 (BLS12-381 Fq, 384 bit) and N = 24 (MNT6753, 768 bit).
 
 Every chain is ONE asm statement, so the carry flag never has to survive between
 statements.  ptxas fuses each mad.lo.cc/madc.hi.cc pair into a single IMAD.WIDE.U32(.X):
@@ -124,7 +124,7 @@ def main(path):
     s = ("// GENERATED by tools/gen_fp_asm.py -- do not edit.\n"
          "// PTX carry-chain primitives (device only) for N-limb Montgomery arithmetic.\n"
          "#pragma once\n#include <cstdint>\n\nnamespace ws {\n\n#ifdef __CUDA_ARCH__\n\n")
-    for N in (8, 24):
+    for N in (8, 12, 24):
         s += "// ======================= N = %d =======================\n" % N
         s += gen(N) + "\n"
     s += "#endif  // __CUDA_ARCH__\n\n}  // namespace ws\n"

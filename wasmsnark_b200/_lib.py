@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwasmsnark_b200.so")
 
 WS_OK = 0
-FIELD_BN128_FQ, FIELD_BN128_FR, FIELD_MNT6753_FQ = 0, 1, 2
+FIELD_BN128_FQ, FIELD_BN128_FR, FIELD_MNT6753_FQ, FIELD_BLS12381_FQ, FIELD_BLS12381_FR = 0, 1, 2, 3, 4
 OP_MUL, OP_ADD, OP_SUB, OP_SQUARE, OP_TOMONT, OP_FROMMONT, OP_INVERSE = range(7)
 
 
@@ -60,6 +60,16 @@ SIGNATURES = {
     "ws_set_key_cache": (_i, [_vp, _i]),
     "ws_bn128_groth16_verify": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp]),
     "ws_bn128_pairing": (_i, [_vp, _vp, _vp]),
+    "ws_bls12381_fq2_mul_batch": (_i, [_vp, _vp, _vp, _vp, _sz]),
+    "ws_bls12381_g1_multiexp": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "ws_bls12381_g1_multiexp_dev": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp]),
+    "ws_bls12381_g1_affine": (_i, [_vp, _vp, _vp, _sz, _i]),
+    "ws_bls12381_g2_multiexp": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "ws_bls12381_g2_multiexp_dev": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp]),
+    "ws_bls12381_g2_affine": (_i, [_vp, _vp, _vp, _sz, _i]),
+    "ws_bls12381_fr_fft": (_i, [_vp, _vp, _sz, _i]),
+    "ws_bls12381_fr_ifft": (_i, [_vp, _vp, _sz, _i]),
+    "ws_bls12381_fr_fft_dev": (_i, [_vp, _vp, _sz, _i, _i, _vp]),
     "ws_bn128_pkey_load": (_i, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),
     "ws_bn128_pkey_free": (None, [_vp]),
     "ws_bn128_pkey_info": (_i, [_vp, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]),

@@ -10,6 +10,9 @@
 #include "ctx.cuh"
 #include "field_kernels.cuh"
 
+namespace ws {
+void bls12381_launch_fp_batch(int field_is_fr, int op, const void* x, const void* y, void* out, size_t n, cudaStream_t st);   // bls12381_g1.cu
+}
 using namespace ws;
 
 #define WS_API __attribute__((visibility("default")))
@@ -43,6 +46,7 @@ WS_API void ws_destroy(ws_ctx* c) {
     for (auto& a : c->arenas)
         if (a.ptr) cudaFree(a.ptr);
     if (c->tw_table) cudaFree(c->tw_table);
+    if (c->tw_table_bls) cudaFree(c->tw_table_bls);
     if (c->lanes_ready) {
         for (int i = 0; i < ws_ctx::NLANES; i++) {
             cudaStreamDestroy(c->lanes[i]);
@@ -82,11 +86,11 @@ WS_API int ws_last_timings(ws_ctx* c, const char** names, float* ms, int cap) {
 // ------------------------------------------------------------------ field batches
 WS_API int ws_fp_batch(ws_ctx* c, int field, int op, const uint8_t* x, const uint8_t* y, uint8_t* out, size_t n) {
     if (!c || !x || !out || (!y && (op == WS_OP_MUL || op == WS_OP_ADD || op == WS_OP_SUB))) return c ? c->fail(WS_E_ARG, "null buffer") : WS_E_ARG;
-    if (field < 0 || field > WS_MNT6753_FQ) return c->fail(WS_E_FIELD, "unknown field id");
+    if (field < 0 || field > WS_BLS12381_FR) return c->fail(WS_E_FIELD, "unknown field id");
     if (op < 0 || op > WS_OP_INVERSE) return c->fail(WS_E_ARG, "unknown op");
     if (n == 0) return WS_OK;
     cudaSetDevice(c->device);
-    size_t esz = field == WS_MNT6753_FQ ? 96 : 32;
+    size_t esz = field == WS_MNT6753_FQ ? 96 : field == WS_BLS12381_FQ ? 48 : 32;
     uint8_t* d = (uint8_t*)c->arena(0, 3 * align256(n * esz));
     if (!d) return c->fail_cuda("workspace");
     uint8_t *dx = d, *dy = d + align256(n * esz), *dr = d + 2 * align256(n * esz);
@@ -95,6 +99,8 @@ WS_API int ws_fp_batch(ws_ctx* c, int field, int op, const uint8_t* x, const uin
     switch (field) {
         case WS_BN128_FQ: launch_fp_batch<BN128_Fq>(op, dx, dy, dr, n, c->stream); break;
         case WS_BN128_FR: launch_fp_batch<BN128_Fr>(op, dx, dy, dr, n, c->stream); break;
+        case WS_BLS12381_FQ: bls12381_launch_fp_batch(0, op, dx, dy, dr, n, c->stream); break;
+        case WS_BLS12381_FR: bls12381_launch_fp_batch(1, op, dx, dy, dr, n, c->stream); break;
         default: launch_fp_batch<MNT6753_Fq>(op, dx, dy, dr, n, c->stream); break;
     }
     cudaMemcpyAsync(out, dr, n * esz, cudaMemcpyDeviceToHost, c->stream);

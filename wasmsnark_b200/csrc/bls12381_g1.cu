@@ -1,0 +1,114 @@
+// bls12381_g1.cu -- BLS12-381 instantiation of the same kernels: 12-limb Fq, 8-limb Fr,
+// G1 multi-scalar multiplication, Fq2 products and the Fr NTT.
+//
+// The reference parameterises its builders the same way:
+//   f1m over q (n64 = 6), frm over r        /root/reference/src/bls12381/build_bls12381.js:20-35  (src/build_f1m.js)
+//   g1m = a-zero Jacobian curve over f1m    /root/reference/src/bls12381/build_bls12381.js:36  (src/build_curve_jacobian_a0.js)
+//   g1m_multiexp                            /root/reference/src/bls12381/build_bls12381.js:37  (src/build_multiexp.js)
+//   fft over frm                            /root/reference/src/bls12381/build_bls12381.js:38  (src/build_fft.js)
+//   f2m = f1m[u]/(u^2 + 1)                  /root/reference/src/bls12381/build_bls12381.js:41  (src/build_f2m.js)
+// No bls12381 WASM image ships in the reference's build/ directory and no JS host drives this curve, so parity
+// for this file is pinned on the big-integer restatement (oracle/bls12381.py) and on the constants of
+// build_bls12381.js (q, r, generators; r * G = O), not on outputs of the reference itself: "parity unpinned".
+// Conventions follow the BN128 path: raw little-endian 32-byte scalars, affine Montgomery points x|y (2 x 48 bytes),
+// x == 0 meaning infinity, result = Jacobian triple X|Y|Z (144 bytes).
+#include "field_kernels.cuh"
+#include "msm_impl.cuh"
+#include "ntt.cuh"
+using namespace ws;
+
+static int log2_exact_u32(uint32_t n) {
+    if (!n || (n & (n - 1))) return -1;
+    int l = 0;
+    while ((1u << l) != n) l++;
+    return l;
+}
+
+static __global__ void __launch_bounds__(128) k_bls_fq2_mul(const BlsFq2* __restrict__ x, const BlsFq2* __restrict__ y, BlsFq2* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    st_vec(out + i, mul(ld_vec(x + i), ld_vec(y + i)));
+}
+
+namespace ws {
+// called from ws_fp_batch (api.cu) for the two BLS12-381 field ids, so the 12-limb kernels live in this translation unit
+void bls12381_launch_fp_batch(int field_is_fr, int op, const void* x, const void* y, void* out, size_t n, cudaStream_t st) {
+    if (field_is_fr) launch_fp_batch<BLS12_381_Fr>(op, x, y, out, n, st);
+    else launch_fp_batch<BLS12_381_Fq>(op, x, y, out, n, st);
+}
+}  // namespace ws
+
+static int bls_fft_dev(ws_ctx* c, void* d_px, size_t n, int odd, int inverse, cudaStream_t st) {
+    int logn = n <= 0xFFFFFFFFull ? log2_exact_u32((uint32_t)n) : -1;
+    if (logn < 0 || logn > 28) return c->fail(WS_E_SIZE, "fft size must be a power of two <= 2^28");
+    TwiddleTableT<BlsFr> T;
+    T.tw = (BlsFr*)c->tw_table_bls;
+    T.logM = c->tw_logM_bls;
+    bool ok = ntt_ensure_table<NttBls12381>(T, logn + 1, st);
+    c->tw_table_bls = T.tw;
+    c->tw_logM_bls = T.logM;
+    if (!ok) return c->fail_cuda("twiddle table");
+    BlsFr* scratch = (BlsFr*)c->arena(2, sizeof(BlsFr) << logn);
+    if (!scratch) return c->fail_cuda("fft scratch");
+    cudaError_t e = ntt_launch<NttBls12381>((BlsFr*)d_px, scratch, logn, odd != 0, inverse != 0, T, st, &c->launches);
+    return e == cudaSuccess ? WS_OK : c->fail_cuda("ntt");
+}
+
+static int bls_fft_host(ws_ctx* c, uint8_t* px, size_t n, int odd, int inverse) {
+    if (!c || !px) return c ? c->fail(WS_E_ARG, "null buffer") : WS_E_ARG;
+    if (!n || n > ((size_t)1 << 28)) return c->fail(WS_E_SIZE, "fft size must be a power of two <= 2^28");
+    cudaSetDevice(c->device);
+    uint8_t* d = (uint8_t*)c->arena(3, n * 32);
+    if (!d) return c->fail_cuda("fft buffer");
+    cudaMemcpyAsync(d, px, n * 32, cudaMemcpyHostToDevice, c->stream);
+    int rc = bls_fft_dev(c, d, n, odd, inverse, c->stream);
+    if (rc) return rc;
+    cudaMemcpyAsync(px, d, n * 32, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) return c->fail_cuda("fft");
+    return WS_OK;
+}
+
+extern "C" {
+WS_API int ws_bls12381_fq2_mul_batch(ws_ctx* c, const uint8_t* x, const uint8_t* y, uint8_t* out, size_t n) {
+    if (!c || !x || !y || !out) return c ? c->fail(WS_E_ARG, "null buffer") : WS_E_ARG;
+    if (n == 0) return WS_OK;
+    cudaSetDevice(c->device);
+    uint8_t* d = (uint8_t*)c->arena(0, 3 * align256(n * 96));
+    if (!d) return c->fail_cuda("workspace");
+    uint8_t *dx = d, *dy = d + align256(n * 96), *dr = d + 2 * align256(n * 96);
+    cudaMemcpyAsync(dx, x, n * 96, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(dy, y, n * 96, cudaMemcpyHostToDevice, c->stream);
+    k_bls_fq2_mul<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>((const BlsFq2*)dx, (const BlsFq2*)dy, (BlsFq2*)dr, n);
+    cudaMemcpyAsync(out, dr, n * 96, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) return c->fail_cuda("fq2_mul_batch");
+    return WS_OK;
+}
+WS_API int ws_bls12381_g1_multiexp(ws_ctx* c, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t out[144]) {
+    return multiexp_host<BlsG1Curve>(c, scalars, points, n, out);
+}
+WS_API int ws_bls12381_g1_multiexp_dev(ws_ctx* c, const void* ds, const void* dp, size_t n, void* dout, int wb, void* stream) {
+    if (!c || !dout || (n && (!ds || !dp))) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
+    cudaSetDevice(c->device);
+    return multiexp_dev<BlsG1Curve>(c, ds, dp, n, dout, wb, stream ? (cudaStream_t)stream : c->stream);
+}
+WS_API int ws_bls12381_g1_affine(ws_ctx* c, const uint8_t* in, uint8_t* out, size_t count, int from_montgomery) {
+    if (!c || !in || !out) return c ? c->fail(WS_E_ARG, "null buffer") : WS_E_ARG;
+    if (count == 0) return WS_OK;
+    cudaSetDevice(c->device);
+    uint8_t* d = (uint8_t*)c->arena(0, 2 * align256(count * 144));
+    if (!d) return c->fail_cuda("workspace");
+    uint8_t* dout = d + align256(count * 144);
+    cudaMemcpyAsync(d, in, count * 144, cudaMemcpyHostToDevice, c->stream);
+    k_affine_points<BlsG1Curve><<<(unsigned)((count + 63) / 64), 64, 0, c->stream>>>((const Jac<BlsG1Curve>*)d, (Jac<BlsG1Curve>*)dout, (int)count, from_montgomery);
+    cudaMemcpyAsync(out, dout, count * 144, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) return c->fail_cuda("affine");
+    return WS_OK;
+}
+WS_API int ws_bls12381_fr_fft(ws_ctx* c, uint8_t* px, size_t n, int odd) { return bls_fft_host(c, px, n, odd, 0); }
+WS_API int ws_bls12381_fr_ifft(ws_ctx* c, uint8_t* px, size_t n, int odd) { return bls_fft_host(c, px, n, odd, 1); }
+WS_API int ws_bls12381_fr_fft_dev(ws_ctx* c, void* d_px, size_t n, int odd, int inverse, void* stream) {
+    if (!c || !d_px) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
+    cudaSetDevice(c->device);
+    return bls_fft_dev(c, d_px, n, odd, inverse, stream ? (cudaStream_t)stream : c->stream);
+}
+}

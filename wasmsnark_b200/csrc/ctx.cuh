@@ -70,6 +70,8 @@ struct ws_ctx {
     bool key_cache = true;
     bool key_tables = true;      // resident proving keys get window tables (prover.cu)
     void* tw_table = nullptr;     // ntt.cuh TwiddleTable storage (Fr*), owned here
+    void* tw_table_bls = nullptr; // same for BLS12-381 Fr (bls12381_g1.cu)
+    int tw_logM_bls = 0;
     int tw_logM = 0;
     int acc_variant = 0;         // tuning hook: launch-bounds variant of the accumulate kernel
     unsigned seg_len = 0;    // 0 = automatic

@@ -52,6 +52,27 @@ struct MntG1Curve {
     }
 };
 
+// BLS12-381: G1 y^2 = x^3 + 4 over the 381-bit field (12 limbs), G2 y^2 = x^3 + 4(1 + u) over Fq2 = Fq[u]/(u^2 + 1);
+// both built by the reference with the a = 0 Jacobian curve module and 32-byte scalars
+// (/root/reference/src/bls12381/build_bls12381.js:33-43).
+using BlsFq = Fp<BLS12_381_Fq>;
+using BlsFr = Fp<BLS12_381_Fr>;
+using BlsFq2 = Fp2T<BLS12_381_Fq>;
+struct BlsG1Curve {
+    using F = BlsFq;
+    static constexpr bool A_ZERO = true;
+    static constexpr bool PROJECTIVE = false;
+    static constexpr int SCALAR_LIMBS = 8;
+    HD static F mul_a(const F& x) { return F::zero(); }
+};
+struct BlsG2Curve {
+    using F = BlsFq2;
+    static constexpr bool A_ZERO = true;
+    static constexpr bool PROJECTIVE = false;
+    static constexpr int SCALAR_LIMBS = 8;
+    HD static F mul_a(const F& x) { return F::zero(); }
+};
+
 template <class C>
 struct Affine {
     using F = typename C::F;

@@ -74,17 +74,19 @@ HD Fp<P> add(const Fp<P>& a, const Fp<P>& b) {
     Fp<P> s, t;
 #ifdef __CUDA_ARCH__
     const Fp<P> m = Fp<P>::modulus();
+    uint32_t bw;
     if constexpr (N == 8) {
         add_n8(s.v, a.v, b.v);
-        uint32_t bw = sub_n8(t.v, s.v, m.v);
-#pragma unroll
-        for (int i = 0; i < N; i++) s.v[i] = bw ? s.v[i] : t.v[i];
+        bw = sub_n8(t.v, s.v, m.v);
+    } else if constexpr (N == 12) {
+        add_n12(s.v, a.v, b.v);
+        bw = sub_n12(t.v, s.v, m.v);
     } else {
         add_n24(s.v, a.v, b.v);
-        uint32_t bw = sub_n24(t.v, s.v, m.v);
-#pragma unroll
-        for (int i = 0; i < N; i++) s.v[i] = bw ? s.v[i] : t.v[i];
+        bw = sub_n24(t.v, s.v, m.v);
     }
+#pragma unroll
+    for (int i = 0; i < N; i++) s.v[i] = bw ? s.v[i] : t.v[i];
 #else
     uint64_t c = 0;
     for (int i = 0; i < N; i++) {
@@ -112,6 +114,9 @@ HD Fp<P> sub(const Fp<P>& a, const Fp<P>& b) {
     if constexpr (N == 8) {
         uint32_t bw = sub_n8(d.v, a.v, b.v);
         addmask_n8(d.v, m.v, bw);
+    } else if constexpr (N == 12) {
+        uint32_t bw = sub_n12(d.v, a.v, b.v);
+        addmask_n12(d.v, m.v, bw);
     } else {
         uint32_t bw = sub_n24(d.v, a.v, b.v);
         addmask_n24(d.v, m.v, bw);
@@ -185,6 +190,17 @@ HD Fp<P> mul_inline(const Fp<P>& A, const Fp<P>& B) {
         uint32_t bw = sub_n8(res.v, e, p);
 #pragma unroll
         for (int i = 0; i < N; i++) res.v[i] = bw ? e[i] : res.v[i];
+    } else if constexpr (N == 12) {
+        WS_ROW0(12)
+#pragma unroll
+        for (int i = 1; i < N; i += 2) {
+            WS_ROW(12, o, e, b[i])
+            if (i + 1 < N) WS_ROW(12, e, o, b[i + 1])
+        }
+        merge_n12(e, o);
+        uint32_t bw = sub_n12(res.v, e, p);
+#pragma unroll
+        for (int i = 0; i < N; i++) res.v[i] = bw ? e[i] : res.v[i];
     } else {
         WS_ROW0(24)
 #pragma unroll
@@ -251,8 +267,8 @@ HD Fp<P> mul_inline(const Fp<P>& A, const Fp<P>& B) {
     return res;
 }
 
-// 24-limb products (~1300 instructions) go out of line: one copy per kernel instead of one per call site
-// keeps ptxas time and code size sane; the 8-limb product stays inline (it is the hot path).
+// 12- and 24-limb products (~330 / ~1300 instructions) go out of line: one copy per kernel instead of one per
+// call site keeps ptxas time and code size sane; the 8-limb product stays inline (it is the hot path).
 template <class P>
 HD_NOINLINE void mul_to(Fp<P>* r, const Fp<P>* a, const Fp<P>* b) { *r = mul_inline(*a, *b); }
 
