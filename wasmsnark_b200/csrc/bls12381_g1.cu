@@ -8,7 +8,7 @@
 //   fft over frm                            /root/reference/src/bls12381/build_bls12381.js:38  (src/build_fft.js)
 //   f2m = f1m[u]/(u^2 + 1)                  /root/reference/src/bls12381/build_bls12381.js:41  (src/build_f2m.js)
 // No bls12381 WASM image ships in the reference's build/ directory and no JS host drives this curve, so parity
-// for this file is pinned on the big-integer restatement (oracle/bls12381.py) and on the constants of
+// for this file is pinned on the big-integer restatement used by tests/test_gpu_bls.py and on the constants of
 // build_bls12381.js (q, r, generators; r * G = O), not on outputs of the reference itself: "parity unpinned".
 // Conventions follow the BN128 path: raw little-endian 32-byte scalars, affine Montgomery points x|y (2 x 48 bytes),
 // x == 0 meaning infinity, result = Jacobian triple X|Y|Z (144 bytes).
