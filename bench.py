@@ -152,13 +152,13 @@ def workload_name():
         LOG2N, "uniform in [0, r)" if SCALARS == "fr" else "uniform raw 256-bit")
 
 
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import ref_wasm
     if not ref_wasm.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (reference not mounted at build time)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref not built (reference not mounted at build time)"})
         return
     cores = usable_cores()
     sample = min(N_PAIRS, 8192 * cores)
@@ -179,7 +179,7 @@ def run_reference(args):
                          "sample": "each step = first %d pairs, %d threads x g1m_multiexp2(w=7) of the reference's WASM image compiled natively (oracle/_ref), partials combined with g1m_add" % (sample, cores)},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def timed_steps(torch, stream, step, steps, flush, barrier, world, dist):
@@ -214,8 +214,17 @@ def main():
     ap.add_argument("--no-ntt", action="store_true")
     ap.add_argument("--no-bls", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result: anything a library prints there (e.g. NCCL's version banner
+    # under NCCL_DEBUG) is sent to stderr instead, and emit() writes the result to the real stdout at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
 
     import torch
     import torch.distributed as dist
@@ -468,7 +477,7 @@ def main():
         bn.ctx.check(lib.ws_bls12381_g1_affine(h, as_ptr(bytes(outb.cpu().numpy())), ctypes.cast(aff, ctypes.c_void_p), 1, 1))
         extra["bls12381"] = {"workload": "BLS12-381 G1 MSM, 2^20 pairs (4096 distinct points tiled, uniform 256-bit scalars), single stream, L2 flushed between steps",
                              "ms_per_msm": ms, "pairs_per_s": nb / (ms * 1e-3), "matches_closed_form": BL.g1_from_affine_std(aff.raw) == want,
-                             "note": "parity unpinned for this curve (no reference image); 12-limb field products are out of line, not tuned"}
+                             "note": "parity unpinned for this curve (no reference image); same kernels as BN128 with 12-limb field elements, launch shapes not tuned"}
         del pts, sc
     if world > 1:
         dist.barrier()
@@ -652,7 +661,7 @@ def main():
                                         "sample": "first %d pairs (%.1f s), reference g1m_multiexp2(w=7) from its WASM image compiled natively, %d threads as src/bn128.js:353-383 splits; single-thread on %d pairs" % (sample, dt, cores, min(sample, 4096))}
             else:
                 line["cpu_baseline"] = {"value": None, "unit": "pairs/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
-        print(json.dumps(line))
+        emit(line)
     for b_ in reversed(bns):
         b_.terminate()
     if world > 1:

@@ -267,13 +267,14 @@ HD Fp<P> mul_inline(const Fp<P>& A, const Fp<P>& B) {
     return res;
 }
 
-// 12- and 24-limb products (~330 / ~1300 instructions) go out of line: one copy per kernel instead of one per
-// call site keeps ptxas time and code size sane; the 8-limb product stays inline (it is the hot path).
+// Big products go out of line -- one copy per kernel instead of one per call site keeps ptxas time and code size
+// sane: always for 24 limbs (~1300 instructions); for 12 limbs (~330) only under the quadratic extension (mul_ool,
+// used by fp2.cuh: a G2 point addition would inline 30 of them).  The 8-limb product stays inline (the hot path).
 template <class P>
 HD_NOINLINE void mul_to(Fp<P>* r, const Fp<P>* a, const Fp<P>* b) { *r = mul_inline(*a, *b); }
 
 template <class P>
-HD Fp<P> mul(const Fp<P>& a, const Fp<P>& b) {
+HD Fp<P> mul_ool(const Fp<P>& a, const Fp<P>& b) {
     if constexpr (P::N > 8) {
         Fp<P> r;
         mul_to<P>(&r, &a, &b);
@@ -281,6 +282,12 @@ HD Fp<P> mul(const Fp<P>& a, const Fp<P>& b) {
     } else {
         return mul_inline(a, b);
     }
+}
+
+template <class P>
+HD Fp<P> mul(const Fp<P>& a, const Fp<P>& b) {
+    if constexpr (P::N > 12) return mul_ool(a, b);
+    else return mul_inline(a, b);
 }
 
 template <class P>

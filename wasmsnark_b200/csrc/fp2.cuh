@@ -35,24 +35,24 @@ HD Fp2T<P> dbl(const Fp2T<P>& a) { return Fp2T<P>{dbl(a.c0), dbl(a.c1)}; }
 
 template <class P>
 HD Fp2T<P> mul(const Fp2T<P>& x, const Fp2T<P>& y) {
-    Fp<P> A = mul(x.c0, y.c0);
-    Fp<P> B = mul(x.c1, y.c1);
-    Fp<P> C = mul(add(x.c0, x.c1), add(y.c0, y.c1));
+    Fp<P> A = mul_ool(x.c0, y.c0);
+    Fp<P> B = mul_ool(x.c1, y.c1);
+    Fp<P> C = mul_ool(add(x.c0, x.c1), add(y.c0, y.c1));
     return Fp2T<P>{sub(A, B), sub(C, add(A, B))};
 }
 
 template <class P>
 HD Fp2T<P> sqr(const Fp2T<P>& x) {
     // (x0 + x1)(x0 - x1), 2 x0 x1
-    Fp<P> AB = mul(x.c0, x.c1);
-    Fp<P> r0 = mul(add(x.c0, x.c1), sub(x.c0, x.c1));
+    Fp<P> AB = mul_ool(x.c0, x.c1);
+    Fp<P> r0 = mul_ool(add(x.c0, x.c1), sub(x.c0, x.c1));
     return Fp2T<P>{r0, dbl(AB)};
 }
 
 template <class P>
 HD Fp2T<P> inv(const Fp2T<P>& x) {
     Fp<P> t = inv(add(sqr(x.c0), sqr(x.c1)));
-    return Fp2T<P>{mul(x.c0, t), neg(mul(x.c1, t))};
+    return Fp2T<P>{mul_ool(x.c0, t), neg(mul_ool(x.c1, t))};
 }
 
 template <class P>
