@@ -496,7 +496,9 @@ def main():
         class Lane:
             """one context + its own resident key, stream and buffers (like one of the reference's prover instances)"""
 
-            def __init__(self, b_, strm):
+            def __init__(self, b_, strm, pk=None, h_w=None, rs=None):
+                pk, h_w, rs = (pk_syn if pk is None else pk), (h_w_syn if h_w is None else h_w), (rs_syn if rs is None else rs)
+                self.h_w = h_w
                 self.bn, self.stream, self.st = b_, strm, ctypes.c_void_p(strm.cuda_stream)
                 self.key = ctypes.c_void_p()
                 t0 = time.perf_counter()
@@ -523,11 +525,41 @@ def main():
 
             def prove_e2e(self):
                 with torch.cuda.stream(self.stream):
-                    self.d_w.copy_(h_w, non_blocking=True)
+                    self.d_w.copy_(self.h_w, non_blocking=True)
                 self.prove()
                 with torch.cuda.stream(self.stream):
                     self.h_proof.copy_(self.d_proof, non_blocking=True)
 
+        pk_syn, h_w_syn, rs_syn = pk, h_w, rs
+        # ---- BASELINE configs[3]: the reference's example/bn128 proving_key.bin + witness.bin (staged next to the
+        # reference image by oracle/build_ref.py), point ranges sharded over the ranks, r = s = 0 => proof_good0.json
+        example = None
+        ex_dir = os.path.join(ROOT, "oracle", "_ref", "example_bn128")
+        if os.path.exists(os.path.join(ex_dir, "proving_key.bin")):
+            pk_e = open(os.path.join(ex_dir, "proving_key.bin"), "rb").read()
+            wit_e = open(os.path.join(ex_dir, "witness.bin"), "rb").read()
+            good = json.load(open(os.path.join(ROOT, "tests", "golden", "example_bn128.golden.json")))
+            Le = Lane(bns[0], streams[0], pk_e, torch.frombuffer(bytearray(wit_e), dtype=torch.uint8).pin_memory(), bytes(64))
+            for _ in range(W):
+                Le.prove()
+            torch.cuda.synchronize()
+            ex_ms = timed_steps(torch, stream, Le.prove, K, flush, barrier, world, dist) / K
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(K):
+                Le.prove_e2e()
+            streams[0].synchronize()
+            barrier()
+            ex_e2e = (time.perf_counter() - t0) / K
+            pb = bytes(Le.d_proof.cpu().numpy())
+            got = {"pi_a": bn.bin2g1(pb[0:96]), "pi_b": bn.bin2g2(pb[96:288]), "pi_c": bn.bin2g1(pb[288:384])}
+            kinfo = O.parse_pkey(pk_e)
+            example = {"workload": "example/bn128 proving_key.bin + witness.bin (BASELINE configs[3]): nVars %d, domainSize %d, r = s = 0" % (kinfo["nVars"], kinfo["domainSize"]),
+                       "ms_per_proof_single_stream": ex_ms, "proofs_per_s": 1000.0 / ex_ms, "e2e_ms_per_proof": 1000 * ex_e2e,
+                       "bit_exact_vs_proof_good0": all(got[k2] == good[k2] for k2 in ("pi_a", "pi_b", "pi_c")),
+                       "shard": "point ranges x%d, all_gather of 768-byte partial records" % world, "key_load_s": Le.load_s}
+            bns[0].lib.ws_bn128_pkey_free(Le.key)
+            del Le
         NP = min(NF, 2)       # proofs in flight (each lane holds its own resident key + tables)
         lanesP = [Lane(bns[i], streams[i]) for i in range(NP)]
         load_s = lanesP[0].load_s
@@ -608,7 +640,7 @@ def main():
                        "pkey_bytes": len(pk), "witness_bytes": len(wit), "shard": "point ranges x%d, all_gather of 768-byte partial records" % world, "scaling": "strong (one fixed-size proof over %d GPUs)" % world},
             "e2e": {"value": 1.0 / pe2e, "unit": "proofs/s", "h2d_bytes_per_step": len(wit), "d2h_bytes_per_step": 384, "ms_per_proof": 1000 * pe2e,
                     "note": "witness from pinned host memory each proof, two proofs in flight; proving key resident (loaded once per context: %.2f s incl. host-side row regrouping and window tables)" % load_s},
-            "dropin_call": dropin, "stages_ms": pstages, "repeatable_bit_exact": same, "algorithmic_bytes": alg_bytes,
+            "example_key": example, "dropin_call": dropin, "stages_ms": pstages, "repeatable_bit_exact": same, "algorithmic_bytes": alg_bytes,
             "hbm_frac": (alg_bytes / (pms * 1e-3) / 1e9) / peaks()[0],
             "gpu_launches_per_proof": int(prove_launches) // K, "keygen_s": gen_s,
         }
