@@ -479,6 +479,39 @@ def main():
                              "ms_per_msm": ms, "pairs_per_s": nb / (ms * 1e-3), "matches_closed_form": BL.g1_from_affine_std(aff.raw) == want,
                              "note": "parity unpinned for this curve (no reference image); same kernels as BN128 with 12-limb field elements, launch shapes not tuned"}
         del pts, sc
+    # ---- BASELINE configs[4]: MNT6753 (768-bit, 24-limb) G1 MSM 2^18 -- wide-limb correctness path, timed for the record
+    if not args.no_bls and rank == 0:
+        from oracle import mnt6753 as MN
+        nm, distinct = 1 << 18, 1024
+        rnd = random.Random(0x6753)
+        a0, d0 = rnd.randrange(MN.R_ORDER), rnd.randrange(MN.R_ORDER)
+        P, Dp = MN.times_scalar(MN.G1_GEN, a0), MN.times_scalar(MN.G1_GEN, d0)
+        base = []
+        for _ in range(distinct):
+            base.append(MN.affine_bytes_m(P))
+            P = MN.add(P, Dp)
+        pts = torch.frombuffer(bytearray(b"".join(base)), dtype=torch.uint8).view(distinct, 192).cuda().repeat(nm // distinct, 1).contiguous()
+        sc_np = np.random.default_rng(0x6753).integers(0, 256, size=(nm, 96), dtype=np.uint8)
+        sc_np[:, 94:] = 0                                     # 752-bit raw scalars
+        sc = torch.from_numpy(sc_np).cuda()
+        outm = torch.zeros(288, dtype=torch.uint8, device="cuda")
+
+        def step_mnt():
+            bn.ctx.check(lib.ws_mnt6753_g1_multiexp_dev(h, sc.data_ptr(), pts.data_ptr(), nm, outm.data_ptr(), 0, st))
+        for _ in range(W):
+            step_mnt()
+        torch.cuda.synchronize()
+        ms = timed_steps(torch, stream, step_mnt, K, flush, lambda: torch.cuda.synchronize(), 1, dist) / K
+        limbs = sc_np.view("<u4").reshape(nm // distinct, distinct, 24).astype(np.uint64).sum(axis=0)
+        tot = [sum(int(limbs[j, k]) << (32 * k) for k in range(24)) for j in range(distinct)]
+        want = MN.times_scalar(MN.G1_GEN, sum(t * (a0 + j * d0) for j, t in enumerate(tot)) % MN.R_ORDER)
+        aff = ctypes.create_string_buffer(288)
+        bn.ctx.check(lib.ws_mnt6753_g1_affine(h, as_ptr(bytes(outm.cpu().numpy())), ctypes.cast(aff, ctypes.c_void_p), 1, 1))
+        got = tuple(int.from_bytes(aff.raw[96 * i:96 * i + 96], "little") for i in range(3))
+        extra["mnt6753"] = {"workload": "MNT6753 G1 MSM, 2^18 pairs (BASELINE configs[4]; 1024 distinct points tiled, 752-bit raw scalars), single stream, L2 flushed between steps",
+                            "ms_per_msm": ms, "pairs_per_s": nm / (ms * 1e-3), "matches_closed_form": got == MN.affine_result(want),
+                            "note": "wide-limb correctness path: 24-limb products out of line, kernels spill; not tuned"}
+        del pts, sc
     if world > 1:
         dist.barrier()
 

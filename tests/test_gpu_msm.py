@@ -82,6 +82,30 @@ def test_small_sets_vs_oracle(bn, g):
             assert dec(aff(dev_multiexp(bn, g, sb, pb, len(sc), c, T))) == want, (c, T, len(sc))
 
 
+@pytest.mark.parametrize("g", [1, 2])
+def test_adversarial_4096_and_independent_points(bn, g):
+    """SURVEY 8d C2 side sets: n = 4096 drawn from 8 base points with duplicates, P / -P pairs, infinity entries and
+    the scalars {0, 1, r-1, r, 2^256-1, ...} (every bucket sees repeated and cancelling points); and a set of
+    independent k_i * G points (no arithmetic-progression structure).  Oracle: its own Pippenger."""
+    from test_host_math import gen_points
+    from test_host_msm import adversarial
+    rnd = random.Random(4096 + g)
+    F = O.Fq if g == 1 else O.Fq2
+    gen = O.G1_GEN if g == 1 else O.G2_GEN
+    enc = util.g1_affine_m if g == 1 else util.g2_affine_m
+    dec = util.g1_result_tuple if g == 1 else util.g2_result_tuple
+    aff = bn.g1_affine if g == 1 else bn.g2_affine
+    fn = bn.g1_multiexp if g == 1 else bn.g2_multiexp
+    n_ind = 1536 if g == 1 else 384
+    ind = gen_points(F, gen, rnd, n_ind)
+    for sc, ps in (adversarial(F, gen, rnd, 4096 if g == 1 else 1024), ([rnd.getrandbits(256) for _ in range(n_ind)], ind)):
+        want = O.pt_affine(F, O.multiexp(F, sc, ps))
+        sb = b"".join(b32(s) for s in sc)
+        pb = b"".join(enc(P) for P in ps)
+        assert dec(aff(fn(sb, pb))) == want
+        assert dec(aff(dev_multiexp(bn, g, sb, pb, len(sc), 9, 5))) == want
+
+
 def test_group_identities_from_reference_suite(bn):
     """test/bn128.js:84-185 through the MSM entry points: r * G = infinity, 10 * P = P added ten times,
     P + (-P) = infinity, for G1 and G2."""

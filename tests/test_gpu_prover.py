@@ -62,11 +62,14 @@ def test_fft_rejects_bad_sizes(bn):
             bn.fft(bytes(32 * n))
 
 
-def test_fft_interleave_identity_2p16(bn):
-    """test/fft.js:71-121 at N = 2^16: FFT_2N(x | 0) = interleave(FFT_N(x), FFT_N(x, odd))."""
-    n = 1 << 16
+@pytest.mark.parametrize("logn", [16, 20])
+def test_fft_interleave_identity(bn, logn):
+    """test/fft.js:71-121 at N = 2^16 and 2^20: FFT_2N(x | 0) = interleave(FFT_N(x), FFT_N(x, odd))."""
+    n = 1 << logn
     rng = np.random.Generator(np.random.PCG64(0xB203))
-    x = b"".join((int.from_bytes(rng.bytes(40), "little") % O.R_ORDER).to_bytes(32, "little") for _ in range(n))
+    raw = np.frombuffer(rng.bytes(32 * n), dtype=np.uint8).reshape(n, 32).copy()
+    raw[:, 31] &= 0x1F                                       # < 2^253 < r: canonical residues
+    x = raw.tobytes()
     big = np.frombuffer(bn.fft(x + bytes(32 * n)), dtype=np.uint8).reshape(2 * n, 32)
     even = np.frombuffer(bn.fft(x, 0), dtype=np.uint8).reshape(n, 32)
     odd = np.frombuffer(bn.fft(x, 1), dtype=np.uint8).reshape(n, 32)

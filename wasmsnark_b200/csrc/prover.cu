@@ -15,6 +15,8 @@
 #include <cuda_runtime.h>
 #include <sys/random.h>
 #include <cstdio>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -411,6 +413,15 @@ static int pkey_load(ws_ctx* c, const uint8_t* pkey, size_t len, ws_pkey** out, 
           pPC + nC * 64 <= len && pPH + (size_t)dom * 64 <= len))
         return c->fail(WS_E_ARG, "proving key sections out of bounds");
     cudaSetDevice(c->device);
+    const bool trace = getenv("WS_TRACE_LOAD") != nullptr;     // stage times of the key load on stderr
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        cudaStreamSynchronize(c->stream);
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ws pkey_load] %-14s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
     std::vector<uint32_t> rs, sg;
     std::vector<uint8_t> cf;
     ws_pkey* k = new ws_pkey();
@@ -424,15 +435,23 @@ static int pkey_load(ws_ctx* c, const uint8_t* pkey, size_t len, ws_pkey** out, 
     shard_range(nv, rank, world, &k->v_lo, &k->v_cnt);
     shard_range((uint32_t)nC, rank, world, &k->c_lo, &k->c_cnt);
     shard_range(dom, rank, world, &k->h_lo, &k->h_cnt);
-    // the reference slices polsA as [pPolsA, pPolsA + pPolsB) (src/bn128.js:592); the section proper ends at pPolsB
-    if (!build_csr(pkey + pA, pB - pA, nv, dom, rs, sg, cf) || !upload_csr(rs, sg, cf, k->polA, c->stream)) {
+    // the reference slices polsA as [pPolsA, pPolsA + pPolsB) (src/bn128.js:592); the section proper ends at pPolsB.
+    // The two sections are regrouped by row on two host threads.
+    std::vector<uint32_t> rs2, sg2;
+    std::vector<uint8_t> cf2;
+    bool okA = false, okB = false;
+    std::thread tb([&] { okB = build_csr(pkey + pB, pPA - pB, nv, dom, rs2, sg2, cf2); });
+    okA = build_csr(pkey + pA, pB - pA, nv, dom, rs, sg, cf);
+    tb.join();
+    if (!okA || !upload_csr(rs, sg, cf, k->polA, c->stream)) {
         pkey_release(k);
         return c->fail(WS_E_ARG, "polsA section malformed (or out of device memory)");
     }
-    if (!build_csr(pkey + pB, pPA - pB, nv, dom, rs, sg, cf) || !upload_csr(rs, sg, cf, k->polB, c->stream)) {
+    if (!okB || !upload_csr(rs2, sg2, cf2, k->polB, c->stream)) {
         pkey_release(k);
         return c->fail(WS_E_ARG, "polsB section malformed (or out of device memory)");
     }
+    lap("csr A+B");
     const size_t vc = k->v_cnt, cc = k->c_cnt, hc = k->h_cnt;
     size_t oA = 0, oB1 = oA + align256(vc * 64 + 64), oB2 = oB1 + align256(vc * 64 + 64), oC = oB2 + align256(vc * 128 + 64),
            oH = oC + align256(cc * 64 + 64), tot = oH + align256(hc * 64 + 64);
@@ -457,8 +476,10 @@ static int pkey_load(ws_ctx* c, const uint8_t* pkey, size_t len, ws_pkey** out, 
         pkey_release(k);
         return c->fail_cuda("proving key upload");
     }
+    lap("points h2d");
     if (c->key_tables) {
         build_key_tables(c, k);
+        lap("window tables");
         if (cudaMalloc(&k->fixed_tables, sizeof(FixedBaseTables)) == cudaSuccess) {
             k_build_fixed_tables<<<(D1_WINDOWS + D2_WINDOWS + 63) / 64, 64, 0, c->stream>>>(k->fixed, k->fixed_tables);
             if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
@@ -470,6 +491,7 @@ static int pkey_load(ws_ctx* c, const uint8_t* pkey, size_t len, ws_pkey** out, 
             cudaGetLastError();
             k->fixed_tables = nullptr;
         }
+        lap("fixed tables");
     }
     *out = k;
     return WS_OK;
