@@ -209,6 +209,12 @@ int ws_bn128_pkey_load(ws_ctx* ctx, const uint8_t* pkey, size_t pkey_len, ws_pke
  * about 13x the key's point bytes): all digit windows of an MSM then share one bucket set and the result needs no
  * doublings.  on = 0 disables them for keys loaded afterwards (same results, table-free MSM).  Default on.       */
 int ws_set_key_tables(ws_ctx* ctx, int on);
+/* Tuning hook: on != 0 runs the prover's one dependent chain (constructLC -> five NTTs -> H MSM; the reference's
+ * CALC_H task and the multiexp that waits for it, src/bn128.js:607-622) on an internal high-priority stream, forked
+ * from and joined to the caller's stream, so the four witness MSMs on the side streams do not stretch it.  Same
+ * results.  Measured at 2^20 constraints: the chain ends 3x earlier but the proof takes the same 21.5 ms (the GPU
+ * is throughput-bound), so the default is off. */
+int ws_set_h_priority(ws_ctx* ctx, int on);
 void ws_bn128_pkey_free(ws_pkey* key);
 int ws_bn128_pkey_info(const ws_pkey* key, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size);
 int ws_bn128_groth16_prove_key(ws_ctx* ctx, const ws_pkey* key, const uint8_t* witness, size_t witness_len,

@@ -58,6 +58,7 @@ SIGNATURES = {
     "ws_bn128_groth16_prove": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
     "ws_set_key_tables": (_i, [_vp, _i]),
     "ws_set_key_cache": (_i, [_vp, _i]),
+    "ws_set_h_priority": (_i, [_vp, _i]),
     "ws_bn128_groth16_verify": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp]),
     "ws_bn128_pairing": (_i, [_vp, _vp, _vp]),
     "ws_bls12381_fq2_mul_batch": (_i, [_vp, _vp, _vp, _vp, _sz]),

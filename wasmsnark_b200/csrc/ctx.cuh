@@ -48,13 +48,20 @@ struct ws_ctx {
     cudaEvent_t fork_ev = nullptr;
     bool lanes_ready = false;
     bool pre_pending = false;   // prover: (r, s) products already in flight on lanes[4]
+    bool h_priority = false;    // prover: run the H chain on the high-priority lane (ws_set_h_priority)
+    cudaEvent_t h_done = nullptr;
     bool ensure_lanes() {
         if (lanes_ready) return true;
+        int prio_least = 0, prio_greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
         for (int i = 0; i < NLANES; i++) {
-            if (cudaStreamCreateWithFlags(&lanes[i], cudaStreamNonBlocking) != cudaSuccess) return false;
+            // lanes[5] carries the H chain (LC, five NTTs, H MSM) at the highest priority: its blocks are scheduled
+            // ahead of the four witness MSMs on lanes 0..3, so the one dependent chain of a proof is not stretched
+            if (cudaStreamCreateWithPriority(&lanes[i], cudaStreamNonBlocking, i == 5 ? prio_greatest : prio_least) != cudaSuccess) return false;
             if (cudaEventCreateWithFlags(&lane_done[i], cudaEventDisableTiming) != cudaSuccess) return false;
         }
         if (cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming) != cudaSuccess) return false;
+        if (cudaEventCreateWithFlags(&h_done, cudaEventDisableTiming) != cudaSuccess) return false;
         lanes_ready = true;
         return true;
     }

@@ -578,9 +578,16 @@ static int prove_partials_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_witn
         cudaEventRecord(c->lane_done[lane], ls);
     }
     if (rc) return rc;
-    if ((rc = calc_h_dev(c, k->polA, k->polB, (const Fr*)d_witness, nv, k->logn, h, work, st))) return rc;
-    if ((rc = msm_g1_run(c, h + k->h_lo, k->tH ? k->tH : (const void*)k->H, k->h_cnt, nullptr, rH, st, 1, k->tc_h))) return rc;
-    c->timer.mark("msm:H", st);
+    // the dependent chain (LC -> NTTs -> H MSM) runs on the high-priority lane, forked from / joined to `st`
+    cudaStream_t hs = c->h_priority ? c->lanes[5] : st;
+    if (hs != st) cudaStreamWaitEvent(hs, c->fork_ev, 0);
+    if ((rc = calc_h_dev(c, k->polA, k->polB, (const Fr*)d_witness, nv, k->logn, h, work, hs))) return rc;
+    if ((rc = msm_g1_run(c, h + k->h_lo, k->tH ? k->tH : (const void*)k->H, k->h_cnt, nullptr, rH, hs, 1, k->tc_h))) return rc;
+    c->timer.mark("msm:H", hs);
+    if (hs != st) {
+        cudaEventRecord(c->h_done, hs);
+        cudaStreamWaitEvent(st, c->h_done, 0);
+    }
     for (int lane = 0; lane < 4; lane++) cudaStreamWaitEvent(st, c->lane_done[lane], 0);
     c->timer.mark("msm:A,B1,B2,C (side streams)", st);
     return cudaGetLastError() == cudaSuccess ? WS_OK : c->fail_cuda("prove");
@@ -720,6 +727,11 @@ static int fft_host(ws_ctx* c, uint8_t* px, size_t n, int odd, int inverse) {
 WS_API int ws_bn128_fr_fft(ws_ctx* c, uint8_t* px, size_t n, int odd) { return fft_host(c, px, n, odd, 0); }
 WS_API int ws_bn128_fr_ifft(ws_ctx* c, uint8_t* px, size_t n, int odd) { return fft_host(c, px, n, odd, 1); }
 
+WS_API int ws_set_h_priority(ws_ctx* c, int on) {
+    if (!c) return WS_E_ARG;
+    c->h_priority = on != 0;
+    return WS_OK;
+}
 WS_API int ws_set_key_tables(ws_ctx* c, int on) {
     if (!c) return WS_E_ARG;
     c->key_tables = on != 0;
