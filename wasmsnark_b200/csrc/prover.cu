@@ -201,43 +201,43 @@ static __global__ void __launch_bounds__(128) k_assemble_pre(const FixedPoints* 
     }
 }
 
-// After the multi-scalar multiplications: 3 warps.
-//   warp 0: pi_a = A + alfa1 + r*delta1, s*pi_a        (src/bn128.js:670-673, :691)
-//   warp 1: pib1 = B1 + beta1 + s*delta1, r*pib1       (:680-683, :695)
-//   warp 2: pi_b = B2 + beta2 + s*delta2               (:675-678)
-//   then    pi_c = C + H + s*pi_a + r*pib1 - (r*s)*delta1   (:686-704), affine + fromMontgomery (:706-712)
-static __global__ void __launch_bounds__(96) k_assemble_post(AssembleArgs g, const PreProducts* __restrict__ pre) {
-    __shared__ G1X s_spia, s_rpib1;
+// After the multi-scalar multiplications: 4 warps, three phases.
+//   phase 1  warp 0: pi_a = A + alfa1 + r*delta1          (src/bn128.js:670-673)
+//            warp 1: pib1 = B1 + beta1 + s*delta1         (:680-683)
+//            warp 2: pi_b = B2 + beta2 + s*delta2         (:675-678)
+//            warp 3: C + H - (r*s)*delta1                 (:686-688, :699-704)
+//   phase 2  warp 0: s*pi_a   warp 1: r*pib1              (:691, :695; warp-cooperative scalar multiplications)
+//            warp 2: pi_b -> affine, fromMontgomery       warp 3: pi_a -> affine  (:706-712; inversions off the critical path)
+//   phase 3  pi_c = phase-1 sum + s*pi_a + r*pib1, affine + fromMontgomery
+static __global__ void __launch_bounds__(128) k_assemble_post(AssembleArgs g, const PreProducts* __restrict__ pre) {
+    __shared__ G1X s_pia, s_pib1, s_spia, s_rpib1, s_pic0;
+    __shared__ G2X s_pib;
     __shared__ uint8_t s_rs[64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < 64) s_rs[threadIdx.x] = g.rs[threadIdx.x];
-    __syncthreads();
     const uint8_t* r = s_rs;
     const uint8_t* s = s_rs + 32;
+    if (lane == 0) {
+        if (warp == 0) s_pia = padd_call<G1Curve>(pre->rd1, padd_call<G1Curve>(load_fixed<G1Curve>(g.fx->alfa1), *g.A));
+        else if (warp == 1) s_pib1 = padd_call<G1Curve>(pre->sd1, padd_call<G1Curve>(load_fixed<G1Curve>(g.fx->beta1), *g.B1));
+        else if (warp == 2) s_pib = padd_call<G2Curve>(pre->sd2, padd_call<G2Curve>(load_fixed<G2Curve>(g.fx->beta2), *g.B2));
+        else s_pic0 = padd_call<G1Curve>(pneg<G1Curve>(pre->rsd1), padd_call<G1Curve>(*g.H, *g.C));
+    }
+    __syncthreads();
     if (warp == 0) {
-        G1X pia = padd_call<G1Curve>(load_fixed<G1Curve>(g.fx->alfa1), *g.A);
-        pia = padd_call<G1Curve>(pre->rd1, pia);
-        G1X v = times_scalar_w4_warp<G1Curve>(pia, s, 32);
-        if (lane == 0) {
-            s_spia = v;
-            *g.pi_a = affine_std<G1Curve>(pia);
-        }
+        G1X v = times_scalar_w4_warp<G1Curve>(s_pia, s, 32);
+        if (lane == 0) s_spia = v;
     } else if (warp == 1) {
-        G1X pib1 = padd_call<G1Curve>(load_fixed<G1Curve>(g.fx->beta1), *g.B1);
-        pib1 = padd_call<G1Curve>(pre->sd1, pib1);
-        G1X v = times_scalar_w4_warp<G1Curve>(pib1, r, 32);
+        G1X v = times_scalar_w4_warp<G1Curve>(s_pib1, r, 32);
         if (lane == 0) s_rpib1 = v;
     } else if (lane == 0) {
-        G2X pib = padd_call<G2Curve>(load_fixed<G2Curve>(g.fx->beta2), *g.B2);
-        pib = padd_call<G2Curve>(pre->sd2, pib);
-        *g.pi_b = affine_std<G2Curve>(pib);
+        if (warp == 2) *g.pi_b = affine_std<G2Curve>(s_pib);
+        else *g.pi_a = affine_std<G1Curve>(s_pia);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        G1X pic = padd_call<G1Curve>(*g.H, *g.C);
-        pic = padd_call<G1Curve>(s_spia, pic);
+        G1X pic = padd_call<G1Curve>(s_spia, s_pic0);
         pic = padd_call<G1Curve>(s_rpib1, pic);
-        pic = padd_call<G1Curve>(pneg<G1Curve>(pre->rsd1), pic);
         *g.pi_c = affine_std<G1Curve>(pic);
     }
 }
@@ -649,7 +649,7 @@ static int prove_finish_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_all, i
     g.pi_b = (Jac<G2Curve>*)(d_out + 96);
     g.pi_c = (Jac<G1Curve>*)(d_out + 288);
     c->launches += 1 + (world > 1 ? 1 : 0);
-    k_assemble_post<<<1, 96, 0, st>>>(g, (const PreProducts*)c->arena(6, sizeof(PreProducts)));
+    k_assemble_post<<<1, 128, 0, st>>>(g, (const PreProducts*)c->arena(6, sizeof(PreProducts)));
     c->timer.mark("assemble", st);
     return cudaGetLastError() == cudaSuccess ? WS_OK : c->fail_cuda("prove");
 }
