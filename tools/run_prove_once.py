@@ -1,5 +1,5 @@
 """Profiling driver: a few Groth16 proofs on a synthetic key (for ncu launch lists / kernel captures).
-usage: python tools/run_prove_once.py [log2 constraints] [reps]"""
+usage: python tools/run_prove_once.py [log2 constraints] [reps] [tables 0/1] [accumulate variant] [h priority 0/1] [back-to-back loops]"""
 import ctypes
 import os
 import sys
@@ -17,7 +17,8 @@ lg = int(sys.argv[1]) if len(sys.argv) > 1 else 18
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 tables = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 variant = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-hprio = int(sys.argv[5]) if len(sys.argv) > 5 else 1
+hprio = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+loops = int(sys.argv[6]) if len(sys.argv) > 6 else 10
 pk, wit = gen_synth_key.make(1 << lg, 58, 1 << lg, seed=0xB204)
 bn = build_bn128(0)
 key = ctypes.c_void_p()
@@ -40,10 +41,11 @@ for r in range(reps):
 bn.lib.ws_set_profiling(bn.ctx.h, 0)
 torch.cuda.synchronize()
 t0 = time.perf_counter()
-for r in range(10):
+for r in range(loops):
     bn.ctx.check(bn.lib.ws_bn128_groth16_prove_dev(bn.ctx.h, key, d_w.data_ptr(), d_rs.data_ptr(), d_out.data_ptr(), None))
 torch.cuda.synchronize()
-print("h_priority=%d: %.3f ms per proof (10 back to back on the context stream, host clock)" % (hprio, (time.perf_counter() - t0) * 100))
+if loops:
+    print("h_priority=%d: %.3f ms per proof (%d back to back on the context stream, host clock)" % (hprio, (time.perf_counter() - t0) * 1000 / loops, loops))
 proof = bytes(d_out.cpu().numpy()).hex()
 print("proof sha:", __import__("hashlib").sha256(bytes.fromhex(proof)).hexdigest()[:16])
 print("prove 2^%d variant %d:" % (lg, variant), " ".join("%s=%.3f" % kv for kv in t), "total=%.3f" % sum(v for _, v in t))
