@@ -55,3 +55,15 @@ def test_product_package_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src.replace("the oracle/", ""), f
+
+
+def test_node_addon_type_checks_against_the_header():
+    """node/wasmsnark_b200_addon.c (the N-API binding of INTEGRATION.md) cannot be built here -- no Node.js -- but
+    it must at least compile against include/wasmsnark_b200.h and a declaration-only N-API stub."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    assert cc, "no C compiler"
+    r = subprocess.run([cc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I" + os.path.join(ROOT, "tests", "host", "napi_stub"),
+                        "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "node", "wasmsnark_b200_addon.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
