@@ -74,4 +74,7 @@ function groth16GenProof(witness, provingKey, cb) {
     else return p;
 }
 
-module.exports = { buildBn128, groth16GenProof, genZKSnarkProof: groth16GenProof };
+// snarkjs proof.json as shipped in example/bn128/proof_good.json
+const proofJson = (p) => JSON.stringify({ pi_a: p.pi_a, pi_b: p.pi_b, pi_c: p.pi_c, protocol: "groth" }, null, 1);
+
+module.exports = { buildBn128, groth16GenProof, genZKSnarkProof: groth16GenProof, proofJson };

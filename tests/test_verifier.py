@@ -67,6 +67,15 @@ def test_verify_same_verdicts_as_reference():
     assert seen == {True, False}
 
 
+def test_proof_json_shape_matches_the_shipped_example():
+    from wasmsnark_b200 import proof_json
+    g = json.load(open(os.path.join(GOLD, "example_bn128.verify.json")))
+    good = g["cases"][0]["proof"]
+    back = json.loads(proof_json(good))
+    assert list(back.keys()) == ["pi_a", "pi_b", "pi_c", "protocol"] and back["protocol"] == "groth"      # example/bn128/proof_good.json
+    assert groth16Verify(g["verification_key"], g["cases"][0]["public"], back)
+
+
 def test_verify_tamper_sweep():
     """flipping any single proof coordinate to another curve point's, or any one public input, must reject"""
     g = json.load(open(os.path.join(GOLD, "example_bn128.verify.json")))

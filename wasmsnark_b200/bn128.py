@@ -181,6 +181,13 @@ def groth16GenProof(witness, provingKey, cb=None, device=0):
 genZKSnarkProof = groth16GenProof
 
 
+def proof_json(proof):
+    """The snarkjs proof.json the reference's example ships (example/bn128/proof_good.json): the prover's object
+    plus "protocol": "groth", as text."""
+    import json
+    return json.dumps({"pi_a": proof["pi_a"], "pi_b": proof["pi_b"], "pi_c": proof["pi_c"], "protocol": "groth"}, indent=1)
+
+
 def _le32(v):
     return int(v).to_bytes(32, "little")
 
