@@ -31,18 +31,19 @@ __device__ __forceinline__ F lane_pick4(int lane, const F& a0, const F& a1, cons
     return select(lane == 0, a0, select(lane == 1, a1, select(lane == 2, a2, a3)));
 }
 
-// 2p [dbl-2008-s-1, a = 0]: 3 product levels instead of 9 sequential products.  All lanes: identical p in, identical 2p out.
+// 2p [dbl-2008-s-1; the a ZZ^2 term joins level 1 when a != 0]: 3 product levels instead of 9-10 sequential products.
+// All lanes: identical p in, identical 2p out.
 template <class C>
 __device__ __forceinline__ XYZZ<C> pdbl_warp4(const XYZZ<C>& p) {
     using F = typename C::F;
-    if (!C::A_ZERO) return pdbl_call<C>(p);
     if (p.is_inf()) return p;
     const int lane = threadIdx.x & 31;
     F U = dbl(p.y);
-    // level 1: V = U^2 | XX = X^2
-    F r1 = sqr(select(lane == 0, U, p.x));
+    // level 1: V = U^2 | XX = X^2 | (a != 0) ZZ^2
+    F r1 = sqr(lane_pick4<F>(lane, U, p.x, p.zz, p.zz));
     F V = shfl_bcast_struct(r1, 0), XX = shfl_bcast_struct(r1, 1);
     F M = add(dbl(XX), XX);
+    if (!C::A_ZERO) M = add(M, C::mul_a(shfl_bcast_struct(r1, 2)));
     // level 2: W = U V | S = X V | MM = M^2 | ZZ3 = V ZZ
     F r2 = mul(lane_pick4<F>(lane, U, p.x, M, V), lane_pick4<F>(lane, V, V, M, p.zz));
     F W = shfl_bcast_struct(r2, 0), S = shfl_bcast_struct(r2, 1), MM = shfl_bcast_struct(r2, 2), ZZ3 = shfl_bcast_struct(r2, 3);
