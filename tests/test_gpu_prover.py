@@ -116,6 +116,22 @@ def test_synth_small_calch_and_proofs(bn):
     bn.lib.ws_set_key_tables(bn.ctx.h, 1)
 
 
+def test_h_priority_hook_gives_the_same_proof(bn):
+    """ws_set_h_priority only moves the H chain to another stream: same bytes."""
+    pk = open(os.path.join(GOLD, "synth_small.pkey.bin"), "rb").read()
+    wit = open(os.path.join(GOLD, "synth_small.witness.bin"), "rb").read()
+    g = json.load(open(os.path.join(GOLD, "synth_small.golden.json")))
+    r, s = bytes.fromhex(g["r"]), bytes.fromhex(g["s"])
+    key = bn.load_proving_key(pk)
+    try:
+        bn.lib.ws_set_h_priority(bn.ctx.h, 1)
+        for _ in range(3):
+            assert bn.groth16GenProof(wit, key, r=r, s=s) == g["proof_rs"]
+    finally:
+        bn.lib.ws_set_h_priority(bn.ctx.h, 0)
+        key.free()
+
+
 def test_stateless_call_key_cache(bn):
     """ws_bn128_groth16_prove keeps the previous call's uploaded key, keyed by content: same key -> reused, a key of
     the same length with different content -> replaced (never a stale proof), cache off -> same bytes."""
