@@ -53,6 +53,7 @@ WS_API void ws_destroy(ws_ctx* c) {
             cudaEventDestroy(c->lane_done[i]);
         }
         cudaEventDestroy(c->fork_ev);
+        cudaEventDestroy(c->h_done);
     }
     cudaStreamDestroy(c->stream);
     delete c;
