@@ -182,6 +182,35 @@ def run_reference(args, emit):
     emit(line)
 
 
+def verifier_line(reps=10):
+    """the host-side Groth16 verifier on the reference's example proof, next to the reference's own
+    groth16Verify (its WASM image compiled natively) on the same host core.  CPU only."""
+    from wasmsnark_b200 import groth16Verify
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "example_bn128.verify.json")))
+    vk, c = g["verification_key"], g["cases"][0]
+    ok = groth16Verify(vk, c["public"], c["proof"])
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ok = groth16Verify(vk, c["public"], c["proof"]) and ok
+    ms = 1000 * (time.perf_counter() - t0) / reps
+    bad = not groth16Verify(vk, g["cases"][2]["public"], g["cases"][2]["proof"])
+    out = {"workload": "groth16Verify on example/bn128 (58 public inputs, 4 pairings), one host core", "ms_per_verify": ms,
+           "accepts_good_rejects_tampered": bool(ok and bad), "reference_ms_per_verify": None}
+    try:
+        from oracle import ref_wasm
+        if ref_wasm.available():
+            m = ref_wasm.RefInstance(pages=1000)
+            ref_wasm.groth16_verify(vk, c["public"], c["proof"], inst=m)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                ref_wasm.groth16_verify(vk, c["public"], c["proof"], inst=m)
+            out["reference_ms_per_verify"] = 1000 * (time.perf_counter() - t0) / 3
+            m.close()
+    except Exception as e:      # noqa: BLE001 -- the reference leg is optional
+        out["reference_error"] = str(e)[:200]
+    return out
+
+
 def timed_steps(torch, stream, step, steps, flush, barrier, world, dist):
     """K steps, each bracketed by its own CUDA-event pair on the launch stream, L2 flushed in between
     (outside the pairs); returns (sum of step times in ms, max over ranks)."""
@@ -679,6 +708,8 @@ def main():
         for ln in lanesP:
             ln.bn.lib.ws_bn128_pkey_free(ln.key)
 
+    if rank == 0 and not args.no_prove:
+        extra["verifier"] = verifier_line()
     if rank == 0:
         serial_ms = total_ms / K
         ms_per_step = pipe_ms / K

@@ -53,6 +53,10 @@ def more(b, tag):
     if b.get("bls12381"):
         out.append("| BLS12-381 G1 MSM 2^20 (SURVEY 8f rank 4, parity unpinned) | %.1f ms (%.1f M pairs/s); closed form: %s |"
                    % (b["bls12381"]["ms_per_msm"], b["bls12381"]["pairs_per_s"] / 1e6, b["bls12381"]["matches_closed_form"]))
+    if b.get("verifier"):
+        v = b["verifier"]
+        out.append("| host-side `groth16Verify` on the example proof (SURVEY 8f rank 3), one core | %.1f ms per verification (reference image compiled natively: %s ms); accepts good / rejects tampered: %s |"
+                   % (v["ms_per_verify"], "%.1f" % v["reference_ms_per_verify"] if v.get("reference_ms_per_verify") else "n/a", v["accepts_good_rejects_tampered"]))
     rows = []
     for n_, f in ((1, "%s_bench_n1.json"), (2, "%s_bench_n2.json"), (4, "%s_bench_n4.json"), (8, "%s_bench_n8.json")):
         fp = os.path.join(P, f % tag)

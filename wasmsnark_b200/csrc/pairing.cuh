@@ -38,6 +38,94 @@ static inline F2 mul_xi(const F2& a) {
     return F2{sub(n0, a.c1), add(n1, a.c0)};
 }
 
+// Inverse of a Montgomery residue x = a R by the binary "almost inverse" (Kaliski): phase 1 yields x^-1 2^k mod p with
+// 256 <= k <= 512 using only shifts and subtractions; the result a^-1 R = x^-1 R^2 = (x^-1 2^k) 2^(512-k) follows by
+// modular doublings.  ~10x cheaper on a CPU than the a^(p-2) ladder the kernels use; inverse(0) = 0 like f1m_inverse.
+struct U256 {
+    uint64_t w[4];
+};
+static inline bool u_is_zero(const U256& a) { return (a.w[0] | a.w[1] | a.w[2] | a.w[3]) == 0; }
+static inline bool u_gt(const U256& a, const U256& b) {
+    for (int i = 3; i >= 0; i--)
+        if (a.w[i] != b.w[i]) return a.w[i] > b.w[i];
+    return false;
+}
+static inline uint64_t u_add(U256& a, const U256& b) {   // a += b, returns carry
+    unsigned __int128 c = 0;
+    for (int i = 0; i < 4; i++) {
+        c += (unsigned __int128)a.w[i] + b.w[i];
+        a.w[i] = (uint64_t)c;
+        c >>= 64;
+    }
+    return (uint64_t)c;
+}
+static inline void u_sub(U256& a, const U256& b) {       // a -= b (a >= b)
+    unsigned __int128 bw = 0;
+    for (int i = 0; i < 4; i++) {
+        unsigned __int128 d = (unsigned __int128)a.w[i] - b.w[i] - bw;
+        a.w[i] = (uint64_t)d;
+        bw = (uint64_t)(d >> 64) & 1;
+    }
+}
+static inline void u_shr1(U256& a) {
+    for (int i = 0; i < 3; i++) a.w[i] = (a.w[i] >> 1) | (a.w[i + 1] << 63);
+    a.w[3] >>= 1;
+}
+static inline uint64_t u_shl1(U256& a) {                 // returns the bit shifted out
+    uint64_t out = a.w[3] >> 63;
+    for (int i = 3; i > 0; i--) a.w[i] = (a.w[i] << 1) | (a.w[i - 1] >> 63);
+    a.w[0] <<= 1;
+    return out;
+}
+static inline Fq fq_inv_fast(const Fq& x) {
+    U256 p, u, v, r{{0, 0, 0, 0}}, s{{1, 0, 0, 0}};
+    for (int i = 0; i < 4; i++) {
+        p.w[i] = BN128_Fq::mod(2 * i) | ((uint64_t)BN128_Fq::mod(2 * i + 1) << 32);
+        v.w[i] = x.v[2 * i] | ((uint64_t)x.v[2 * i + 1] << 32);
+    }
+    if (u_is_zero(v)) return x;
+    u = p;
+    int k = 0;
+    // invariants: x r = -u 2^k, x s = v 2^k (mod p); r, s < 2p fit 256 bits because p < 2^254
+    while (!u_is_zero(v)) {
+        if (!(u.w[0] & 1)) {
+            u_shr1(u);
+            u_shl1(s);
+        } else if (!(v.w[0] & 1)) {
+            u_shr1(v);
+            u_shl1(r);
+        } else if (u_gt(u, v)) {
+            u_sub(u, v);
+            u_shr1(u);
+            u_add(r, s);
+            u_shl1(s);
+        } else {
+            u_sub(v, u);
+            u_shr1(v);
+            u_add(s, r);
+            u_shl1(r);
+        }
+        k++;
+    }
+    if (!u_gt(p, r)) u_sub(r, p);           // r in [0, 2p) -> [0, p)
+    U256 t = p;
+    u_sub(t, r);                            // x^-1 2^k = p - r
+    for (; k < 512; k++) {                  // times 2^(512 - k)
+        u_shl1(t);                          // t < p < 2^254: no bit is lost
+        if (!u_gt(p, t)) u_sub(t, p);
+    }
+    Fq out;
+    for (int i = 0; i < 4; i++) {
+        out.v[2 * i] = (uint32_t)t.w[i];
+        out.v[2 * i + 1] = (uint32_t)(t.w[i] >> 32);
+    }
+    return out;
+}
+static inline F2 f2_inv_fast(const F2& x) {              // 1 / (c0^2 + c1^2) * (c0, -c1)   (src/build_f2m.js:275-333)
+    Fq t = fq_inv_fast(add(sqr(x.c0), sqr(x.c1)));
+    return F2{mul(x.c0, t), neg(mul(x.c1, t))};
+}
+
 // ---------------------------------------------------------------- Fq6 = Fq2[v]/(v^3 - xi)
 struct F6 {
     F2 a0, a1, a2;
@@ -61,7 +149,7 @@ static inline F6 inv(const F6& x) {
     F2 B = sub(mul_xi(sqr(x.a2)), mul(x.a0, x.a1));
     F2 C = sub(sqr(x.a1), mul(x.a0, x.a2));
     F2 t = add(mul(x.a0, A), mul_xi(add(mul(x.a2, B), mul(x.a1, C))));
-    F2 ti = inv(t);
+    F2 ti = f2_inv_fast(t);
     return F6{mul(A, ti), mul(B, ti), mul(C, ti)};
 }
 
@@ -156,7 +244,7 @@ static inline void batch_inv(F2* d, int n) {
         pre[i] = acc;
         acc = mul(acc, d[i]);
     }
-    acc = inv(acc);
+    acc = f2_inv_fast(acc);
     for (int i = n - 1; i >= 0; i--) {
         F2 t = mul(acc, pre[i]);
         acc = mul(acc, d[i]);
