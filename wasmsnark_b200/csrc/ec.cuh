@@ -27,14 +27,14 @@ struct G1Curve {
     static constexpr bool A_ZERO = true;
     static constexpr bool PROJECTIVE = false;   // external triple is Jacobian (x = X/Z^2, y = Y/Z^3)
     static constexpr int SCALAR_LIMBS = 8;
-    HD static F mul_a(const F& x) { return F::zero(); }
+    HD static F mul_a(const F&) { return F::zero(); }
 };
 struct G2Curve {
     using F = Fq2;
     static constexpr bool A_ZERO = true;
     static constexpr bool PROJECTIVE = false;
     static constexpr int SCALAR_LIMBS = 8;
-    HD static F mul_a(const F& x) { return F::zero(); }
+    HD static F mul_a(const F&) { return F::zero(); }
 };
 
 // MNT6753 G1: y^2 = x^3 + 11 x + b over the 753-bit field (24 limbs); the reference builds it with
@@ -63,14 +63,14 @@ struct BlsG1Curve {
     static constexpr bool A_ZERO = true;
     static constexpr bool PROJECTIVE = false;
     static constexpr int SCALAR_LIMBS = 8;
-    HD static F mul_a(const F& x) { return F::zero(); }
+    HD static F mul_a(const F&) { return F::zero(); }
 };
 struct BlsG2Curve {
     using F = BlsFq2;
     static constexpr bool A_ZERO = true;
     static constexpr bool PROJECTIVE = false;
     static constexpr int SCALAR_LIMBS = 8;
-    HD static F mul_a(const F& x) { return F::zero(); }
+    HD static F mul_a(const F&) { return F::zero(); }
 };
 
 template <class C>
