@@ -117,7 +117,64 @@ def gen(N):
     w("        : %s);" % ", ".join('"r"(t[%d])' % i for i in range(N)))
     w("}")
     w("")
+    if N == 8:
+        gen_from_variants(N, w)
     return "\n".join(L)
+
+
+def shift_mad_from_ins(N, K):
+    """shift_mad_n with the products of pairs k < K known to be zero (the dedicated squaring skips a_j * a_i, j < i):
+    those positions only move O down by two limbs and carry.  Operands: 0..N-1 O, N = E0, N+1.. = a[2k] (k >= K), last = bi."""
+    H = N // 2
+    ins = ["add.cc.u32 %%%d, %%%d, %%1;" % (N, N)]
+    bi = N + 1 + (H - K)
+    for k in range(H):
+        last = k == H - 1
+        s_lo = "0" if last else "%%%d" % (2 * k + 2)
+        s_hi = "0" if last else "%%%d" % (2 * k + 3)
+        if k < K:
+            ins.append("addc.cc.u32 %%%d, %s, 0;" % (2 * k, s_lo))
+            ins.append("addc.cc.u32 %%%d, %s, 0;" % (2 * k + 1, s_hi))
+        else:
+            a = N + 1 + (k - K)
+            ins.append("madc.lo.cc.u32 %%%d, %%%d, %%%d, %s;" % (2 * k, a, bi, s_lo))
+            ins.append("%s %%%d, %%%d, %%%d, %s;" % ("madc.hi.u32" if last else "madc.hi.cc.u32", 2 * k + 1, a, bi, s_hi))
+    return ins
+
+
+def cmad_from_ins(N, K):
+    """cmad_n starting at pair K (lower limbs untouched).  Operands: 0..N-1 acc, N = carry out, N+1.. = a[2k] (k >= K), last = bi."""
+    H = N // 2
+    bi = N + 1 + (H - K)
+    ins = []
+    for k in range(K, H):
+        a = N + 1 + (k - K)
+        ins.append("%s %%%d, %%%d, %%%d, %%%d;" % ("mad.lo.cc.u32" if k == K else "madc.lo.cc.u32", 2 * k, a, bi, 2 * k))
+        ins.append("madc.hi.cc.u32 %%%d, %%%d, %%%d, %%%d;" % (2 * k + 1, a, bi, 2 * k + 1))
+    ins.append("addc.u32 %%%d, 0, 0;" % N)
+    return ins
+
+
+def gen_from_variants(N, w):
+    H = N // 2
+    sfx = str(N)
+    w("// ---- variants for the dedicated squaring: products of pairs k < K are known to be zero ----")
+    w("template <int K> __device__ __forceinline__ void shift_mad_from_n%s(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi);" % sfx)
+    w("template <int K> __device__ __forceinline__ uint32_t cmad_from_n%s(uint32_t* acc, const uint32_t* a, uint32_t bi);" % sfx)
+    for K in range(H):
+        w("template <> __device__ __forceinline__ void shift_mad_from_n%s<%d>(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi) {" % (sfx, K))
+        w('    asm("%s"' % " ".join(shift_mad_from_ins(N, K)))
+        w("        : %s, \"+r\"(E[0])" % ", ".join('"+r"(O[%d])' % i for i in range(N)))
+        w("        : %s, \"r\"(bi));" % ", ".join('"r"(a[%d])' % (2 * k) for k in range(K, H)))
+        w("}")
+        w("template <> __device__ __forceinline__ uint32_t cmad_from_n%s<%d>(uint32_t* acc, const uint32_t* a, uint32_t bi) {" % (sfx, K))
+        w("    uint32_t c;")
+        w('    asm("%s"' % " ".join(cmad_from_ins(N, K)))
+        w("        : %s, \"=&r\"(c)" % ", ".join('"+r"(acc[%d])' % i for i in range(N)))
+        w("        : %s, \"r\"(bi));" % ", ".join('"r"(a[%d])' % (2 * k) for k in range(K, H)))
+        w("    return c;")
+        w("}")
+    w("")
 
 
 def main(path):

@@ -290,8 +290,78 @@ HD Fp<P> mul(const Fp<P>& a, const Fp<P>& b) {
     else return mul_inline(a, b);
 }
 
+// Dedicated squaring for the 8-limb fields (device): a_i a_j, i != j, is computed once and doubled, so the product
+// part needs 36 limb products instead of 64 (the 72 of the reduction stay): 108 instead of 137 IMAD-class instructions.
+// Row i of the interleaved scheme multiplies a_i by the vector (0, .., 0, a_i, 2 a_{>i}) -- the limbs of the doubled
+// number d = 2a, with the bit that a_i shifts into d_{i+1} cleared -- through the chain variants that skip the zero
+// products (fp_asm.cuh: shift_mad_from / cmad_from).  Needs two spare bits in the top limb (p < 2^254: the doubled
+// early rows stay below 2^288, the nine limbs of the two accumulators; a 255-bit modulus such as BLS12-381 Fr overflows
+// them, so it keeps sqr = mul).
+// tests/test_fp_asm_model.py runs this composition on the generated instruction lists in a Python model.
+#ifdef __CUDA_ARCH__
 template <class P>
-HD Fp<P> sqr(const Fp<P>& a) { return mul(a, a); }
+__device__ __forceinline__ Fp<P> sqr_inline8(const Fp<P>& A) {
+    constexpr int N = 8;
+    static_assert(P::N == N && P::BITS <= 254, "8 limbs with two spare top bits");
+    Fp<P> res;
+    uint32_t e[N], o[N], d[N];
+    const Fp<P> M = Fp<P>::modulus();
+    const uint32_t* a = A.v;
+    const uint32_t* p = M.v;
+    d[0] = 0;
+#pragma unroll
+    for (int j = 1; j < N; j++) d[j] = __funnelshift_l(a[j - 1], a[j], 1);
+#define WS_SQR_X(i)                                                                                   \
+    uint32_t x[N + 1];                                                                                \
+    _Pragma("unroll") for (int j = 0; j < N; j++)                                                     \
+        x[j] = j < (i) ? 0u : (j == (i) ? a[(i)] : (j == (i) + 1 ? (d[j] & ~1u) : d[j]));             \
+    x[N] = 0;
+#define WS_SQR_REDUCE(E, O)                                                                           \
+    {                                                                                                 \
+        uint32_t m = E[0] * P::NP0;                                                                   \
+        cmad_n8(O, p + 1, m);                                                                         \
+        O[N - 1] += cmad_n8(E, p, m);                                                                 \
+    }
+#define WS_SQR_ROW(i, E, O)                                                                           \
+    {                                                                                                 \
+        WS_SQR_X(i)                                                                                   \
+        shift_mad_from_n8<((i) >> 1)>(E, O, x + 1, a[(i)]);                                           \
+        if constexpr ((((i) + 1) >> 1) < N / 2) O[N - 1] += cmad_from_n8<(((i) + 1) >> 1)>(E, x, a[(i)]); \
+        WS_SQR_REDUCE(E, O)                                                                           \
+    }
+    {
+        WS_SQR_X(0)
+        mul_n8(e, x, a[0]);
+        mul_n8(o, x + 1, a[0]);
+        WS_SQR_REDUCE(e, o)
+    }
+    WS_SQR_ROW(1, o, e)
+    WS_SQR_ROW(2, e, o)
+    WS_SQR_ROW(3, o, e)
+    WS_SQR_ROW(4, e, o)
+    WS_SQR_ROW(5, o, e)
+    WS_SQR_ROW(6, e, o)
+    WS_SQR_ROW(7, o, e)
+#undef WS_SQR_X
+#undef WS_SQR_REDUCE
+#undef WS_SQR_ROW
+    merge_n8(e, o);
+    uint32_t bw = sub_n8(res.v, e, p);
+#pragma unroll
+    for (int i = 0; i < N; i++) res.v[i] = bw ? e[i] : res.v[i];
+    return res;
+}
+#endif
+
+template <class P>
+HD Fp<P> sqr(const Fp<P>& a) {
+#if defined(__CUDA_ARCH__) && !defined(WS_NO_DEDICATED_SQR)
+    if constexpr (P::N == 8 && P::BITS <= 254) return sqr_inline8(a);
+    else return mul(a, a);
+#else
+    return mul(a, a);
+#endif
+}
 
 template <class P>
 HD Fp<P> to_mont(const Fp<P>& a) { return mul(a, Fp<P>::r2()); }
