@@ -41,7 +41,7 @@ N_PAIRS = 1 << LOG2N
 PROVE_LOG2 = int(os.environ.get("WS_BENCH_PROVE_LOG2", "20"))       # constraints (domain size) of the synthetic key
 ALG_BYTES_PER_PAIR = 96          # 32 B scalar + 64 B affine point
 KERNELS_PER_MSM = 18             # digits, 2x3 scan, scatter, 3 task-table, accumulate, 2 combine, segreduce, seg2, bitsum, final
-NCU_TRAFFIC_BYTES = 649606144   # k_msm_accumulate<G1>, n = 2^20: measured once per round with ncu (profiles/)
+NCU_TRAFFIC_BYTES = 656826368   # k_msm_accumulate<G1>, n = 2^20: measured once per round with ncu (profiles/)
 NFLIGHT = max(1, int(os.environ.get("WS_BENCH_INFLIGHT", "4")))   # MSMs in flight for the throughput number
 SCALARS = os.environ.get("WS_BENCH_SCALARS", "fr")      # "fr": uniform in [0, r) ; "raw256": uniform 256-bit
 
@@ -737,11 +737,12 @@ def main():
                          "frac": achieved / peak if achieved else None, "traffic": NCU_TRAFFIC_BYTES if (LOG2N == 20 and world == 1) else None,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_ncu_accumulate_g1_2p20.txt)", "peak_source": which,
                          "kernel_ms": acc_ms, "algorithmic_bytes_per_launch": ALG_BYTES_PER_PAIR * cnt,
-                         "note": "integer-multiply bound, not HBM bound: 8M+2S Montgomery products (137 IMAD each) per pair per window",
+                         "note": "integer-multiply bound, not HBM bound: 8M+2S Montgomery products per pair per window (137 IMAD-class instructions per product, 111 per dedicated squaring)",
                          "compute_side": {"montgomery_products_per_s": (10.0 * 16 * cnt) / (acc_ms * 1e-3) if acc_ms > 0 else None,
-                                          "imad_wide_ceiling_products_per_s": 148 * 4 * 8 * 1.965e9 / 137,
-                                          "frac_of_imad_ceiling": ((10.0 * 16 * cnt) / (acc_ms * 1e-3)) / (148 * 4 * 8 * 1.965e9 / 137) if acc_ms > 0 else None,
-                                          "ncu_fmaheavy_pipe_busy_pct": 83.2, "ncu_simt_lanes_per_warp": 31.7,
+                                          "imad_per_product_avg": (8 * 137 + 2 * 111) / 10.0,
+                                          "imad_wide_ceiling_products_per_s": 148 * 4 * 8 * 1.965e9 / ((8 * 137 + 2 * 111) / 10.0),
+                                          "frac_of_imad_ceiling": ((10.0 * 16 * cnt) / (acc_ms * 1e-3)) / (148 * 4 * 8 * 1.965e9 / ((8 * 137 + 2 * 111) / 10.0)) if acc_ms > 0 else None,
+                                          "ncu_fmaheavy_pipe_busy_pct": 81.5, "ncu_simt_lanes_per_warp": 31.7,
                                           "source": "profiles/r1_ncu_accumulate_g1_2p20.txt"}},
             "stages_ms": {k: v / K for k, v in stage_ms.items()},
         }

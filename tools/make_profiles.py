@@ -68,6 +68,10 @@ def more(b, tag):
     if rows:
         out += ["", "## Scaling runs (torchrun, one rank per GPU; MSM line = weak scaling, Groth16 = one fixed 2^20 proof sharded)", "",
                 "| GPUs | MSM M pairs/s | ms per step | e2e M pairs/s | Groth16 proofs/s | proof latency ms |", "|---|---|---|---|---|---|"] + rows
+    rf = b.get("roofline", {})
+    if rf.get("traffic") and os.path.exists(os.path.join(P, "%s_ncu_accumulate_g1_2p20.txt" % tag)):
+        out += ["", "Note: `roofline.traffic` in `%s_bench_n1.json` (%d B) is the constant bench.py carried when that line was recorded; the ncu capture"
+                " committed here was taken afterwards on the same code and reads the value in the table above (bench.py now carries it)." % (tag, rf["traffic"])]
     lb = os.path.join(P, "%s_launches_bench_msm.csv" % tag)
     if os.path.exists(lb):
         t, tot, a = launch_table(lb)
