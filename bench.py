@@ -16,7 +16,10 @@ Montgomery G1 points.
             bounded sample over the host cores, split as src/bn128.js:353-383 does
 Same JSON line, key "groth16": the other half of BASELINE's metric -- full Groth16 proofs/s on a synthetic
 2^20-constraint key (tools/gen_synth_key.py), device-resident key + witness (value) and through the
-host-buffer call with the resident key (e2e); key "ntt": BASELINE configs[2], 2^22 forward + inverse.
+host-buffer call with the resident key (e2e), plus "example_key" (BASELINE configs[3]: the reference's example key,
+checked against proof_good0.json) and "dropin_call" (the stateless groth16GenProof(witness, provingKey) call);
+key "ntt": BASELINE configs[2], 2^22 forward + inverse; "mnt6753": configs[4] MSM 2^18; "bls12381": G1 MSM 2^20;
+"verifier": host-side groth16Verify next to the reference's.
 `--impl reference` runs only the CPU arm and prints the same line shape.
 N > 1 (torchrun, one rank per GPU): one MSM of N * 2^20 pairs, contiguous point ranges of 2^20 pairs per rank (the
 reference's worker split), one all_gather of the 96-byte partial sums over NCCL, tiny on-device combine: per-GPU
@@ -395,7 +398,7 @@ def main():
     pipe_ms = float(t.item())
 
     # ---- end to end through the host-buffer ABI (pinned host memory; H2D + D2H inside): K blocking calls
-    #      issued from two host threads, one context each (world == 1), so one call's H2D overlaps the other's compute
+    #      issued from one host thread per context (world == 1), so one call's H2D overlaps the others' compute
     out_hosts = [torch.zeros(96, dtype=torch.uint8).pin_memory() for _ in range(NF)]
     out_host = out_hosts[0]
 
