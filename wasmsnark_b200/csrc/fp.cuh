@@ -88,19 +88,28 @@ HD Fp<P> add(const Fp<P>& a, const Fp<P>& b) {
 #pragma unroll
     for (int i = 0; i < N; i++) s.v[i] = bw ? s.v[i] : t.v[i];
 #else
-    uint64_t c = 0;
-    for (int i = 0; i < N; i++) {
-        c += (uint64_t)a.v[i] + b.v[i];
-        s.v[i] = (uint32_t)c;
-        c >>= 32;
+    // host: 64-bit limbs
+    constexpr int M = N / 2;
+    typedef unsigned __int128 u128;
+    uint64_t sw[M], tw[M];
+    u128 c = 0;
+    for (int i = 0; i < M; i++) {
+        c += (u128)(a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32)) + (b.v[2 * i] | ((uint64_t)b.v[2 * i + 1] << 32));
+        sw[i] = (uint64_t)c;
+        c >>= 64;
     }
-    int64_t bw = 0;
-    for (int i = 0; i < N; i++) {
-        int64_t d = (int64_t)s.v[i] - P::mod(i) + bw;
-        t.v[i] = (uint32_t)d;
-        bw = d >> 32;
+    uint64_t bw = 0;
+    for (int i = 0; i < M; i++) {
+        u128 d = (u128)sw[i] - (P::mod(2 * i) | ((uint64_t)P::mod(2 * i + 1) << 32)) - bw;
+        tw[i] = (uint64_t)d;
+        bw = (uint64_t)(d >> 64) & 1;
     }
-    if (!bw) s = t;
+    for (int i = 0; i < M; i++) {
+        uint64_t w = bw ? sw[i] : tw[i];
+        s.v[2 * i] = (uint32_t)w;
+        s.v[2 * i + 1] = (uint32_t)(w >> 32);
+    }
+    (void)t;
 #endif
     return s;
 }
@@ -122,19 +131,25 @@ HD Fp<P> sub(const Fp<P>& a, const Fp<P>& b) {
         addmask_n24(d.v, m.v, bw);
     }
 #else
-    int64_t bw = 0;
-    for (int i = 0; i < N; i++) {
-        int64_t t = (int64_t)a.v[i] - b.v[i] + bw;
-        d.v[i] = (uint32_t)t;
-        bw = t >> 32;
+    constexpr int M = N / 2;
+    typedef unsigned __int128 u128;
+    uint64_t dw[M], bw = 0;
+    for (int i = 0; i < M; i++) {
+        u128 t = (u128)(a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32)) - (b.v[2 * i] | ((uint64_t)b.v[2 * i + 1] << 32)) - bw;
+        dw[i] = (uint64_t)t;
+        bw = (uint64_t)(t >> 64) & 1;
     }
     if (bw) {
-        uint64_t c = 0;
-        for (int i = 0; i < N; i++) {
-            c += (uint64_t)d.v[i] + P::mod(i);
-            d.v[i] = (uint32_t)c;
-            c >>= 32;
+        u128 c = 0;
+        for (int i = 0; i < M; i++) {
+            c += (u128)dw[i] + (P::mod(2 * i) | ((uint64_t)P::mod(2 * i + 1) << 32));
+            dw[i] = (uint64_t)c;
+            c >>= 64;
         }
+    }
+    for (int i = 0; i < M; i++) {
+        d.v[2 * i] = (uint32_t)dw[i];
+        d.v[2 * i + 1] = (uint32_t)(dw[i] >> 32);
     }
 #endif
     return d;

@@ -74,6 +74,8 @@ WS_API int ws_bn128_groth16_verify(const uint8_t vk_alfa_1[64], const uint8_t vk
         return WS_OK;
     if (!rd_g1(ic, &icp)) return WS_OK;
     XYZZ<G1Curve> acc = icp.inf ? XYZZ<G1Curve>::inf() : XYZZ<G1Curve>{icp.x, icp.y, Fq::one(), Fq::one()};
+    std::vector<Affine<G1Curve>> pts;
+    std::vector<const uint8_t*> scs;
     for (size_t i = 0; i < n_inputs; i++) {
         const uint8_t* s = inputs + 32 * i;
         uint32_t w[8];
@@ -89,8 +91,34 @@ WS_API int ws_bn128_groth16_verify(const uint8_t vk_alfa_1[64], const uint8_t vk
         if (!lt) return WS_OK;
         if (!rd_g1(ic + 64 * (i + 1), &icp)) return WS_OK;
         if (icp.inf) continue;
-        XYZZ<G1Curve> t = times_scalar<G1Curve>(XYZZ<G1Curve>{icp.x, icp.y, Fq::one(), Fq::one()}, s, 32);
-        acc = padd_call<G1Curve>(acc, t);
+        pts.push_back(Affine<G1Curve>{icp.x, icp.y});
+        scs.push_back(s);
+    }
+    // vk_x = IC[0] + sum input_i IC[i+1].  The reference adds g1m_timesScalar results one by one (:774-776); the same
+    // group element comes out of one small bucket pass: 4-bit windows, 15 buckets, mixed additions.
+    {
+        constexpr int C = 4, NB = (1 << C) - 1;
+        XYZZ<G1Curve> sum = XYZZ<G1Curve>::inf();
+        for (int win = 256 / C - 1; win >= 0; win--) {
+            for (int d = 0; d < C; d++) sum = pdbl_call<G1Curve>(sum);
+            XYZZ<G1Curve> bucket[NB];
+            bool used = false;
+            for (int b = 0; b < NB; b++) bucket[b] = XYZZ<G1Curve>::inf();
+            for (size_t i = 0; i < pts.size(); i++) {
+                unsigned dig = (scs[i][win >> 1] >> ((win & 1) * 4)) & 15u;
+                if (!dig) continue;
+                bucket[dig - 1] = pmadd<G1Curve>(bucket[dig - 1], pts[i]);
+                used = true;
+            }
+            if (!used) continue;
+            XYZZ<G1Curve> run = XYZZ<G1Curve>::inf(), tot = XYZZ<G1Curve>::inf();
+            for (int b = NB - 1; b >= 0; b--) {       // sum_b (b + 1) bucket[b] by running sums
+                run = padd_call<G1Curve>(run, bucket[b]);
+                tot = padd_call<G1Curve>(tot, run);
+            }
+            sum = padd_call<G1Curve>(sum, tot);
+        }
+        acc = padd_call<G1Curve>(acc, sum);
     }
     Jac<G1Curve> ax = to_affine<G1Curve>(acc);
     G1A vkx{ax.x, ax.y, ax.z.is_zero()};
