@@ -106,7 +106,7 @@ Files
 * `%s_ncu_accumulate_g1_2p20.txt` -- `ncu --set full --clock-control none -k regex:k_msm_accumulate` on `tools/run_msm_once.py 20 3` (summary of the raw page, tools/ncu_summary.py).
 * `%s_ncu_ntt_pass_2p22.txt` -- same for two `k_ntt_pass64` launches (radix-64 passes) of a 2^22 transform, `tools/run_ntt_once.py 22 1`.
 * `%s_launches_msm_2p20.csv`, `%s_launches_prove_2p20.csv` -- `ncu --metrics gpu__time_duration.sum --clock-control none` launch lists (cold-cache, serialised: compare SHARES, not absolutes).
-* `r1_sass_fp_mul.txt` -- SASS opcode histogram of the BN128 Montgomery product kernel (`cuobjdump -sass`): 137 IMAD-class instructions, one `IMAD.WIDE.U32(.X)` per limb product.
+* `r1_sass_fp_mul.txt` -- SASS opcode histogram of the BN128 Montgomery product kernel (`cuobjdump -sass`): 137 IMAD-class instructions, one `IMAD.WIDE.U32(.X)` per limb product; `r1_sass_fp_sqr.txt` -- the same for the dedicated squaring: 111.
 * `r1_bench_n2_prove2p18.json`, `r1_bench_n4.json`, `r1_bench_n8.json` -- N = 2 / 4 / 8 runs under torchrun (NCCL) from earlier in the round; `r1_bench_n1_reference_arm.json` -- `bench.py --impl reference`.
 
 ## Headline (BASELINE configs[1], G1 MSM n = 2^20, scalars uniform in [0, r))
