@@ -10,8 +10,9 @@
  * are plain and are consumed as raw 256-bit integers (never reduced).
  *
  * Return value: 0 on success, a negative WS_E_* code otherwise (ws_last_error() gives text).
- * The library never falls back to a CPU implementation: without a usable CUDA device
- * ws_create fails with WS_E_CUDA.
+ * The proving path never falls back to a CPU implementation: without a usable CUDA device
+ * ws_create fails with WS_E_CUDA.  Only the Groth16 verifier / pairing entry points are host code, by design
+ * (four pairings are not data-parallel work); they take no ws_ctx.
  *
  * Threading: a ws_ctx owns one CUDA device, one stream set and one workspace; calls on the
  * same ctx must be serialised by the caller (the reference likewise has one in-flight command
