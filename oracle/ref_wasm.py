@@ -203,6 +203,15 @@ class RefBn128:
     def calcH(self, signals, polsA, polsB, nSignals, domainSize):
         return self.workers[0].cmd_calc_h(signals, polsA, polsB, nSignals, domainSize)
 
+    def _msm_results(self, signals, sec, nPublic):
+        h = self.calcH(signals, sec["polsA"], sec["polsB"], sec["nSignals"], sec["domainSize"])
+        rH = self.g1_multiexp(h, sec["pointsH"])
+        rA = self.g1_multiexp(signals, sec["pointsA"])
+        rB1 = self.g1_multiexp(signals, sec["pointsB1"])
+        rB2 = self.g2_multiexp(signals, sec["pointsB2"])
+        rC = self.g1_multiexp(signals[(nPublic + 1) * 32:], sec["pointsC"])
+        return rH, rA, rB1, rB2, rC
+
     def g1_affine_std(self, p96):
         """g1m_affine + g1m_fromMontgomery (src/bn128.js:706-712)."""
         m = self.main
@@ -235,12 +244,9 @@ class RefBn128:
         beta2 = pkey[232:360]
         delta2 = pkey[360:488]
 
-        h = self.calcH(signals, polsA, polsB, nSignals, domainSize)
-        rH = self.g1_multiexp(h, pointsH)
-        rA = self.g1_multiexp(signals, pointsA)
-        rB1 = self.g1_multiexp(signals, pointsB1)
-        rB2 = self.g2_multiexp(signals, pointsB2)
-        rC = self.g1_multiexp(signals[(nPublic + 1) * 32:], pointsC)
+        sec = {"polsA": polsA, "polsB": polsB, "nSignals": nSignals, "domainSize": domainSize, "pointsA": pointsA,
+               "pointsB1": pointsB1, "pointsB2": pointsB2, "pointsC": pointsC, "pointsH": pointsH}
+        rH, rA, rB1, rB2, rC = self._msm_results(signals, sec, nPublic)
 
         m = self.main
         c = m.call
@@ -314,6 +320,81 @@ class RefBn128:
         if raw:
             return ba, bb, bc
         return format_proof(ba, bb, bc)
+
+
+class RefBn128Pool(RefBn128):
+    """RefBn128 with the reference's worker pool (src/bn128.js:173-265): W instances of the image, one host
+    thread each (ctypes releases the GIL inside the image).  Task graph of groth16GenProof as the reference
+    builds it (src/bn128.js:607-622): CALC_H is ONE task on one worker (:569-578); every multiexp is split
+    into W contiguous ranges (:353-372), one task each; the H multiexp is queued when CALC_H resolves; the
+    partial points are added serially on the main instance (:376-380).  Used by the golden-vector scripts and
+    as bench.py's CPU baseline (Web-Worker-parallel arm); concurrency=1 is the single-threaded arm."""
+
+    def __init__(self, concurrency=8, pages=PAGES):
+        from concurrent.futures import ThreadPoolExecutor
+        import queue
+        self.main = RefInstance(pages=1000)
+        self.pr0 = self.main.alloc(192)
+        self.pr1 = self.main.alloc(192)
+        self.concurrency = max(1, concurrency)
+        self.workers = [RefInstance(pages=pages) for _ in range(self.concurrency)]
+        self._free = queue.Queue()
+        for w in self.workers:
+            self._free.put(w)
+        self.ex = ThreadPoolExecutor(max_workers=self.concurrency)
+
+    def close(self):
+        self.ex.shutdown(wait=True)
+        super().close()
+
+    def _task(self, fn):
+        """postAction (src/bn128.js:272-300): the task runs on whichever worker is free."""
+        def run():
+            wk = self._free.get()
+            try:
+                return fn(wk)
+            finally:
+                self._free.put(wk)
+        return self.ex.submit(run)
+
+    def _multiexp_async(self, g, scalars, points, psize):
+        nPoints = len(scalars) // 32
+        W = self.concurrency
+        per = nPoints // W
+        futs = []
+        for i in range(W):
+            n = per if i < W - 1 else nPoints - per * (W - 1)
+            s = scalars[i * per * 32: i * per * 32 + n * 32]
+            p = points[i * per * psize: i * per * psize + n * psize]
+            futs.append(self._task((lambda wk, s=s, p=p, n=n: wk.cmd_g1_multiexp(s, p, n)) if g == 1 else
+                                   (lambda wk, s=s, p=p, n=n: wk.cmd_g2_multiexp(s, p, n))))
+        return futs
+
+    def _combine(self, g, futs):
+        m = self.main
+        pfx = "g1m" if g == 1 else "g2m"
+        m.call(pfx + "_zero", self.pr0)
+        for f in futs:
+            m.put(self.pr1, f.result())
+            m.call(pfx + "_add", self.pr0, self.pr1, self.pr0)
+        return m.get(self.pr0, 96 if g == 1 else 192)
+
+    def _multiexp(self, g, scalars, points, psize, variant=None):
+        return self._combine(g, self._multiexp_async(g, scalars, points, psize))
+
+    def calcH(self, signals, polsA, polsB, nSignals, domainSize):
+        return self._task(lambda wk: wk.cmd_calc_h(signals, polsA, polsB, nSignals, domainSize)).result()
+
+    def _msm_results(self, signals, sec, nPublic):
+        """the five multiexps with CALC_H in flight beside them (src/bn128.js:607-622)."""
+        fh = self._task(lambda wk: wk.cmd_calc_h(signals, sec["polsA"], sec["polsB"], sec["nSignals"], sec["domainSize"]))
+        fA = self._multiexp_async(1, signals, sec["pointsA"], 64)
+        fB1 = self._multiexp_async(1, signals, sec["pointsB1"], 64)
+        fB2 = self._multiexp_async(2, signals, sec["pointsB2"], 128)
+        fC = self._multiexp_async(1, signals[(nPublic + 1) * 32:], sec["pointsC"], 64)
+        h = fh.result()
+        fH = self._multiexp_async(1, h, sec["pointsH"], 64)
+        return self._combine(1, fH), self._combine(1, fA), self._combine(1, fB1), self._combine(2, fB2), self._combine(1, fC)
 
 
 def groth16_verify(verification_key, inputs, proof, inst=None):

@@ -12,6 +12,27 @@ LIB_PATH = os.path.join(_HERE, "libwasmsnark_b200.so")
 WS_OK = 0
 FIELD_BN128_FQ, FIELD_BN128_FR, FIELD_MNT6753_FQ, FIELD_BLS12381_FQ, FIELD_BLS12381_FR = 0, 1, 2, 3, 4
 OP_MUL, OP_ADD, OP_SUB, OP_SQUARE, OP_TOMONT, OP_FROMMONT, OP_INVERSE = range(7)
+# bytes per element of each field id (ws_fp_batch reads / writes n * size bytes)
+FIELD_ELEMENT_BYTES = {FIELD_BN128_FQ: 32, FIELD_BN128_FR: 32, FIELD_MNT6753_FQ: 96, FIELD_BLS12381_FQ: 48, FIELD_BLS12381_FR: 32}
+_BINARY_OPS = (OP_MUL, OP_ADD, OP_SUB)
+
+
+def fp_batch(ctx, field, op, x, y=None):
+    """ws_fp_batch with the buffer lengths checked against the field's element size (shared by the curve mirrors)."""
+    esz = FIELD_ELEMENT_BYTES.get(field)
+    if esz is None:
+        raise ValueError("unknown field id %r" % (field,))
+    if len(x) % esz:
+        raise ValueError("x must be a whole number of %d-byte elements" % esz)
+    if op in _BINARY_OPS:
+        if y is None or len(y) != len(x):
+            raise ValueError("y must have the same length as x for a binary op")
+    elif y is not None and len(y) != len(x):
+        raise ValueError("y, if given, must have the same length as x")
+    n = len(x) // esz
+    out = ctypes.create_string_buffer(max(1, n * esz))
+    ctx.check(ctx.lib.ws_fp_batch(ctx.h, field, op, as_ptr(x), as_ptr(y), ctypes.cast(out, ctypes.c_void_p), n))
+    return out.raw[:n * esz]
 
 
 class LibraryNotBuilt(RuntimeError):

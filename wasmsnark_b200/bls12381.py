@@ -61,13 +61,11 @@ class Bls12381:
         return buf.raw
 
     def fp_batch(self, field, op, x, y=None):
-        esz = 48 if field == _lib.FIELD_BLS12381_FQ else 32
-        n = len(x) // esz
-        out = ctypes.create_string_buffer(max(1, n * esz))
-        self.ctx.check(self.lib.ws_fp_batch(self.ctx.h, field, op, as_ptr(x), as_ptr(y), ctypes.cast(out, ctypes.c_void_p), n))
-        return out.raw[:n * esz]
+        return _lib.fp_batch(self.ctx, field, op, x, y)
 
     def fq2_mul_batch(self, x, y):
+        if len(x) % 96 or len(y) != len(x):
+            raise ValueError("x and y must be the same whole number of 96-byte Fq2 elements")
         n = len(x) // 96
         out = ctypes.create_string_buffer(max(1, n * 96))
         self.ctx.check(self.lib.ws_bls12381_fq2_mul_batch(self.ctx.h, as_ptr(x), as_ptr(y), ctypes.cast(out, ctypes.c_void_p), n))

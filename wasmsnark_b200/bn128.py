@@ -82,6 +82,8 @@ class Bn128:
 
     def calcH(self, signals, polsA, polsB, nSignals, domainSize):
         """src/bn128.js:569-578 -> worker CALC_H (:126-166): domainSize*32 bytes, non-Montgomery."""
+        if len(signals) < nSignals * 32:
+            raise ValueError("signals shorter than nSignals * 32 bytes")
         out = ctypes.create_string_buffer(domainSize * 32)
         self.ctx.check(self.lib.ws_bn128_calc_h(self.ctx.h, as_ptr(signals), as_ptr(polsA), len(polsA), as_ptr(polsB), len(polsB),
                                                 nSignals, domainSize, ctypes.cast(out, ctypes.c_void_p)))
@@ -98,6 +100,9 @@ class Bn128:
         load_proving_key().  r, s: 32-byte strings injected for tests (None => CSPRNG like the
         reference; the values used are kept in self._pr / self._ps like src/bn128.js:663-664 when
         injected).  Returns {pi_a, pi_b, pi_c} as decimal strings (src/bn128.js:714-718)."""
+        for nm, v in (("r", r), ("s", s)):
+            if v is not None and len(v) != 32:
+                raise ValueError("%s must be exactly 32 bytes" % nm)
         pa = ctypes.create_string_buffer(96)
         pb = ctypes.create_string_buffer(192)
         pc = ctypes.create_string_buffer(96)
@@ -117,13 +122,11 @@ class Bn128:
 
     # -- field batches (WASM exports f1m_*/frm_*; batch forms fft_mulN etc.)
     def fp_batch(self, field, op, x, y=None):
-        esz = 96 if field == _lib.FIELD_MNT6753_FQ else 32
-        n = len(x) // esz
-        out = ctypes.create_string_buffer(max(1, n * esz))
-        self.ctx.check(self.lib.ws_fp_batch(self.ctx.h, field, op, as_ptr(x), as_ptr(y), ctypes.cast(out, ctypes.c_void_p), n))
-        return out.raw[:n * esz]
+        return _lib.fp_batch(self.ctx, field, op, x, y)
 
     def fq2_mul_batch(self, x, y):
+        if len(x) % 64 or len(y) != len(x):
+            raise ValueError("x and y must be the same whole number of 64-byte Fq2 elements")
         n = len(x) // 64
         out = ctypes.create_string_buffer(max(1, n * 64))
         self.ctx.check(self.lib.ws_bn128_fq2_mul_batch(self.ctx.h, as_ptr(x), as_ptr(y), ctypes.cast(out, ctypes.c_void_p), n))

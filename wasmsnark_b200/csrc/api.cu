@@ -47,6 +47,7 @@ WS_API void ws_destroy(ws_ctx* c) {
         if (a.ptr) cudaFree(a.ptr);
     if (c->tw_table) cudaFree(c->tw_table);
     if (c->tw_table_bls) cudaFree(c->tw_table_bls);
+    if (c->busy_ev) cudaEventDestroy(c->busy_ev);
     if (c->lanes_ready) {
         for (int i = 0; i < ws_ctx::NLANES; i++) {
             cudaStreamDestroy(c->lanes[i]);
@@ -64,12 +65,14 @@ WS_API const char* ws_last_error(const ws_ctx* c) { return c ? c->err.c_str() : 
 WS_API unsigned long long ws_kernel_launches(const ws_ctx* c) { return c ? c->launches : 0; }
 
 WS_API int ws_set_profiling(ws_ctx* c, int on) {
+    WsLock ws_lock_(c);
     if (!c) return WS_E_ARG;
     c->timer.enabled = on != 0;
     return WS_OK;
 }
 
 WS_API int ws_last_timings(ws_ctx* c, const char** names, float* ms, int cap) {
+    WsLock ws_lock_(c);
     if (!c) return WS_E_ARG;
     cudaSetDevice(c->device);
     if (cudaStreamSynchronize(c->timer.last_stream) != cudaSuccess) return c->fail_cuda("sync");
@@ -86,6 +89,7 @@ WS_API int ws_last_timings(ws_ctx* c, const char** names, float* ms, int cap) {
 
 // ------------------------------------------------------------------ field batches
 WS_API int ws_fp_batch(ws_ctx* c, int field, int op, const uint8_t* x, const uint8_t* y, uint8_t* out, size_t n) {
+    WsLock ws_lock_(c);
     if (!c || !x || !out || (!y && (op == WS_OP_MUL || op == WS_OP_ADD || op == WS_OP_SUB))) return c ? c->fail(WS_E_ARG, "null buffer") : WS_E_ARG;
     if (field < 0 || field > WS_BLS12381_FR) return c->fail(WS_E_FIELD, "unknown field id");
     if (op < 0 || op > WS_OP_INVERSE) return c->fail(WS_E_ARG, "unknown op");
@@ -110,6 +114,7 @@ WS_API int ws_fp_batch(ws_ctx* c, int field, int op, const uint8_t* x, const uin
 }
 
 WS_API int ws_bn128_fq2_mul_batch(ws_ctx* c, const uint8_t* x, const uint8_t* y, uint8_t* out, size_t n) {
+    WsLock ws_lock_(c);
     if (!c || !x || !y || !out) return c ? c->fail(WS_E_ARG, "null buffer") : WS_E_ARG;
     if (n == 0) return WS_OK;
     cudaSetDevice(c->device);
@@ -126,12 +131,14 @@ WS_API int ws_bn128_fq2_mul_batch(ws_ctx* c, const uint8_t* x, const uint8_t* y,
 
 // test / tuning hook: force the task cap T (0 = automatic)
 WS_API int ws_set_msm_task_cap(ws_ctx* c, unsigned T) {
+    WsLock ws_lock_(c);
     if (!c) return WS_E_ARG;
     c->force_T = T;
     return WS_OK;
 }
 
 WS_API int ws_set_msm_acc_variant(ws_ctx* c, int v) {
+    WsLock ws_lock_(c);
     if (!c) return WS_E_ARG;
     c->acc_variant = v;
     return WS_OK;
@@ -139,6 +146,7 @@ WS_API int ws_set_msm_acc_variant(ws_ctx* c, int v) {
 
 // test / tuning hook: buckets per reduce segment (power of two)
 WS_API int ws_set_msm_seg_len(ws_ctx* c, unsigned L) {
+    WsLock ws_lock_(c);
     if (!c || (L & (L - 1))) return WS_E_ARG;   // 0 = automatic
     c->seg_len = L;
     return WS_OK;

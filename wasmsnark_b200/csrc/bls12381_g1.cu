@@ -50,11 +50,13 @@ static int bls_fft_dev(ws_ctx* c, void* d_px, size_t n, int odd, int inverse, cu
     if (!ok) return c->fail_cuda("twiddle table");
     BlsFr* scratch = (BlsFr*)c->arena(2, sizeof(BlsFr) << logn);
     if (!scratch) return c->fail_cuda("fft scratch");
+    WsStreamScope chain(c, st);
     cudaError_t e = ntt_launch<NttBls12381>((BlsFr*)d_px, scratch, logn, odd != 0, inverse != 0, T, st, &c->launches);
     return e == cudaSuccess ? WS_OK : c->fail_cuda("ntt");
 }
 
 static int bls_fft_host(ws_ctx* c, uint8_t* px, size_t n, int odd, int inverse) {
+    WsLock ws_lock_(c);
     if (!c || !px) return c ? c->fail(WS_E_ARG, "null buffer") : WS_E_ARG;
     if (!n || n > ((size_t)1 << 28)) return c->fail(WS_E_SIZE, "fft size must be a power of two <= 2^28");
     cudaSetDevice(c->device);
@@ -70,6 +72,7 @@ static int bls_fft_host(ws_ctx* c, uint8_t* px, size_t n, int odd, int inverse) 
 
 extern "C" {
 WS_API int ws_bls12381_fq2_mul_batch(ws_ctx* c, const uint8_t* x, const uint8_t* y, uint8_t* out, size_t n) {
+    WsLock ws_lock_(c);
     if (!c || !x || !y || !out) return c ? c->fail(WS_E_ARG, "null buffer") : WS_E_ARG;
     if (n == 0) return WS_OK;
     cudaSetDevice(c->device);
@@ -84,14 +87,17 @@ WS_API int ws_bls12381_fq2_mul_batch(ws_ctx* c, const uint8_t* x, const uint8_t*
     return WS_OK;
 }
 WS_API int ws_bls12381_g1_multiexp(ws_ctx* c, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t out[144]) {
+    WsLock ws_lock_(c);
     return multiexp_host<BlsG1Curve>(c, scalars, points, n, out);
 }
 WS_API int ws_bls12381_g1_multiexp_dev(ws_ctx* c, const void* ds, const void* dp, size_t n, void* dout, int wb, void* stream) {
+    WsLock ws_lock_(c);
     if (!c || !dout || (n && (!ds || !dp))) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
     cudaSetDevice(c->device);
     return multiexp_dev<BlsG1Curve>(c, ds, dp, n, dout, wb, stream ? (cudaStream_t)stream : c->stream);
 }
 WS_API int ws_bls12381_g1_affine(ws_ctx* c, const uint8_t* in, uint8_t* out, size_t count, int from_montgomery) {
+    WsLock ws_lock_(c);
     if (!c || !in || !out) return c ? c->fail(WS_E_ARG, "null buffer") : WS_E_ARG;
     if (count == 0) return WS_OK;
     cudaSetDevice(c->device);
@@ -107,6 +113,7 @@ WS_API int ws_bls12381_g1_affine(ws_ctx* c, const uint8_t* in, uint8_t* out, siz
 WS_API int ws_bls12381_fr_fft(ws_ctx* c, uint8_t* px, size_t n, int odd) { return bls_fft_host(c, px, n, odd, 0); }
 WS_API int ws_bls12381_fr_ifft(ws_ctx* c, uint8_t* px, size_t n, int odd) { return bls_fft_host(c, px, n, odd, 1); }
 WS_API int ws_bls12381_fr_fft_dev(ws_ctx* c, void* d_px, size_t n, int odd, int inverse, void* stream) {
+    WsLock ws_lock_(c);
     if (!c || !d_px) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
     cudaSetDevice(c->device);
     return bls_fft_dev(c, d_px, n, odd, inverse, stream ? (cudaStream_t)stream : c->stream);

@@ -7,14 +7,17 @@ using namespace ws;
 
 extern "C" {
 WS_API int ws_bls12381_g2_multiexp(ws_ctx* c, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t out[288]) {
+    WsLock ws_lock_(c);
     return multiexp_host<BlsG2Curve>(c, scalars, points, n, out);
 }
 WS_API int ws_bls12381_g2_multiexp_dev(ws_ctx* c, const void* ds, const void* dp, size_t n, void* dout, int wb, void* stream) {
+    WsLock ws_lock_(c);
     if (!c || !dout || (n && (!ds || !dp))) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
     cudaSetDevice(c->device);
     return multiexp_dev<BlsG2Curve>(c, ds, dp, n, dout, wb, stream ? (cudaStream_t)stream : c->stream);
 }
 WS_API int ws_bls12381_g2_affine(ws_ctx* c, const uint8_t* in, uint8_t* out, size_t count, int from_montgomery) {
+    WsLock ws_lock_(c);
     if (!c || !in || !out) return c ? c->fail(WS_E_ARG, "null buffer") : WS_E_ARG;
     if (count == 0) return WS_OK;
     cudaSetDevice(c->device);

@@ -1,6 +1,7 @@
 // ctx.cuh -- the library context: device, stream, growable HBM arenas, stage timer.
 #pragma once
 #include <cuda_runtime.h>
+#include <mutex>
 #include <string>
 
 #include "../../include/wasmsnark_b200.h"
@@ -40,6 +41,27 @@ struct Arena {
 struct ws_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    // Thread safety (the reference queues any number of commands, src/bn128.js:282-300): every C-ABI entry point
+    // holds `mu` for the duration of the call, so host threads sharing a context are serialised -- blocking calls
+    // run one after the other; asynchronous *_dev calls are additionally chained on the device through `busy_ev`
+    // (they share the context's workspace arenas): work enqueued on a different stream than the previous call's
+    // first waits for that call's work.
+    std::recursive_mutex mu;
+    cudaEvent_t busy_ev = nullptr;
+    cudaStream_t busy_stream = nullptr;
+    bool busy = false;
+    void enter_stream(cudaStream_t st) {
+        if (busy && busy_stream != st) cudaStreamWaitEvent(st, busy_ev, 0);
+    }
+    void leave_stream(cudaStream_t st) {
+        if (!busy_ev && cudaEventCreateWithFlags(&busy_ev, cudaEventDisableTiming) != cudaSuccess) {
+            busy_ev = nullptr;
+            return;
+        }
+        cudaEventRecord(busy_ev, st);
+        busy_stream = st;
+        busy = true;
+    }
     ws::Arena arenas[16];
     // side streams for the prover: independent MSMs and the r/s fixed-base products run concurrently
     static constexpr int NLANES = 6;
@@ -110,4 +132,26 @@ struct ws_ctx {
         err = std::string(where) + ": " + cudaGetErrorString(e);
         return WS_E_CUDA;
     }
+};
+
+// Holds the context's mutex for the duration of one C-ABI call (null ctx: no-op, the caller returns WS_E_ARG).
+struct WsLock {
+    ws_ctx* c;
+    explicit WsLock(ws_ctx* c_) : c(c_) {
+        if (c) c->mu.lock();
+    }
+    ~WsLock() {
+        if (c) c->mu.unlock();
+    }
+    WsLock(const WsLock&) = delete;
+    WsLock& operator=(const WsLock&) = delete;
+};
+// Orders one asynchronous call's work after the previous call's on the device (see ws_ctx::busy_ev).
+struct WsStreamScope {
+    ws_ctx* c;
+    cudaStream_t st;
+    WsStreamScope(ws_ctx* c_, cudaStream_t st_) : c(c_), st(st_) { c->enter_stream(st); }
+    ~WsStreamScope() { c->leave_stream(st); }
+    WsStreamScope(const WsStreamScope&) = delete;
+    WsStreamScope& operator=(const WsStreamScope&) = delete;
 };

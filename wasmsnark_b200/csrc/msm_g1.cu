@@ -20,14 +20,17 @@ int msm_table_choose_c(size_t n) {
 
 extern "C" {
 WS_API int ws_bn128_g1_multiexp(ws_ctx* c, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t out[96]) {
+    WsLock ws_lock_(c);
     return multiexp_host<G1Curve>(c, scalars, points, n, out);
 }
 WS_API int ws_bn128_g1_multiexp_dev(ws_ctx* c, const void* ds, const void* dp, size_t n, void* dout, int wb, void* stream) {
+    WsLock ws_lock_(c);
     if (!c || !dout || (n && (!ds || !dp))) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
     cudaSetDevice(c->device);
     return multiexp_dev<G1Curve>(c, ds, dp, n, dout, wb, stream ? (cudaStream_t)stream : c->stream);
 }
 WS_API int ws_bn128_g1_sum_dev(ws_ctx* c, const void* d_parts, int count, void* d_out, void* stream) {
+    WsLock ws_lock_(c);
     if (!c || !d_parts || !d_out || count < 0) return c ? c->fail(WS_E_ARG, "bad argument") : WS_E_ARG;
     cudaSetDevice(c->device);
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
@@ -35,6 +38,7 @@ WS_API int ws_bn128_g1_sum_dev(ws_ctx* c, const void* d_parts, int count, void* 
     return cudaGetLastError() == cudaSuccess ? WS_OK : c->fail_cuda("sum_points");
 }
 WS_API int ws_bn128_g1_affine(ws_ctx* c, const uint8_t* in, uint8_t* out, size_t count, int from_montgomery) {
+    WsLock ws_lock_(c);
     if (!c || !in || !out) return c ? c->fail(WS_E_ARG, "null buffer") : WS_E_ARG;
     if (count == 0) return WS_OK;
     cudaSetDevice(c->device);
@@ -48,11 +52,13 @@ WS_API int ws_bn128_g1_affine(ws_ctx* c, const uint8_t* in, uint8_t* out, size_t
     return WS_OK;
 }
 WS_API int ws_bn128_g1_build_table_dev(ws_ctx* c, const void* d_points, size_t n, int table_c, void* d_table, void* stream) {
+    WsLock ws_lock_(c);
     if (!c || !d_points || !d_table) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
     cudaSetDevice(c->device);
     return build_table_dev<G1Curve>(c, d_points, n, table_c, d_table, stream ? (cudaStream_t)stream : c->stream);
 }
 WS_API int ws_bn128_g1_multiexp_table_dev(ws_ctx* c, const void* ds, const void* d_table, size_t n, int table_c, void* dout, void* stream) {
+    WsLock ws_lock_(c);
     if (!c || !dout || (n && (!ds || !d_table))) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
     if (table_c < 8 || table_c > 22) return c->fail(WS_E_ARG, "table window bits must be in 8..22");
     cudaSetDevice(c->device);

@@ -34,6 +34,18 @@ inline int multiexp_dev(ws_ctx* c, const void* d_scalars, const void* d_points, 
     if (!base) return c->fail_cuda("msm workspace");
     MsmWorkspace w;
     msm_carve<C>(p, base, &w);
+    // a public entry (own_timer): chain after the previous asynchronous call on this context (shared arenas)
+    struct Chain {
+        ws_ctx* c;
+        cudaStream_t st;
+        bool on;
+        Chain(ws_ctx* c_, cudaStream_t st_, bool on_) : c(c_), st(st_), on(on_) {
+            if (on) c->enter_stream(st);
+        }
+        ~Chain() {
+            if (on) c->leave_stream(st);
+        }
+    } chain(c, st, own_timer);
     if (own_timer) c->timer.begin(st);
     cudaError_t e = msm_launch<C>(p, w, (const uint32_t*)d_scalars, (const Affine<C>*)d_points, (XYZZ<C>*)d_out_xyzz, (Jac<C>*)d_out, st, own_timer ? &c->timer : nullptr, &c->launches, c->acc_variant);
     if (e != cudaSuccess) return c->fail_cuda("msm launch");
@@ -42,6 +54,7 @@ inline int multiexp_dev(ws_ctx* c, const void* d_scalars, const void* d_points, 
 
 template <class C>
 inline int multiexp_host(ws_ctx* c, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t* out) {
+    WsLock ws_lock_(c);
     if (!c || !out || (n && (!scalars || !points))) return c ? c->fail(WS_E_ARG, "null buffer") : WS_E_ARG;
     cudaSetDevice(c->device);
     constexpr size_t PS = sizeof(Affine<C>), OS = sizeof(Jac<C>), SS = 4 * C::SCALAR_LIMBS;
@@ -49,12 +62,13 @@ inline int multiexp_host(ws_ctx* c, const uint8_t* scalars, const uint8_t* point
     if (!d) return c->fail_cuda("input workspace");
     uint8_t *ds = d, *dp = d + align256(n * SS), *dout = dp + align256(n * PS);
     if (n) {
-        cudaMemcpyAsync(ds, scalars, n * SS, cudaMemcpyHostToDevice, c->stream);
-        cudaMemcpyAsync(dp, points, n * PS, cudaMemcpyHostToDevice, c->stream);
+        if (cudaMemcpyAsync(ds, scalars, n * SS, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+            cudaMemcpyAsync(dp, points, n * PS, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+            return c->fail_cuda("multiexp: host-to-device copy");
     }
     int rc = multiexp_dev<C>(c, ds, dp, n, dout, 0, c->stream);
     if (rc) return rc;
-    cudaMemcpyAsync(out, dout, OS, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaMemcpyAsync(out, dout, OS, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return c->fail_cuda("multiexp: device-to-host copy");
     if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) return c->fail_cuda("multiexp");
     return WS_OK;
 }

@@ -36,6 +36,7 @@ static __global__ void __launch_bounds__(64) k_mnt_fq3_mul(const MntFq3* __restr
 
 extern "C" {
 WS_API int ws_mnt6753_fq3_mul_batch(ws_ctx* c, const uint8_t* x, const uint8_t* y, uint8_t* out, size_t n) {
+    WsLock ws_lock_(c);
     if (!c || !x || !y || !out) return c ? c->fail(WS_E_ARG, "null buffer") : WS_E_ARG;
     if (n == 0) return WS_OK;
     cudaSetDevice(c->device);
@@ -50,14 +51,17 @@ WS_API int ws_mnt6753_fq3_mul_batch(ws_ctx* c, const uint8_t* x, const uint8_t* 
     return WS_OK;
 }
 WS_API int ws_mnt6753_g1_multiexp(ws_ctx* c, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t out[288]) {
+    WsLock ws_lock_(c);
     return multiexp_host<MntG1Curve>(c, scalars, points, n, out);
 }
 WS_API int ws_mnt6753_g1_multiexp_dev(ws_ctx* c, const void* ds, const void* dp, size_t n, void* dout, int wb, void* stream) {
+    WsLock ws_lock_(c);
     if (!c || !dout || (n && (!ds || !dp))) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
     cudaSetDevice(c->device);
     return multiexp_dev<MntG1Curve>(c, ds, dp, n, dout, wb, stream ? (cudaStream_t)stream : c->stream);
 }
 WS_API int ws_mnt6753_g1_affine(ws_ctx* c, const uint8_t* in, uint8_t* out, size_t count, int from_montgomery) {
+    WsLock ws_lock_(c);
     if (!c || !in || !out) return c ? c->fail(WS_E_ARG, "null buffer") : WS_E_ARG;
     if (count == 0) return WS_OK;
     cudaSetDevice(c->device);

@@ -269,10 +269,13 @@ struct MillerState {
     G1A P;
     G2A Q, T;
 };
-// d[i] <- 1/d[i] for n <= 8 non-zero values with one field inversion
-static inline void batch_inv(F2* d, int n) {
+// d[i] <- 1/d[i] for n <= 8 values with one field inversion.  Returns false (d untouched) if any d[i] is zero: a zero
+// would otherwise zero EVERY inverse of the batch, i.e. one degenerate pair would corrupt the slopes of the others.
+static inline bool batch_inv(F2* d, int n) {
     F2 pre[8];
     F2 acc = F2::one();
+    for (int i = 0; i < n; i++)
+        if (d[i].is_zero()) return false;
     for (int i = 0; i < n; i++) {
         pre[i] = acc;
         acc = mul(acc, d[i]);
@@ -283,6 +286,7 @@ static inline void batch_inv(F2* d, int n) {
         acc = mul(acc, d[i]);
         d[i] = t;
     }
+    return true;
 }
 // T <- T + R along the chord/tangent of slope lam, multiplying the line into f
 static inline void step_apply(MillerState& s, const F2& lam, const F2& rx, F12& f) {
@@ -291,24 +295,31 @@ static inline void step_apply(MillerState& s, const F2& lam, const F2& rx, F12& 
     s.T.y = sub(mul(lam, sub(s.T.x, x3)), s.T.y);
     s.T.x = x3;
 }
-static inline void steps_double(MillerState** st, int n, F12& f) {
+// The affine walk has no formula for a vertical line: T = +-R in an addition step or y_T = 0 in a doubling step.  Neither
+// can happen for Q in the order-r subgroup (the loop count stays below r); it can for a twist point outside it (the
+// BN254 twist cofactor has small factors) -- the steps then report failure and the caller rejects the input.
+static inline bool steps_double(MillerState** st, int n, F12& f) {
     F2 den[8];
     for (int i = 0; i < n; i++) den[i] = dbl(st[i]->T.y);
-    batch_inv(den, n);
+    if (!batch_inv(den, n)) return false;
     for (int i = 0; i < n; i++) {
         F2 x2 = sqr(st[i]->T.x);
         step_apply(*st[i], mul(add(dbl(x2), x2), den[i]), st[i]->T.x, f);
     }
+    return true;
 }
-static inline void steps_add(MillerState** st, const G2A* R, int n, F12& f) {
+static inline bool steps_add(MillerState** st, const G2A* R, int n, F12& f) {
     F2 den[8];
     for (int i = 0; i < n; i++) den[i] = sub(R[i].x, st[i]->T.x);
-    batch_inv(den, n);
+    if (!batch_inv(den, n)) return false;
     for (int i = 0; i < n; i++) step_apply(*st[i], mul(sub(R[i].y, st[i]->T.y), den[i]), R[i].x, f);
+    return true;
 }
 
 // prod_i f_{6z+2,Q_i}(P_i) * (the two Frobenius lines): one shared squaring and one shared inversion per step
-static inline F12 miller_product(const G1A* P, const G2A* Q, int n) {
+// *ok = false: a degenerate step was met (some Q_i is not in the order-r subgroup); the returned value is meaningless.
+static inline F12 miller_product(const G1A* P, const G2A* Q, int n, bool* ok) {
+    *ok = true;
     MillerState all[8];
     MillerState* st[8];
     G2A q0[8], q1[8], q2[8];
@@ -326,11 +337,12 @@ static inline F12 miller_product(const G1A* P, const G2A* Q, int n) {
     if (!m) return f;
     for (int b = 1; b < pairing_consts::ATE_LOOP_BITS; b++) {
         f = sqr(f);
-        steps_double(st, m, f);
-        if (pairing_consts::ATE_LOOP[b]) steps_add(st, q0, m, f);
+        if (!steps_double(st, m, f) || (pairing_consts::ATE_LOOP[b] && !steps_add(st, q0, m, f))) {
+            *ok = false;
+            return f;
+        }
     }
-    steps_add(st, q1, m, f);
-    steps_add(st, q2, m, f);
+    if (!steps_add(st, q1, m, f) || !steps_add(st, q2, m, f)) *ok = false;
     return f;
 }
 
@@ -352,7 +364,10 @@ static inline F12 final_exponentiation(const F12& f) {
     return mul(frobenius(mul(conj(e), l), 3), r);
 }
 
-static inline F12 pairing(const G1A& P, const G2A& Q) { return final_exponentiation(miller_product(&P, &Q, 1)); }
+static inline F12 pairing(const G1A& P, const G2A& Q, bool* ok) {
+    F12 f = miller_product(&P, &Q, 1, ok);
+    return *ok ? final_exponentiation(f) : F12::one();
+}
 
 }  // namespace pairing
 }  // namespace ws

@@ -696,14 +696,19 @@ static int prove_host(ws_ctx* c, const ws_pkey* k, const uint8_t* witness, size_
 extern "C" {
 
 WS_API int ws_bn128_fr_fft_dev(ws_ctx* c, void* d_px, size_t n, int odd, int inverse, void* stream) {
+    WsLock ws_lock_(c);
     if (!c || !d_px) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
     int logn = n <= 0xFFFFFFFFull ? log2_exact((uint32_t)n) : -1;
     if (logn < 0 || logn > 28) return c->fail(WS_E_SIZE, "fft size must be a power of two <= 2^28");
     cudaSetDevice(c->device);
+    // BN128 Fr has 2-adicity 28: the odd (coset) transform needs w_{2n}, which does not exist for n = 2^28
+    // (the reference's table ends at w[28] as well, src/build_fft.js:29-57)
+    if (odd && logn == 28) return c->fail(WS_E_SIZE, "odd fft of size 2^28 needs a 2^29-th root of unity");
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    if (!ensure_twiddles(c, logn + 1, st)) return c->fail_cuda("twiddle table");
+    if (!ensure_twiddles(c, logn + (odd ? 1 : 0), st)) return c->fail_cuda("twiddle table");
     Fr* scratch = (Fr*)c->arena(2, sizeof(Fr) << logn);
     if (!scratch) return c->fail_cuda("fft scratch");
+    WsStreamScope chain(c, st);
     c->timer.begin(st);
     cudaError_t e = ntt_launch((Fr*)d_px, scratch, logn, odd != 0, inverse != 0, twiddles(c), st, &c->launches);
     c->timer.mark("ntt", st);
@@ -711,6 +716,7 @@ WS_API int ws_bn128_fr_fft_dev(ws_ctx* c, void* d_px, size_t n, int odd, int inv
 }
 
 static int fft_host(ws_ctx* c, uint8_t* px, size_t n, int odd, int inverse) {
+    WsLock ws_lock_(c);
     if (!c || !px) return c ? c->fail(WS_E_ARG, "null buffer") : WS_E_ARG;
     int logn = n <= 0xFFFFFFFFull ? log2_exact((uint32_t)n) : -1;
     if (logn < 0 || logn > 28) return c->fail(WS_E_SIZE, "fft size must be a power of two <= 2^28");
@@ -728,42 +734,52 @@ WS_API int ws_bn128_fr_fft(ws_ctx* c, uint8_t* px, size_t n, int odd) { return f
 WS_API int ws_bn128_fr_ifft(ws_ctx* c, uint8_t* px, size_t n, int odd) { return fft_host(c, px, n, odd, 1); }
 
 WS_API int ws_set_h_priority(ws_ctx* c, int on) {
+    WsLock ws_lock_(c);
     if (!c) return WS_E_ARG;
     c->h_priority = on != 0;
     return WS_OK;
 }
 WS_API int ws_set_key_tables(ws_ctx* c, int on) {
+    WsLock ws_lock_(c);
     if (!c) return WS_E_ARG;
     c->key_tables = on != 0;
     return WS_OK;
 }
 WS_API int ws_bn128_pkey_load(ws_ctx* c, const uint8_t* pkey, size_t len, ws_pkey** out) {
+    WsLock ws_lock_(c);
     if (!c || !pkey || !out) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
     *out = nullptr;
     return pkey_load(c, pkey, len, out);
 }
 WS_API int ws_bn128_pkey_load_shard(ws_ctx* c, const uint8_t* pkey, size_t len, int rank, int world, ws_pkey** out) {
+    WsLock ws_lock_(c);
     if (!c || !pkey || !out) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
     *out = nullptr;
     return pkey_load(c, pkey, len, out, rank, world);
 }
 WS_API int ws_bn128_groth16_partials_dev(ws_ctx* c, const ws_pkey* k, const void* d_witness, void* d_partials, void* stream) {
+    WsLock ws_lock_(c);
     if (!c || !k || !d_witness || !d_partials) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
     if (k->ctx != c) return c->fail(WS_E_ARG, "proving key belongs to another context");
     if (((uintptr_t)d_witness | (uintptr_t)d_partials) & 15) return c->fail(WS_E_ARG, "device pointers must be 16-byte aligned");
     cudaSetDevice(c->device);
+    WsStreamScope chain(c, stream ? (cudaStream_t)stream : c->stream);
     return prove_partials_dev(c, k, (const uint8_t*)d_witness, (uint8_t*)d_partials, stream ? (cudaStream_t)stream : c->stream);
 }
 WS_API int ws_bn128_groth16_prepare_dev(ws_ctx* c, const ws_pkey* k, const void* d_rs, void* stream) {
+    WsLock ws_lock_(c);
     if (!c || !k || !d_rs) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
     if (k->ctx != c) return c->fail(WS_E_ARG, "proving key belongs to another context");
     cudaSetDevice(c->device);
+    WsStreamScope chain(c, stream ? (cudaStream_t)stream : c->stream);
     return prove_pre_dev(c, k, (const uint8_t*)d_rs, stream ? (cudaStream_t)stream : c->stream);
 }
 WS_API int ws_bn128_groth16_finish_dev(ws_ctx* c, const ws_pkey* k, const void* d_all_partials, int world, const void* d_rs, void* d_out, void* stream) {
+    WsLock ws_lock_(c);
     if (!c || !k || !d_all_partials || !d_rs || !d_out || world < 1) return c ? c->fail(WS_E_ARG, "bad argument") : WS_E_ARG;
     if (k->ctx != c) return c->fail(WS_E_ARG, "proving key belongs to another context");
     cudaSetDevice(c->device);
+    WsStreamScope chain(c, stream ? (cudaStream_t)stream : c->stream);
     return prove_finish_dev(c, k, (const uint8_t*)d_all_partials, world, (const uint8_t*)d_rs, (uint8_t*)d_out, stream ? (cudaStream_t)stream : c->stream);
 }
 WS_API void ws_bn128_pkey_free(ws_pkey* k) {
@@ -782,6 +798,7 @@ WS_API int ws_bn128_pkey_info(const ws_pkey* k, uint32_t* n_vars, uint32_t* n_pu
 
 WS_API int ws_bn128_calc_h(ws_ctx* c, const uint8_t* signals, const uint8_t* polsA, size_t lenA, const uint8_t* polsB, size_t lenB, uint32_t n_signals,
                            uint32_t domain_size, uint8_t* out) {
+    WsLock ws_lock_(c);
     if (!c || !signals || !polsA || !polsB || !out) return c ? c->fail(WS_E_ARG, "null buffer") : WS_E_ARG;
     int logn = log2_exact(domain_size);
     if (logn < 0 || logn > 27) return c->fail(WS_E_SIZE, "domainSize must be a power of two <= 2^27");
@@ -817,6 +834,7 @@ WS_API int ws_bn128_calc_h(ws_ctx* c, const uint8_t* signals, const uint8_t* pol
 
 WS_API int ws_bn128_groth16_prove_key(ws_ctx* c, const ws_pkey* k, const uint8_t* witness, size_t wlen, const uint8_t* r, const uint8_t* s, uint8_t pi_a[96],
                                       uint8_t pi_b[192], uint8_t pi_c[96]) {
+    WsLock ws_lock_(c);
     if (!c || !k || !witness || !pi_a || !pi_b || !pi_c) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
     if (k->ctx != c) return c->fail(WS_E_ARG, "proving key belongs to another context");
     return prove_host(c, k, witness, wlen, r, s, pi_a, pi_b, pi_c);
@@ -863,6 +881,7 @@ static unsigned long long key_fingerprint(const uint8_t* p, size_t n) {
 static void cached_key_free(void* k) { pkey_release((ws_pkey*)k); }
 
 WS_API int ws_set_key_cache(ws_ctx* c, int on) {
+    WsLock ws_lock_(c);
     if (!c) return WS_E_ARG;
     c->key_cache = on != 0;
     if (!on && c->cached_key) {
@@ -876,6 +895,7 @@ WS_API int ws_set_key_cache(ws_ctx* c, int on) {
 
 WS_API int ws_bn128_groth16_prove(ws_ctx* c, const uint8_t* witness, size_t wlen, const uint8_t* pkey, size_t plen, const uint8_t* r, const uint8_t* s,
                                   uint8_t pi_a[96], uint8_t pi_b[192], uint8_t pi_c[96]) {
+    WsLock ws_lock_(c);
     if (!c || !witness || !pkey || !pi_a || !pi_b || !pi_c) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
     if (!c->key_cache) {
         ws_pkey* k = nullptr;
@@ -909,10 +929,12 @@ WS_API int ws_bn128_groth16_prove(ws_ctx* c, const uint8_t* witness, size_t wlen
 }
 
 WS_API int ws_bn128_groth16_prove_dev(ws_ctx* c, const ws_pkey* k, const void* d_witness, const void* d_rs, void* d_out, void* stream) {
+    WsLock ws_lock_(c);
     if (!c || !k || !d_witness || !d_rs || !d_out) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
     if (k->ctx != c) return c->fail(WS_E_ARG, "proving key belongs to another context");
     if (((uintptr_t)d_witness | (uintptr_t)d_out) & 15) return c->fail(WS_E_ARG, "device pointers must be 16-byte aligned");
     cudaSetDevice(c->device);
+    WsStreamScope chain(c, stream ? (cudaStream_t)stream : c->stream);
     return prove_dev(c, k, (const uint8_t*)d_witness, (const uint8_t*)d_rs, (uint8_t*)d_out, stream ? (cudaStream_t)stream : c->stream);
 }
 

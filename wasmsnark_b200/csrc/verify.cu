@@ -50,7 +50,9 @@ WS_API int ws_bn128_pairing(const uint8_t p[64], const uint8_t q[128], uint8_t o
     G1A P;
     G2A Q;
     if (!rd_g1(p, &P) || !rd_g2(q, &Q)) return WS_E_ARG;
-    F12 e = ws::pairing::pairing(P, Q);
+    bool ok = true;
+    F12 e = ws::pairing::pairing(P, Q, &ok);
+    if (!ok) return WS_E_ARG;          // Q outside the order-r subgroup of the twist (vertical line in the Miller loop)
     for (int i = 0; i < 6; i++) {   // reference ftm layout: c0.(a0,a1,a2), c1.(a0,a1,a2), each (re, im)
         const F6& h = i < 3 ? e.c0 : e.c1;
         const F2& a = (i % 3) == 0 ? h.a0 : (i % 3) == 1 ? h.a1 : h.a2;
@@ -124,7 +126,9 @@ WS_API int ws_bn128_groth16_verify(const uint8_t vk_alfa_1[64], const uint8_t vk
     G1A vkx{ax.x, ax.y, ax.z.is_zero()};
     G1A Ps[4] = {A, negate(vkx), negate(C), negate(alfa)};
     G2A Qs[4] = {B, gamma, delta, beta};
-    F12 e = final_exponentiation(miller_product(Ps, Qs, 4));
-    *valid = (e == F12::one()) ? 1 : 0;
+    bool ok = true;
+    F12 ml = miller_product(Ps, Qs, 4, &ok);
+    if (!ok) return WS_OK;             // a G2 input outside the order-r subgroup: reject (*valid stays 0)
+    *valid = (final_exponentiation(ml) == F12::one()) ? 1 : 0;
     return WS_OK;
 }
