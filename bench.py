@@ -1,37 +1,42 @@
 #!/usr/bin/env python3
-"""bench.py -- BASELINE.json metric on B200.   python bench.py --gpus N --steps K --warmup W
+"""bench.py -- BASELINE.json's metric on B200.   python bench.py --gpus N --steps K --warmup W
 
-Primary line (BASELINE configs[1]): BN128 G1 multi-scalar multiplication, n = 2^20 scalar-point pairs.
-One step = one pass of the hot path over one batch of synthetic input: sum s_i * P_i for 2^20 uniformly
-random scalars in [0, r) (set WS_BENCH_SCALARS=raw256 for uniform raw 256-bit integers) and 2^20 affine
-Montgomery G1 points.
-  value     pairs/s, inputs resident in HBM when the timed region starts (device-pointer C ABI), K steps with
-            WS_BENCH_INFLIGHT (default 4) MSMs in flight on as many contexts/streams, one CUDA-event pair around them;
-            "latency" holds the one-at-a-time figure (per-step events, L2 flushed between steps)
-  e2e       pairs/s through the host-buffer C ABI call ws_bn128_g1_multiexp: pinned host buffers, H2D of
-            scalars + points and D2H of the 96-byte result inside the timed region (one host thread per context)
-  roofline  dominant kernel k_msm_accumulate: 96 algorithmic bytes per pair / its CUDA-event
-            duration on the launch stream, against the measured HBM copy peak (MEASURED_PEAKS.json)
-  cpu_baseline  the reference's own g1m_multiexp2 (w = 7; its WASM image compiled natively, oracle/_ref) on a
-            bounded sample over the host cores, split as src/bn128.js:353-383 does
-Same JSON line, key "groth16": the other half of BASELINE's metric -- full Groth16 proofs/s on a synthetic
-2^20-constraint key (tools/gen_synth_key.py), device-resident key + witness (value) and through the
-host-buffer call with the resident key (e2e), plus "example_key" (BASELINE configs[3]: the reference's example key,
-checked against proof_good0.json) and "dropin_call" (the stateless groth16GenProof(witness, provingKey) call);
-key "ntt": BASELINE configs[2], 2^22 forward + inverse; "mnt6753": configs[4] MSM 2^18; "bls12381": G1 MSM 2^20;
-"verifier": host-side groth16Verify next to the reference's.
-`--impl reference` runs only the CPU arm and prints the same line shape.
-N > 1 (torchrun, one rank per GPU): one MSM of N * 2^20 pairs, contiguous point ranges of 2^20 pairs per rank (the
-reference's worker split), one all_gather of the 96-byte partial sums over NCCL, tiny on-device combine: per-GPU
-work is fixed, so the MSM line is WEAK scaling; the "groth16" object is one fixed 2^20-constraint proof sharded
-over the N GPUs (strong scaling of its latency).
+Primary line: **Groth16 proofs/sec, BN128, 2^20 constraints** (BASELINE.json `metric`, first half) -- STRONG scaling:
+the workload is one fixed-size proof whatever N is.  One step = one full proof of the synthetic 2^20-constraint key of
+tools/gen_synth_key.py (nVars = domainSize = 2^20, nPublic = 58, seed 0xB204) with fixed (r, s); the proof is compared
+with the one the REFERENCE's own code computed for the same inputs (tests/golden/synth_2p20.golden.json) before
+anything is timed.
+  value     proofs/s, key + witness resident in HBM, WS_BENCH_PROOFS_INFLIGHT (default 2) proofs in flight (one
+            context + resident key each), K proofs inside one CUDA-event pair, max over ranks
+  latency   one proof at a time (per-proof CUDA events, L2 flushed between proofs)
+  e2e       proofs/s through the host-buffer C ABI: N = 1 -- the blocking ws_bn128_groth16_prove_key(witness) from one
+            host thread per context, witness in pinned host memory, H2D + D2H inside the timed region; `e2e.pageable` is
+            the same from ordinary pageable memory, `dropin_call` the stateless ws_bn128_groth16_prove(witness, pkey)
+            (the literal groth16GenProof(witness, provingKey), key handed over on every call);
+            N > 1 -- parallel.ShardedProver: per proof, H2D of the witness ranges the rank needs, the sharded proof
+            (H on one rank per proof, rotating; NCCL send/recv of the h slices; one all_gather of 768-byte records),
+            D2H of the proof
+  roofline  the dominant kernel of a proof, k_msm_accumulate<G1> (4 launches per proof, window-table form): 96
+            algorithmic bytes per pair / its CUDA-event duration on the launch stream, timed alone on the
+            key's A section with the witness scalars, against the measured HBM copy peak (MEASURED_PEAKS.json);
+            `traffic` and the pipe utilisation are read from the ncu summary committed under profiles/
+  cpu_baseline  the reference's own groth16GenProof (its WASM image compiled natively, oracle/_ref, driven as
+            src/bn128.js:580-720 drives it, worker pool = all host cores) on a bounded sample: the same generator's
+            2^16-constraint key, scaled by 2^16/2^20 (the reference's cost per constraint does not fall with size --
+            fixed-window multiexp, n log n FFT -- so this over-states its 2^20 rate); plus the single-threaded figure
+Extra objects on the same line: "msm" (BASELINE configs[1], G1 MSM 2^20 pairs, the second half of the metric, with its
+own roofline / cpu_baseline / e2e; N > 1: the same 2^20 pairs split N ways = strong, and "msm_weak"), "ntt" (configs[2]),
+"example_key" (configs[3], checked against proof_good0.json), "mnt6753" (configs[4]), "bls12381", "verifier".
+`--impl reference` runs only the CPU arm (rank 0) and prints the same line shape.
 """
 import argparse
 import ctypes
 import json
 import os
+import re
 import subprocess
 import sys
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -39,14 +44,27 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
-LOG2N = int(os.environ.get("WS_BENCH_LOG2N", "20"))
+LOG2N = int(os.environ.get("WS_BENCH_LOG2N", "20"))                 # MSM pairs
 N_PAIRS = 1 << LOG2N
 PROVE_LOG2 = int(os.environ.get("WS_BENCH_PROVE_LOG2", "20"))       # constraints (domain size) of the synthetic key
+CPU_SAMPLE_LOG2 = int(os.environ.get("WS_BENCH_CPU_SAMPLE_LOG2", "16"))
 ALG_BYTES_PER_PAIR = 96          # 32 B scalar + 64 B affine point
-KERNELS_PER_MSM = 18             # digits, 2x3 scan, scatter, 3 task-table, accumulate, 2 combine, segreduce, seg2, bitsum, final
-NCU_TRAFFIC_BYTES = 656826368   # k_msm_accumulate<G1>, n = 2^20: measured once per round with ncu (profiles/)
-NFLIGHT = max(1, int(os.environ.get("WS_BENCH_INFLIGHT", "4")))   # MSMs in flight for the throughput number
+NFLIGHT = max(1, int(os.environ.get("WS_BENCH_INFLIGHT", "4")))     # MSMs in flight for the MSM throughput number
+NPROOFS = max(1, int(os.environ.get("WS_BENCH_PROOFS_INFLIGHT", "2")))
 SCALARS = os.environ.get("WS_BENCH_SCALARS", "fr")      # "fr": uniform in [0, r) ; "raw256": uniform 256-bit
+RS = bytes(range(1, 65))          # r | s injected into every timed proof (the golden proof uses the same)
+DTYPE = "u32 limbs (256-bit Montgomery)"
+
+
+def metric_name():
+    return "Groth16 proofs/sec (BN128, 2^%d constraints)" % PROVE_LOG2
+
+
+def workload_config():
+    """identical in the GPU arm and the reference arm"""
+    return {"workload": "BN128 Groth16 full prove, synthetic proving key nVars = domainSize = 2^%d, nPublic = 58 (tools/gen_synth_key.py seed 0xB204), "
+                        "witness 6.7%% zeros / 3.1%% ones / 10%% < 2^32 / rest uniform < r, fixed (r, s)" % PROVE_LOG2,
+            "log2_constraints": PROVE_LOG2, "n_public": 58}
 
 
 def make_inputs(n, seed=0xB201, dist=None, offset=0):
@@ -72,7 +90,43 @@ def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
     except Exception:
-        return 6650.0, "fallback"
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def read_ncu_summary(kernel_substr, prefer=("r2", "r1")):
+    """Metrics of the first kernel whose name contains `kernel_substr` from the newest profiles/<tag>_ncu_*.txt summary
+    (tools/ncu_summary.py format).  Returns (dict name -> float in base units, path) or ({}, None)."""
+    pdir = os.path.join(ROOT, "profiles")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
+    try:
+        names = sorted(os.listdir(pdir))
+    except OSError:
+        return {}, None
+    for tag in prefer:
+        for fn in names:
+            if not (fn.startswith(tag + "_ncu_") and fn.endswith(".txt")):
+                continue
+            cur, out = None, {}
+            for line in open(os.path.join(pdir, fn)):
+                if line.startswith("== kernel:"):
+                    if out:
+                        break
+                    cur = line if kernel_substr in line else None
+                    continue
+                if cur is None:
+                    continue
+                f = line.split()
+                if len(f) < 2:
+                    continue
+                try:
+                    val = float(f[-1].replace(",", ""))
+                except ValueError:
+                    continue
+                unit = f[-2] if len(f) >= 3 else ""
+                out[f[0]] = val * scale.get(unit, 1.0)
+            if out:
+                return out, os.path.join("profiles", fn)
+    return {}, None
 
 
 class ClockSampler:
@@ -105,11 +159,10 @@ class ClockSampler:
             for nm, v in zip(names, f[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
-
-
-_POOLS = {}
+        busy = sorted(x for x in sm if x > 0)
+        # median over the upper half of the samples: the sampler also sees the idle gaps between the bench's phases
+        top = busy[len(busy) // 2:] if busy else []
+        return {"sm_mhz": top[len(top) // 2] if top else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def usable_cores():
@@ -131,10 +184,12 @@ def usable_cores():
     return n
 
 
-def cpu_reference_arm(scalars, points, sample_pairs, threads):
-    """The reference's g1m_multiexp2 over `threads` workers on the first `sample_pairs` pairs.  The worker pool
-    (one instance of the reference's image per thread) is built once, as buildBn128() does; the timed part is
-    what Bn128.g1_multiexp does: split, post the slices, run, add the partial points."""
+# ------------------------------------------------------------------------------------------------ CPU arms (oracle/_ref)
+_POOLS = {}
+
+
+def cpu_msm_arm(scalars, points, sample_pairs, threads):
+    """The reference's g1m_multiexp2 over `threads` workers on the first `sample_pairs` pairs (src/bn128.js:353-383)."""
     import util
     pool = _POOLS.get(threads)
     if pool is None:
@@ -146,43 +201,81 @@ def cpu_reference_arm(scalars, points, sample_pairs, threads):
     return sample_pairs / dt, dt
 
 
-def metric_name():
-    return "BN128 G1-MSM scalar-point pairs/sec (n=2^%d)" % LOG2N
+class CpuProver:
+    """The reference's groth16GenProof on a 2^k-constraint key of the bench's generator, worker pool of `threads`."""
+
+    def __init__(self, k, threads):
+        import gen_synth_key
+        from oracle import ref_wasm
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        import make_golden_2p20
+        self.k, self.threads = k, threads
+        self.pk, self.wit = gen_synth_key.make(1 << k, 58, 1 << k, seed=0xB204)
+        self.pool = ref_wasm.RefBn128Pool(concurrency=threads, pages=make_golden_2p20.pages_for(self.pk, self.wit))
+
+    def prove(self):
+        t0 = time.perf_counter()
+        proof = self.pool.groth16GenProof(self.wit, self.pk, r=RS[:32], s=RS[32:])
+        return time.perf_counter() - t0, proof
+
+    def close(self):
+        self.pool.close()
 
 
-def workload_name():
-    return "BN128 G1 MSM, 2^%d scalar-point pairs (BASELINE configs[1]): scalars %s, affine Montgomery points" % (
-        LOG2N, "uniform in [0, r)" if SCALARS == "fr" else "uniform raw 256-bit")
+def cpu_prover_baseline(cores):
+    """cpu_baseline object of the primary line: all cores on the 2^CPU_SAMPLE_LOG2 sample, one thread on a 2^13 sample."""
+    k = min(CPU_SAMPLE_LOG2, PROVE_LOG2)
+    scale = (1 << k) / float(1 << PROVE_LOG2)
+    cp = CpuProver(k, cores)
+    cp.prove() if k <= 12 else None                  # tiny samples: touch the pool once
+    dt, _ = cp.prove()
+    cp.close()
+    k1 = min(13, k)
+    c1 = CpuProver(k1, 1)
+    dt1, _ = c1.prove()
+    c1.close()
+    return {"value": scale / dt, "unit": "proofs/s", "cores": cores, "kind": "reference",
+            "single_thread_value": ((1 << k1) / float(1 << PROVE_LOG2)) / dt1,
+            "sample": "reference groth16GenProof (its WASM image compiled natively, oracle/_ref; worker pool of %d threads as src/bn128.js:353-383,569-622 schedules it) "
+                      "on the same generator's 2^%d-constraint key: %.2f s per proof, scaled by 2^%d/2^%d; single thread: 2^%d-constraint key, %.2f s" % (cores, k, dt, k, PROVE_LOG2, k1, dt1),
+            "sample_seconds": dt, "sample_log2_constraints": k}
 
 
 def run_reference(args, emit):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference: the reference's own CPU prover on the box's host cores, rank 0 only; each step = one proof of the
+    bounded sample key, the value scaled to proofs/s at 2^PROVE_LOG2 constraints."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     from oracle import ref_wasm
     if not ref_wasm.available():
         emit({"impl": "reference", "unavailable": "oracle/_ref not built (reference not mounted at build time)"})
         return
     cores = usable_cores()
-    sample = min(N_PAIRS, 8192 * cores)
-    scalars, points, _, _ = make_inputs(sample)
-    vals = []
-    for k in range(args.warmup + args.steps):
-        v, dt = cpu_reference_arm(scalars, points, sample, cores)
-        if k >= args.warmup:
-            vals.append((v, dt))
-    v = sum(x for x, _ in vals) / len(vals)
-    ms = 1000.0 * sum(d for _, d in vals) / len(vals)
-    line = {
-        "impl": "reference", "metric": metric_name(), "value": v, "unit": "pairs/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (256-bit Montgomery)", "data": "synthetic",
-        "config": {"workload": workload_name(), "sample_pairs": sample},
-        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "reference",
-                         "sample": "each step = first %d pairs, %d threads x g1m_multiexp2(w=7) of the reference's WASM image compiled natively (oracle/_ref), partials combined with g1m_add" % (sample, cores)},
-        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    emit(line)
+    k = min(CPU_SAMPLE_LOG2, PROVE_LOG2)
+    total = max(1, args.steps) + max(0, args.warmup)
+    cp = CpuProver(k, cores)
+    dt, _ = cp.prove()                               # first warm-up step doubles as the budget probe
+    while dt * total > 240.0 and k > 10:             # keep the whole run within a few minutes
+        cp.close()
+        k -= 1
+        cp = CpuProver(k, cores)
+        dt, _ = cp.prove()
+    for _ in range(max(0, args.warmup - 1)):
+        cp.prove()
+    times = [cp.prove()[0] for _ in range(max(1, args.steps))]
+    cp.close()
+    scale = (1 << k) / float(1 << PROVE_LOG2)
+    mean = sum(times) / len(times)
+    v = scale / mean
+    emit({
+        "impl": "reference", "metric": metric_name(), "value": v, "unit": "proofs/s", "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
+        "ms_per_step": 1000.0 * mean / scale, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+        "config": workload_config(),
+        "cpu_baseline": {"value": v, "unit": "proofs/s", "cores": cores, "kind": "reference",
+                         "sample": "each step = the reference's groth16GenProof (WASM image compiled natively, oracle/_ref; %d worker threads, CALC_H one task, every multiexp split %d ways, src/bn128.js:353-383,569-622) "
+                                   "on the same generator's 2^%d-constraint key (%.2f s per step), scaled by 2^%d/2^%d to the 2^%d-constraint workload" % (cores, cores, k, mean, k, PROVE_LOG2, PROVE_LOG2)},
+        "e2e": {"value": v, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    })
 
 
 def verifier_line(reps=10):
@@ -214,25 +307,590 @@ def verifier_line(reps=10):
     return out
 
 
-def timed_steps(torch, stream, step, steps, flush, barrier, world, dist):
-    """K steps, each bracketed by its own CUDA-event pair on the launch stream, L2 flushed in between
-    (outside the pairs); returns (sum of step times in ms, max over ranks)."""
-    evs = []
-    barrier()
-    for _ in range(steps):
-        flush.fill_(1)
+# ------------------------------------------------------------------------------------------------ GPU arm
+class Env:
+    """torch / distributed state shared by the sections"""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists)")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.W = max(3, args.warmup)
+        self.K = max(1, args.steps)
+        self.stream = torch.cuda.Stream()            # a real (non-legacy) stream: the library launches on it
+        torch.cuda.set_stream(self.stream)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        from wasmsnark_b200 import build_bn128
+        nctx = max(NFLIGHT, NPROOFS)
+        self.bns = [build_bn128(self.local) for _ in range(nctx)]
+        self.streams = [self.stream] + [torch.cuda.Stream() for _ in range(nctx - 1)]
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def launches(self):
+        return sum(b.lib.ws_kernel_launches(b.ctx.h) for b in self.bns)
+
+    def timed_serial(self, step, steps, stream=None):
+        """`steps` steps, each bracketed by its own CUDA-event pair on the launch stream, L2 flushed in between (outside
+        the pairs); returns the mean step time in ms, max over ranks."""
+        torch = self.torch
+        stream = stream or self.stream
+        evs = []
+        self.barrier()
+        for _ in range(steps):
+            self.flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            step()
+            e1.record(stream)
+            evs.append((e0, e1))
+            torch.cuda.synchronize()
+        self.barrier()
+        return self.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs)) / steps
+
+    def timed_pipelined(self, body, nstreams):
+        """one CUDA-event pair on the main stream around `body`, which enqueues work on streams[0 .. nstreams); returns ms,
+        max over ranks"""
+        torch = self.torch
+        self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        step()
-        e1.record(stream)
+        e0.record(self.stream)
+        for sx in self.streams[1:nstreams]:
+            sx.wait_event(e0)
+        body()
+        for sx in self.streams[1:nstreams]:
+            ej = torch.cuda.Event()
+            ej.record(sx)
+            self.stream.wait_event(ej)
+        e1.record(self.stream)
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1))
+
+
+def section_groth16(env, args):
+    """The primary line's numbers.  Returns (dict of line fields, extras dict)."""
+    torch, dist, world, rank, K, W = env.torch, env.dist, env.world, env.rank, env.K, env.W
+    import gen_synth_key
+    from wasmsnark_b200._lib import as_ptr
+    from wasmsnark_b200.parallel import ShardedProver
+    nv = dom = 1 << PROVE_LOG2
+    t0 = time.perf_counter()
+    pk, wit = gen_synth_key.make(nv, 58, dom, seed=0xB204)
+    gen_s = time.perf_counter() - t0
+    h_w = torch.frombuffer(bytearray(wit), dtype=torch.uint8).pin_memory()
+
+    class Lane:
+        """one context + its own resident key (shard), stream and buffers -- like one of the reference's prover instances"""
+
+        def __init__(self, bn, stream, pk_b=pk, h_wit=h_w, rs=RS):
+            self.bn, self.stream, self.h_w = bn, stream, h_wit
+            t0 = time.perf_counter()
+            self.sp = ShardedProver(bn, pk_b, rank, world)
+            self.load_s = time.perf_counter() - t0
+            with torch.cuda.stream(stream):
+                self.d_w = h_wit.cuda()
+                self.d_rs = torch.frombuffer(bytearray(rs), dtype=torch.uint8).cuda()
+                self.d_proof = torch.zeros(384, dtype=torch.uint8, device="cuda")
+            self.h_proof = torch.zeros(384, dtype=torch.uint8).pin_memory()
+            self.h2d = 0
+
+        def prove(self, idx=0):
+            self.sp.prove_dev(self.d_w, self.d_rs, self.d_proof, self.stream, owner=idx % world)
+
+        def prove_e2e(self, idx=0):
+            """N > 1 e2e step: host -> device copy of what this rank needs of the witness, the proof, device -> host"""
+            self.h2d = self.sp.upload_witness(self.d_w, self.h_w, idx % world, self.stream)
+            self.prove(idx)
+            with torch.cuda.stream(self.stream):
+                self.h_proof.copy_(self.d_proof, non_blocking=True)
+
+        def free(self):
+            self.sp.free()
+
+    out = {}
+    # ---- BASELINE configs[3]: the reference's example key (staged by oracle/build_ref.py), r = s = 0 => proof_good0.json
+    ex_dir = os.path.join(ROOT, "oracle", "_ref", "example_bn128")
+    example = None
+    if os.path.exists(os.path.join(ex_dir, "proving_key.bin")):
+        from oracle import bn128 as O
+        pk_e = open(os.path.join(ex_dir, "proving_key.bin"), "rb").read()
+        wit_e = open(os.path.join(ex_dir, "witness.bin"), "rb").read()
+        good = json.load(open(os.path.join(ROOT, "tests", "golden", "example_bn128.golden.json")))
+        Le = Lane(env.bns[0], env.streams[0], pk_e, torch.frombuffer(bytearray(wit_e), dtype=torch.uint8).pin_memory(), bytes(64))
+        for i in range(W):
+            Le.prove(i)
+        torch.cuda.synchronize()
+        ctr = [0]
+
+        def ex_step():
+            Le.prove(ctr[0])
+            ctr[0] += 1
+        ex_ms = env.timed_serial(ex_step, K)
+        pb = bytes(Le.d_proof.cpu().numpy())
+        bn0 = env.bns[0]
+        got = {"pi_a": bn0.bin2g1(pb[0:96]), "pi_b": bn0.bin2g2(pb[96:288]), "pi_c": bn0.bin2g1(pb[288:384])}
+        kinfo = O.parse_pkey(pk_e)
+        example = {"workload": "example/bn128 proving_key.bin + witness.bin (BASELINE configs[3]): nVars %d, domainSize %d, r = s = 0" % (kinfo["nVars"], kinfo["domainSize"]),
+                   "ms_per_proof_single_stream": ex_ms, "proofs_per_s": 1000.0 / ex_ms,
+                   "bit_exact_vs_proof_good0": all(got[k2] == good[k2] for k2 in ("pi_a", "pi_b", "pi_c")), "key_load_s": Le.load_s}
+        if not example["bit_exact_vs_proof_good0"]:
+            raise SystemExit("PARITY FAILURE: example/bn128 proof differs from proof_good0.json")
+        Le.free()
+        del Le
+    # ---- the 2^PROVE_LOG2 key
+    NP = NPROOFS
+    lanes = [Lane(env.bns[i], env.streams[i]) for i in range(NP)]
+    L0 = lanes[0]
+    L0.prove(0)
+    torch.cuda.synchronize()
+    proof_bytes = bytes(L0.d_proof.cpu().numpy())
+    # parity of what is timed: the reference's own proof for these inputs
+    gold_path = os.path.join(ROOT, "tests", "golden", "synth_2p%d.golden.json" % PROVE_LOG2)
+    golden_ok = None
+    if os.path.exists(gold_path):
+        gold = json.load(open(gold_path))
+        bn0 = env.bns[0]
+        got = {"pi_a": bn0.bin2g1(proof_bytes[0:96]), "pi_b": bn0.bin2g2(proof_bytes[96:288]), "pi_c": bn0.bin2g1(proof_bytes[288:384])}
+        golden_ok = got == gold["proof"] and gold["r"] + gold["s"] == RS.hex()
+        if not golden_ok:
+            raise SystemExit("PARITY FAILURE: the 2^%d-constraint proof differs from the reference's (tests/golden)" % PROVE_LOG2)
+    for i in range(1, world):                       # every owner position gives the same bytes
+        L0.prove(i)
+        torch.cuda.synchronize()
+        if bytes(L0.d_proof.cpu().numpy()) != proof_bytes:
+            raise SystemExit("PARITY FAILURE: proof depends on the H owner")
+    if world > 1:                                   # and every rank holds the same proof
+        allp = [None] * world
+        dist.all_gather_object(allp, proof_bytes)
+        if any(p != proof_bytes for p in allp):
+            raise SystemExit("PARITY FAILURE: ranks disagree on the proof")
+    # stage stamps of one proof (single GPU: the whole proof is one call on one context)
+    pstages = {}
+    if world == 1:
+        bn0 = env.bns[0]
+        bn0.lib.ws_set_profiling(bn0.ctx.h, 1)
+        for i in range(W):
+            L0.prove(i)
+        torch.cuda.synchronize()
+        pstages = dict(bn0.ctx.timings())
+        bn0.lib.ws_set_profiling(bn0.ctx.h, 0)
+    else:
+        for i in range(W):
+            L0.prove(i)
+    sampler = ClockSampler(env.local) if rank == 0 else None
+    # latency: one proof at a time
+    ctr = [0]
+
+    def lat_step():
+        L0.prove(ctr[0])
+        ctr[0] += 1
+    lat_ms = env.timed_serial(lat_step, K)
+    # throughput: K proofs, NP in flight (alternating lanes), one event pair around all of them
+    for k in range(NP * W):
+        lanes[k % NP].prove(k)
+    env.barrier()
+    l0 = env.launches()
+    ms_total = env.timed_pipelined(lambda: [lanes[k % NP].prove(k) for k in range(K)], NP)
+    launches = env.launches() - l0
+    pms = ms_total / K
+    # ---- e2e
+    e2e = {}
+    if world == 1:
+        # the blocking host-buffer call from one host thread per context, witness in pinned memory
+        outs = [[ctypes.create_string_buffer(n) for n in (96, 192, 96)] for _ in range(NP)]
+        keys = [ln.sp.key for ln in lanes]
+
+        def host_call(i, wptr):
+            b = lanes[i].bn
+            b.ctx.check(b.lib.ws_bn128_groth16_prove_key(b.ctx.h, keys[i], wptr, len(wit), as_ptr(RS[:32]), as_ptr(RS[32:]), *outs[i]))
+
+        def e2e_run(wptr, calls):
+            per = -(-calls // NP)
+
+            def worker(i):
+                for _ in range(per):
+                    host_call(i, wptr)
+            th = [threading.Thread(target=worker, args=(i,)) for i in range(NP)]
+            env.barrier()
+            t0 = time.perf_counter()
+            [x.start() for x in th]
+            [x.join() for x in th]
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / (per * NP), per * NP
+        pinned_ptr = ctypes.c_void_p(h_w.data_ptr())
+        e2e_run(pinned_ptr, NP * 2)
+        e_s, e_steps = e2e_run(pinned_ptr, K)
+        if (outs[0][0].raw + outs[0][1].raw + outs[0][2].raw) != proof_bytes:
+            raise SystemExit("PARITY FAILURE: host-buffer call returned another proof")
+        pageable = bytes(wit)
+        e2e_run(as_ptr(pageable), NP)
+        p_s, _ = e2e_run(as_ptr(pageable), K)
+        e2e = {"value": 1.0 / e_s, "unit": "proofs/s", "h2d_bytes_per_step": len(wit), "d2h_bytes_per_step": 384, "ms_per_proof": 1000 * e_s, "steps": e_steps,
+               "timer": "host perf_counter around %d blocking ws_bn128_groth16_prove_key calls (K rounded up to whole rounds), %d in flight from as many host threads / contexts; witness in pinned host memory, key resident" % (e_steps, NP),
+               "pageable": {"value": 1.0 / p_s, "ms_per_proof": 1000 * p_s, "note": "the same calls with the witness in ordinary pageable memory (a Python bytes object): staged through the library's pinned ring by 4 host threads"}}
+    else:
+        for k in range(NP * 2):
+            lanes[k % NP].prove_e2e(k)
+        env.barrier()
+        t0 = time.perf_counter()
+        h2d = 0
+        for k in range(K):
+            lanes[k % NP].prove_e2e(k)
+            h2d += lanes[k % NP].h2d
+        for sx in env.streams[:NP]:
+            sx.synchronize()
+        env.barrier()
+        e_s = env.max_over_ranks((time.perf_counter() - t0) / K)
+        tot_h2d = torch.tensor([float(h2d) / K], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tot_h2d)
+        e2e = {"value": 1.0 / e_s, "unit": "proofs/s", "h2d_bytes_per_step": int(tot_h2d.item()), "d2h_bytes_per_step": 384 * world, "ms_per_proof": 1000 * e_s, "steps": K,
+               "timer": "host perf_counter around K proofs through parallel.ShardedProver, %d in flight; per proof and rank: H2D of the witness ranges the rank needs from pinned memory (whole witness on the H owner), sharded proof, D2H of the proof; max over ranks; bytes summed over ranks" % NP}
+    # ---- the literal drop-in call: groth16GenProof(witness, provingKey), both host byte buffers on every call
+    dropin = None
+    if world == 1:
+        bn0 = env.bns[0]
+        pa, pb_, pc = (ctypes.create_string_buffer(n) for n in (96, 192, 96))
+
+        def dropin_call():
+            bn0.ctx.check(bn0.lib.ws_bn128_groth16_prove(bn0.ctx.h, as_ptr(wit), len(wit), as_ptr(pk), len(pk), as_ptr(RS[:32]), as_ptr(RS[32:]), pa, pb_, pc))
+        t0 = time.perf_counter()
+        dropin_call()
+        first_s = time.perf_counter() - t0
+        for _ in range(W):
+            dropin_call()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            dropin_call()
+        rep_s = (time.perf_counter() - t0) / K
+        dropin = {"first_call_s": first_s, "repeat_call_ms": 1000 * rep_s, "proofs_per_s": 1.0 / rep_s, "proof_matches_resident_path": (pa.raw + pb_.raw + pc.raw) == proof_bytes,
+                  "note": "blocking ws_bn128_groth16_prove(witness, pkey), pageable host buffers, one call at a time; the first call parses / uploads the key and builds its tables, "
+                          "repeats start the proof with the cached key while host threads fingerprint the %d-byte key buffer" % len(pk)}
+        bn0.lib.ws_set_key_cache(bn0.ctx.h, 0)
+        bn0.lib.ws_set_key_cache(bn0.ctx.h, 1)
+    clocks = sampler.stop() if sampler else None
+    alg_bytes = (len(pk) - 40) + len(wit) + 64 * (4 * dom + 2 * dom) + 3 * 32 * 2 * dom
+    out["line"] = {
+        "value": 1000.0 / pms, "ms_per_step": pms, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
+        "latency": {"ms_per_proof_single_stream": lat_ms, "proofs_per_s": 1000.0 / lat_ms,
+                    "note": "one proof at a time, per-proof CUDA events, L2 flushed (256 MiB fill) between proofs"},
+        "config_extra": {"pkey_bytes": len(pk), "witness_bytes": len(wit), "in_flight": "%d proofs (one context + resident key%s each)" % (NP, " shard" if world > 1 else ""),
+                         "parallelism": ("point ranges of A, B1, B2, C, hExps x%d (src/bn128.js:353-361 split); H on one rank per proof (rotating), NCCL send/recv of h slices, one all_gather of 768-byte partial records, assembly on every rank" % world) if world > 1 else "single GPU",
+                         "l2": "key sections + window tables (5.5 GB) and MSM workspaces are far larger than the 126 MB L2; the latency run also flushes L2 between proofs",
+                         "bit_exact_vs_reference_golden": golden_ok, "key_load_s": L0.load_s, "keygen_s": gen_s},
+        "stages_ms": pstages, "dropin_call": dropin, "example_key": example,
+        "algorithmic_bytes_per_proof": alg_bytes, "hbm_frac_whole_proof": (alg_bytes / (pms * 1e-3) / 1e9) / peaks()[0],
+    }
+    # ---- roofline of the dominant kernel: k_msm_accumulate<G1>, window-table form, timed alone on the A section
+    if rank == 0:
+        from oracle import bn128 as O
+        bn0 = env.bns[0]
+        lib, h = bn0.lib, bn0.ctx.h
+        kinfo = O.parse_pkey(pk)
+        a0 = kinfo["pPointsA"]
+        npts = nv
+        tc = 20 if npts >= (1 << 20) else max(8, npts.bit_length() - 1)
+        Wn = lib.ws_msm_table_windows(tc)
+        st = ctypes.c_void_p(env.stream.cuda_stream)
+        d_pts = torch.frombuffer(bytearray(pk[a0:a0 + 64 * npts]), dtype=torch.uint8).cuda()
+        d_tab = torch.empty(Wn * npts * 64, dtype=torch.uint8, device="cuda")
+        d_o = torch.zeros(256, dtype=torch.uint8, device="cuda")
+        d_wit = h_w.cuda()
+        bn0.ctx.check(lib.ws_bn128_g1_build_table_dev(h, d_pts.data_ptr(), npts, tc, d_tab.data_ptr(), st))
+        lib.ws_set_profiling(h, 1)
+        acc, tot, reps = 0.0, {}, max(3, min(K, 10))
+        for i in range(3 + reps):
+            env.flush.fill_(1)
+            bn0.ctx.check(lib.ws_bn128_g1_multiexp_table_dev(h, d_wit.data_ptr(), d_tab.data_ptr(), npts, tc, d_o.data_ptr(), st))
+            tm = bn0.ctx.timings()
+            if i >= 3:
+                for nm, ms in tm:
+                    tot[nm] = tot.get(nm, 0.0) + ms / reps
+        lib.ws_set_profiling(h, 0)
+        acc = tot.get("accumulate", 0.0)
+        peak, which = peaks()
+        ncu, src = read_ncu_summary("k_msm_accumulate<G1Curve")
+        achieved = (ALG_BYTES_PER_PAIR * npts) / (acc * 1e-3) / 1e9 if acc > 0 else None
+        traffic = (ncu.get("dram__bytes_read.sum", 0) + ncu.get("dram__bytes_write.sum", 0)) or None
+        out["roofline"] = {"bound": "hbm", "kernel": "k_msm_accumulate<G1> (window-table form, c = %d: %d windows share one bucket set)" % (tc, Wn), "achieved": achieved, "peak": peak,
+                           "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": traffic, "traffic_source": src, "peak_source": which, "kernel_ms": acc,
+                           "algorithmic_bytes_per_launch": ALG_BYTES_PER_PAIR * npts, "launches_per_proof": 4,
+                           "stages_ms_of_this_msm": tot,
+                           "note": "integer-multiply bound, not HBM bound: one 8M+2S mixed addition (137 IMAD-class instructions per product, 111 per squaring) per non-zero digit; timed alone, A section of the key with the witness as scalars",
+                           "ncu": {"fmaheavy_pipe_busy_pct": ncu.get("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+                                   "kernel_ms_under_ncu": ncu.get("gpu__time_duration.sum"), "source": src}}
+        del d_pts, d_tab, d_wit
+    for ln in lanes:
+        ln.free()
+    return out
+
+
+def section_msm(env, args, strong=True):
+    """BASELINE configs[1]: G1 MSM of 2^LOG2N pairs.  N > 1: strong = the same 2^LOG2N pairs split over the ranks."""
+    torch, dist, world, rank, K, W = env.torch, env.dist, env.world, env.rank, env.K, env.W
+    from wasmsnark_b200.parallel import shard_range
+    from oracle import bn128 as O
+    import util
+    total_pairs = N_PAIRS if strong else N_PAIRS * world
+    lo, cnt = shard_range(total_pairs, rank, world)
+    scalars, points, P0, D = make_inputs(cnt, offset=lo)
+    h_s = torch.frombuffer(bytearray(scalars), dtype=torch.uint8).pin_memory()
+    h_p = torch.frombuffer(bytearray(points), dtype=torch.uint8).pin_memory()
+    NF = NFLIGHT
+    bns, streams = env.bns[:NF], env.streams[:NF]
+    bn = bns[0]
+    lib, h = bn.lib, bn.ctx.h
+    st = ctypes.c_void_p(env.stream.cuda_stream)
+    d_s, d_p = h_s.cuda(), h_p.cuda()
+    d_out = torch.zeros(256, dtype=torch.uint8, device="cuda")
+    gathered = torch.zeros(world * 96, dtype=torch.uint8, device="cuda") if world > 1 else None
+
+    def step_dev():
+        bn.ctx.check(lib.ws_bn128_g1_multiexp_dev(h, d_s.data_ptr(), d_p.data_ptr(), cnt, d_out.data_ptr(), 0, st))
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, d_out[:96])
+            bn.ctx.check(lib.ws_bn128_g1_sum_dev(h, gathered.data_ptr(), world, d_out.data_ptr(), st))
+    # correctness of what is being timed (closed form of sum s_i (P0 + i D))
+    step_dev()
+    torch.cuda.synchronize()
+    sc = [int.from_bytes(scalars[32 * i:32 * i + 32], "little") for i in range(cnt)]
+    moments = [sum(sc) % O.R_ORDER, sum((lo + i) * v for i, v in enumerate(sc)) % O.R_ORDER]
+    del sc
+    if world > 1:
+        allm = [None] * world
+        dist.all_gather_object(allm, moments)
+        moments = [sum(m[0] for m in allm) % O.R_ORDER, sum(m[1] for m in allm) % O.R_ORDER]
+    if rank == 0:
+        want = O.pt_affine(O.Fq, O.pt_add(O.Fq, O.pt_times_scalar(O.Fq, (P0[0], P0[1], 1), moments[0]), O.pt_times_scalar(O.Fq, (D[0], D[1], 1), moments[1])))
+        if util.g1_result_tuple(bn.g1_affine(bytes(d_out[:96].cpu().numpy()))) != want:
+            raise SystemExit("PARITY FAILURE: MSM result differs from the oracle")
+    lib.ws_set_profiling(h, 1)
+    for _ in range(W):
+        step_dev()
+    stage_ms = {}
+
+    def step_prof():
+        step_dev()
+    evs = []
+    env.barrier()
+    for _ in range(K):
+        env.flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(env.stream)
+        step_dev()
+        e1.record(env.stream)
         evs.append((e0, e1))
         torch.cuda.synchronize()
-    barrier()
-    total = sum(a.elapsed_time(b) for a, b in evs)
-    t = torch.tensor([total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+        for nm, ms in bn.ctx.timings():
+            stage_ms[nm] = stage_ms.get(nm, 0.0) + ms / K
+    env.barrier()
+    serial_ms = env.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs)) / K
+    lib.ws_set_profiling(h, 0)
+    # pipelined throughput: NF contexts / streams in rotation, inputs rotate over 4 device copies (> L2)
+    in_sets = [(d_s, d_p)] + [(d_s.clone(), d_p.clone()) for _ in range(3)]
+    lanes = [(bns[i], streams[i], ctypes.c_void_p(streams[i].cuda_stream), d_out if i == 0 else torch.zeros(256, dtype=torch.uint8, device="cuda"),
+              gathered if i == 0 else (torch.zeros(world * 96, dtype=torch.uint8, device="cuda") if world > 1 else None)) for i in range(NF)]
+
+    def step_pipe(k):
+        b_, strm, stp, dout, gath = lanes[k % NF]
+        ds_, dp_ = in_sets[k & 3]
+        with torch.cuda.stream(strm):
+            b_.ctx.check(b_.lib.ws_bn128_g1_multiexp_dev(b_.ctx.h, ds_.data_ptr(), dp_.data_ptr(), cnt, dout.data_ptr(), 0, stp))
+            if world > 1:
+                dist.all_gather_into_tensor(gath, dout[:96])
+                b_.ctx.check(b_.lib.ws_bn128_g1_sum_dev(b_.ctx.h, gath.data_ptr(), world, dout.data_ptr(), stp))
+    for k in range(NF * W):
+        step_pipe(k)
+    l0 = env.launches()
+    pipe_ms = env.timed_pipelined(lambda: [step_pipe(k) for k in range(K)], NF) / K
+    launches = env.launches() - l0
+    out = {"workload": "BN128 G1 MSM, 2^%d scalar-point pairs (BASELINE configs[1]): scalars %s, affine Montgomery points%s" % (
+               LOG2N + (0 if strong else world.bit_length() - 1), "uniform in [0, r)" if SCALARS == "fr" else "uniform raw 256-bit",
+               "" if world == 1 else (" -- STRONG: the same pairs split over %d ranks" % world if strong else " -- WEAK: 2^%d pairs per rank" % LOG2N)),
+           "value": total_pairs / (pipe_ms * 1e-3), "unit": "pairs/s", "ms_per_step": pipe_ms, "pairs": total_pairs, "pairs_per_gpu": cnt,
+           "in_flight": "%d MSMs (contexts / streams in rotation), inputs rotate over 4 device copies (> L2)" % NF,
+           "latency": {"ms_per_msm_single_stream": serial_ms, "pairs_per_s": total_pairs / (serial_ms * 1e-3)},
+           "stages_ms": stage_ms, "gpu_launches": int(launches), "bit_exact_vs_oracle": True}
+    if strong:
+        # e2e through the host-buffer ABI (pinned host memory; H2D + D2H inside), one host thread per context
+        out_hosts = [torch.zeros(96, dtype=torch.uint8).pin_memory() for _ in range(NF)]
+
+        def host_call(i):
+            b_ = bns[i]
+            b_.ctx.check(b_.lib.ws_bn128_g1_multiexp(b_.ctx.h, h_s.data_ptr(), h_p.data_ptr(), cnt, out_hosts[i].data_ptr()))
+
+        def exchange(i):
+            b_, strm, stp, dout, gath = lanes[i]
+            with torch.cuda.stream(strm):
+                dout[:96].copy_(out_hosts[i], non_blocking=True)
+                dist.all_gather_into_tensor(gath, dout[:96])
+                b_.ctx.check(b_.lib.ws_bn128_g1_sum_dev(b_.ctx.h, gath.data_ptr(), world, dout.data_ptr(), stp))
+                out_hosts[i].copy_(dout[:96], non_blocking=True)
+
+        def e2e_round():
+            th = [threading.Thread(target=host_call, args=(i,)) for i in range(NF)]
+            [x.start() for x in th]
+            [x.join() for x in th]
+            if world > 1:
+                for i in range(NF):
+                    exchange(i)
+                for i in range(NF):
+                    streams[i].synchronize()
+        for _ in range(2):
+            e2e_round()
+        env.barrier()
+        KE = -(-K // NF)
+        t0 = time.perf_counter()
+        for _ in range(KE):
+            e2e_round()
+        env.barrier()
+        e_s = env.max_over_ranks((time.perf_counter() - t0) / (KE * NF))
+        out["e2e"] = {"value": total_pairs / e_s, "unit": "pairs/s", "h2d_bytes_per_step": 96 * total_pairs, "d2h_bytes_per_step": 96 * world, "ms_per_step": 1000 * e_s,
+                      "timer": "host perf_counter around rounds of %d concurrent blocking ws_bn128_g1_multiexp calls (pinned host buffers)%s, max over ranks" % (NF, ", partials exchanged with one all_gather" if world > 1 else "")}
+    if rank == 0 and strong:
+        acc = stage_ms.get("accumulate", 0.0)
+        peak, which = peaks()
+        achieved = (ALG_BYTES_PER_PAIR * cnt) / (acc * 1e-3) / 1e9 if acc > 0 else None
+        ncu, src = read_ncu_summary("k_msm_accumulate<G1Curve")
+        out["roofline"] = {"bound": "hbm", "kernel": "k_msm_accumulate<G1> (table-free form: 16 digit windows + carry window)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                           "frac": achieved / peak if achieved else None, "kernel_ms": acc, "algorithmic_bytes_per_launch": ALG_BYTES_PER_PAIR * cnt, "peak_source": which,
+                           "traffic": ((ncu.get("dram__bytes_read.sum", 0) + ncu.get("dram__bytes_write.sum", 0)) or None) if (LOG2N == 20 and world == 1) else None, "traffic_source": src}
+        if not args.no_cpu_baseline:
+            from oracle import ref_wasm
+            if ref_wasm.available():
+                cores = usable_cores()
+                sample = min(cnt, 8192 * cores)
+                v1, _ = cpu_msm_arm(scalars, points, min(sample, 4096), 1)
+                v, dt = cpu_msm_arm(scalars, points, sample, cores)
+                out["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "reference", "single_thread_value": v1,
+                                       "sample": "first %d pairs (%.1f s), reference g1m_multiexp2(w=7) from its WASM image compiled natively, %d threads as src/bn128.js:353-383 splits; single thread on %d pairs" % (sample, dt, cores, min(sample, 4096))}
+    del in_sets
+    return out
+
+
+def section_ntt(env):
+    """BASELINE configs[2]: Fr NTT 2^22 forward + inverse (rank 0; a transform of this size is not sharded)."""
+    torch = env.torch
+    bn = env.bns[0]
+    lib, h = bn.lib, bn.ctx.h
+    st = ctypes.c_void_p(env.stream.cuda_stream)
+    n22 = 1 << 22
+    x = torch.randint(0, 256, (n22, 32), dtype=torch.uint8, device="cuda")
+    x[:, 31] &= 0x1F
+    x0 = x.clone()
+
+    def step_ntt():
+        bn.ctx.check(lib.ws_bn128_fr_fft_dev(h, x.data_ptr(), n22, 0, 0, st))
+        bn.ctx.check(lib.ws_bn128_fr_fft_dev(h, x.data_ptr(), n22, 0, 1, st))
+    for _ in range(env.W):
+        step_ntt()
+    torch.cuda.synchronize()
+    ok = bool(torch.equal(x, x0))
+    evs = []
+    for _ in range(env.K):
+        env.flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(env.stream)
+        step_ntt()
+        e1.record(env.stream)
+        evs.append((e0, e1))
+        torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs) / env.K
+    peak, which = peaks()
+    ach = 536870912 / (ms * 1e-3) / 1e9
+    ncu, src = read_ncu_summary("k_ntt_pass64")
+    return {"workload": "BN128 Fr NTT 2^22 forward + inverse round trip (BASELINE configs[2])", "ms_per_round_trip": ms, "elements_per_s": 2 * n22 / (ms * 1e-3), "round_trip_bit_exact": ok,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes": 536870912, "peak_source": which,
+                         "note": "integer-multiply bound: n/2 log2 n Montgomery products per transform; 5 passes, each reads and writes every element once, no trailing copy",
+                         "ncu": {"fmaheavy_pipe_busy_pct": ncu.get("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"), "source": src}}}
+
+
+def section_other_curves(env):
+    """SURVEY 8f rank 4 (BLS12-381 G1 MSM 2^20) and BASELINE configs[4] (MNT6753 G1 MSM 2^18), rank 0, single stream."""
+    import random
+    import numpy as np
+    torch = env.torch
+    from wasmsnark_b200._lib import as_ptr
+    from oracle import bls12381 as BL
+    from oracle import mnt6753 as MN
+    bn = env.bns[0]
+    lib, h = bn.lib, bn.ctx.h
+    st = ctypes.c_void_p(env.stream.cuda_stream)
+    out = {}
+    nb, distinct = 1 << 20, 4096
+    rnd = random.Random(0xB15)
+    a0, d0 = rnd.randrange(BL.R_ORDER), rnd.randrange(BL.R_ORDER)
+    P, Dp = BL.pt_mul(BL.Fq, BL.G1_GEN, a0), BL.pt_mul(BL.Fq, BL.G1_GEN, d0)
+    base = []
+    for _ in range(distinct):
+        base.append(BL.g1_bytes(P))
+        P = BL.pt_add(BL.Fq, P, Dp)
+    pts = torch.frombuffer(bytearray(b"".join(base)), dtype=torch.uint8).view(distinct, 96).cuda().repeat(nb // distinct, 1).contiguous()
+    sc_np = np.random.default_rng(0xB15).integers(0, 256, size=(nb, 32), dtype=np.uint8)
+    sc = torch.from_numpy(sc_np).cuda()
+    outb = torch.zeros(144, dtype=torch.uint8, device="cuda")
+
+    def step_bls():
+        bn.ctx.check(lib.ws_bls12381_g1_multiexp_dev(h, sc.data_ptr(), pts.data_ptr(), nb, outb.data_ptr(), 0, st))
+    for _ in range(env.W):
+        step_bls()
+    torch.cuda.synchronize()
+    ms = env.timed_serial(step_bls, env.K)
+    limbs = sc_np.view("<u4").reshape(nb // distinct, distinct, 8).astype(np.uint64).sum(axis=0)
+    tot = [sum(int(limbs[j, k]) << (32 * k) for k in range(8)) for j in range(distinct)]
+    want = BL.pt_mul(BL.Fq, BL.G1_GEN, sum(t * (a0 + j * d0) for j, t in enumerate(tot)) % BL.R_ORDER)
+    aff = ctypes.create_string_buffer(144)
+    bn.ctx.check(lib.ws_bls12381_g1_affine(h, as_ptr(bytes(outb.cpu().numpy())), ctypes.cast(aff, ctypes.c_void_p), 1, 1))
+    out["bls12381"] = {"workload": "BLS12-381 G1 MSM, 2^20 pairs (4096 distinct points tiled, uniform 256-bit scalars), single stream, L2 flushed between steps",
+                       "ms_per_msm": ms, "pairs_per_s": nb / (ms * 1e-3), "matches_closed_form": BL.g1_from_affine_std(aff.raw) == want,
+                       "note": "same kernels as BN128 with 12-limb field elements; launch shapes not tuned"}
+    del pts, sc
+    nm, distinct = 1 << 18, 1024
+    rnd = random.Random(0x6753)
+    a0, d0 = rnd.randrange(MN.R_ORDER), rnd.randrange(MN.R_ORDER)
+    P, Dp = MN.times_scalar(MN.G1_GEN, a0), MN.times_scalar(MN.G1_GEN, d0)
+    base = []
+    for _ in range(distinct):
+        base.append(MN.affine_bytes_m(P))
+        P = MN.add(P, Dp)
+    pts = torch.frombuffer(bytearray(b"".join(base)), dtype=torch.uint8).view(distinct, 192).cuda().repeat(nm // distinct, 1).contiguous()
+    sc_np = np.random.default_rng(0x6753).integers(0, 256, size=(nm, 96), dtype=np.uint8)
+    sc_np[:, 94:] = 0                                     # 752-bit raw scalars
+    sc = torch.from_numpy(sc_np).cuda()
+    outm = torch.zeros(288, dtype=torch.uint8, device="cuda")
+
+    def step_mnt():
+        bn.ctx.check(lib.ws_mnt6753_g1_multiexp_dev(h, sc.data_ptr(), pts.data_ptr(), nm, outm.data_ptr(), 0, st))
+    for _ in range(env.W):
+        step_mnt()
+    torch.cuda.synchronize()
+    ms = env.timed_serial(step_mnt, env.K)
+    limbs = sc_np.view("<u4").reshape(nm // distinct, distinct, 24).astype(np.uint64).sum(axis=0)
+    tot = [sum(int(limbs[j, k]) << (32 * k) for k in range(24)) for j in range(distinct)]
+    want = MN.times_scalar(MN.G1_GEN, sum(t * (a0 + j * d0) for j, t in enumerate(tot)) % MN.R_ORDER)
+    aff = ctypes.create_string_buffer(288)
+    bn.ctx.check(lib.ws_mnt6753_g1_affine(h, as_ptr(bytes(outm.cpu().numpy())), ctypes.cast(aff, ctypes.c_void_p), 1, 1))
+    got = tuple(int.from_bytes(aff.raw[96 * i:96 * i + 96], "little") for i in range(3))
+    out["mnt6753"] = {"workload": "MNT6753 G1 MSM, 2^18 pairs (BASELINE configs[4]; 1024 distinct points tiled, 752-bit raw scalars), single stream, L2 flushed between steps",
+                      "ms_per_msm": ms, "pairs_per_s": nm / (ms * 1e-3), "matches_closed_form": got == MN.affine_result(want),
+                      "note": "wide-limb path: 24-limb field elements"}
+    return out
 
 
 def main():
@@ -242,10 +900,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-prove", action="store_true")
+    ap.add_argument("--no-msm", action="store_true")
     ap.add_argument("--no-ntt", action="store_true")
-    ap.add_argument("--no-bls", action="store_true")
+    ap.add_argument("--no-bls", action="store_true", help="skip the BLS12-381 / MNT6753 MSM lines")
+    ap.add_argument("--only-prove", action="store_true", help="primary line only (profiling runs)")
     args = ap.parse_args()
+    if args.only_prove:
+        args.no_msm = args.no_ntt = args.no_bls = args.no_cpu_baseline = True
     # stdout carries exactly ONE line, the JSON result: anything a library prints there (e.g. NCCL's version banner
     # under NCCL_DEBUG) is sent to stderr instead, and emit() writes the result to the real stdout at the end.
     sys.stdout.flush()
@@ -258,515 +919,44 @@ def main():
     if args.impl == "reference":
         return run_reference(args, emit)
 
-    import torch
-    import torch.distributed as dist
-    from wasmsnark_b200 import build_bn128
-    from wasmsnark_b200.parallel import shard_range
-    from wasmsnark_b200._lib import as_ptr
-    import util
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    W = max(3, args.warmup)
-    K = args.steps
-
-    # weak scaling: the job is one MSM of world * 2^LOG2N pairs; rank r holds the contiguous range [r * 2^LOG2N, (r+1) * 2^LOG2N)
-    TOTAL_PAIRS = N_PAIRS * world
-    lo, cnt = shard_range(TOTAL_PAIRS, rank, world)
-    assert cnt == N_PAIRS
-    scalars, points, P0, D = make_inputs(cnt, offset=lo)
-    h_s = torch.frombuffer(bytearray(scalars), dtype=torch.uint8).pin_memory()
-    h_p = torch.frombuffer(bytearray(points), dtype=torch.uint8).pin_memory()
-    stream = torch.cuda.Stream()            # a real (non-legacy) stream: the library launches on it
-    torch.cuda.set_stream(stream)
-    st = ctypes.c_void_p(stream.cuda_stream)
-    d_s, d_p = h_s.cuda(), h_p.cuda()
-    d_out = torch.zeros(256, dtype=torch.uint8, device="cuda")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    bn = build_bn128(local)
-    lib, h = bn.lib, bn.ctx.h
-    gathered = torch.zeros(world * 96, dtype=torch.uint8, device="cuda") if world > 1 else None
-
-    def step_dev():
-        bn.ctx.check(lib.ws_bn128_g1_multiexp_dev(h, d_s.data_ptr(), d_p.data_ptr(), cnt, d_out.data_ptr(), 0, st))
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, d_out[:96])
-            bn.ctx.check(lib.ws_bn128_g1_sum_dev(h, gathered.data_ptr(), world, d_out.data_ptr(), st))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- correctness of what is being timed (closed form of sum s_i (P0 + i D))
-    step_dev()
-    torch.cuda.synchronize()
-    from oracle import bn128 as O
-    sc = [int.from_bytes(scalars[32 * i:32 * i + 32], "little") for i in range(cnt)]
-    moments = [sum(sc) % O.R_ORDER, sum((lo + i) * v for i, v in enumerate(sc)) % O.R_ORDER]     # sum s_i, sum i_global * s_i
-    del sc
-    if world > 1:
-        allm = [None] * world
-        dist.all_gather_object(allm, moments)
-        moments = [sum(m[0] for m in allm) % O.R_ORDER, sum(m[1] for m in allm) % O.R_ORDER]
-    if rank == 0:
-        want = O.pt_affine(O.Fq, O.pt_add(O.Fq, O.pt_times_scalar(O.Fq, (P0[0], P0[1], 1), moments[0]), O.pt_times_scalar(O.Fq, (D[0], D[1], 1), moments[1])))
-        got = util.g1_result_tuple(bn.g1_affine(bytes(d_out[:96].cpu().numpy())))
-        if got != want:
-            raise SystemExit("PARITY FAILURE: MSM result differs from the oracle")
-
-    # ---- device-resident timing (per-stage events on for the roofline numerator's denominator)
-    sampler = ClockSampler(local) if rank == 0 else None
-    lib.ws_set_profiling(h, 1)
-    for _ in range(W):
-        step_dev()
-    stage_ms = {}
-
-    barrier()
-    evs = []
-    for _ in range(K):
-        flush.fill_(1)                      # L2 flush (256 MiB), outside the timed events
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        step_dev()
-        e1.record(stream)
-        evs.append((e0, e1))
-        torch.cuda.synchronize()
-        for nm, ms in bn.ctx.timings():
-            stage_ms[nm] = stage_ms.get(nm, 0.0) + ms
-    barrier()
-    total_ms = sum(a.elapsed_time(b) for a, b in evs)
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    lib.ws_set_profiling(h, 0)
-
-    # ---- pipelined throughput: the same K steps, alternating between two contexts (own stream + workspace each,
-    #      like two of the reference's workers), so the single-warp tail of one MSM (window Horner) runs under the
-    #      next one's bucket accumulation.  Inputs rotate over 4 device copies (384 MiB > L2) instead of a flush.
-    NF = NFLIGHT
-    bns = [bn] + [build_bn128(local) for _ in range(NF - 1)]
-    streams = [stream] + [torch.cuda.Stream() for _ in range(NF - 1)]
-    in_sets = [(d_s, d_p)] + [(d_s.clone(), d_p.clone()) for _ in range(3)]
-    lanes = []
-    for i in range(NF):
-        lanes.append((bns[i], streams[i], ctypes.c_void_p(streams[i].cuda_stream), d_out if i == 0 else torch.zeros(256, dtype=torch.uint8, device="cuda"),
-                      gathered if i == 0 else (torch.zeros(world * 96, dtype=torch.uint8, device="cuda") if world > 1 else None)))
-
-    def step_pipe(k):
-        b_, strm, stp, dout, gath = lanes[k % NF]
-        ds_, dp_ = in_sets[k & 3]
-        with torch.cuda.stream(strm):
-            b_.ctx.check(b_.lib.ws_bn128_g1_multiexp_dev(b_.ctx.h, ds_.data_ptr(), dp_.data_ptr(), cnt, dout.data_ptr(), 0, stp))
-            if world > 1:
-                dist.all_gather_into_tensor(gath, dout[:96])
-                b_.ctx.check(b_.lib.ws_bn128_g1_sum_dev(b_.ctx.h, gath.data_ptr(), world, dout.data_ptr(), stp))
-    def all_launches():
-        return sum(b_.lib.ws_kernel_launches(b_.ctx.h) for b_ in bns)
-
-    def fork_join(body):
-        """one CUDA-event pair around `body`, which enqueues work on all the lane streams"""
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for sx in streams[1:]:
-            sx.wait_event(e0)
-        body()
-        for sx in streams[1:]:
-            ej = torch.cuda.Event()
-            ej.record(sx)
-            stream.wait_event(ej)
-        e1.record(stream)
-        return e0, e1
-    for k in range(NF * W):
-        step_pipe(k)
-    barrier()
-    launches0 = all_launches()
-    e0, e1 = fork_join(lambda: [step_pipe(k) for k in range(K)])
-    msm_launches = all_launches() - launches0
-    barrier()
-    pipe_ms = e0.elapsed_time(e1)
-    t = torch.tensor([pipe_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    pipe_ms = float(t.item())
-
-    # ---- end to end through the host-buffer ABI (pinned host memory; H2D + D2H inside): K blocking calls
-    #      issued from one host thread per context (world == 1), so one call's H2D overlaps the others' compute
-    out_hosts = [torch.zeros(96, dtype=torch.uint8).pin_memory() for _ in range(NF)]
-    out_host = out_hosts[0]
-
-    import threading
-
-    def host_call(b_, oh):
-        b_.ctx.check(b_.lib.ws_bn128_g1_multiexp(b_.ctx.h, h_s.data_ptr(), h_p.data_ptr(), cnt, oh.data_ptr()))
-
-    def exchange(i):
-        """N > 1: the rank's partial (already on the host, as the C ABI returned it) goes back to the device for the
-        single all_gather + on-device combine, and the combined point returns to the host."""
-        b_, strm, stp, dout, gath = lanes[i]
-        with torch.cuda.stream(strm):
-            dout[:96].copy_(out_hosts[i], non_blocking=True)
-            dist.all_gather_into_tensor(gath, dout[:96])
-            b_.ctx.check(b_.lib.ws_bn128_g1_sum_dev(b_.ctx.h, gath.data_ptr(), world, dout.data_ptr(), stp))
-            out_hosts[i].copy_(dout[:96], non_blocking=True)
-
-    def e2e_round(ncalls):
-        """`ncalls` (<= NF) blocking host-buffer calls issued concurrently from as many host threads (one context
-        each), then -- N > 1 only -- the exchanges, in a fixed order on the main thread so that every rank issues
-        the same collective sequence."""
-        th = [threading.Thread(target=host_call, args=(bns[i], out_hosts[i])) for i in range(ncalls)]
-        [x.start() for x in th]
-        [x.join() for x in th]
-        if world > 1:
-            for i in range(ncalls):
-                exchange(i)
-            for i in range(ncalls):
-                streams[i].synchronize()
-    for _ in range(W):
-        e2e_round(NF)
-    barrier()
-    KE = -(-K // NF) * NF   # e2e steps: K rounded up to whole rounds of NF concurrent calls (a ragged last round would idle contexts)
-    t0 = time.perf_counter()
-    if world == 1:          # free-running: each host thread issues its share of the KE calls back to back
-        def worker(i, n_calls):
-            for _ in range(n_calls):
-                host_call(bns[i], out_hosts[i])
-        th = [threading.Thread(target=worker, args=(i, KE // NF)) for i in range(NF)]
-        [x.start() for x in th]
-        [x.join() for x in th]
-    else:
-        for _ in range(KE // NF):
-            e2e_round(NF)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    clocks = sampler.stop() if sampler else None
-    del in_sets
-
+    env = Env(args)
+    world, rank = env.world, env.rank
+    g = section_groth16(env, args)
     extra = {}
-    # ---- BASELINE configs[2]: Fr NTT 2^22 forward + inverse (rank 0 only; the transform is not sharded)
-    if not args.no_ntt and rank == 0:
-        n22 = 1 << 22
-        x = torch.randint(0, 256, (n22, 32), dtype=torch.uint8, device="cuda")
-        x[:, 31] &= 0x1F
-        x0 = x.clone()
-
-        def step_ntt():
-            bn.ctx.check(lib.ws_bn128_fr_fft_dev(h, x.data_ptr(), n22, 0, 0, st))
-            bn.ctx.check(lib.ws_bn128_fr_fft_dev(h, x.data_ptr(), n22, 0, 1, st))
-        for _ in range(W):
-            step_ntt()
-        torch.cuda.synchronize()
-        ok = bool(torch.equal(x, x0))
-        ms = timed_steps(torch, stream, step_ntt, K, flush, lambda: torch.cuda.synchronize(), 1, dist) / K
-        peak, which = peaks()
-        ach = 536870912 / (ms * 1e-3) / 1e9
-        extra["ntt"] = {"workload": "BN128 Fr NTT 2^22 forward + inverse round trip (BASELINE configs[2])", "ms_per_round_trip": ms,
-                        "elements_per_s": 2 * n22 / (ms * 1e-3), "round_trip_bit_exact": ok,
-                        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                                     "algorithmic_bytes": 536870912, "note": "integer-multiply bound: n/2 log2 n Montgomery products per transform"}}
-        del x, x0
-    # ---- SURVEY 8f rank 4: the same MSM kernels instantiated for BLS12-381 G1 (12-limb field), 2^20 pairs, rank 0 only
-    if not args.no_bls and rank == 0:
-        import random
-        import numpy as np
-        from oracle import bls12381 as BL
-        nb, distinct = 1 << 20, 4096
-        rnd = random.Random(0xB15)
-        a0, d0 = rnd.randrange(BL.R_ORDER), rnd.randrange(BL.R_ORDER)
-        P, Dp = BL.pt_mul(BL.Fq, BL.G1_GEN, a0), BL.pt_mul(BL.Fq, BL.G1_GEN, d0)
-        base = []
-        for _ in range(distinct):
-            base.append(BL.g1_bytes(P))
-            P = BL.pt_add(BL.Fq, P, Dp)
-        pts = torch.frombuffer(bytearray(b"".join(base)), dtype=torch.uint8).view(distinct, 96).cuda().repeat(nb // distinct, 1).contiguous()
-        sc_np = np.random.default_rng(0xB15).integers(0, 256, size=(nb, 32), dtype=np.uint8)
-        sc = torch.from_numpy(sc_np).cuda()
-        outb = torch.zeros(144, dtype=torch.uint8, device="cuda")
-
-        def step_bls():
-            bn.ctx.check(lib.ws_bls12381_g1_multiexp_dev(h, sc.data_ptr(), pts.data_ptr(), nb, outb.data_ptr(), 0, st))
-        for _ in range(W):
-            step_bls()
-        torch.cuda.synchronize()
-        ms = timed_steps(torch, stream, step_bls, K, flush, lambda: torch.cuda.synchronize(), 1, dist) / K
-        # closed form: sum_j (sum of the scalars that met point j) * (a0 + j d0) * G
-        limbs = sc_np.view("<u4").reshape(nb // distinct, distinct, 8).astype(np.uint64).sum(axis=0)
-        tot = [sum(int(limbs[j, k]) << (32 * k) for k in range(8)) for j in range(distinct)]
-        want = BL.pt_mul(BL.Fq, BL.G1_GEN, sum(t * (a0 + j * d0) for j, t in enumerate(tot)) % BL.R_ORDER)
-        aff = ctypes.create_string_buffer(144)
-        bn.ctx.check(lib.ws_bls12381_g1_affine(h, as_ptr(bytes(outb.cpu().numpy())), ctypes.cast(aff, ctypes.c_void_p), 1, 1))
-        extra["bls12381"] = {"workload": "BLS12-381 G1 MSM, 2^20 pairs (4096 distinct points tiled, uniform 256-bit scalars), single stream, L2 flushed between steps",
-                             "ms_per_msm": ms, "pairs_per_s": nb / (ms * 1e-3), "matches_closed_form": BL.g1_from_affine_std(aff.raw) == want,
-                             "note": "parity unpinned for this curve (no reference image); same kernels as BN128 with 12-limb field elements, launch shapes not tuned"}
-        del pts, sc
-    # ---- BASELINE configs[4]: MNT6753 (768-bit, 24-limb) G1 MSM 2^18 -- wide-limb correctness path, timed for the record
-    if not args.no_bls and rank == 0:
-        from oracle import mnt6753 as MN
-        nm, distinct = 1 << 18, 1024
-        rnd = random.Random(0x6753)
-        a0, d0 = rnd.randrange(MN.R_ORDER), rnd.randrange(MN.R_ORDER)
-        P, Dp = MN.times_scalar(MN.G1_GEN, a0), MN.times_scalar(MN.G1_GEN, d0)
-        base = []
-        for _ in range(distinct):
-            base.append(MN.affine_bytes_m(P))
-            P = MN.add(P, Dp)
-        pts = torch.frombuffer(bytearray(b"".join(base)), dtype=torch.uint8).view(distinct, 192).cuda().repeat(nm // distinct, 1).contiguous()
-        sc_np = np.random.default_rng(0x6753).integers(0, 256, size=(nm, 96), dtype=np.uint8)
-        sc_np[:, 94:] = 0                                     # 752-bit raw scalars
-        sc = torch.from_numpy(sc_np).cuda()
-        outm = torch.zeros(288, dtype=torch.uint8, device="cuda")
-
-        def step_mnt():
-            bn.ctx.check(lib.ws_mnt6753_g1_multiexp_dev(h, sc.data_ptr(), pts.data_ptr(), nm, outm.data_ptr(), 0, st))
-        for _ in range(W):
-            step_mnt()
-        torch.cuda.synchronize()
-        ms = timed_steps(torch, stream, step_mnt, K, flush, lambda: torch.cuda.synchronize(), 1, dist) / K
-        limbs = sc_np.view("<u4").reshape(nm // distinct, distinct, 24).astype(np.uint64).sum(axis=0)
-        tot = [sum(int(limbs[j, k]) << (32 * k) for k in range(24)) for j in range(distinct)]
-        want = MN.times_scalar(MN.G1_GEN, sum(t * (a0 + j * d0) for j, t in enumerate(tot)) % MN.R_ORDER)
-        aff = ctypes.create_string_buffer(288)
-        bn.ctx.check(lib.ws_mnt6753_g1_affine(h, as_ptr(bytes(outm.cpu().numpy())), ctypes.cast(aff, ctypes.c_void_p), 1, 1))
-        got = tuple(int.from_bytes(aff.raw[96 * i:96 * i + 96], "little") for i in range(3))
-        extra["mnt6753"] = {"workload": "MNT6753 G1 MSM, 2^18 pairs (BASELINE configs[4]; 1024 distinct points tiled, 752-bit raw scalars), single stream, L2 flushed between steps",
-                            "ms_per_msm": ms, "pairs_per_s": nm / (ms * 1e-3), "matches_closed_form": got == MN.affine_result(want),
-                            "note": "wide-limb correctness path: 24-limb products out of line, kernels spill; not tuned"}
-        del pts, sc
+    if not args.no_msm:
+        extra["msm"] = section_msm(env, args, strong=True)
+        if world > 1:
+            env.barrier()
+            extra["msm_weak"] = section_msm(env, args, strong=False)
     if world > 1:
-        dist.barrier()
-
-    # ---- Groth16 full prove on a synthetic 2^PROVE_LOG2-constraint key
-    if not args.no_prove:
-        import gen_synth_key
-        from oracle import bn128 as O
-        nv = dom = 1 << PROVE_LOG2
-        t0 = time.perf_counter()
-        pk, wit = gen_synth_key.make(nv, 58, dom, seed=0xB204)
-        gen_s = time.perf_counter() - t0
-        h_w = torch.frombuffer(bytearray(wit), dtype=torch.uint8).pin_memory()
-        rs = bytes(range(1, 65))
-
-        class Lane:
-            """one context + its own resident key, stream and buffers (like one of the reference's prover instances)"""
-
-            def __init__(self, b_, strm, pk=None, h_w=None, rs=None):
-                pk, h_w, rs = (pk_syn if pk is None else pk), (h_w_syn if h_w is None else h_w), (rs_syn if rs is None else rs)
-                self.h_w = h_w
-                self.bn, self.stream, self.st = b_, strm, ctypes.c_void_p(strm.cuda_stream)
-                self.key = ctypes.c_void_p()
-                t0 = time.perf_counter()
-                b_.ctx.check(b_.lib.ws_bn128_pkey_load_shard(b_.ctx.h, as_ptr(pk), len(pk), rank, world, ctypes.byref(self.key)))
-                self.load_s = time.perf_counter() - t0
-                with torch.cuda.stream(strm):
-                    self.d_w = h_w.cuda()
-                    self.d_rs = torch.frombuffer(bytearray(rs), dtype=torch.uint8).cuda()
-                    self.d_part = torch.zeros(768, dtype=torch.uint8, device="cuda")
-                    self.d_all = torch.zeros(768 * world, dtype=torch.uint8, device="cuda")
-                    self.d_proof = torch.zeros(384, dtype=torch.uint8, device="cuda")
-                self.h_proof = torch.zeros(384, dtype=torch.uint8).pin_memory()
-
-            def prove(self):
-                b_, hh = self.bn, self.bn.ctx.h
-                with torch.cuda.stream(self.stream):
-                    b_.ctx.check(b_.lib.ws_bn128_groth16_prepare_dev(hh, self.key, self.d_rs.data_ptr(), self.st))
-                    b_.ctx.check(b_.lib.ws_bn128_groth16_partials_dev(hh, self.key, self.d_w.data_ptr(), self.d_part.data_ptr(), self.st))
-                    src = self.d_part
-                    if world > 1:
-                        dist.all_gather_into_tensor(self.d_all, self.d_part)
-                        src = self.d_all
-                    b_.ctx.check(b_.lib.ws_bn128_groth16_finish_dev(hh, self.key, src.data_ptr(), world, self.d_rs.data_ptr(), self.d_proof.data_ptr(), self.st))
-
-            def prove_e2e(self):
-                with torch.cuda.stream(self.stream):
-                    self.d_w.copy_(self.h_w, non_blocking=True)
-                self.prove()
-                with torch.cuda.stream(self.stream):
-                    self.h_proof.copy_(self.d_proof, non_blocking=True)
-
-        pk_syn, h_w_syn, rs_syn = pk, h_w, rs
-        # ---- BASELINE configs[3]: the reference's example/bn128 proving_key.bin + witness.bin (staged next to the
-        # reference image by oracle/build_ref.py), point ranges sharded over the ranks, r = s = 0 => proof_good0.json
-        example = None
-        ex_dir = os.path.join(ROOT, "oracle", "_ref", "example_bn128")
-        if os.path.exists(os.path.join(ex_dir, "proving_key.bin")):
-            pk_e = open(os.path.join(ex_dir, "proving_key.bin"), "rb").read()
-            wit_e = open(os.path.join(ex_dir, "witness.bin"), "rb").read()
-            good = json.load(open(os.path.join(ROOT, "tests", "golden", "example_bn128.golden.json")))
-            Le = Lane(bns[0], streams[0], pk_e, torch.frombuffer(bytearray(wit_e), dtype=torch.uint8).pin_memory(), bytes(64))
-            for _ in range(W):
-                Le.prove()
-            torch.cuda.synchronize()
-            ex_ms = timed_steps(torch, stream, Le.prove, K, flush, barrier, world, dist) / K
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(K):
-                Le.prove_e2e()
-            streams[0].synchronize()
-            barrier()
-            ex_e2e = (time.perf_counter() - t0) / K
-            pb = bytes(Le.d_proof.cpu().numpy())
-            got = {"pi_a": bn.bin2g1(pb[0:96]), "pi_b": bn.bin2g2(pb[96:288]), "pi_c": bn.bin2g1(pb[288:384])}
-            kinfo = O.parse_pkey(pk_e)
-            example = {"workload": "example/bn128 proving_key.bin + witness.bin (BASELINE configs[3]): nVars %d, domainSize %d, r = s = 0" % (kinfo["nVars"], kinfo["domainSize"]),
-                       "ms_per_proof_single_stream": ex_ms, "proofs_per_s": 1000.0 / ex_ms, "e2e_ms_per_proof": 1000 * ex_e2e,
-                       "bit_exact_vs_proof_good0": all(got[k2] == good[k2] for k2 in ("pi_a", "pi_b", "pi_c")),
-                       "shard": "point ranges x%d, all_gather of 768-byte partial records" % world, "key_load_s": Le.load_s}
-            bns[0].lib.ws_bn128_pkey_free(Le.key)
-            del Le
-        NP = min(NF, 2)       # proofs in flight (each lane holds its own resident key + tables)
-        lanesP = [Lane(bns[i], streams[i]) for i in range(NP)]
-        load_s = lanesP[0].load_s
-        L0 = lanesP[0]
-        lib.ws_set_profiling(h, 1)
-        for _ in range(W):
-            L0.prove()
-        torch.cuda.synchronize()
-        pstages = dict(bn.ctx.timings()) if world == 1 else {}
-        lib.ws_set_profiling(h, 0)
-        # single-stream latency: one proof at a time, per-proof CUDA events, L2 flushed between proofs
-        lat_ms = timed_steps(torch, stream, L0.prove, K, flush, barrier, world, dist) / K
-        proof_bytes = bytes(L0.d_proof.cpu().numpy())
-        # throughput: the same K proofs, two in flight (alternating lanes), one CUDA-event pair around all of them
-        for k in range(NP * W):
-            lanesP[k % NP].prove()
-        barrier()
-        pl0 = all_launches()
-        e0, e1 = fork_join(lambda: [lanesP[k % NP].prove() for k in range(K)])
-        prove_launches = all_launches() - pl0
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        pms = float(t.item()) / K
-        # e2e: witness from pinned host memory -> device and the proof back to the host for every proof, two in flight
-        for k in range(2 * NP):
-            lanesP[k % NP].prove_e2e()
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(K):
-            lanesP[k % NP].prove_e2e()
-        for sx in streams:
-            sx.synchronize()
-        barrier()
-        pe2e = (time.perf_counter() - t0) / K
-        t = torch.tensor([pe2e], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        pe2e = float(t.item())
-        # the literal drop-in call: groth16GenProof(witness, provingKey) with both as host byte buffers on every call
-        # (src/bn128.js:580); the library fingerprints the key buffer and reuses the uploaded key of the previous call
-        dropin = None
-        if world == 1:
-            pa, pb, pc = (ctypes.create_string_buffer(nb) for nb in (96, 192, 96))
-
-            def dropin_call():
-                bn.ctx.check(lib.ws_bn128_groth16_prove(h, as_ptr(wit), len(wit), as_ptr(pk), len(pk), as_ptr(rs[:32]), as_ptr(rs[32:]), pa, pb, pc))
-            t0 = time.perf_counter()
-            dropin_call()
-            first_s = time.perf_counter() - t0
-            for _ in range(W):
-                dropin_call()
-            t0 = time.perf_counter()
-            for _ in range(K):
-                dropin_call()
-            rep_s = (time.perf_counter() - t0) / K
-            dropin = {"first_call_s": first_s, "repeat_call_ms": 1000 * rep_s, "proofs_per_s": 1.0 / rep_s,
-                      "proof_matches_resident_path": (pa.raw + pb.raw + pc.raw) == proof_bytes,
-                      "note": "blocking ws_bn128_groth16_prove(witness, pkey) with host buffers, one call at a time; first call parses/uploads the key and builds its tables, repeats hash the %d-byte key buffer and reuse it" % len(pk)}
-            lib.ws_set_key_cache(h, 0)
-            lib.ws_set_key_cache(h, 1)
-        step_prove = L0.prove
-        d_proof = L0.d_proof
-        key_h = None
-        # parity of what was timed: the oracle's proof needs minutes at 2^20 in pure Python, so the check here is
-        # the reference image on the SAME key at a size it finishes (tests/ cover the rest); at 2^20 we verify
-        # determinism across ranks and that two runs agree bit for bit.
-        step_prove()
-        torch.cuda.synchronize()
-        same = bytes(d_proof.cpu().numpy()) == proof_bytes
-        alg_bytes = (len(pk) - 40) + len(wit) + 64 * (4 * dom + 2 * dom) + 3 * 32 * 2 * dom
-        extra["groth16"] = {
-            "metric": "Groth16 proofs/sec (BN128, 2^%d constraints)" % PROVE_LOG2, "value": 1000.0 / pms, "unit": "proofs/s", "ms_per_proof": pms,
-            "in_flight": "%d proofs (one context each, with its own resident key + window tables)" % NP,
-            "latency": {"ms_per_proof_single_stream": lat_ms, "proofs_per_s": 1000.0 / lat_ms},
-            "config": {"workload": "synthetic proving key nVars = domainSize = 2^%d, nPublic = 58 (tools/gen_synth_key.py), key resident in HBM" % PROVE_LOG2,
-                       "pkey_bytes": len(pk), "witness_bytes": len(wit), "shard": "point ranges x%d, all_gather of 768-byte partial records" % world, "scaling": "strong (one fixed-size proof over %d GPUs)" % world},
-            "e2e": {"value": 1.0 / pe2e, "unit": "proofs/s", "h2d_bytes_per_step": len(wit), "d2h_bytes_per_step": 384, "ms_per_proof": 1000 * pe2e,
-                    "note": "witness from pinned host memory each proof, two proofs in flight; proving key resident (loaded once per context: %.2f s incl. host-side row regrouping and window tables)" % load_s},
-            "example_key": example, "dropin_call": dropin, "stages_ms": pstages, "repeatable_bit_exact": same, "algorithmic_bytes": alg_bytes,
-            "hbm_frac": (alg_bytes / (pms * 1e-3) / 1e9) / peaks()[0],
-            "gpu_launches_per_proof": int(prove_launches) // K, "keygen_s": gen_s,
-        }
-        for ln in lanesP:
-            ln.bn.lib.ws_bn128_pkey_free(ln.key)
-
-    if rank == 0 and not args.no_prove:
-        extra["verifier"] = verifier_line()
+        env.dist.barrier()
     if rank == 0:
-        serial_ms = total_ms / K
-        ms_per_step = pipe_ms / K
-        value = TOTAL_PAIRS / (ms_per_step * 1e-3)
-        acc_ms = stage_ms.get("accumulate", 0.0) / K
-        peak, which = peaks()
-        achieved = (ALG_BYTES_PER_PAIR * cnt) / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else None
-        line = {
-            "metric": metric_name(), "value": value, "unit": "pairs/s",
-            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (256-bit Montgomery)", "data": "synthetic",
-            "config": {"workload": workload_name(), "pairs": TOTAL_PAIRS, "pairs_per_gpu": N_PAIRS,
-                       "parallelism": "one MSM of %d x 2^%d pairs, contiguous point range per GPU + one all_gather of 96-B partials + on-device combine" % (world, LOG2N) if world > 1 else "single GPU",
-                       "in_flight": "%d MSMs (that many contexts / streams in rotation; K steps inside one CUDA-event pair, max over ranks)" % NF,
-                       "l2": "inputs rotate over 4 device copies (384 MiB > 126 MB L2); the single-stream latency run flushes L2 between steps",
-                       "bit_exact_vs_oracle": True},
-            "latency": {"ms_per_msm_single_stream": serial_ms, "pairs_per_s": TOTAL_PAIRS / (serial_ms * 1e-3),
-                        "note": "one MSM at a time, per-step CUDA events, L2 flushed (256 MiB fill) between steps"},
-            "clocks": clocks,
-            "e2e": {"value": TOTAL_PAIRS / (e2e_s / KE), "unit": "pairs/s", "h2d_bytes_per_step": 96 * cnt, "d2h_bytes_per_step": 96,
-                    "ms_per_step": 1000.0 * e2e_s / KE, "steps": KE,
-                    "timer": "host perf_counter around %d blocking C-ABI calls (K rounded up to whole rounds) issued %d at a time from as many host threads / contexts, max over ranks" % (KE, NF)},
-            "gpu_launches": int(msm_launches) + (K if world > 1 else 0),
-            "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate<G1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if achieved else None, "traffic": NCU_TRAFFIC_BYTES if (LOG2N == 20 and world == 1) else None,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_ncu_accumulate_g1_2p20.txt)", "peak_source": which,
-                         "kernel_ms": acc_ms, "algorithmic_bytes_per_launch": ALG_BYTES_PER_PAIR * cnt,
-                         "note": "integer-multiply bound, not HBM bound: 8M+2S Montgomery products per pair per window (137 IMAD-class instructions per product, 111 per dedicated squaring)",
-                         "compute_side": {"montgomery_products_per_s": (10.0 * 16 * cnt) / (acc_ms * 1e-3) if acc_ms > 0 else None,
-                                          "imad_per_product_avg": (8 * 137 + 2 * 111) / 10.0,
-                                          "imad_wide_ceiling_products_per_s": 148 * 4 * 8 * 1.965e9 / ((8 * 137 + 2 * 111) / 10.0),
-                                          "frac_of_imad_ceiling": ((10.0 * 16 * cnt) / (acc_ms * 1e-3)) / (148 * 4 * 8 * 1.965e9 / ((8 * 137 + 2 * 111) / 10.0)) if acc_ms > 0 else None,
-                                          "ncu_fmaheavy_pipe_busy_pct": 81.5, "ncu_simt_lanes_per_warp": 31.7,
-                                          "source": "profiles/r1_ncu_accumulate_g1_2p20.txt"}},
-            "stages_ms": {k: v / K for k, v in stage_ms.items()},
-        }
+        if not args.no_ntt:
+            extra["ntt"] = section_ntt(env)
+        if not args.no_bls:
+            extra.update(section_other_curves(env))
+        if not args.only_prove:
+            extra["verifier"] = verifier_line()
+        gl = g["line"]
+        cfg = workload_config()
+        cfg.update(gl.pop("config_extra"))
+        line = {"metric": metric_name(), "value": gl.pop("value"), "unit": "proofs/s", "n_gpus": world, "steps": env.K, "warmup": env.W, "ms_per_step": gl.pop("ms_per_step"),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic", "config": cfg}
+        line.update(gl)
+        line["roofline"] = g.get("roofline")
         line.update(extra)
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             from oracle import ref_wasm
             if ref_wasm.available():
-                cores = usable_cores()
-                sample = min(N_PAIRS, 8192 * cores)
-                v1, _ = cpu_reference_arm(scalars, points, min(sample, 4096), 1)
-                v, dt = cpu_reference_arm(scalars, points, sample, cores)
-                line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "reference", "single_thread_value": v1,
-                                        "sample": "first %d pairs (%.1f s), reference g1m_multiexp2(w=7) from its WASM image compiled natively, %d threads as src/bn128.js:353-383 splits; single-thread on %d pairs" % (sample, dt, cores, min(sample, 4096))}
+                line["cpu_baseline"] = cpu_prover_baseline(usable_cores())
             else:
-                line["cpu_baseline"] = {"value": None, "unit": "pairs/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+                line["cpu_baseline"] = {"value": None, "unit": "proofs/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
         emit(line)
-    for b_ in reversed(bns):
+    for b_ in reversed(env.bns):
         b_.terminate()
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        env.dist.barrier()
+        env.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

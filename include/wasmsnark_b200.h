@@ -14,9 +14,12 @@
  * ws_create fails with WS_E_CUDA.  Only the Groth16 verifier / pairing entry points are host code, by design
  * (four pairings are not data-parallel work); they take no ws_ctx.
  *
- * Threading: a ws_ctx owns one CUDA device, one stream set and one workspace; calls on the
- * same ctx must be serialised by the caller (the reference likewise has one in-flight command
- * per worker, src/bn128.js:272-300).  Different ctx objects are independent.
+ * Threading: a ws_ctx owns one CUDA device, one stream set and one workspace and is thread-safe:
+ * every entry point holds the context's mutex for the duration of the call, so blocking calls from
+ * several host threads queue up like the reference's actionQueue (src/bn128.js:272-300), and the
+ * asynchronous *_dev calls -- which share the context's workspace -- are additionally chained on the
+ * device (work enqueued on another stream than the previous call's first waits for it).  Use one
+ * ctx per stream of work that should run concurrently.  Different ctx objects are independent.
  */
 #ifndef WASMSNARK_B200_H
 #define WASMSNARK_B200_H
@@ -234,11 +237,48 @@ int ws_bn128_groth16_prove_dev(ws_ctx* ctx, const ws_pkey* key, const void* d_wi
 #define WS_PARTIALS_BYTES 768
 int ws_bn128_pkey_load_shard(ws_ctx* ctx, const uint8_t* pkey, size_t pkey_len, int rank, int world, ws_pkey** out);
 int ws_bn128_groth16_partials_dev(ws_ctx* ctx, const ws_pkey* key, const void* d_witness, void* d_partials, void* stream);
+/* The same, split so that H (the reference's single CALC_H task, src/bn128.js:569-578) is computed by ONE rank per
+ * proof and handed to the others -- what strong scaling over the GPUs of a box needs (every rank repeating the five
+ * NTTs caps the speed-up):
+ *   ws_bn128_groth16_witness_msms_dev  starts the rank's A, B1, B2, C partial MSMs on the context's side streams, forked
+ *        from `stream` at this point; d_witness is an nVars*32-byte device buffer of which only the ranges
+ *        ws_bn128_pkey_shard_info reports need to hold data.  Writes slots A, B1, C, B2 of d_partials.
+ *   ws_bn128_groth16_h_dev             h = coefficients n..2n-1 of A*B (domainSize*32 bytes, plain form) from the WHOLE
+ *        witness, on `stream` -- run by the proof's H owner only; the caller then ships h[h_lo, h_lo + h_cnt) to every
+ *        rank (NCCL send/recv, or a peer copy inside one process: see ws_multi_* below).
+ *   ws_bn128_groth16_h_msm_dev         the rank's H partial MSM over its slice d_h_shard (h_cnt*32 bytes), on `stream`,
+ *        then joins the side streams: afterwards d_partials is complete in stream order (all_gather + finish as above).
+ * ws_bn128_pkey_shard_info: range = {v_lo, v_cnt, c_lo, c_cnt, h_lo, h_cnt} -- witness element ranges [v_lo, v_lo+v_cnt)
+ * (A/B1/B2) and [c_lo, c_lo+c_cnt) (C; c_lo already includes the nPublic+1 offset), h range [h_lo, h_lo+h_cnt).       */
+int ws_bn128_groth16_witness_msms_dev(ws_ctx* ctx, const ws_pkey* key, const void* d_witness, void* d_partials, void* stream);
+int ws_bn128_groth16_h_dev(ws_ctx* ctx, const ws_pkey* key, const void* d_witness, void* d_h, void* stream);
+int ws_bn128_groth16_h_msm_dev(ws_ctx* ctx, const ws_pkey* key, const void* d_h_shard, void* d_partials, void* stream);
+int ws_bn128_pkey_shard_info(const ws_pkey* key, uint32_t range[6]);
 /* optional, before partials: starts the products that depend only on (r, s) and the key's fixed points
  * (r*delta1, s*delta1, (r*s)*delta1, s*delta2; src/bn128.js:672-702) on a side stream so that they overlap
  * the multi-scalar multiplications; finish_dev picks the result up (or computes it itself if not prepared). */
 int ws_bn128_groth16_prepare_dev(ws_ctx* ctx, const ws_pkey* key, const void* d_rs, void* stream);
 int ws_bn128_groth16_finish_dev(ws_ctx* ctx, const ws_pkey* key, const void* d_all_partials, int world, const void* d_rs, void* d_out, void* stream);
+
+/* ---- all the GPUs of one box behind one handle (one process, one blocking call) -------------------------------
+ * Replaces buildBn128() + the worker pool as a whole (src/bn128.js:173-265): ws_multi_create(ngpus) opens one ws_ctx
+ * per GPU (ngpus <= 0: every visible device) with peer access between them; the calls below are the reference's
+ * Bn128.groth16GenProof / g1_multiexp / g2_multiexp with their worker split (:353-415, :580-720) mapped onto the
+ * GPUs: contiguous point ranges per GPU, H (the single CALC_H task, :569-578) computed by one GPU per proof -- rotating
+ * from proof to proof -- and shipped slice-wise to the others with peer copies over NVLink, the partial points copied
+ * to GPU 0, added and assembled there.  Host buffers, blocking, thread-safe (calls on one handle are serialised).
+ * ws_multi_bn128_groth16_prove is stateless like ws_bn128_groth16_prove: the key's shards stay on the GPUs between
+ * calls and are reused when the caller's key buffer has the same length and content fingerprint (hashed on the host
+ * while the GPUs already work on the proof).  Results are bit-identical to the single-GPU calls.              */
+typedef struct ws_multi ws_multi;
+int ws_multi_create(int ngpus, ws_multi** out);
+void ws_multi_destroy(ws_multi* m);
+int ws_multi_gpus(const ws_multi* m);
+const char* ws_multi_last_error(const ws_multi* m);
+int ws_multi_bn128_groth16_prove(ws_multi* m, const uint8_t* witness, size_t witness_len, const uint8_t* pkey, size_t pkey_len,
+                                 const uint8_t* r, const uint8_t* s, uint8_t pi_a[96], uint8_t pi_b[192], uint8_t pi_c[96]);
+int ws_multi_bn128_g1_multiexp(ws_multi* m, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t out[96]);
+int ws_multi_bn128_g2_multiexp(ws_multi* m, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t out[192]);
 
 /* Number of this library's CUDA kernels launched on the context so far (MSM, NTT and prover paths). */
 unsigned long long ws_kernel_launches(const ws_ctx* ctx);
@@ -251,6 +291,8 @@ int ws_set_msm_task_cap(ws_ctx* ctx, unsigned cap);
 int ws_set_msm_seg_len(ws_ctx* ctx, unsigned len);
 /* Tuning/test hook: occupancy variant (launch bounds) of the bucket-accumulation kernel; 0 = default. */
 int ws_set_msm_acc_variant(ws_ctx* ctx, int variant);
+/* Tuning/test hook: occupancy variant of the radix-64 NTT pass (0: 4 blocks/SM, 1: 5, 2: 6). */
+int ws_set_ntt_variant(ws_ctx* ctx, int variant);
 
 /* Elapsed device time (ms, CUDA events on the launch stream) of the kernels enqueued by the last
  * *_dev / host call on this ctx, split per pipeline stage; names[i] are static strings.

@@ -248,3 +248,211 @@ def test_random_rs_proof_accepted_by_reference_verifier(bn):
     assert not ref_wasm.groth16_verify(vk, pub, p1)
     assert not bn.groth16Verify(vk, pub, p1)
     key.free()
+
+
+# ---------------------------------------------------------------------------------------------------- round 2
+def _synth_small():
+    pk = open(os.path.join(GOLD, "synth_small.pkey.bin"), "rb").read()
+    wit = open(os.path.join(GOLD, "synth_small.witness.bin"), "rb").read()
+    g = json.load(open(os.path.join(GOLD, "synth_small.golden.json")))
+    return pk, wit, g
+
+
+@pytest.mark.parametrize("logn", [3, 8, 9, 13, 15, 18])
+def test_fft_in_place_pass_counts_and_variants(bn, logn):
+    """Every pass schedule of ntt_launch lands in the caller's buffer without a trailing copy (odd and even pass counts,
+    one and two scratch buffers), and the occupancy variants of the radix-64 pass compute the same bytes."""
+    n = 1 << logn
+    rng = np.random.Generator(np.random.PCG64(logn))
+    raw = np.frombuffer(rng.bytes(32 * n), dtype=np.uint8).reshape(n, 32).copy()
+    raw[:, 31] &= 0x1F
+    x = raw.tobytes()
+    base = {}
+    try:
+        for variant in (0, 1, 2):
+            bn.lib.ws_set_ntt_variant(bn.ctx.h, variant)
+            for odd in (0, 1):
+                y = bn.fft(x, odd)
+                assert bn.ifft(bn.fft(x, 0), 0) == x
+                if variant == 0:
+                    base[odd] = y
+                    if logn <= 9:
+                        xs = [O.from_mont(int.from_bytes(x[32 * i:32 * i + 32], "little"), O.R_ORDER) for i in range(n)]
+                        assert from_mont_list(y) == O.fft(xs, odd)
+                else:
+                    assert y == base[odd]
+    finally:
+        bn.lib.ws_set_ntt_variant(bn.ctx.h, 0)
+
+
+def test_fft_2p28_odd_is_rejected_not_garbage(bn):
+    """BN128 Fr has 2-adicity 28: fft(n = 2^28, odd) would need a 2^29-th root of unity.  The size check
+    comes before any allocation."""
+    import ctypes
+    from wasmsnark_b200._lib import WsError
+    with pytest.raises(WsError):
+        bn.ctx.check(bn.lib.ws_bn128_fr_fft_dev(bn.ctx.h, ctypes.c_void_p(256), 1 << 28, 1, 0, None))
+
+
+def test_split_prover_entry_points_equal_the_single_call(bn):
+    """witness_msms_dev + h_dev + h_msm_dev (the strong-scaling split: H computed once and handed over) on shards 0/2 and
+    1/2 of one GPU, h copied slice-wise like the NCCL / peer-copy hand-over would, against the golden proof."""
+    import ctypes
+    import torch
+    from wasmsnark_b200._lib import as_ptr
+    pk, wit, g = _synth_small()
+    world = 2
+    d_w = torch.frombuffer(bytearray(wit), dtype=torch.uint8).cuda()
+    d_rs = torch.frombuffer(bytearray(bytes.fromhex(g["r"]) + bytes.fromhex(g["s"])), dtype=torch.uint8).cuda()
+    d_all = torch.zeros(768 * world, dtype=torch.uint8, device="cuda")
+    d_out = torch.zeros(384, dtype=torch.uint8, device="cuda")
+    keys, ranges = [], []
+    for r in range(world):
+        k = ctypes.c_void_p()
+        bn.ctx.check(bn.lib.ws_bn128_pkey_load_shard(bn.ctx.h, as_ptr(pk), len(pk), r, world, ctypes.byref(k)))
+        rg = (ctypes.c_uint32 * 6)()
+        bn.lib.ws_bn128_pkey_shard_info(k, rg)
+        keys.append(k)
+        ranges.append(tuple(rg))
+    domain = 256
+    assert [rg[4:6] for rg in ranges] == [(0, 128), (128, 128)]
+    d_h = torch.zeros(domain * 32, dtype=torch.uint8, device="cuda")
+    bn.ctx.check(bn.lib.ws_bn128_groth16_h_dev(bn.ctx.h, keys[1], d_w.data_ptr(), d_h.data_ptr(), None))      # rank 1 owns H
+    torch.cuda.synchronize()
+    bn.ctx.timings()
+    k = O.parse_pkey(pk)
+    want_h = bn.calcH(wit, pk[k["pPolsA"]:k["pPolsB"]], pk[k["pPolsB"]:k["pPointsA"]], k["nVars"], k["domainSize"])
+    assert bytes(d_h.cpu().numpy()) == want_h
+    for r in range(world):
+        # a non-owner only holds the hull of its witness ranges and its slice of h
+        from wasmsnark_b200.parallel import witness_hull
+        lo, cnt = witness_hull(ranges[r])
+        w_r = torch.zeros_like(d_w)
+        w_r[32 * lo:32 * (lo + cnt)] = d_w[32 * lo:32 * (lo + cnt)]
+        h_r = torch.zeros_like(d_h)
+        h_lo, h_cnt = ranges[r][4], ranges[r][5]
+        h_r[32 * h_lo:32 * (h_lo + h_cnt)] = d_h[32 * h_lo:32 * (h_lo + h_cnt)]
+        torch.cuda.synchronize()
+        part = d_all[768 * r:]
+        bn.ctx.check(bn.lib.ws_bn128_groth16_witness_msms_dev(bn.ctx.h, keys[r], w_r.data_ptr(), part.data_ptr(), None))
+        bn.ctx.check(bn.lib.ws_bn128_groth16_h_msm_dev(bn.ctx.h, keys[r], h_r.data_ptr() + 32 * h_lo, part.data_ptr(), None))
+        bn.ctx.timings()
+        torch.cuda.synchronize()
+    bn.ctx.check(bn.lib.ws_bn128_groth16_finish_dev(bn.ctx.h, keys[0], d_all.data_ptr(), world, d_rs.data_ptr(), d_out.data_ptr(), None))
+    bn.ctx.timings()
+    torch.cuda.synchronize()
+    out = bytes(d_out.cpu().numpy())
+    assert {"pi_a": bn.bin2g1(out[:96]), "pi_b": bn.bin2g2(out[96:288]), "pi_c": bn.bin2g1(out[288:])} == g["proof_rs"]
+    for k_ in keys:
+        bn.lib.ws_bn128_pkey_free(k_)
+
+
+def test_context_is_thread_safe(bn):
+    """Several host threads proving / multiplying on ONE context (the reference queues any number of commands,
+    src/bn128.js:282-300; the Node addon runs proofs on libuv worker threads): every result is the right one."""
+    import threading
+    pk, wit, g = _synth_small()
+    r, s = bytes.fromhex(g["r"]), bytes.fromhex(g["s"])
+    key = bn.load_proving_key(pk)
+    errors = []
+
+    def prover(n):
+        try:
+            for _ in range(n):
+                assert bn.groth16GenProof(wit, key, r=r, s=s) == g["proof_rs"]
+        except Exception as e:       # noqa: BLE001
+            errors.append(e)
+
+    def stateless(n):
+        try:
+            for _ in range(n):
+                assert bn.groth16GenProof(wit, pk, r=r, s=s) == g["proof_rs"]
+        except Exception as e:       # noqa: BLE001
+            errors.append(e)
+
+    def ffts(n):
+        try:
+            x = bytes(range(32)) * 64
+            want = bn.fft(x)
+            for _ in range(n):
+                assert bn.fft(x) == want
+        except Exception as e:       # noqa: BLE001
+            errors.append(e)
+    th = [threading.Thread(target=f, args=(6,)) for f in (prover, prover, stateless, ffts)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    key.free()
+    assert not errors, errors
+
+
+def test_stateless_call_from_pageable_memory_large_witness(bn):
+    """The pinned staging ring (host_io.cuh) is only used above 1 MiB: a 2^15-signal witness from ordinary bytes objects
+    through the stateless call, twice (second call: cached key, fingerprint overlapped), equals the resident-key proof."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tools"))
+    import gen_synth_key
+    nv = 1 << 15
+    pk, wit = gen_synth_key.make(nv + 1000, 7, nv, seed=5)
+    assert len(wit) > (1 << 20)
+    r, s = bytes(range(32)), bytes(range(32, 64))
+    key = bn.load_proving_key(pk)
+    want = bn.groth16GenProof(wit, key, r=r, s=s)
+    key.free()
+    for _ in range(3):
+        assert bn.groth16GenProof(bytes(wit), bytes(pk), r=r, s=s) == want
+    assert bn.groth16GenProof(bytearray(wit), bytearray(pk), r=r, s=s) == want
+
+
+def test_multi_handle_on_the_visible_gpus():
+    """ws_multi_*: the one-process multi-GPU handle (all visible GPUs; 1 on a single-GPU box, where the code path is the
+    same with n = 1).  Golden proofs, MSMs against the single-context results, stateless key replacement."""
+    import torch
+    from wasmsnark_b200 import build_bn128, build_bn128_multi
+    import util
+    pk, wit, g = _synth_small()
+    r, s = bytes.fromhex(g["r"]), bytes.fromhex(g["s"])
+    m = build_bn128_multi(0)
+    bn1 = build_bn128(0)
+    try:
+        assert m.ngpus == torch.cuda.device_count()
+        for _ in range(3):          # H owner rotates over the GPUs
+            assert m.groth16GenProof(wit, pk, r=r, s=s) == g["proof_rs"]
+        assert m.groth16GenProof(wit, pk, r=bytes(32), s=bytes(32)) == g["proof_r0s0"]
+        k = O.parse_pkey(pk)
+        a = k["pPointsA"]
+        pk3 = pk[:a + 64] + pk[a + 128:a + 192] + pk[a + 64:a + 128] + pk[a + 192:]      # same length, other content
+        assert m.groth16GenProof(wit, pk3, r=r, s=s) == bn1.groth16GenProof(wit, pk3, r=r, s=s) != g["proof_rs"]
+        assert m.groth16GenProof(wit, pk, r=r, s=s) == g["proof_rs"]
+        n = 5000
+        aff, P0, D = util.arith_points(O.Fq, O.G1_GEN, n, 11)
+        rnd = random.Random(12)
+        sc = [rnd.getrandbits(256) for _ in range(n)]
+        sb, pb = b"".join(util.b32(v) for v in sc), util.g1_points_bytes(aff)
+        assert util.g1_result_tuple(bn1.g1_affine(m.g1_multiexp(sb, pb))) == util.closed_form_sum(sc, P0, D)
+        g2p = b"".join(util.g2_affine_m(O.pt_times_scalar(O.Fq2, (O.G2_GEN[0], O.G2_GEN[1], O.Fq2.one), rnd.randrange(1, O.R_ORDER))) for _ in range(40))
+        sb2 = b"".join(util.b32(rnd.getrandbits(256)) for _ in range(40))
+        assert bn1.g2_affine(m.g2_multiexp(sb2, g2p)) == bn1.g2_affine(bn1.g2_multiexp(sb2, g2p))
+    finally:
+        m.terminate()
+        bn1.terminate()
+
+
+def test_golden_proof_2p20_constraints(bn):
+    """BASELINE's headline config: the 2^20-constraint synthetic key (tools/gen_synth_key.make(2^20, 58, 2^20, seed 0xB204))
+    with the bench's (r, s) against the proof the REFERENCE's own code computed for it (tests/golden/make_golden_2p20.py,
+    pkey sha256 pinned).  Key generation dominates (~20 s of host time)."""
+    import hashlib
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tools"))
+    import gen_synth_key
+    gold = json.load(open(os.path.join(GOLD, "synth_2p20.golden.json")))
+    k = gold["log2_constraints"]
+    pk, wit = gen_synth_key.make(1 << k, gold["n_public"], 1 << k, seed=gold["seed"])
+    assert hashlib.sha256(pk).hexdigest() == gold["pkey_sha256"]
+    assert hashlib.sha256(wit).hexdigest() == gold["witness_sha256"]
+    key = bn.load_proving_key(pk)
+    try:
+        proof = bn.groth16GenProof(wit, key, r=bytes.fromhex(gold["r"]), s=bytes.fromhex(gold["s"]))
+    finally:
+        key.free()
+    assert proof == gold["proof"]

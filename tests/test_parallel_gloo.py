@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from oracle import bn128 as O
-from wasmsnark_b200.parallel import all_gather_records, shard_range
+from wasmsnark_b200.parallel import all_gather_records, scatter_slices, shard_range, witness_hull
 
 
 def test_shard_range_matches_reference_split():
@@ -62,3 +62,41 @@ def test_two_rank_sharded_sum_equals_unsharded():
     assert all(p.exitcode == 0 for p in procs)
     assert sorted(r for r, _ in got) == [0, 1]
     assert all(res == want for _, res in got)
+
+
+def _scatter_worker(rank, world, port, n_elems, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ok = True
+    full = torch.arange(n_elems * 32, dtype=torch.int64).remainder(251).to(torch.uint8)          # what the H owner computed
+    for owner in range(world):                    # the owner rotates from proof to proof
+        buf = full.clone() if rank == owner else torch.full((n_elems * 32,), 255, dtype=torch.uint8)
+        scatter_slices(buf, 32, n_elems, owner, rank, world)
+        lo, cnt = shard_range(n_elems, rank, world)
+        ok &= bool(torch.equal(buf[lo * 32:(lo + cnt) * 32], full[lo * 32:(lo + cnt) * 32]))
+        if rank != owner:                         # nothing outside the slice was written
+            rest = torch.cat([buf[:lo * 32], buf[(lo + cnt) * 32:]])
+            ok &= bool((rest == 255).all())
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_h_slices_reach_every_rank_from_a_rotating_owner():
+    """The H hand-over of the sharded prover (parallel.scatter_slices) on a world_size-2 gloo group, uneven split."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + random.randrange(2000)
+    procs = [ctx.Process(target=_scatter_worker, args=(r, 2, port, 37, q)) for r in range(2)]
+    [p.start() for p in procs]
+    got = [q.get(timeout=120) for _ in range(2)]
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert sorted(got) == [(0, True), (1, True)]
+
+
+def test_witness_hull_covers_both_point_ranges():
+    # (v_lo, v_cnt, c_lo incl. the nPublic + 1 offset, c_cnt, h_lo, h_cnt)
+    assert witness_hull((100, 50, 130, 40, 0, 0)) == (100, 70)
+    assert witness_hull((0, 10, 59, 5, 0, 0)) == (0, 64)
+    assert witness_hull((0, 0, 0, 0, 0, 0)) == (0, 0)

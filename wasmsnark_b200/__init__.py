@@ -5,4 +5,4 @@ libwasmsnark_b200.so (include/wasmsnark_b200.h).  All proving-path arithmetic ru
 CUDA kernels with no CPU fallback; only the Groth16 verifier (four pairings) is host code.
 """
 from ._lib import load_library, LibraryNotBuilt  # noqa: F401
-from .bn128 import Bn128, ProvingKey, build_bn128, groth16GenProof, genZKSnarkProof, groth16Verify, pairing, proof_json  # noqa: F401
+from .bn128 import Bn128, MultiBn128, ProvingKey, build_bn128, build_bn128_multi, groth16GenProof, genZKSnarkProof, groth16Verify, pairing, proof_json  # noqa: F401

@@ -243,6 +243,63 @@ def pairing(p, q):
     return [int.from_bytes(out.raw[32 * i:32 * i + 32], "little") for i in range(12)]
 
 
+class MultiBn128:
+    """All the GPUs of one box behind one object (ws_multi_*): the reference's `Bn128` with its worker pool mapped
+    onto the GPUs (src/bn128.js:173-265, :353-415, :580-720).  One process, blocking calls, host buffers."""
+    bin2int, bin2g1, bin2g2 = Bn128.bin2int, Bn128.bin2g1, Bn128.bin2g2
+
+    def __init__(self, ngpus=0):
+        self.lib = _lib.load_library()
+        h = ctypes.c_void_p()
+        rc = self.lib.ws_multi_create(ngpus, ctypes.byref(h))
+        if rc != _lib.WS_OK:
+            raise _lib.WsError(rc, "ws_multi_create failed (asked for %d GPUs)" % ngpus)
+        self.h = h
+        self.ngpus = self.lib.ws_multi_gpus(h)
+
+    def terminate(self):
+        if self.h:
+            self.lib.ws_multi_destroy(self.h)
+            self.h = None
+
+    def _check(self, rc):
+        if rc != _lib.WS_OK:
+            raise _lib.WsError(rc, (self.lib.ws_multi_last_error(self.h) or b"").decode())
+
+    def _multiexp(self, fn, scalars, points, psize, osize):
+        if len(scalars) % 32:
+            raise ValueError("scalars must be n*32 bytes")
+        n = len(scalars) // 32
+        if len(points) < n * psize:
+            raise ValueError("points buffer too short for %d scalars" % n)
+        out = ctypes.create_string_buffer(osize)
+        self._check(fn(self.h, as_ptr(scalars), as_ptr(points), n, ctypes.cast(out, ctypes.c_void_p)))
+        return out.raw
+
+    def g1_multiexp(self, scalars, points):
+        return self._multiexp(self.lib.ws_multi_bn128_g1_multiexp, scalars, points, 64, 96)
+
+    def g2_multiexp(self, scalars, points):
+        return self._multiexp(self.lib.ws_multi_bn128_g2_multiexp, scalars, points, 128, 192)
+
+    def groth16GenProof(self, signals, pkey, r=None, s=None, raw=False):
+        """src/bn128.js:580-720 over all the GPUs of the handle; pkey: proving_key.bin bytes."""
+        for nm, v in (("r", r), ("s", s)):
+            if v is not None and len(v) != 32:
+                raise ValueError("%s must be exactly 32 bytes" % nm)
+        pa, pb, pc = ctypes.create_string_buffer(96), ctypes.create_string_buffer(192), ctypes.create_string_buffer(96)
+        outs = [ctypes.cast(x, ctypes.c_void_p) for x in (pa, pb, pc)]
+        self._check(self.lib.ws_multi_bn128_groth16_prove(self.h, as_ptr(signals), len(signals), as_ptr(pkey), len(pkey), as_ptr(r), as_ptr(s), *outs))
+        if raw:
+            return pa.raw, pb.raw, pc.raw
+        return {"pi_a": self.bin2g1(pa.raw), "pi_b": self.bin2g2(pb.raw), "pi_c": self.bin2g1(pc.raw)}
+
+
+def build_bn128_multi(ngpus=0):
+    """buildBn128() with the worker pool = the GPUs of the box (ngpus <= 0: all visible devices)."""
+    return MultiBn128(ngpus)
+
+
 def build_bn128(device=0):
     """index.js:20-22 / src/bn128.js:173-265 `buildBn128()`."""
     return Bn128(device)

@@ -48,6 +48,7 @@ WS_API void ws_destroy(ws_ctx* c) {
     if (c->tw_table) cudaFree(c->tw_table);
     if (c->tw_table_bls) cudaFree(c->tw_table_bls);
     if (c->busy_ev) cudaEventDestroy(c->busy_ev);
+    c->stager.destroy();
     if (c->lanes_ready) {
         for (int i = 0; i < ws_ctx::NLANES; i++) {
             cudaStreamDestroy(c->lanes[i]);
@@ -141,6 +142,13 @@ WS_API int ws_set_msm_acc_variant(ws_ctx* c, int v) {
     WsLock ws_lock_(c);
     if (!c) return WS_E_ARG;
     c->acc_variant = v;
+    return WS_OK;
+}
+
+WS_API int ws_set_ntt_variant(ws_ctx* c, int v) {
+    WsLock ws_lock_(c);
+    if (!c) return WS_E_ARG;
+    c->ntt_variant = v;
     return WS_OK;
 }
 

@@ -48,10 +48,11 @@ static int bls_fft_dev(ws_ctx* c, void* d_px, size_t n, int odd, int inverse, cu
     c->tw_table_bls = T.tw;
     c->tw_logM_bls = T.logM;
     if (!ok) return c->fail_cuda("twiddle table");
-    BlsFr* scratch = (BlsFr*)c->arena(2, sizeof(BlsFr) << logn);
+    BlsFr* scratch = (BlsFr*)c->arena(2, 2 * (sizeof(BlsFr) << logn));
     if (!scratch) return c->fail_cuda("fft scratch");
     WsStreamScope chain(c, st);
-    cudaError_t e = ntt_launch<NttBls12381>((BlsFr*)d_px, scratch, logn, odd != 0, inverse != 0, T, st, &c->launches);
+    cudaError_t e = ntt_launch<NttBls12381>((const BlsFr*)d_px, (BlsFr*)d_px, scratch, scratch + ((size_t)1 << logn), logn, odd != 0, inverse != 0, T, st,
+                                            &c->launches, c->ntt_variant);
     return e == cudaSuccess ? WS_OK : c->fail_cuda("ntt");
 }
 

@@ -5,6 +5,7 @@
 #include <string>
 
 #include "../../include/wasmsnark_b200.h"
+#include "host_io.cuh"
 
 namespace ws {
 
@@ -88,6 +89,7 @@ struct ws_ctx {
         return true;
     }
     ws::StageTimer timer;
+    ws::PinnedStager stager;     // pageable caller buffers -> device (host_io.cuh)
     std::string err;
     unsigned long long launches = 0;   // kernels of this library launched so far (ws_kernel_launches)
     unsigned force_T = 0;
@@ -103,6 +105,7 @@ struct ws_ctx {
     int tw_logM_bls = 0;
     int tw_logM = 0;
     int acc_variant = 0;         // tuning hook: launch-bounds variant of the accumulate kernel
+    int ntt_variant = 0;         // tuning hook: occupancy variant of the radix-64 NTT pass (ws_set_ntt_variant)
     unsigned seg_len = 0;    // 0 = automatic
 
     // Arena `slot` grown to at least `bytes` (contents are scratch: not preserved on growth).

@@ -532,14 +532,16 @@ static int calc_h_dev(ws_ctx* c, const DevCsr& pa, const DevCsr& pb, const Fr* d
     k_csr_lc<<<(n + 127) / 128, 128, 0, st>>>(pa.row_start, pa.sig, pa.coef, sM, A, n);
     k_csr_lc<<<(n + 127) / 128, 128, 0, st>>>(pb.row_start, pb.sig, pb.coef, sM, B, n);
     c->timer.mark("h:lc", st);
-    cudaMemcpyAsync(Ao, A, sizeof(Fr) * n, cudaMemcpyDeviceToDevice, st);
-    cudaMemcpyAsync(Bo, B, sizeof(Fr) * n, cudaMemcpyDeviceToDevice, st);
-    ntt_launch(Ao, scratch, logn, 0, 1, T, st, &c->launches);
-    ntt_launch(Bo, scratch, logn, 0, 1, T, st, &c->launches);
-    ntt_launch(Ao, scratch, logn, 1, 0, T, st, &c->launches);
-    ntt_launch(Bo, scratch, logn, 1, 0, T, st, &c->launches);
+    const int nv = c->ntt_variant;
+    // A, B keep the evaluations on the even domain; Ao, Bo receive the coefficients (out-of-place inverse transform:
+    // no copy), then become the evaluations on the odd coset in place (P is free until the product and serves as the
+    // second scratch buffer an odd pass count needs)
+    ntt_launch<NttBn128>(A, Ao, scratch, nullptr, logn, 0, 1, T, st, &c->launches, nv);
+    ntt_launch<NttBn128>(B, Bo, scratch, nullptr, logn, 0, 1, T, st, &c->launches, nv);
+    ntt_launch<NttBn128>(Ao, Ao, scratch, P, logn, 1, 0, T, st, &c->launches, nv);
+    ntt_launch<NttBn128>(Bo, Bo, scratch, P, logn, 1, 0, T, st, &c->launches, nv);
     k_interleave_mul<<<(n + 127) / 128, 128, 0, st>>>(A, B, Ao, Bo, P, n);
-    ntt_launch(P, scratch, logn + 1, 0, 1, T, st, &c->launches);
+    ntt_launch<NttBn128>(P, P, scratch, A, logn + 1, 0, 1, T, st, &c->launches, nv);     // A|B (2n, contiguous) are dead now
     c->launches += 5;      // to_mont, 2 x csr_lc, interleave_mul, from_mont
     k_fr_from_mont<<<(n + 127) / 128, 128, 0, st>>>(P + n, d_h, n);
     c->timer.mark("h:ntt", st);
@@ -549,48 +551,76 @@ static int calc_h_dev(ws_ctx* c, const DevCsr& pa, const DevCsr& pb, const Fr* d
 // The five partial sums of this key's shard, as XYZZ records: A | B1 | C | H (128 bytes each) | B2 (256).
 constexpr size_t PARTIALS_BYTES = 4 * sizeof(G1X) + sizeof(G2X);   // 768
 
-static int prove_partials_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_witness, uint8_t* d_partials, cudaStream_t st) {
-    const uint32_t nv = k->n_vars, n = k->domain;
-    const size_t work_elems = (size_t)nv + 9 * (size_t)n + 64;
-    uint8_t* base = (uint8_t*)c->arena(2, work_elems * 32);
-    if (!base || !c->ensure_lanes()) return c->fail_cuda("prover workspace");
-    Fr* h = (Fr*)base;
-    Fr* work = h + n;
-    G1X* rA = (G1X*)d_partials;
-    G1X* rB1 = rA + 1;
-    G1X* rC = rB1 + 1;
-    G1X* rH = rC + 1;
-    G2X* rB2 = (G2X*)(rH + 1);
-    c->timer.begin(st);
-    // The four witness MSMs do not depend on H: they go to side streams (own workspace each) and run
-    // while the H pipeline (LC + 5 NTTs) and the H MSM proceed on `st` -- the reference's promise
-    // graph (src/bn128.js:607-622), with streams instead of workers.
+struct PartialSlots {
+    G1X *rA, *rB1, *rC, *rH;
+    G2X* rB2;
+    explicit PartialSlots(uint8_t* d_partials) {
+        rA = (G1X*)d_partials;
+        rB1 = rA + 1;
+        rC = rB1 + 1;
+        rH = rC + 1;
+        rB2 = (G2X*)(rH + 1);
+    }
+};
+
+// The four witness MSMs of this key's shard (A, B1, C over G1; B2 over G2) on side streams forked from `st` at this
+// point, each with its own workspace -- the reference's promise graph (src/bn128.js:607-622), with streams instead of
+// workers.  They do not depend on H.  prove_h_msm_dev (or prove_join_dev) joins them back into `st`.
+static int prove_witness_msms_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_witness, uint8_t* d_partials, cudaStream_t st) {
+    if (!c->ensure_lanes()) return c->fail_cuda("prover streams");
+    PartialSlots p(d_partials);
     cudaEventRecord(c->fork_ev, st);
     const uint8_t* wv = d_witness + 32 * (size_t)k->v_lo;
     int rc = 0;
     for (int lane = 0; lane < 4 && !rc; lane++) {
         cudaStream_t ls = c->lanes[lane];
         cudaStreamWaitEvent(ls, c->fork_ev, 0);
-        if (lane == 0) rc = msm_g2_run(c, wv, k->tB2 ? k->tB2 : (const void*)k->B2, k->v_cnt, nullptr, rB2, ls, 8 + lane, k->tc_v);
-        else if (lane == 1) rc = msm_g1_run(c, wv, k->tA ? k->tA : (const void*)k->A, k->v_cnt, nullptr, rA, ls, 8 + lane, k->tc_v);
-        else if (lane == 2) rc = msm_g1_run(c, wv, k->tB1 ? k->tB1 : (const void*)k->B1, k->v_cnt, nullptr, rB1, ls, 8 + lane, k->tc_v);
-        else rc = msm_g1_run(c, d_witness + 32 * ((size_t)k->n_public + 1 + k->c_lo), k->tC ? k->tC : (const void*)k->C, k->c_cnt, nullptr, rC, ls, 8 + lane, k->tc_c);
+        if (lane == 0) rc = msm_g2_run(c, wv, k->tB2 ? k->tB2 : (const void*)k->B2, k->v_cnt, nullptr, p.rB2, ls, 8 + lane, k->tc_v);
+        else if (lane == 1) rc = msm_g1_run(c, wv, k->tA ? k->tA : (const void*)k->A, k->v_cnt, nullptr, p.rA, ls, 8 + lane, k->tc_v);
+        else if (lane == 2) rc = msm_g1_run(c, wv, k->tB1 ? k->tB1 : (const void*)k->B1, k->v_cnt, nullptr, p.rB1, ls, 8 + lane, k->tc_v);
+        else rc = msm_g1_run(c, d_witness + 32 * ((size_t)k->n_public + 1 + k->c_lo), k->tC ? k->tC : (const void*)k->C, k->c_cnt, nullptr, p.rC, ls, 8 + lane, k->tc_c);
         cudaEventRecord(c->lane_done[lane], ls);
     }
     if (rc) return rc;
-    // the dependent chain (LC -> NTTs -> H MSM) runs on the high-priority lane, forked from / joined to `st`
+    return cudaGetLastError() == cudaSuccess ? WS_OK : c->fail_cuda("prove: witness MSMs");
+}
+
+// h = coefficients n..2n-1 of A*B for the WHOLE domain (the reference's CALC_H task), from the whole witness, on `st`.
+static int prove_h_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_witness, Fr* d_h, cudaStream_t st) {
+    const uint32_t nv = k->n_vars, n = k->domain;
+    const size_t work_elems = (size_t)nv + 8 * (size_t)n + 64;
+    Fr* work = (Fr*)c->arena(2, work_elems * 32);
+    if (!work) return c->fail_cuda("prover workspace");
+    return calc_h_dev(c, k->polA, k->polB, (const Fr*)d_witness, nv, k->logn, d_h, work, st);
+}
+
+// The H MSM of this key's shard: d_h_shard = h[h_lo .. h_lo + h_cnt), on `st`; then the side streams of the witness
+// MSMs are joined into `st`, after which the 768-byte record is complete in stream order.
+static int prove_h_msm_dev(ws_ctx* c, const ws_pkey* k, const Fr* d_h_shard, uint8_t* d_partials, cudaStream_t st) {
+    PartialSlots p(d_partials);
+    int rc = msm_g1_run(c, d_h_shard, k->tH ? k->tH : (const void*)k->H, k->h_cnt, nullptr, p.rH, st, 1, k->tc_h);
+    if (rc) return rc;
+    c->timer.mark("msm:H", st);
+    for (int lane = 0; lane < 4; lane++) cudaStreamWaitEvent(st, c->lane_done[lane], 0);
+    c->timer.mark("msm:A,B1,B2,C (side streams)", st);
+    return cudaGetLastError() == cudaSuccess ? WS_OK : c->fail_cuda("prove: H MSM");
+}
+
+static int prove_partials_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_witness, uint8_t* d_partials, cudaStream_t st) {
+    Fr* h = (Fr*)c->arena(7, ((size_t)k->domain + 8) * 32);
+    if (!h || !c->ensure_lanes()) return c->fail_cuda("prover workspace");
+    c->timer.begin(st);
+    int rc = prove_witness_msms_dev(c, k, d_witness, d_partials, st);
+    if (rc) return rc;
+    // the dependent chain (LC -> NTTs -> H MSM) optionally runs on the high-priority lane, forked from / joined to `st`
     cudaStream_t hs = c->h_priority ? c->lanes[5] : st;
     if (hs != st) cudaStreamWaitEvent(hs, c->fork_ev, 0);
-    if ((rc = calc_h_dev(c, k->polA, k->polB, (const Fr*)d_witness, nv, k->logn, h, work, hs))) return rc;
-    if ((rc = msm_g1_run(c, h + k->h_lo, k->tH ? k->tH : (const void*)k->H, k->h_cnt, nullptr, rH, hs, 1, k->tc_h))) return rc;
-    c->timer.mark("msm:H", hs);
+    if ((rc = prove_h_dev(c, k, d_witness, h, hs))) return rc;
     if (hs != st) {
         cudaEventRecord(c->h_done, hs);
         cudaStreamWaitEvent(st, c->h_done, 0);
     }
-    for (int lane = 0; lane < 4; lane++) cudaStreamWaitEvent(st, c->lane_done[lane], 0);
-    c->timer.mark("msm:A,B1,B2,C (side streams)", st);
-    return cudaGetLastError() == cudaSuccess ? WS_OK : c->fail_cuda("prove");
+    return prove_h_msm_dev(c, k, h + k->h_lo, d_partials, st);
 }
 
 // Starts the (r, s)-only products on a side stream; `st` must have d_rs ready at this point.
@@ -664,8 +694,11 @@ static int prove_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_witness, cons
     return prove_finish_dev(c, k, part, 1, d_rs, d_out, st);
 }
 
-static int prove_host(ws_ctx* c, const ws_pkey* k, const uint8_t* witness, size_t wlen, const uint8_t* r, const uint8_t* s, uint8_t* pi_a, uint8_t* pi_b,
-                      uint8_t* pi_c) {
+// The blocking host-buffer call in two halves, so that the stateless entry point can fingerprint the caller's key
+// buffer on the host while the GPU already works.
+//   prove_host_enqueue  stages the witness to the device (pinned ring for pageable memory) and enqueues the proof
+//   prove_host_collect  waits and copies the 384 result bytes out
+static int prove_host_enqueue(ws_ctx* c, const ws_pkey* k, const uint8_t* witness, size_t wlen, const uint8_t* r, const uint8_t* s) {
     if (wlen < (size_t)k->n_vars * 32) return c->fail(WS_E_ARG, "witness shorter than nVars * 32 bytes");
     cudaSetDevice(c->device);
     uint8_t rs[64];
@@ -679,17 +712,29 @@ static int prove_host(ws_ctx* c, const ws_pkey* k, const uint8_t* witness, size_
     if (!d) return c->fail_cuda("witness buffer");
     uint8_t* d_rs = d + align256(wbytes);
     uint8_t* d_out = d_rs + 256;
-    cudaMemcpyAsync(d, witness, wbytes, cudaMemcpyHostToDevice, c->stream);
-    cudaMemcpyAsync(d_rs, rs, 64, cudaMemcpyHostToDevice, c->stream);
-    int rc = prove_dev(c, k, d, d_rs, d_out, c->stream);
-    if (rc) return rc;
+    if (c->stager.upload(d, witness, wbytes, c->stream, c->device) != cudaSuccess) return c->fail_cuda("witness upload");
+    if (cudaMemcpyAsync(d_rs, rs, 64, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return c->fail_cuda("r, s upload");   // pageable: staged before return
+    return prove_dev(c, k, d, d_rs, d_out, c->stream);
+}
+
+static int prove_host_collect(ws_ctx* c, const ws_pkey* k, uint8_t* pi_a, uint8_t* pi_b, uint8_t* pi_c) {
+    size_t wbytes = (size_t)k->n_vars * 32;
+    uint8_t* d = (uint8_t*)c->arena(3, align256(wbytes) + 1024);
+    uint8_t* d_out = d + align256(wbytes) + 256;
     uint8_t outb[384];
-    cudaMemcpyAsync(outb, d_out, 384, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaMemcpyAsync(outb, d_out, 384, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return c->fail_cuda("proof download");
     if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) return c->fail_cuda("prove");
     memcpy(pi_a, outb, 96);
     memcpy(pi_b, outb + 96, 192);
     memcpy(pi_c, outb + 288, 96);
     return WS_OK;
+}
+
+static int prove_host(ws_ctx* c, const ws_pkey* k, const uint8_t* witness, size_t wlen, const uint8_t* r, const uint8_t* s, uint8_t* pi_a, uint8_t* pi_b,
+                      uint8_t* pi_c) {
+    int rc = prove_host_enqueue(c, k, witness, wlen, r, s);
+    if (rc) return rc;
+    return prove_host_collect(c, k, pi_a, pi_b, pi_c);
 }
 
 // ============================================================================ C ABI
@@ -706,11 +751,12 @@ WS_API int ws_bn128_fr_fft_dev(ws_ctx* c, void* d_px, size_t n, int odd, int inv
     if (odd && logn == 28) return c->fail(WS_E_SIZE, "odd fft of size 2^28 needs a 2^29-th root of unity");
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     if (!ensure_twiddles(c, logn + (odd ? 1 : 0), st)) return c->fail_cuda("twiddle table");
-    Fr* scratch = (Fr*)c->arena(2, sizeof(Fr) << logn);
+    Fr* scratch = (Fr*)c->arena(2, 2 * (sizeof(Fr) << logn));       // two buffers: an odd pass count needs both
     if (!scratch) return c->fail_cuda("fft scratch");
     WsStreamScope chain(c, st);
     c->timer.begin(st);
-    cudaError_t e = ntt_launch((Fr*)d_px, scratch, logn, odd != 0, inverse != 0, twiddles(c), st, &c->launches);
+    cudaError_t e = ntt_launch<NttBn128>((const Fr*)d_px, (Fr*)d_px, scratch, scratch + ((size_t)1 << logn), logn, odd != 0, inverse != 0, twiddles(c), st,
+                                         &c->launches, c->ntt_variant);
     c->timer.mark("ntt", st);
     return e == cudaSuccess ? WS_OK : c->fail_cuda("ntt");
 }
@@ -765,6 +811,48 @@ WS_API int ws_bn128_groth16_partials_dev(ws_ctx* c, const ws_pkey* k, const void
     cudaSetDevice(c->device);
     WsStreamScope chain(c, stream ? (cudaStream_t)stream : c->stream);
     return prove_partials_dev(c, k, (const uint8_t*)d_witness, (uint8_t*)d_partials, stream ? (cudaStream_t)stream : c->stream);
+}
+WS_API int ws_bn128_groth16_witness_msms_dev(ws_ctx* c, const ws_pkey* k, const void* d_witness, void* d_partials, void* stream) {
+    WsLock ws_lock_(c);
+    if (!c || !k || !d_witness || !d_partials) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
+    if (k->ctx != c) return c->fail(WS_E_ARG, "proving key belongs to another context");
+    if (((uintptr_t)d_witness | (uintptr_t)d_partials) & 15) return c->fail(WS_E_ARG, "device pointers must be 16-byte aligned");
+    cudaSetDevice(c->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    c->enter_stream(st);            // the matching leave_stream is in ws_bn128_groth16_h_msm_dev, which joins the side streams
+    c->timer.begin(st);
+    return prove_witness_msms_dev(c, k, (const uint8_t*)d_witness, (uint8_t*)d_partials, st);
+}
+WS_API int ws_bn128_groth16_h_dev(ws_ctx* c, const ws_pkey* k, const void* d_witness, void* d_h, void* stream) {
+    WsLock ws_lock_(c);
+    if (!c || !k || !d_witness || !d_h) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
+    if (k->ctx != c) return c->fail(WS_E_ARG, "proving key belongs to another context");
+    if (((uintptr_t)d_witness | (uintptr_t)d_h) & 15) return c->fail(WS_E_ARG, "device pointers must be 16-byte aligned");
+    cudaSetDevice(c->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    return prove_h_dev(c, k, (const uint8_t*)d_witness, (Fr*)d_h, st);
+}
+WS_API int ws_bn128_groth16_h_msm_dev(ws_ctx* c, const ws_pkey* k, const void* d_h_shard, void* d_partials, void* stream) {
+    WsLock ws_lock_(c);
+    if (!c || !k || !d_partials || (k->h_cnt && !d_h_shard)) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
+    if (k->ctx != c) return c->fail(WS_E_ARG, "proving key belongs to another context");
+    if (((uintptr_t)d_h_shard | (uintptr_t)d_partials) & 15) return c->fail(WS_E_ARG, "device pointers must be 16-byte aligned");
+    if (!c->lanes_ready) return c->fail(WS_E_ARG, "ws_bn128_groth16_witness_msms_dev must be called first");
+    cudaSetDevice(c->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    int rc = prove_h_msm_dev(c, k, (const Fr*)d_h_shard, (uint8_t*)d_partials, st);
+    c->leave_stream(st);
+    return rc;
+}
+WS_API int ws_bn128_pkey_shard_info(const ws_pkey* k, uint32_t range[6]) {
+    if (!k || !range) return WS_E_ARG;
+    range[0] = k->v_lo;
+    range[1] = k->v_cnt;
+    range[2] = k->n_public + 1 + k->c_lo;
+    range[3] = k->c_cnt;
+    range[4] = k->h_lo;
+    range[5] = k->h_cnt;
+    return WS_OK;
 }
 WS_API int ws_bn128_groth16_prepare_dev(ws_ctx* c, const ws_pkey* k, const void* d_rs, void* stream) {
     WsLock ws_lock_(c);
@@ -909,23 +997,37 @@ WS_API int ws_bn128_groth16_prove(ws_ctx* c, const uint8_t* witness, size_t wlen
     // The reference is handed the same proving key on every call and re-slices / re-posts it each time
     // (src/bn128.js:581-604).  Here the parsed, uploaded key (with its window tables) of the previous call is
     // kept and reused when the caller's buffer has the same length and content fingerprint.
-    unsigned long long fp = key_fingerprint(pkey, plen);
-    if (!c->cached_key || c->cached_len != plen || c->cached_fp != fp) {
-        cudaSetDevice(c->device);
-        if (c->cached_key) {
-            cudaStreamSynchronize(c->stream);
-            pkey_release((ws_pkey*)c->cached_key);
-            c->cached_key = nullptr;
-        }
-        ws_pkey* k = nullptr;
-        int rc = pkey_load(c, pkey, plen, &k);
-        if (rc) return rc;
-        c->cached_key = k;
-        c->cached_fp = fp;
-        c->cached_len = plen;
-        c->cached_key_free = cached_key_free;
+    // The whole buffer is fingerprinted on every call (a sampled hash could miss an in-place edit), but not on the
+    // critical path: when an entry of the same length exists, the proof is enqueued with it FIRST and the host threads
+    // hash the caller's buffer while the GPU works; only a mismatch (a different key) discards that proof, reloads
+    // and proves again.  r and s are drawn once so that both attempts would use the same values.
+    uint8_t rs[64];
+    if (r) memcpy(rs, r, 32);
+    else if (getrandom(rs, 32, 0) != 32) return c->fail(WS_E_ARG, "getrandom failed");
+    if (s) memcpy(rs + 32, s, 32);
+    else if (getrandom(rs + 32, 32, 0) != 32) return c->fail(WS_E_ARG, "getrandom failed");
+    bool optimistic = c->cached_key && c->cached_len == plen;
+    if (optimistic && prove_host_enqueue(c, (const ws_pkey*)c->cached_key, witness, wlen, rs, rs + 32) != WS_OK) {
+        cudaStreamSynchronize(c->stream);       // e.g. a same-length key with another nVars: decide after the fingerprint
+        cudaGetLastError();
+        optimistic = false;
     }
-    return prove_host(c, (const ws_pkey*)c->cached_key, witness, wlen, r, s, pi_a, pi_b, pi_c);
+    unsigned long long fp = key_fingerprint(pkey, plen);
+    if (optimistic && c->cached_fp == fp) return prove_host_collect(c, (const ws_pkey*)c->cached_key, pi_a, pi_b, pi_c);
+    cudaSetDevice(c->device);
+    if (c->cached_key) {
+        cudaStreamSynchronize(c->stream);
+        pkey_release((ws_pkey*)c->cached_key);
+        c->cached_key = nullptr;
+    }
+    ws_pkey* k = nullptr;
+    int rc = pkey_load(c, pkey, plen, &k);
+    if (rc) return rc;
+    c->cached_key = k;
+    c->cached_fp = fp;
+    c->cached_len = plen;
+    c->cached_key_free = cached_key_free;
+    return prove_host(c, k, witness, wlen, rs, rs + 32, pi_a, pi_b, pi_c);
 }
 
 WS_API int ws_bn128_groth16_prove_dev(ws_ctx* c, const ws_pkey* k, const void* d_witness, const void* d_rs, void* d_out, void* stream) {

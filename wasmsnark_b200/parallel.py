@@ -1,11 +1,19 @@
-"""Multi-GPU plumbing: one process per GPU, torch.distributed for the exchange step.
+"""Multi-GPU plumbing, one process per GPU (torchrun), torch.distributed / NCCL for the exchange steps.
 
-The reference parallelises every multiexp by giving each worker a contiguous point range --
-floor(n / W) points each, the last worker takes the remainder -- and adding the W partial points on
-the main thread (/root/reference/src/bn128.js:353-383).  The same split is used across ranks here;
-the serial add loop becomes one all_gather of fixed-size partial records followed by a tiny on-device
-combine (elliptic-curve addition is not an NCCL reduction operator, so all_gather + local reduce is
-the single-collective equivalent of an all-reduce).
+The reference parallelises a proof like this (/root/reference/src/bn128.js):
+  * every multiexp is split over the W workers by contiguous point ranges -- floor(n / W) points each, the last
+    worker takes the remainder -- and the W partial points are added on the main thread (:353-383);
+  * CALC_H (constructLC + five FFTs) is ONE task on ONE worker (:569-578); the H multiexp is queued when it
+    resolves (:607-622).
+The same structure is used across ranks here:
+  * `shard_range` is the reference's split; each rank keeps only its ranges of A, B1, B2, C, hExps in HBM;
+  * per proof ONE rank -- the H owner, rotating from proof to proof so that a pipeline of proofs loads all ranks
+    equally -- computes h and sends every other rank its slice h[h_lo, h_lo + h_cnt) (NCCL send/recv over NVLink,
+    4 MiB per rank at 2^20 constraints / 8 GPUs);
+  * every rank runs its five partial MSMs; one all_gather of the 768-byte partial records; every rank adds the
+    records and runs the final assembly (elliptic-curve addition is not an NCCL reduction operator, so
+    all_gather + on-device add is the single-collective equivalent of an all-reduce of partial sums).
+The one-process form of the same split (peer copies instead of NCCL) is ws_multi_* in the C ABI.
 """
 import ctypes
 
@@ -37,25 +45,107 @@ def all_gather_records(record, world, group=None):
     return out
 
 
+def scatter_slices(buf, elem_bytes, n_elems, owner, rank, world, group=None):
+    """The H hand-over: `buf` is a 1-D uint8 tensor of n_elems * elem_bytes bytes on every rank; on `owner` it holds
+    the whole array, afterwards every rank holds ITS shard_range slice at the slice's natural offset (the rest of
+    `buf` is untouched on non-owners).  One send per non-owner rank from the owner, one receive on each of them;
+    works on gloo (CPU tensors) and NCCL (CUDA tensors, ordered on the current stream)."""
+    import torch.distributed as dist
+    if world == 1:
+        return
+    ops = []
+    if rank == owner:
+        for r in range(world):
+            if r == owner:
+                continue
+            lo, cnt = shard_range(n_elems, r, world)
+            if cnt:
+                ops.append(dist.P2POp(dist.isend, buf[lo * elem_bytes:(lo + cnt) * elem_bytes], r, group))
+    else:
+        lo, cnt = shard_range(n_elems, rank, world)
+        if cnt:
+            ops.append(dist.P2POp(dist.irecv, buf[lo * elem_bytes:(lo + cnt) * elem_bytes], owner, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()          # NCCL: orders the current stream after the transfer (does not block the host)
+
+
+def witness_hull(key_ranges):
+    """(first element, count) of the witness range a non-owner rank needs: the hull of its A/B1/B2 range and its C range
+    (ws_bn128_pkey_shard_info)."""
+    v_lo, v_cnt, c_lo, c_cnt = key_ranges[:4]
+    lo = min(v_lo, c_lo)
+    hi = max(v_lo + v_cnt, c_lo + c_cnt)
+    return lo, max(0, hi - lo)
+
+
 class ShardedProver:
-    """Groth16 prover with the proving key's point sections range-sharded over the ranks of a
-    torch.distributed group (NCCL).  Every rank ends up with the same proof."""
+    """Groth16 prover over the ranks of a torch.distributed group (NCCL), structured like the reference's worker pool:
+    point sections range-sharded, H computed by one rank per proof (rotating).  Every rank ends up with the same
+    proof, bit-identical to the single-GPU one.  All device work of a proof is enqueued on ONE torch.cuda.Stream given
+    by the caller (the library launches on it, NCCL orders itself against it): no host synchronisation inside."""
 
     def __init__(self, bn, pkey_bytes, rank, world, group=None):
+        import torch
         from ._lib import as_ptr
         self.bn, self.rank, self.world, self.group = bn, rank, world, group
         self.key = ctypes.c_void_p()
         bn.ctx.check(bn.lib.ws_bn128_pkey_load_shard(bn.ctx.h, as_ptr(pkey_bytes), len(pkey_bytes), rank, world, ctypes.byref(self.key)))
+        a, b, c = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+        bn.lib.ws_bn128_pkey_info(self.key, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        self.n_vars, self.n_public, self.domain = a.value, b.value, c.value
+        rg = (ctypes.c_uint32 * 6)()
+        bn.lib.ws_bn128_pkey_shard_info(self.key, rg)
+        self.ranges = tuple(rg)
+        dev = torch.device("cuda", bn.ctx.device)
+        self.d_h = torch.zeros(self.domain * 32, dtype=torch.uint8, device=dev)
+        self.d_part = torch.zeros(768, dtype=torch.uint8, device=dev)
+        self.d_all = torch.zeros(768 * world, dtype=torch.uint8, device=dev)
+        self.count = 0
 
-    def prove_dev(self, d_witness, d_rs, d_out, stream_ptr):
-        """d_witness / d_rs / d_out: CUDA uint8 tensors (nVars*32, 64, 384 bytes)."""
+    def next_owner(self):
+        """H owner of the next proof: the same sequence on every rank."""
+        o = self.count % self.world
+        self.count += 1
+        return o
+
+    def upload_witness(self, d_witness, h_witness, owner, stream):
+        """Host -> device copy of what this rank needs of the witness for a proof owned by `owner`: everything on the
+        owner (the LC step reads every signal), the hull of its point ranges elsewhere.  h_witness: pinned uint8 tensor."""
         import torch
-        bn = self.bn
-        part = torch.empty(768, dtype=torch.uint8, device=d_witness.device)
-        bn.ctx.check(bn.lib.ws_bn128_groth16_prepare_dev(bn.ctx.h, self.key, d_rs.data_ptr(), stream_ptr))
-        bn.ctx.check(bn.lib.ws_bn128_groth16_partials_dev(bn.ctx.h, self.key, d_witness.data_ptr(), part.data_ptr(), stream_ptr))
-        allp = all_gather_records(part, self.world, self.group)
-        bn.ctx.check(bn.lib.ws_bn128_groth16_finish_dev(bn.ctx.h, self.key, allp.data_ptr(), self.world, d_rs.data_ptr(), d_out.data_ptr(), stream_ptr))
+        with torch.cuda.stream(stream):
+            if self.rank == owner:
+                d_witness.copy_(h_witness, non_blocking=True)
+                return h_witness.numel()
+            lo, cnt = witness_hull(self.ranges)
+            if cnt:
+                d_witness[lo * 32:(lo + cnt) * 32].copy_(h_witness[lo * 32:(lo + cnt) * 32], non_blocking=True)
+            return cnt * 32
+
+    def prove_dev(self, d_witness, d_rs, d_out, stream, owner=None):
+        """d_witness / d_rs / d_out: CUDA uint8 tensors (nVars*32, 64, 384 bytes); stream: the torch.cuda.Stream all of
+        the proof's work is ordered on (required).  owner: the rank that computes H (default: rotates)."""
+        import torch
+        if stream is None or not hasattr(stream, "cuda_stream"):
+            raise ValueError("prove_dev needs a torch.cuda.Stream")
+        if owner is None:
+            owner = self.next_owner()
+        bn, h, lib = self.bn, self.bn.ctx.h, self.bn.lib
+        st = ctypes.c_void_p(stream.cuda_stream)
+        h_lo, h_cnt = self.ranges[4], self.ranges[5]
+        with torch.cuda.stream(stream):
+            bn.ctx.check(lib.ws_bn128_groth16_prepare_dev(h, self.key, d_rs.data_ptr(), st))
+            bn.ctx.check(lib.ws_bn128_groth16_witness_msms_dev(h, self.key, d_witness.data_ptr(), self.d_part.data_ptr(), st))
+            if self.rank == owner:
+                bn.ctx.check(lib.ws_bn128_groth16_h_dev(h, self.key, d_witness.data_ptr(), self.d_h.data_ptr(), st))
+            scatter_slices(self.d_h, 32, self.domain, owner, self.rank, self.world, self.group)
+            bn.ctx.check(lib.ws_bn128_groth16_h_msm_dev(h, self.key, self.d_h.data_ptr() + 32 * h_lo, self.d_part.data_ptr(), st))
+            src = self.d_part
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_gather_into_tensor(self.d_all, self.d_part, group=self.group)
+                src = self.d_all
+            bn.ctx.check(lib.ws_bn128_groth16_finish_dev(h, self.key, src.data_ptr(), self.world, d_rs.data_ptr(), d_out.data_ptr(), st))
         return d_out
 
     def free(self):
