@@ -33,7 +33,11 @@ const g1bin = (e) => cat([int2bin(e[0]), int2bin(e[1])]);                       
 const g2bin = (e) => cat([int2bin(e[0][0]), int2bin(e[0][1]), int2bin(e[1][0]), int2bin(e[1][1])]);      // setG2Affine :509-513
 
 class Bn128 {
-    constructor(device) { this.h = native.create(device || 0); }
+    // opts: a device index, or { device, gpus } -- gpus > 1 (0 = all) spreads every proof / multiexp over that many GPUs
+    constructor(opts) {
+        const o = typeof opts === "object" && opts !== null ? opts : { device: opts };
+        this.h = native.create(o.device || 0, o.gpus === undefined ? 1 : o.gpus);
+    }
     groth16GenProof(signals, pkey, r, s) {
         return new Promise((resolve, reject) => {
             native.prove(this.h, signals, pkey, r || null, s || null, (err, p) => {
@@ -64,7 +68,7 @@ class Bn128 {
     terminate() { native.destroy(this.h); this.h = null; }
 }
 
-async function buildBn128(device) { return new Bn128(device); }
+async function buildBn128(opts) { return new Bn128(opts); }
 
 let shared = null;
 function groth16GenProof(witness, provingKey, cb) {

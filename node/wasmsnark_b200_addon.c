@@ -8,8 +8,14 @@
  *     cc -shared -fPIC -I$(node -p "require('node:path').dirname(process.execPath)+'/../include/node'") \
  *        -I../include wasmsnark_b200_addon.c -L../wasmsnark_b200 -lwasmsnark_b200 -o wasmsnark_b200.node
  *
+ * Threading: prove() runs the blocking C call on a libuv worker thread and any number of proofs may be in flight on
+ * one handle, as with the reference's promise API; that is safe because every C-ABI entry point holds its context's
+ * mutex for the duration of the call (include/wasmsnark_b200.h, "Threading") -- overlapping calls on one handle queue
+ * up in arrival order like the reference's actionQueue (src/bn128.js:282-300).
+ *
  * Exports:
- *   create(device) -> external handle                       buildBn128()            src/bn128.js:173-265
+ *   create(device, ngpus) -> external handle                buildBn128()            src/bn128.js:173-265
+ *        ngpus > 1 (or 0 = all): proofs and multiexps use every GPU of the box (ws_multi_*, the worker pool = the GPUs)
  *   destroy(handle)                                         Bn128.terminate()       src/bn128.js:562-566
  *   prove(handle, witness, pkey, r|null, s|null, cb)        Bn128.groth16GenProof   src/bn128.js:580-720
  *        cb(err, {pi_a: ArrayBuffer(96), pi_b: ArrayBuffer(192), pi_c: ArrayBuffer(96)})   (async work)
@@ -65,32 +71,47 @@ static napi_value throw_ws(napi_env env, ws_ctx* c, int rc) {
     return NULL;
 }
 
+/* one handle = one single-GPU context (always) + optionally the multi-GPU handle the heavy calls go through */
+typedef struct {
+    ws_ctx* c;
+    ws_multi* m;
+} handle_t;
+
 static void finalize_ctx(napi_env env, void* data, void* hint) {
     (void)env;
     (void)hint;
-    ws_destroy((ws_ctx*)data);
+    handle_t* h = (handle_t*)data;
+    if (h->m) ws_multi_destroy(h->m);
+    ws_destroy(h->c);
+    free(h);
 }
 
 static napi_value Create(napi_env env, napi_callback_info info) {
-    size_t argc = 1;
-    napi_value argv[1];
+    size_t argc = 2;
+    napi_value argv[2];
     CHECK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
-    int32_t device = 0;
+    int32_t device = 0, ngpus = 1;
     if (argc >= 1) napi_get_value_int32(env, argv[0], &device);
-    ws_ctx* c = NULL;
-    int rc = ws_create(device, &c);
-    if (rc) {
-        napi_throw_error(env, "WASMSNARK_B200", "no usable CUDA device (ws_create failed); there is no CPU fallback");
+    if (argc >= 2) napi_get_value_int32(env, argv[1], &ngpus);
+    handle_t* h = (handle_t*)calloc(1, sizeof *h);
+    if (!h || ws_create(device, &h->c) || (ngpus != 1 && ws_multi_create(ngpus, &h->m))) {
+        if (h && h->c) ws_destroy(h->c);
+        free(h);
+        napi_throw_error(env, "WASMSNARK_B200", "no usable CUDA device (ws_create / ws_multi_create failed); there is no CPU fallback");
         return NULL;
     }
     napi_value ext;
-    CHECK(napi_create_external(env, c, finalize_ctx, NULL, &ext));
+    CHECK(napi_create_external(env, h, finalize_ctx, NULL, &ext));
     return ext;
 }
 
-static ws_ctx* ctx_arg(napi_env env, napi_value v) {
+static handle_t* handle_arg(napi_env env, napi_value v) {
     void* p = NULL;
-    return napi_get_value_external(env, v, &p) == napi_ok ? (ws_ctx*)p : NULL;
+    return napi_get_value_external(env, v, &p) == napi_ok ? (handle_t*)p : NULL;
+}
+static ws_ctx* ctx_arg(napi_env env, napi_value v) {
+    handle_t* h = handle_arg(env, v);
+    return h ? h->c : NULL;
 }
 
 /* ---- prove: blocking C call wrapped in napi_async_work (the reference resolves a Promise from its workers) */
@@ -98,6 +119,7 @@ typedef struct {
     napi_async_work work;
     napi_ref cb, wit_ref, key_ref;
     ws_ctx* ctx;
+    ws_multi* multi;
     uint8_t *wit, *key;
     size_t wit_len, key_len;
     uint8_t r[32], s[32];
@@ -109,8 +131,14 @@ typedef struct {
 static void prove_execute(napi_env env, void* data) {
     (void)env;
     prove_job* j = (prove_job*)data;
-    j->rc = ws_bn128_groth16_prove(j->ctx, j->wit, j->wit_len, j->key, j->key_len, j->have_r ? j->r : NULL, j->have_s ? j->s : NULL, j->pi_a, j->pi_b, j->pi_c);
-    if (j->rc) strncpy(j->err, ws_last_error(j->ctx), sizeof j->err - 1);
+    const uint8_t *r = j->have_r ? j->r : NULL, *s = j->have_s ? j->s : NULL;
+    if (j->multi) {
+        j->rc = ws_multi_bn128_groth16_prove(j->multi, j->wit, j->wit_len, j->key, j->key_len, r, s, j->pi_a, j->pi_b, j->pi_c);
+        if (j->rc) strncpy(j->err, ws_multi_last_error(j->multi), sizeof j->err - 1);
+    } else {
+        j->rc = ws_bn128_groth16_prove(j->ctx, j->wit, j->wit_len, j->key, j->key_len, r, s, j->pi_a, j->pi_b, j->pi_c);
+        if (j->rc) strncpy(j->err, ws_last_error(j->ctx), sizeof j->err - 1);
+    }
 }
 
 static void prove_complete(napi_env env, napi_status status, void* data) {
@@ -149,7 +177,9 @@ static napi_value Prove(napi_env env, napi_callback_info info) {
         return NULL;
     }
     prove_job* j = (prove_job*)calloc(1, sizeof *j);
-    j->ctx = ctx_arg(env, argv[0]);
+    handle_t* hd = handle_arg(env, argv[0]);
+    j->ctx = hd ? hd->c : NULL;
+    j->multi = hd ? hd->m : NULL;
     uint8_t* p;
     size_t l;
     if (!j->ctx || !get_buffer(env, argv[1], &j->wit, &j->wit_len) || !get_buffer(env, argv[2], &j->key, &j->key_len)) {
@@ -174,7 +204,8 @@ static napi_value Multiexp(napi_env env, napi_callback_info info, int g2) {
     size_t argc = 3;
     napi_value argv[3];
     CHECK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
-    ws_ctx* c = ctx_arg(env, argv[0]);
+    handle_t* hd = handle_arg(env, argv[0]);
+    ws_ctx* c = hd ? hd->c : NULL;
     uint8_t *sc, *pt;
     size_t sl, pl;
     if (!c || !get_buffer(env, argv[1], &sc, &sl) || !get_buffer(env, argv[2], &pt, &pl) || sl % 32 || pl < (sl / 32) * (g2 ? 128 : 64)) {
@@ -182,8 +213,17 @@ static napi_value Multiexp(napi_env env, napi_callback_info info, int g2) {
         return NULL;
     }
     uint8_t out[192];
-    int rc = g2 ? ws_bn128_g2_multiexp(c, sc, pt, sl / 32, out) : ws_bn128_g1_multiexp(c, sc, pt, sl / 32, out);
-    if (rc) return throw_ws(env, c, rc);
+    int rc;
+    if (hd->m) {
+        rc = g2 ? ws_multi_bn128_g2_multiexp(hd->m, sc, pt, sl / 32, out) : ws_multi_bn128_g1_multiexp(hd->m, sc, pt, sl / 32, out);
+        if (rc) {
+            napi_throw_error(env, "WASMSNARK_B200", ws_multi_last_error(hd->m));
+            return NULL;
+        }
+    } else {
+        rc = g2 ? ws_bn128_g2_multiexp(c, sc, pt, sl / 32, out) : ws_bn128_g1_multiexp(c, sc, pt, sl / 32, out);
+        if (rc) return throw_ws(env, c, rc);
+    }
     return make_ab(env, out, g2 ? 192 : 96);
 }
 static napi_value G1Multiexp(napi_env env, napi_callback_info info) { return Multiexp(env, info, 0); }

@@ -150,3 +150,28 @@ def test_fft_round_trip_2p20_and_bad_sizes(bls):
     assert y != xb and bls.ifft(y) == xb
     with pytest.raises(WsError):
         bls.fft(bytes(32 * 3))
+
+
+def test_reference_group_relations_through_the_msm_abi(bls):
+    """The reference's own BLS12-381 group tests hold no vectors, only relations (test/bls12381.js:289-389): 4G by
+    additions == 4G by doublings, 10 G by timesScalar == ten additions of G, r G == infinity, for G1 and G2, on the
+    generators its module builds (src/bls12381/build_bls12381.js:117-152).  The same relations, evaluated by the GPU
+    kernels through the MSM entry points (a sum of k copies of G with scalar 1 is k additions; a single pair is a
+    timesScalar).  This is all the reference offers for this curve: parity stays UNPINNED."""
+    for g1 in (True, False):
+        G = B.G1_GEN if g1 else B.G2_GEN
+        gb = B.g1_bytes(G) if g1 else B.g2_bytes(G)
+        msm = bls.g1_multiexp if g1 else bls.g2_multiexp
+        aff = bls.g1_affine if g1 else bls.g2_affine
+        dec = B.g1_from_affine_std if g1 else B.g2_from_affine_std
+        one, two, four, ten = (le(v, 32) for v in (1, 2, 4, 10))
+
+        def point(scalars, npts):
+            return dec(aff(msm(b"".join(scalars), gb * npts), 1))
+        g2x = point([two], 1)
+        assert point([one] * 4, 4) == point([four], 1) == point([two, two], 2)          # G+G+G+G == 2(2G)
+        assert point([one] * 10, 10) == point([ten], 1)                                   # timesScalar(10) == 10 additions
+        assert g2x is not None and point([one], 1) == G
+        assert point([le(B.R_ORDER, 32)], 1) is None                                      # r G == infinity
+        assert point([le(B.R_ORDER - 1, 32), one], 2) is None                             # (r - 1) G + G
+        assert point([four, le(B.R_ORDER - 4, 32)], 2) is None                            # g?m_sub(4G, 4G) is zero
