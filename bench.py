@@ -6,7 +6,7 @@ the workload is one fixed-size proof whatever N is.  One step = one full proof o
 tools/gen_synth_key.py (nVars = domainSize = 2^20, nPublic = 58, seed 0xB204) with fixed (r, s); the proof is compared
 with the one the REFERENCE's own code computed for the same inputs (tests/golden/synth_2p20.golden.json) before
 anything is timed.
-  value     proofs/s, key + witness resident in HBM, WS_BENCH_PROOFS_INFLIGHT (default 2) proofs in flight (one
+  value     proofs/s, key + witness resident in HBM, WS_BENCH_PROOFS_INFLIGHT (default 3; 4 from N = 4) proofs in flight (one
             context + resident key each), K proofs inside one CUDA-event pair, max over ranks
   latency   one proof at a time (per-proof CUDA events, L2 flushed between proofs)
   e2e       proofs/s through the host-buffer C ABI: N = 1 -- the blocking ws_bn128_groth16_prove_key(witness) from one
@@ -50,7 +50,9 @@ PROVE_LOG2 = int(os.environ.get("WS_BENCH_PROVE_LOG2", "20"))       # constraint
 CPU_SAMPLE_LOG2 = int(os.environ.get("WS_BENCH_CPU_SAMPLE_LOG2", "16"))
 ALG_BYTES_PER_PAIR = 96          # 32 B scalar + 64 B affine point
 NFLIGHT = max(1, int(os.environ.get("WS_BENCH_INFLIGHT", "4")))     # MSMs in flight for the MSM throughput number
-NPROOFS = max(1, int(os.environ.get("WS_BENCH_PROOFS_INFLIGHT", "2")))
+_WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+# proofs in flight per rank: the fewer points a rank holds, the larger the share of dependent-chain latency in a proof
+NPROOFS = max(1, int(os.environ.get("WS_BENCH_PROOFS_INFLIGHT", "3" if _WORLD <= 2 else "4")))
 SCALARS = os.environ.get("WS_BENCH_SCALARS", "fr")      # "fr": uniform in [0, r) ; "raw256": uniform 256-bit
 RS = bytes(range(1, 65))          # r | s injected into every timed proof (the golden proof uses the same)
 DTYPE = "u32 limbs (256-bit Montgomery)"
@@ -347,12 +349,24 @@ class Env:
     def launches(self):
         return sum(b.lib.ws_kernel_launches(b.ctx.h) for b in self.bns)
 
-    def timed_serial(self, step, steps, stream=None):
+    def timed_serial(self, step, steps, stream=None, local=False):
         """`steps` steps, each bracketed by its own CUDA-event pair on the launch stream, L2 flushed in between (outside
-        the pairs); returns the mean step time in ms, max over ranks."""
+        the pairs); returns the mean step time in ms, max over ranks.  local=True: a section only one rank runs -- no
+        collective anywhere inside."""
         torch = self.torch
         stream = stream or self.stream
         evs = []
+        if local:
+            torch.cuda.synchronize()
+            for _ in range(steps):
+                self.flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                step()
+                e1.record(stream)
+                evs.append((e0, e1))
+                torch.cuda.synchronize()
+            return sum(a.elapsed_time(b) for a, b in evs) / steps
         self.barrier()
         for _ in range(steps):
             self.flush.fill_(1)
@@ -851,7 +865,7 @@ def section_other_curves(env):
     for _ in range(env.W):
         step_bls()
     torch.cuda.synchronize()
-    ms = env.timed_serial(step_bls, env.K)
+    ms = env.timed_serial(step_bls, env.K, local=True)
     limbs = sc_np.view("<u4").reshape(nb // distinct, distinct, 8).astype(np.uint64).sum(axis=0)
     tot = [sum(int(limbs[j, k]) << (32 * k) for k in range(8)) for j in range(distinct)]
     want = BL.pt_mul(BL.Fq, BL.G1_GEN, sum(t * (a0 + j * d0) for j, t in enumerate(tot)) % BL.R_ORDER)
@@ -880,7 +894,7 @@ def section_other_curves(env):
     for _ in range(env.W):
         step_mnt()
     torch.cuda.synchronize()
-    ms = env.timed_serial(step_mnt, env.K)
+    ms = env.timed_serial(step_mnt, env.K, local=True)
     limbs = sc_np.view("<u4").reshape(nm // distinct, distinct, 24).astype(np.uint64).sum(axis=0)
     tot = [sum(int(limbs[j, k]) << (32 * k) for k in range(24)) for j in range(distinct)]
     want = MN.times_scalar(MN.G1_GEN, sum(t * (a0 + j * d0) for j, t in enumerate(tot)) % MN.R_ORDER)

@@ -258,7 +258,7 @@ def _synth_small():
     return pk, wit, g
 
 
-@pytest.mark.parametrize("logn", [3, 8, 9, 13, 15, 18])
+@pytest.mark.parametrize("logn", [3, 6, 7, 8, 9, 13, 15, 18])
 def test_fft_in_place_pass_counts_and_variants(bn, logn):
     """Every pass schedule of ntt_launch lands in the caller's buffer without a trailing copy (odd and even pass counts,
     one and two scratch buffers), and the occupancy variants of the radix-64 pass compute the same bytes."""
@@ -269,7 +269,7 @@ def test_fft_in_place_pass_counts_and_variants(bn, logn):
     x = raw.tobytes()
     base = {}
     try:
-        for variant in (0, 1, 2):
+        for variant in (0, 1, 2, 3, 4):
             bn.lib.ws_set_ntt_variant(bn.ctx.h, variant)
             for odd in (0, 1):
                 y = bn.fft(x, odd)

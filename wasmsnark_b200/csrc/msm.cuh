@@ -301,6 +301,9 @@ static __global__ void __launch_bounds__(256) k_msm_combine_big(MsmPlan p, const
     }
 }
 
+// a level with at most this many (role, window, group) items runs the warp-cooperative form (~28 warps per SM)
+constexpr uint32_t MSM_LEVEL_WARP_MAX = 4096;
+
 template <class C>
 static __global__ void __launch_bounds__(128, (sizeof(typename C::F) == 32 ? 4 : 1)) k_msm_segreduce(MsmPlan p, const uint32_t* __restrict__ tstart, const XYZZ<C>* __restrict__ partials,
                                                               XYZZ<C>* __restrict__ pool) {
@@ -319,6 +322,60 @@ static __global__ void __launch_bounds__(128) k_msm_level(MsmPlan p, int l, XYZZ
     int role = idx / per_role;
     uint32_t i = idx - role * per_role;
     msm_level_body<C>(p, l, i / p.Sl[l], i % p.Sl[l], role, pool);
+}
+
+// The same level with ONE WARP per (role, window, group) and warp-cooperative additions (warp_ec.cuh: the independent
+// products of an addition on 4 lanes, 4 product levels deep instead of 14 sequential products).  Used for the small
+// upper levels, where there are too few items to fill the machine and the level is pure dependent-chain latency: a
+// cooperative addition has ~1/3 of the latency of a sequential one at 8x the pipe time, which is free up there.
+template <class C>
+static __global__ void __launch_bounds__(128) k_msm_level_warp(MsmPlan p, int l, XYZZ<C>* pool) {
+    const uint32_t idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // warp-uniform
+    const uint32_t per_role = (uint32_t)p.nwin * p.Sl[l];
+    if (idx >= (uint32_t)l * per_role) return;
+    const int role = idx / per_role, lane = threadIdx.x & 31;
+    const uint32_t i = idx - role * per_role, w = i / p.Sl[l], g = i % p.Sl[l];
+    const uint32_t G = p.G[l], Sin = p.Sl[l - 1], Sout = p.Sl[l];
+    const size_t in_per = (size_t)Sin * p.nwin, out_per = (size_t)Sout * p.nwin;
+    const size_t ib = (size_t)w * Sin + (size_t)g * G, ob = (size_t)w * Sout + g;
+    if (role > 0) {
+        const XYZZ<C>* in = pool + p.offC[l - 1] + (size_t)(role - 1) * in_per;
+        XYZZ<C> acc = in[ib];
+#pragma unroll 1
+        for (uint32_t j = 1; j < G; j++) acc = padd_warp4<C>(acc, in[ib + j]);
+        if (lane == 0) pool[p.offC[l] + (size_t)(role - 1) * out_per + ob] = acc;
+        return;
+    }
+    const XYZZ<C>* inT = pool + p.offT[l - 1];
+    XYZZ<C> run = XYZZ<C>::inf(), acc = XYZZ<C>::inf();
+#pragma unroll 1
+    for (int j = (int)G - 1; j >= 1; j--) {
+        run = padd_warp4<C>(run, inT[ib + j]);
+        acc = padd_warp4<C>(acc, run);
+    }
+    run = padd_warp4<C>(run, inT[ib]);
+    if (lane == 0) {
+        pool[p.offC[l] + (size_t)(l - 1) * out_per + ob] = acc;
+        pool[p.offT[l] + ob] = run;
+    }
+}
+
+// window value from the plane sums (msm_window_value) with warp-cooperative doublings / additions; all lanes return it
+template <class C>
+__device__ __forceinline__ XYZZ<C> msm_window_value_warp(const MsmPlan& p, uint32_t w, const XYZZ<C>* bits) {
+    const XYZZ<C>* bw = bits + (size_t)w * msm_nplanes(p);
+    XYZZ<C> acc = XYZZ<C>::inf();
+#pragma unroll 1
+    for (int k = p.logSK - 1; k >= 0; k--) {
+        acc = pdbl_warp4<C>(acc);
+        acc = padd_warp4<C>(acc, bw[p.nlev + k]);
+    }
+#pragma unroll 1
+    for (int l = p.nlev; l >= 1; l--) {
+        for (uint32_t x = p.G[l]; x > 1; x >>= 1) acc = pdbl_warp4<C>(acc);
+        acc = padd_warp4<C>(acc, bw[l - 1]);
+    }
+    return acc;
 }
 
 // plane sums over the top level (at most 32 groups per window): grid (nwin, nplanes), one warp each.
@@ -348,7 +405,15 @@ static __global__ void __launch_bounds__(32) k_msm_bitsum(MsmPlan p, const XYZZ<
 // Montgomery -- the reference's g1m_multiexp result format (callers normalise with g1_affine).
 template <class C>
 static __global__ void __launch_bounds__(160) k_msm_final(MsmPlan p, const XYZZ<C>* __restrict__ bits, XYZZ<C>* R, XYZZ<C>* out_xyzz, Jac<C>* out_jac) {
-    for (int w = threadIdx.x; w < p.nwin; w += blockDim.x) R[w] = msm_window_value<C>(p, w, bits);
+    if (p.nwin <= (int)(blockDim.x >> 5)) {       // few windows (one with a window table): one warp per window, cooperative chain
+        const int w = threadIdx.x >> 5;
+        if (w < p.nwin) {
+            XYZZ<C> v = msm_window_value_warp<C>(p, w, bits);
+            if ((threadIdx.x & 31) == 0) R[w] = v;
+        }
+    } else {
+        for (int w = threadIdx.x; w < p.nwin; w += blockDim.x) R[w] = msm_window_value<C>(p, w, bits);
+    }
     __syncthreads();
     if (threadIdx.x < 32) {      // one full warp: the doublings are 3-lane cooperative (warp_ec.cuh)
         MsmPlanLite pl{p.nwin, p.c};
@@ -547,7 +612,8 @@ inline cudaError_t msm_launch(const MsmPlan& p, const MsmWorkspace& w, const uin
     mark("segreduce");
     for (int l = 2; l <= p.nlev; l++) {
         uint32_t nt = (uint32_t)l * (uint32_t)p.nwin * p.Sl[l];
-        k_msm_level<C><<<(nt + 127) / 128, 128, 0, st>>>(p, l, (X*)w.pool);
+        if (nt <= MSM_LEVEL_WARP_MAX) k_msm_level_warp<C><<<(nt + 3) / 4, 128, 0, st>>>(p, l, (X*)w.pool);     // one warp per item
+        else k_msm_level<C><<<(nt + 127) / 128, 128, 0, st>>>(p, l, (X*)w.pool);
     }
     k_msm_bitsum<C><<<dim3(p.nwin, msm_nplanes(p)), 32, 0, st>>>(p, (const X*)w.pool, (X*)w.bits);
     mark("bitsum");

@@ -149,22 +149,50 @@ int load_keys(ws_multi* m, const uint8_t* pkey, size_t plen, unsigned long long 
 int enqueue_proof(ws_multi* m, const uint8_t* witness, const uint8_t* rs) {
     const int n = m->n;
     const int owner = (int)(m->proofs++ % (unsigned long long)n);
-    // 1. inputs + the four witness MSMs everywhere (the owner needs the whole witness for the LC step)
-    for (int g = 0; g < n; g++) {
+    // 1. inputs + the four witness MSMs everywhere (the owner needs the whole witness for the LC step); one host thread
+    //    per GPU, so that the staging copies of the (pageable) witness run side by side
+    std::vector<int> rc1(n, WS_OK);
+    std::vector<std::string> err1(n);
+    auto stage1 = [&](int g) {
         cudaSetDevice(m->dev[g]);
         const uint32_t* r = m->range[g];
         if (g == owner) {
-            if (m->stager[g].upload(m->d_wit[g], witness, (size_t)m->n_vars * 32, m->st[g], m->dev[g]) != cudaSuccess) return m->fail(WS_E_CUDA, "witness upload");
+            if (m->stager[g].upload(m->d_wit[g], witness, (size_t)m->n_vars * 32, m->st[g], m->dev[g]) != cudaSuccess) {
+                rc1[g] = WS_E_CUDA;
+                err1[g] = "witness upload";
+                return;
+            }
         } else {
             uint32_t lo = std::min(r[0], r[2]), hi = std::max(r[0] + r[1], r[2] + r[3]);
-            if (hi > lo && m->stager[g].upload(m->d_wit[g] + (size_t)lo * 32, witness + (size_t)lo * 32, (size_t)(hi - lo) * 32, m->st[g], m->dev[g]) != cudaSuccess)
-                return m->fail(WS_E_CUDA, "witness upload");
+            if (hi > lo && m->stager[g].upload(m->d_wit[g] + (size_t)lo * 32, witness + (size_t)lo * 32, (size_t)(hi - lo) * 32, m->st[g], m->dev[g]) != cudaSuccess) {
+                rc1[g] = WS_E_CUDA;
+                err1[g] = "witness upload";
+                return;
+            }
         }
-        if (g == 0 && cudaMemcpyAsync(m->d_small[0] + OFF_RS, rs, 64, cudaMemcpyHostToDevice, m->st[0]) != cudaSuccess) return m->fail(WS_E_CUDA, "r, s upload");
-        int rc;
-        if (g == 0 && (rc = ws_bn128_groth16_prepare_dev(m->ctx[0], m->key[0], m->d_small[0] + OFF_RS, m->st[0]))) return m->fail_ctx(0, rc);
-        if ((rc = ws_bn128_groth16_witness_msms_dev(m->ctx[g], m->key[g], m->d_wit[g], m->d_small[g] + OFF_PART, m->st[g]))) return m->fail_ctx(g, rc);
+        int rc = WS_OK;
+        if (g == 0) {
+            if (cudaMemcpyAsync(m->d_small[0] + OFF_RS, rs, 64, cudaMemcpyHostToDevice, m->st[0]) != cudaSuccess) {
+                rc1[g] = WS_E_CUDA;
+                err1[g] = "r, s upload";
+                return;
+            }
+            rc = ws_bn128_groth16_prepare_dev(m->ctx[0], m->key[0], m->d_small[0] + OFF_RS, m->st[0]);
+        }
+        if (!rc) rc = ws_bn128_groth16_witness_msms_dev(m->ctx[g], m->key[g], m->d_wit[g], m->d_small[g] + OFF_PART, m->st[g]);
+        if (rc) {
+            rc1[g] = rc;
+            err1[g] = std::string("gpu ") + std::to_string(m->dev[g]) + ": " + ws_last_error(m->ctx[g]);
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int g = 1; g < n; g++) th.emplace_back(stage1, g);
+        stage1(0);
+        for (auto& x : th) x.join();
     }
+    for (int g = 0; g < n; g++)
+        if (rc1[g]) return m->fail(rc1[g], err1[g]);
     // 2. H on its owner
     cudaSetDevice(m->dev[owner]);
     int rc = ws_bn128_groth16_h_dev(m->ctx[owner], m->key[owner], m->d_wit[owner], m->d_h[owner], m->st[owner]);
