@@ -88,6 +88,26 @@ def make_inputs(n, seed=0xB201, dist=None, offset=0):
     return scalars, util.g1_points_bytes(aff), P0, D
 
 
+def synth_key(log2):
+    """(pkey, witness, seconds) of the bench's synthetic key; WS_BENCH_KEY_CACHE=<dir> keeps the generated bytes on disk
+    between bench invocations on one box (profiling sessions run bench.py several times)."""
+    import gen_synth_key
+    cache = os.environ.get("WS_BENCH_KEY_CACHE")
+    t0 = time.perf_counter()
+    if cache:
+        fp, fw = os.path.join(cache, "synth_2p%d.pkey.bin" % log2), os.path.join(cache, "synth_2p%d.witness.bin" % log2)
+        if os.path.exists(fp) and os.path.exists(fw):
+            return open(fp, "rb").read(), open(fw, "rb").read(), time.perf_counter() - t0
+    pk, wit = gen_synth_key.make(1 << log2, 58, 1 << log2, seed=0xB204)
+    if cache and int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        os.makedirs(cache, exist_ok=True)
+        for path, data in ((fp, pk), (fw, wit)):
+            with open(path + ".tmp", "wb") as f:
+                f.write(data)
+            os.replace(path + ".tmp", path)
+    return pk, wit, time.perf_counter() - t0
+
+
 def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
@@ -207,12 +227,11 @@ class CpuProver:
     """The reference's groth16GenProof on a 2^k-constraint key of the bench's generator, worker pool of `threads`."""
 
     def __init__(self, k, threads):
-        import gen_synth_key
         from oracle import ref_wasm
         sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
         import make_golden_2p20
         self.k, self.threads = k, threads
-        self.pk, self.wit = gen_synth_key.make(1 << k, 58, 1 << k, seed=0xB204)
+        self.pk, self.wit, _ = synth_key(k)
         self.pool = ref_wasm.RefBn128Pool(concurrency=threads, pages=make_golden_2p20.pages_for(self.pk, self.wit))
 
     def prove(self):
@@ -401,22 +420,19 @@ class Env:
 def section_groth16(env, args):
     """The primary line's numbers.  Returns (dict of line fields, extras dict)."""
     torch, dist, world, rank, K, W = env.torch, env.dist, env.world, env.rank, env.K, env.W
-    import gen_synth_key
     from wasmsnark_b200._lib import as_ptr
     from wasmsnark_b200.parallel import ShardedProver
     nv = dom = 1 << PROVE_LOG2
-    t0 = time.perf_counter()
-    pk, wit = gen_synth_key.make(nv, 58, dom, seed=0xB204)
-    gen_s = time.perf_counter() - t0
+    pk, wit, gen_s = synth_key(PROVE_LOG2)
     h_w = torch.frombuffer(bytearray(wit), dtype=torch.uint8).pin_memory()
 
     class Lane:
         """one context + its own resident key (shard), stream and buffers -- like one of the reference's prover instances"""
 
-        def __init__(self, bn, stream, pk_b=pk, h_wit=h_w, rs=RS):
+        def __init__(self, bn, stream, pk_b=pk, h_wit=h_w, rs=RS, group=None):
             self.bn, self.stream, self.h_w = bn, stream, h_wit
             t0 = time.perf_counter()
-            self.sp = ShardedProver(bn, pk_b, rank, world)
+            self.sp = ShardedProver(bn, pk_b, rank, world, group=group)
             self.load_s = time.perf_counter() - t0
             with torch.cuda.stream(stream):
                 self.d_w = h_wit.cuda()
@@ -470,7 +486,11 @@ def section_groth16(env, args):
         del Le
     # ---- the 2^PROVE_LOG2 key
     NP = NPROOFS
-    lanes = [Lane(env.bns[i], env.streams[i]) for i in range(NP)]
+    # one NCCL communicator per lane: collectives of different proofs in flight are then not serialised on one NCCL stream
+    groups = [None] * NP
+    if world > 1 and os.environ.get("WS_BENCH_LANE_GROUPS", "1") != "0":
+        groups = [None] + [dist.new_group(ranks=list(range(world))) for _ in range(NP - 1)]
+    lanes = [Lane(env.bns[i], env.streams[i], group=groups[i]) for i in range(NP)]
     L0 = lanes[0]
     L0.prove(0)
     torch.cuda.synchronize()

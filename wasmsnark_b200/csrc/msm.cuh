@@ -301,8 +301,10 @@ static __global__ void __launch_bounds__(256) k_msm_combine_big(MsmPlan p, const
     }
 }
 
-// a level with at most this many (role, window, group) items runs the warp-cooperative form (~28 warps per SM)
-constexpr uint32_t MSM_LEVEL_WARP_MAX = 4096;
+// a level with at most this many (role, window, group) items runs the warp-cooperative form.  Measured at 2^20 / c = 20: with
+// 4096 (level 3: 3072 warps) a proof is 0.5 ms shorter alone but 0.3 ms longer in a pipeline of proofs -- a cooperative addition
+// holds the multiplier pipe 8x longer per useful product -- so only the levels that cannot fill a wave use it
+constexpr uint32_t MSM_LEVEL_WARP_MAX = 1024;
 
 template <class C>
 static __global__ void __launch_bounds__(128, (sizeof(typename C::F) == 32 ? 4 : 1)) k_msm_segreduce(MsmPlan p, const uint32_t* __restrict__ tstart, const XYZZ<C>* __restrict__ partials,
