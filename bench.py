@@ -424,6 +424,9 @@ def section_groth16(env, args):
     from wasmsnark_b200.parallel import ShardedProver
     nv = dom = 1 << PROVE_LOG2
     pk, wit, gen_s = synth_key(PROVE_LOG2)
+    split = os.environ.get("WS_BENCH_SPLIT", "auto")
+    if split == "auto":
+        split = "balanced" if world >= 4 else "uniform"
     h_w = torch.frombuffer(bytearray(wit), dtype=torch.uint8).pin_memory()
 
     class Lane:
@@ -432,7 +435,7 @@ def section_groth16(env, args):
         def __init__(self, bn, stream, pk_b=pk, h_wit=h_w, rs=RS, group=None):
             self.bn, self.stream, self.h_w = bn, stream, h_wit
             t0 = time.perf_counter()
-            self.sp = ShardedProver(bn, pk_b, rank, world, group=group)
+            self.sp = ShardedProver(bn, pk_b, rank, world, group=group, split=split)
             self.load_s = time.perf_counter() - t0
             with torch.cuda.stream(stream):
                 self.d_w = h_wit.cuda()
@@ -464,7 +467,7 @@ def section_groth16(env, args):
         wit_e = open(os.path.join(ex_dir, "witness.bin"), "rb").read()
         good = json.load(open(os.path.join(ROOT, "tests", "golden", "example_bn128.golden.json")))
         Le = Lane(env.bns[0], env.streams[0], pk_e, torch.frombuffer(bytearray(wit_e), dtype=torch.uint8).pin_memory(), bytes(64))
-        for i in range(W):
+        for i in range(max(W, world)):             # every H owner once: NCCL sets up its peer connections lazily
             Le.prove(i)
         torch.cuda.synchronize()
         ctr = [0]
@@ -625,7 +628,8 @@ def section_groth16(env, args):
         "latency": {"ms_per_proof_single_stream": lat_ms, "proofs_per_s": 1000.0 / lat_ms,
                     "note": "one proof at a time, per-proof CUDA events, L2 flushed (256 MiB fill) between proofs"},
         "config_extra": {"pkey_bytes": len(pk), "witness_bytes": len(wit), "in_flight": "%d proofs (one context + resident key%s each)" % (NP, " shard" if world > 1 else ""),
-                         "parallelism": ("point ranges of A, B1, B2, C, hExps x%d (src/bn128.js:353-361 split); H on one rank per proof (rotating), NCCL send/recv of h slices, one all_gather of 768-byte partial records, assembly on every rank" % world) if world > 1 else "single GPU",
+                         "parallelism": ("%s over %d ranks; H on one rank per proof (rotating), NCCL send/recv of h slices, one all_gather of 768-byte partial records, assembly on every rank" % (
+                             "balanced split: the five point sections laid end to end, cost-weighted, cut into equal contiguous pieces" if split == "balanced" else "uniform split: 1/N of every point section (src/bn128.js:353-361)", world)) if world > 1 else "single GPU",
                          "l2": "key sections + window tables (5.5 GB) and MSM workspaces are far larger than the 126 MB L2; the latency run also flushes L2 between proofs",
                          "bit_exact_vs_reference_golden": golden_ok, "key_load_s": L0.load_s, "keygen_s": gen_s},
         "stages_ms": pstages, "dropin_call": dropin, "example_key": example,

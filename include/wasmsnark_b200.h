@@ -249,11 +249,22 @@ int ws_bn128_groth16_partials_dev(ws_ctx* ctx, const ws_pkey* key, const void* d
  *   ws_bn128_groth16_h_msm_dev         the rank's H partial MSM over its slice d_h_shard (h_cnt*32 bytes), on `stream`,
  *        then joins the side streams: afterwards d_partials is complete in stream order (all_gather + finish as above).
  * ws_bn128_pkey_shard_info: range = {v_lo, v_cnt, c_lo, c_cnt, h_lo, h_cnt} -- witness element ranges [v_lo, v_lo+v_cnt)
- * (A/B1/B2) and [c_lo, c_lo+c_cnt) (C; c_lo already includes the nPublic+1 offset), h range [h_lo, h_lo+h_cnt).       */
+ * (A/B1/B2; their hull if they differ) and [c_lo, c_lo+c_cnt) (C; c_lo already includes the nPublic+1 offset), h range
+ * [h_lo, h_lo+h_cnt).                                                                                                */
 int ws_bn128_groth16_witness_msms_dev(ws_ctx* ctx, const ws_pkey* key, const void* d_witness, void* d_partials, void* stream);
 int ws_bn128_groth16_h_dev(ws_ctx* ctx, const ws_pkey* key, const void* d_witness, void* d_h, void* stream);
 int ws_bn128_groth16_h_msm_dev(ws_ctx* ctx, const ws_pkey* key, const void* d_h_shard, void* d_partials, void* stream);
 int ws_bn128_pkey_shard_info(const ws_pkey* key, uint32_t range[6]);
+/* A partial key with an explicit element range per point section: ranges = {lo, cnt} x 5 in the order A, B1, B2, C, H (A, B1,
+ * B2 index the signals, C the signals after the public ones, H the domain).  Any partition of the points over the ranks
+ * gives the same proof (the sums are associative); wasmsnark_b200/parallel.py (balanced_ranges) and ws_multi_* use it to
+ * give a rank one or two LARGE contiguous pieces -- cut from the five sections laid end to end, weighted by cost per
+ * point -- instead of 1/N of every section: fewer, larger MSMs per rank (wider windows, fewer reduction tails).
+ * Accepted by the partials / split entry points above, like a ws_bn128_pkey_load_shard key.                          */
+int ws_bn128_pkey_load_ranges(ws_ctx* ctx, const uint8_t* pkey, size_t pkey_len, const uint32_t ranges[10], ws_pkey** out);
+/* The balanced partition of a key over n ranks (host code, no GPU): out receives n x 10 values, rank-major, each row in the
+ * layout ws_bn128_pkey_load_ranges takes.  WS_E_ARG for a malformed key header or n outside 1..16.                   */
+int ws_balanced_ranges(const uint8_t* pkey, size_t pkey_len, int n, uint32_t* out);
 /* optional, before partials: starts the products that depend only on (r, s) and the key's fixed points
  * (r*delta1, s*delta1, (r*s)*delta1, s*delta2; src/bn128.js:672-702) on a side stream so that they overlap
  * the multi-scalar multiplications; finish_dev picks the result up (or computes it itself if not prepared). */
@@ -274,9 +285,18 @@ typedef struct ws_multi ws_multi;
 int ws_multi_create(int ngpus, ws_multi** out);
 void ws_multi_destroy(ws_multi* m);
 int ws_multi_gpus(const ws_multi* m);
+/* Point partition for keys loaded afterwards: 0 = uniform (1/N of every section, the reference's worker split,
+ * src/bn128.js:353-361), 1 = balanced (see ws_bn128_pkey_load_ranges).  Default: balanced from 4 GPUs.  Same proofs. */
+int ws_multi_set_split(ws_multi* m, int mode);
 const char* ws_multi_last_error(const ws_multi* m);
 int ws_multi_bn128_groth16_prove(ws_multi* m, const uint8_t* witness, size_t witness_len, const uint8_t* pkey, size_t pkey_len,
                                  const uint8_t* r, const uint8_t* s, uint8_t pi_a[96], uint8_t pi_b[192], uint8_t pi_c[96]);
+/* Resident form (no per-call fingerprint of the key bytes -- at 8 GPUs hashing a 500 MB key takes longer than the proof):
+ * ws_multi_bn128_pkey_load makes `pkey` the handle's resident key (its shards replace the previous key's);
+ * ws_multi_bn128_groth16_prove_resident proves with it.                                                              */
+int ws_multi_bn128_pkey_load(ws_multi* m, const uint8_t* pkey, size_t pkey_len);
+int ws_multi_bn128_groth16_prove_resident(ws_multi* m, const uint8_t* witness, size_t witness_len, const uint8_t* r, const uint8_t* s,
+                                          uint8_t pi_a[96], uint8_t pi_b[192], uint8_t pi_c[96]);
 int ws_multi_bn128_g1_multiexp(ws_multi* m, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t out[96]);
 int ws_multi_bn128_g2_multiexp(ws_multi* m, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t out[192]);
 
@@ -291,7 +311,8 @@ int ws_set_msm_task_cap(ws_ctx* ctx, unsigned cap);
 int ws_set_msm_seg_len(ws_ctx* ctx, unsigned len);
 /* Tuning/test hook: occupancy variant (launch bounds) of the bucket-accumulation kernel; 0 = default. */
 int ws_set_msm_acc_variant(ws_ctx* ctx, int variant);
-/* Tuning/test hook: occupancy variant of the radix-64 NTT pass (0: 4 blocks/SM, 1: 5, 2: 6). */
+/* Tuning/test hook: NTT pass variant -- 0: radix-64, 4 blocks/SM; 1 / 2: 5 / 6 blocks/SM; 3 / 4: warp-local exchange (4 / 5 blocks/SM);
+ * 5 / 6: radix-16 passes (6 / 8 blocks/SM).  Same results. */
 int ws_set_ntt_variant(ws_ctx* ctx, int variant);
 
 /* Elapsed device time (ms, CUDA events on the launch stream) of the kernels enqueued by the last

@@ -269,7 +269,7 @@ def test_fft_in_place_pass_counts_and_variants(bn, logn):
     x = raw.tobytes()
     base = {}
     try:
-        for variant in (0, 1, 2, 3, 4):
+        for variant in (0, 1, 2, 3, 4, 5, 6):
             bn.lib.ws_set_ntt_variant(bn.ctx.h, variant)
             for odd in (0, 1):
                 y = bn.fft(x, odd)
@@ -347,6 +347,51 @@ def test_split_prover_entry_points_equal_the_single_call(bn):
         bn.lib.ws_bn128_pkey_free(k_)
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_balanced_split_emulated_on_one_gpu(bn, world):
+    """ws_bn128_pkey_load_ranges with parallel.balanced_ranges pieces (a rank holds one or two large contiguous pieces of
+    the five sections, some sections not at all), every 'rank' run on this GPU, records concatenated, finish: golden."""
+    import ctypes
+    import torch
+    from wasmsnark_b200._lib import as_ptr
+    from wasmsnark_b200.parallel import balanced_ranges, section_weights
+    pk, wit, g = _synth_small()
+    weights, sizes = section_weights(pk)
+    d_w = torch.frombuffer(bytearray(wit), dtype=torch.uint8).cuda()
+    d_rs = torch.frombuffer(bytearray(bytes.fromhex(g["r"]) + bytes.fromhex(g["s"])), dtype=torch.uint8).cuda()
+    d_all = torch.zeros(768 * world, dtype=torch.uint8, device="cuda")
+    d_out = torch.zeros(384, dtype=torch.uint8, device="cuda")
+    d_h = torch.zeros(256 * 32, dtype=torch.uint8, device="cuda")
+    keys = []
+    for r in range(world):
+        k = ctypes.c_void_p()
+        arr = (ctypes.c_uint32 * 10)(*balanced_ranges(weights, sizes, r, world))
+        bn.ctx.check(bn.lib.ws_bn128_pkey_load_ranges(bn.ctx.h, as_ptr(pk), len(pk), arr, ctypes.byref(k)))
+        keys.append(k)
+    bn.ctx.check(bn.lib.ws_bn128_groth16_h_dev(bn.ctx.h, keys[world - 1], d_w.data_ptr(), d_h.data_ptr(), None))
+    bn.ctx.timings()
+    torch.cuda.synchronize()
+    for r in range(world):
+        rg = (ctypes.c_uint32 * 6)()
+        bn.lib.ws_bn128_pkey_shard_info(keys[r], rg)
+        part = d_all[768 * r:]
+        bn.ctx.check(bn.lib.ws_bn128_groth16_witness_msms_dev(bn.ctx.h, keys[r], d_w.data_ptr(), part.data_ptr(), None))
+        bn.ctx.check(bn.lib.ws_bn128_groth16_h_msm_dev(bn.ctx.h, keys[r], d_h.data_ptr() + 32 * rg[4], part.data_ptr(), None))
+        bn.ctx.timings()
+        torch.cuda.synchronize()
+    bn.ctx.check(bn.lib.ws_bn128_groth16_finish_dev(bn.ctx.h, keys[0], d_all.data_ptr(), world, d_rs.data_ptr(), d_out.data_ptr(), None))
+    bn.ctx.timings()
+    torch.cuda.synchronize()
+    out = bytes(d_out.cpu().numpy())
+    assert {"pi_a": bn.bin2g1(out[:96]), "pi_b": bn.bin2g2(out[96:288]), "pi_c": bn.bin2g1(out[288:])} == g["proof_rs"]
+    # a partial key is refused by the whole-proof entry point
+    from wasmsnark_b200._lib import WsError
+    with pytest.raises(WsError):
+        bn.ctx.check(bn.lib.ws_bn128_groth16_prove_dev(bn.ctx.h, keys[0], d_w.data_ptr(), d_rs.data_ptr(), d_out.data_ptr(), None))
+    for k_ in keys:
+        bn.lib.ws_bn128_pkey_free(k_)
+
+
 def test_context_is_thread_safe(bn):
     """Several host threads proving / multiplying on ONE context (the reference queues any number of commands,
     src/bn128.js:282-300; the Node addon runs proofs on libuv worker threads): every result is the right one."""
@@ -418,6 +463,14 @@ def test_multi_handle_on_the_visible_gpus():
         for _ in range(3):          # H owner rotates over the GPUs
             assert m.groth16GenProof(wit, pk, r=r, s=s) == g["proof_rs"]
         assert m.groth16GenProof(wit, pk, r=bytes(32), s=bytes(32)) == g["proof_r0s0"]
+        for mode in (1, 0):                             # balanced and uniform point partitions
+            m.lib.ws_multi_set_split(m.h, mode)
+            pk_mod = pk[:-64] + pk[-128:-64]            # another key (last H point duplicated): forces a reload with this split
+            assert m.groth16GenProof(wit, pk_mod, r=r, s=s) == bn1.groth16GenProof(wit, pk_mod, r=r, s=s)
+            assert m.groth16GenProof(wit, pk, r=r, s=s) == g["proof_rs"]
+        tok = m.load_proving_key(pk)                    # resident form: no per-call key fingerprint
+        for _ in range(2):
+            assert m.groth16GenProof(wit, tok, r=r, s=s) == g["proof_rs"]
         k = O.parse_pkey(pk)
         a = k["pPointsA"]
         pk3 = pk[:a + 64] + pk[a + 128:a + 192] + pk[a + 64:a + 128] + pk[a + 192:]      # same length, other content

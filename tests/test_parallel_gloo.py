@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from oracle import bn128 as O
-from wasmsnark_b200.parallel import all_gather_records, scatter_slices, shard_range, witness_hull
+from wasmsnark_b200.parallel import all_gather_records, balanced_ranges, scatter_slices, section_weights, shard_range, witness_hull
 
 
 def test_shard_range_matches_reference_split():
@@ -100,3 +100,35 @@ def test_witness_hull_covers_both_point_ranges():
     assert witness_hull((100, 50, 130, 40, 0, 0)) == (100, 70)
     assert witness_hull((0, 10, 59, 5, 0, 0)) == (0, 64)
     assert witness_hull((0, 0, 0, 0, 0, 0)) == (0, 0)
+
+
+def test_balanced_split_partitions_every_section_and_matches_the_c_library():
+    """parallel.balanced_ranges: every point of every section belongs to exactly one rank, pieces are contiguous, the
+    weighted load is even, and the C library (ws_balanced_ranges, what ws_multi_* uses) cuts identically."""
+    import ctypes
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import gen_synth_key
+    from wasmsnark_b200 import _lib
+    pk, _ = gen_synth_key.make(5000, 7, 4096, seed=3)
+    weights, sizes = section_weights(pk)
+    assert weights["B2"] > weights["A"] and weights["B1"] < 100            # the key's B points are 30 % infinity
+    lib = _lib.load_library()
+    for world in (1, 2, 3, 4, 8):
+        rows = [balanced_ranges(weights, sizes, r, world) for r in range(world)]
+        out = (ctypes.c_uint32 * (10 * world))()
+        assert lib.ws_balanced_ranges(_lib.as_ptr(pk), len(pk), world, out) == 0
+        assert [list(out[10 * r:10 * r + 10]) for r in range(world)] == rows
+        loads = []
+        for i, sec in enumerate(("A", "B1", "B2", "C", "H")):
+            pos = 0
+            for r in range(world):
+                lo, cnt = rows[r][2 * i], rows[r][2 * i + 1]
+                if cnt:
+                    assert lo == pos
+                    pos += cnt
+            assert pos == sizes[sec]
+        for r in range(world):
+            loads.append(sum(rows[r][2 * i + 1] * weights[sec] for i, sec in enumerate(("A", "B1", "B2", "C", "H"))))
+        assert max(loads) - min(loads) <= 2 * max(weights.values())
+    assert lib.ws_balanced_ranges(_lib.as_ptr(pk[:100]), 100, 2, (ctypes.c_uint32 * 20)()) != 0

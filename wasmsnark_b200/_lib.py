@@ -104,12 +104,17 @@ SIGNATURES = {
     "ws_bn128_groth16_h_dev": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "ws_bn128_groth16_h_msm_dev": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "ws_bn128_pkey_shard_info": (_i, [_vp, ctypes.POINTER(ctypes.c_uint32)]),
+    "ws_bn128_pkey_load_ranges": (_i, [_vp, _vp, _sz, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(_vp)]),
+    "ws_multi_set_split": (_i, [_vp, _i]),
+    "ws_balanced_ranges": (_i, [_vp, _sz, _i, ctypes.POINTER(ctypes.c_uint32)]),
     "ws_set_ntt_variant": (_i, [_vp, _i]),
     "ws_multi_create": (_i, [_i, ctypes.POINTER(_vp)]),
     "ws_multi_destroy": (None, [_vp]),
     "ws_multi_gpus": (_i, [_vp]),
     "ws_multi_last_error": (ctypes.c_char_p, [_vp]),
     "ws_multi_bn128_groth16_prove": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "ws_multi_bn128_pkey_load": (_i, [_vp, _vp, _sz]),
+    "ws_multi_bn128_groth16_prove_resident": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
     "ws_multi_bn128_g1_multiexp": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "ws_multi_bn128_g2_multiexp": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "ws_bn128_groth16_finish_dev": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),

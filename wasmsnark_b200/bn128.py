@@ -282,14 +282,25 @@ class MultiBn128:
     def g2_multiexp(self, scalars, points):
         return self._multiexp(self.lib.ws_multi_bn128_g2_multiexp, scalars, points, 128, 192)
 
+    RESIDENT = object()       # pass as `pkey` to prove with the key made resident by load_proving_key
+
+    def load_proving_key(self, pkey):
+        """Makes `pkey` the handle's resident key (its shards stay on the GPUs); returns the token to pass as `pkey`."""
+        self._check(self.lib.ws_multi_bn128_pkey_load(self.h, as_ptr(pkey), len(pkey)))
+        return self.RESIDENT
+
     def groth16GenProof(self, signals, pkey, r=None, s=None, raw=False):
-        """src/bn128.js:580-720 over all the GPUs of the handle; pkey: proving_key.bin bytes."""
+        """src/bn128.js:580-720 over all the GPUs of the handle; pkey: proving_key.bin bytes, or the token returned by
+        load_proving_key()."""
         for nm, v in (("r", r), ("s", s)):
             if v is not None and len(v) != 32:
                 raise ValueError("%s must be exactly 32 bytes" % nm)
         pa, pb, pc = ctypes.create_string_buffer(96), ctypes.create_string_buffer(192), ctypes.create_string_buffer(96)
         outs = [ctypes.cast(x, ctypes.c_void_p) for x in (pa, pb, pc)]
-        self._check(self.lib.ws_multi_bn128_groth16_prove(self.h, as_ptr(signals), len(signals), as_ptr(pkey), len(pkey), as_ptr(r), as_ptr(s), *outs))
+        if pkey is self.RESIDENT:
+            self._check(self.lib.ws_multi_bn128_groth16_prove_resident(self.h, as_ptr(signals), len(signals), as_ptr(r), as_ptr(s), *outs))
+        else:
+            self._check(self.lib.ws_multi_bn128_groth16_prove(self.h, as_ptr(signals), len(signals), as_ptr(pkey), len(pkey), as_ptr(r), as_ptr(s), *outs))
         if raw:
             return pa.raw, pb.raw, pc.raw
         return {"pi_a": self.bin2g1(pa.raw), "pi_b": self.bin2g2(pb.raw), "pi_c": self.bin2g1(pc.raw)}

@@ -45,7 +45,7 @@ unsigned long long fingerprint(const uint8_t* p, size_t n) {      // same constr
         return r ^ (r >> 31);
     };
     unsigned hw = std::thread::hardware_concurrency();
-    int nt = (int)std::min<size_t>(std::min<unsigned>(hw ? hw : 1, 8), n / ((size_t)8 << 20));
+    int nt = (int)std::min<size_t>(std::min<unsigned>(hw ? hw : 1, 16), n / ((size_t)8 << 20));
     if (nt <= 1) return one(p, n);
     std::vector<unsigned long long> part(nt);
     std::vector<std::thread> th;
@@ -83,6 +83,7 @@ struct ws_multi {
     uint8_t* d_ms[MAXG] = {};
     size_t ms_cap[MAXG] = {};
     unsigned long long proofs = 0;         // rotates the H owner
+    int balanced_from = 4;                 // GPU count from which the balanced split replaces the uniform one (ws_multi_set_split)
     std::mutex mu;
     std::string err;
     int fail(int code, const std::string& m) {
@@ -107,13 +108,63 @@ void free_keys(ws_multi* m) {
     m->key_len = 0;
 }
 
+// Balanced split (the same construction as wasmsnark_b200/parallel.py: balanced_ranges): the five point sections laid end
+// to end in the order B2, A, B1, C, H, each point weighted by its cost (G2 ~2.8 G1 additions, h is full-width, points at
+// infinity -- x == 0 -- are free: their share is sampled on every 16th point), cut into n equal pieces; a GPU owns the
+// points whose start falls into its piece -- one or two large contiguous pieces instead of 1/n of every section.
+// ranges: [g][10] = {lo, cnt} in section order A, B1, B2, C, H.  Returns false for a malformed header.
+bool balanced_ranges(const uint8_t* pkey, size_t plen, int n, uint32_t (*ranges)[10]) {
+    if (plen < 488) return false;
+    uint32_t h[10];
+    memcpy(h, pkey, 40);
+    const uint64_t nv = h[0], npub = h[1], dom = h[2];
+    if (npub + 1 > nv) return false;
+    // line order B2, A, B1, C, H -> index into the A, B1, B2, C, H layout
+    const int sec[5] = {2, 0, 1, 3, 4};
+    const uint64_t off[5] = {h[7], h[5], h[6], h[8], h[9]}, size[5] = {nv, nv, nv, nv - npub - 1, dom};
+    const uint64_t psize[5] = {128, 64, 64, 64, 64}, xbytes[5] = {64, 32, 32, 32, 32}, base[5] = {280, 100, 100, 100, 120};
+    uint64_t w[5], total = 0;
+    for (int k = 0; k < 5; k++) {
+        if (off[k] + size[k] * psize[k] > plen) return false;
+        uint64_t samples = 0, finite = 0;
+        for (uint64_t i = 0; i < size[k]; i += 16) {
+            const uint8_t* x = pkey + off[k] + i * psize[k];
+            bool nz = false;
+            for (uint64_t b = 0; b < xbytes[k] && !nz; b++) nz = x[b] != 0;
+            samples++;
+            finite += nz;
+        }
+        w[k] = samples ? std::max<uint64_t>(1, base[k] * std::max<uint64_t>(finite, 1) / samples) : base[k];
+        total += w[k] * size[k];
+    }
+    for (int g = 0; g < n; g++) {
+        const uint64_t start = (uint64_t)g * total / n, end = (uint64_t)(g + 1) * total / n;
+        uint64_t o = 0;
+        for (int k = 0; k < 5; k++) {
+            auto cut = [&](uint64_t pos) -> uint64_t {       // first element whose start is >= pos
+                if (pos <= o) return 0;
+                return std::min<uint64_t>(size[k], (pos - o + w[k] - 1) / w[k]);
+            };
+            const uint64_t lo = cut(start), hi = cut(end);
+            ranges[g][2 * sec[k]] = hi > lo ? (uint32_t)lo : 0;
+            ranges[g][2 * sec[k] + 1] = hi > lo ? (uint32_t)(hi - lo) : 0;
+            o += w[k] * size[k];
+        }
+    }
+    return true;
+}
+
 // Loads the key's shards (one host thread per GPU: the row regrouping of the polynomial sections is host work).
 int load_keys(ws_multi* m, const uint8_t* pkey, size_t plen, unsigned long long fp) {
     free_keys(m);
     std::vector<int> rc(m->n, 0);
     std::vector<std::thread> th;
+    uint32_t ranges[MAXG][10];
+    const bool balanced = m->n >= m->balanced_from && balanced_ranges(pkey, plen, m->n, ranges);
     for (int g = 0; g < m->n; g++)
-        th.emplace_back([&, g] { rc[g] = ws_bn128_pkey_load_shard(m->ctx[g], pkey, plen, g, m->n, &m->key[g]); });
+        th.emplace_back([&, g] {
+            rc[g] = balanced ? ws_bn128_pkey_load_ranges(m->ctx[g], pkey, plen, ranges[g], &m->key[g]) : ws_bn128_pkey_load_shard(m->ctx[g], pkey, plen, g, m->n, &m->key[g]);
+        });
     for (auto& x : th) x.join();
     for (int g = 0; g < m->n; g++)
         if (rc[g]) {
@@ -163,7 +214,9 @@ int enqueue_proof(ws_multi* m, const uint8_t* witness, const uint8_t* rs) {
                 return;
             }
         } else {
-            uint32_t lo = std::min(r[0], r[2]), hi = std::max(r[0] + r[1], r[2] + r[3]);
+            uint32_t lo = 0xFFFFFFFFu, hi = 0;
+            if (r[1]) lo = std::min(lo, r[0]), hi = std::max(hi, r[0] + r[1]);
+            if (r[3]) lo = std::min(lo, r[2]), hi = std::max(hi, r[2] + r[3]);
             if (hi > lo && m->stager[g].upload(m->d_wit[g] + (size_t)lo * 32, witness + (size_t)lo * 32, (size_t)(hi - lo) * 32, m->st[g], m->dev[g]) != cudaSuccess) {
                 rc1[g] = WS_E_CUDA;
                 err1[g] = "witness upload";
@@ -203,7 +256,7 @@ int enqueue_proof(ws_multi* m, const uint8_t* witness, const uint8_t* rs) {
         cudaSetDevice(m->dev[g]);
         const uint32_t* r = m->range[g];
         uint8_t* hs = m->d_h[g] + (size_t)r[4] * 32;
-        if (g != owner) {
+        if (g != owner && r[5]) {
             cudaStreamWaitEvent(m->st[g], m->ev_h[owner], 0);
             if (r[5] && cudaMemcpyPeerAsync(hs, m->dev[g], m->d_h[owner] + (size_t)r[4] * 32, m->dev[owner], (size_t)r[5] * 32, m->st[g]) != cudaSuccess)
                 return m->fail(WS_E_CUDA, "peer copy of h");
@@ -342,11 +395,56 @@ WS_API void ws_multi_destroy(ws_multi* m) {
     delete m;
 }
 
+// The balanced partition itself (pure host code, no device): out = n x 10 values.  Exposed so that other hosts of the
+// per-GPU C ABI (one process per GPU) can use exactly the partition ws_multi_* uses, and for the CPU tests.
+WS_API int ws_balanced_ranges(const uint8_t* pkey, size_t plen, int n, uint32_t* out) {
+    if (!pkey || !out || n < 1 || n > MAXG) return WS_E_ARG;
+    uint32_t ranges[MAXG][10];
+    if (!balanced_ranges(pkey, plen, n, ranges)) return WS_E_ARG;
+    memcpy(out, ranges, (size_t)n * 10 * sizeof(uint32_t));
+    return WS_OK;
+}
+
 WS_API int ws_multi_gpus(const ws_multi* m) { return m ? m->n : 0; }
+// mode 0: uniform split (1/n of every section, the reference's worker split); 1: balanced split; applies to keys loaded afterwards
+WS_API int ws_multi_set_split(ws_multi* m, int mode) {
+    if (!m) return WS_E_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    m->balanced_from = mode ? 2 : 1 << 30;
+    return WS_OK;
+}
 WS_API const char* ws_multi_last_error(const ws_multi* m) { return m ? m->err.c_str() : "null handle"; }
 
 WS_API int ws_multi_bn128_g1_multiexp(ws_multi* m, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t out[96]) { return multiexp<1>(m, scalars, points, n, out); }
 WS_API int ws_multi_bn128_g2_multiexp(ws_multi* m, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t out[192]) { return multiexp<2>(m, scalars, points, n, out); }
+
+// Resident form: the key's shards are loaded once (replacing whatever key the handle held) and proofs then take only the
+// witness -- no per-call fingerprint of the key bytes, which at 8 GPUs costs more host time than the proof takes.
+WS_API int ws_multi_bn128_pkey_load(ws_multi* m, const uint8_t* pkey, size_t plen) {
+    if (!m || !pkey) return m ? m->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    for (int g = 0; g < m->n; g++) {
+        cudaSetDevice(m->dev[g]);
+        cudaStreamSynchronize(m->st[g]);
+    }
+    return load_keys(m, pkey, plen, fingerprint(pkey, plen));
+}
+
+WS_API int ws_multi_bn128_groth16_prove_resident(ws_multi* m, const uint8_t* witness, size_t wlen, const uint8_t* r, const uint8_t* s, uint8_t pi_a[96],
+                                                 uint8_t pi_b[192], uint8_t pi_c[96]) {
+    if (!m || !witness || !pi_a || !pi_b || !pi_c) return m ? m->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    if (!m->key[0]) return m->fail(WS_E_ARG, "no resident proving key: call ws_multi_bn128_pkey_load first");
+    if (wlen < (size_t)m->n_vars * 32) return m->fail(WS_E_ARG, "witness shorter than nVars * 32 bytes");
+    uint8_t rs[64];
+    if (r) memcpy(rs, r, 32);
+    else if (getrandom(rs, 32, 0) != 32) return m->fail(WS_E_ARG, "getrandom failed");
+    if (s) memcpy(rs + 32, s, 32);
+    else if (getrandom(rs + 32, 32, 0) != 32) return m->fail(WS_E_ARG, "getrandom failed");
+    int rc = enqueue_proof(m, witness, rs);
+    if (rc) return rc;
+    return collect_proof(m, pi_a, pi_b, pi_c);
+}
 
 WS_API int ws_multi_bn128_groth16_prove(ws_multi* m, const uint8_t* witness, size_t wlen, const uint8_t* pkey, size_t plen, const uint8_t* r, const uint8_t* s,
                                         uint8_t pi_a[96], uint8_t pi_b[192], uint8_t pi_c[96]) {

@@ -315,9 +315,10 @@ struct ws_pkey {
     // point-range shard held by this key object (rank r of w): contiguous ranges, floor(n/w) each and the
     // last rank takes the remainder -- the reference's worker split (src/bn128.js:353-361)
     int rank = 0, world = 1;
-    uint32_t v_lo = 0, v_cnt = 0;     // A / B1 / B2 over the signals
-    uint32_t c_lo = 0, c_cnt = 0;     // C over signals nPublic+1 ..
-    uint32_t h_lo = 0, h_cnt = 0;     // hExps over the domain
+    // element range of each point section held by this key object, in section order A, B1, B2, C, H (SEC_*): A / B1 /
+    // B2 index the signals, C the signals from nPublic+1 on (lo is relative to that), H the domain.  The uniform shard
+    // gives A, B1, B2 the same range; ws_bn128_pkey_load_ranges sets each independently (balanced split, parallel.py).
+    uint32_t lo[5] = {}, cnt[5] = {};
     DevCsr polA, polB;
     uint8_t* points = nullptr;     // one allocation: A | B1 | B2 | C | H, each 256-byte aligned
     G1Affine *A = nullptr, *B1 = nullptr, *C = nullptr, *H = nullptr;
@@ -325,9 +326,14 @@ struct ws_pkey {
     FixedPoints* fixed = nullptr;
     FixedBaseTables* fixed_tables = nullptr;    // comb tables of delta1 / delta2 (built with the window tables)
     // window tables (2^(c w) * P_i, see k_msm_build_table): one per section, built at load; tc_* = window bits, 0 = none
-    void *tA = nullptr, *tB1 = nullptr, *tB2 = nullptr, *tC = nullptr, *tH = nullptr;
-    int tc_v = 0, tc_c = 0, tc_h = 0;
+    void* tab[5] = {};
+    int tc[5] = {};
+    const void* msm_points(int sec) const {
+        if (tab[sec]) return tab[sec];
+        return sec == 0 ? (const void*)A : sec == 1 ? (const void*)B1 : sec == 2 ? (const void*)B2 : sec == 3 ? (const void*)C : (const void*)H;
+    }
 };
+enum { SEC_A = 0, SEC_B1 = 1, SEC_B2 = 2, SEC_C = 3, SEC_H = 4 };
 
 static int log2_exact(uint32_t n) {
     if (n == 0 || (n & (n - 1))) return -1;
@@ -343,11 +349,7 @@ static void pkey_release(ws_pkey* k) {
     cudaFree(k->points);
     cudaFree(k->fixed);
     cudaFree(k->fixed_tables);
-    cudaFree(k->tA);
-    cudaFree(k->tB1);
-    cudaFree(k->tB2);
-    cudaFree(k->tC);
-    cudaFree(k->tH);
+    for (int i = 0; i < 5; i++) cudaFree(k->tab[i]);
     delete k;
 }
 
@@ -360,45 +362,35 @@ static void shard_range(uint32_t n, int rank, int world, uint32_t* lo, uint32_t*
 // Window tables for the five point sections (HBM is plentiful: 13 x the section size at 2^20).  Failure to
 // allocate is not an error: the section then runs the table-free MSM.
 static void build_key_tables(ws_ctx* c, ws_pkey* k) {
-    auto one = [&](const void* pts, size_t cnt, size_t psize, int* tc, void** tab, bool g2) {
-        *tab = nullptr;
-        if (cnt == 0) return;
-        int cc = *tc ? *tc : msm_table_choose_c(cnt);
+    const char* force = getenv("WS_TABLE_C");          // tuning hook: window bits of the tables (default: from the section size)
+    const void* pts[5] = {k->A, k->B1, k->B2, k->C, k->H};
+    for (int sec = 0; sec < 5; sec++) {
+        k->tab[sec] = nullptr;
+        k->tc[sec] = 0;
+        const size_t cnt = k->cnt[sec], psize = sec == SEC_B2 ? 128 : 64;
+        if (cnt == 0) continue;
+        int cc = msm_table_choose_c(cnt);
+        if (force && atoi(force) >= 8 && atoi(force) <= 22) cc = atoi(force);
         int W = msm_table_windows_n(cc);
-        if ((uint64_t)W * cnt >= 0x80000000ull) return;
+        if ((uint64_t)W * cnt >= 0x80000000ull) continue;
         void* t = nullptr;
         if (cudaMalloc(&t, (size_t)W * cnt * psize) != cudaSuccess) {
             cudaGetLastError();
-            return;
+            continue;
         }
-        int rc = g2 ? msm_g2_build_table(c, pts, cnt, cc, t, c->stream) : msm_g1_build_table(c, pts, cnt, cc, t, c->stream);
+        int rc = sec == SEC_B2 ? msm_g2_build_table(c, pts[sec], cnt, cc, t, c->stream) : msm_g1_build_table(c, pts[sec], cnt, cc, t, c->stream);
         if (rc || cudaStreamSynchronize(c->stream) != cudaSuccess) {
             cudaGetLastError();
             cudaFree(t);
-            return;
+            continue;
         }
-        *tc = cc;
-        *tab = t;
-    };
-    one(k->A, k->v_cnt, 64, &k->tc_v, &k->tA, false);
-    if (k->tA) {
-        one(k->B1, k->v_cnt, 64, &k->tc_v, &k->tB1, false);
-        one(k->B2, k->v_cnt, 128, &k->tc_v, &k->tB2, true);
+        k->tc[sec] = cc;
+        k->tab[sec] = t;
     }
-    if (!k->tA || !k->tB1 || !k->tB2) {        // all three share tc_v: all or nothing
-        cudaFree(k->tA);
-        cudaFree(k->tB1);
-        cudaFree(k->tB2);
-        k->tA = k->tB1 = k->tB2 = nullptr;
-        k->tc_v = 0;
-    }
-    one(k->C, k->c_cnt, 64, &k->tc_c, &k->tC, false);
-    if (!k->tC) k->tc_c = 0;
-    one(k->H, k->h_cnt, 64, &k->tc_h, &k->tH, false);
-    if (!k->tH) k->tc_h = 0;
 }
 
-static int pkey_load(ws_ctx* c, const uint8_t* pkey, size_t len, ws_pkey** out, int rank = 0, int world = 1) {
+// ranges: nullptr = the uniform shard of (rank, world); else {lo, cnt} x 5 in section order A, B1, B2, C, H
+static int pkey_load(ws_ctx* c, const uint8_t* pkey, size_t len, ws_pkey** out, int rank = 0, int world = 1, const uint32_t* ranges = nullptr) {
     if (world < 1 || rank < 0 || rank >= world) return c->fail(WS_E_ARG, "bad rank / world");
     if (len < 488) return c->fail(WS_E_ARG, "proving key shorter than its header");
     uint32_t h[10];
@@ -432,9 +424,23 @@ static int pkey_load(ws_ctx* c, const uint8_t* pkey, size_t len, ws_pkey** out, 
     k->logn = logn;
     k->rank = rank;
     k->world = world;
-    shard_range(nv, rank, world, &k->v_lo, &k->v_cnt);
-    shard_range((uint32_t)nC, rank, world, &k->c_lo, &k->c_cnt);
-    shard_range(dom, rank, world, &k->h_lo, &k->h_cnt);
+    const uint32_t sec_n[5] = {nv, nv, nv, (uint32_t)nC, dom};
+    if (ranges) {
+        for (int i = 0; i < 5; i++) {
+            k->lo[i] = ranges[2 * i];
+            k->cnt[i] = ranges[2 * i + 1];
+            if ((uint64_t)k->lo[i] + k->cnt[i] > sec_n[i]) {
+                pkey_release(k);
+                return c->fail(WS_E_ARG, "section range out of bounds");
+            }
+        }
+    } else {
+        shard_range(nv, rank, world, &k->lo[SEC_A], &k->cnt[SEC_A]);
+        k->lo[SEC_B1] = k->lo[SEC_B2] = k->lo[SEC_A];
+        k->cnt[SEC_B1] = k->cnt[SEC_B2] = k->cnt[SEC_A];
+        shard_range((uint32_t)nC, rank, world, &k->lo[SEC_C], &k->cnt[SEC_C]);
+        shard_range(dom, rank, world, &k->lo[SEC_H], &k->cnt[SEC_H]);
+    }
     // the reference slices polsA as [pPolsA, pPolsA + pPolsB) (src/bn128.js:592); the section proper ends at pPolsB.
     // The two sections are regrouped by row on two host threads.
     std::vector<uint32_t> rs2, sg2;
@@ -452,8 +458,8 @@ static int pkey_load(ws_ctx* c, const uint8_t* pkey, size_t len, ws_pkey** out, 
         return c->fail(WS_E_ARG, "polsB section malformed (or out of device memory)");
     }
     lap("csr A+B");
-    const size_t vc = k->v_cnt, cc = k->c_cnt, hc = k->h_cnt;
-    size_t oA = 0, oB1 = oA + align256(vc * 64 + 64), oB2 = oB1 + align256(vc * 64 + 64), oC = oB2 + align256(vc * 128 + 64),
+    const size_t nA = k->cnt[SEC_A], nB1 = k->cnt[SEC_B1], nB2 = k->cnt[SEC_B2], cc = k->cnt[SEC_C], hc = k->cnt[SEC_H];
+    size_t oA = 0, oB1 = oA + align256(nA * 64 + 64), oB2 = oB1 + align256(nB1 * 64 + 64), oC = oB2 + align256(nB2 * 128 + 64),
            oH = oC + align256(cc * 64 + 64), tot = oH + align256(hc * 64 + 64);
     if (cudaMalloc(&k->points, tot) != cudaSuccess || cudaMalloc(&k->fixed, sizeof(FixedPoints)) != cudaSuccess) {
         pkey_release(k);
@@ -464,13 +470,11 @@ static int pkey_load(ws_ctx* c, const uint8_t* pkey, size_t len, ws_pkey** out, 
     k->B2 = (G2Affine*)(k->points + oB2);
     k->C = (G1Affine*)(k->points + oC);
     k->H = (G1Affine*)(k->points + oH);
-    if (vc) {
-        cudaMemcpyAsync(k->A, pkey + pPA + (size_t)k->v_lo * 64, vc * 64, cudaMemcpyHostToDevice, c->stream);
-        cudaMemcpyAsync(k->B1, pkey + pPB1 + (size_t)k->v_lo * 64, vc * 64, cudaMemcpyHostToDevice, c->stream);
-        cudaMemcpyAsync(k->B2, pkey + pPB2 + (size_t)k->v_lo * 128, vc * 128, cudaMemcpyHostToDevice, c->stream);
-    }
-    if (cc) cudaMemcpyAsync(k->C, pkey + pPC + (size_t)k->c_lo * 64, cc * 64, cudaMemcpyHostToDevice, c->stream);
-    if (hc) cudaMemcpyAsync(k->H, pkey + pPH + (size_t)k->h_lo * 64, hc * 64, cudaMemcpyHostToDevice, c->stream);
+    if (nA) cudaMemcpyAsync(k->A, pkey + pPA + (size_t)k->lo[SEC_A] * 64, nA * 64, cudaMemcpyHostToDevice, c->stream);
+    if (nB1) cudaMemcpyAsync(k->B1, pkey + pPB1 + (size_t)k->lo[SEC_B1] * 64, nB1 * 64, cudaMemcpyHostToDevice, c->stream);
+    if (nB2) cudaMemcpyAsync(k->B2, pkey + pPB2 + (size_t)k->lo[SEC_B2] * 128, nB2 * 128, cudaMemcpyHostToDevice, c->stream);
+    if (cc) cudaMemcpyAsync(k->C, pkey + pPC + (size_t)k->lo[SEC_C] * 64, cc * 64, cudaMemcpyHostToDevice, c->stream);
+    if (hc) cudaMemcpyAsync(k->H, pkey + pPH + (size_t)k->lo[SEC_H] * 64, hc * 64, cudaMemcpyHostToDevice, c->stream);
     cudaMemcpyAsync(k->fixed, pkey + 40, 448, cudaMemcpyHostToDevice, c->stream);
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
         pkey_release(k);
@@ -570,15 +574,15 @@ static int prove_witness_msms_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_
     if (!c->ensure_lanes()) return c->fail_cuda("prover streams");
     PartialSlots p(d_partials);
     cudaEventRecord(c->fork_ev, st);
-    const uint8_t* wv = d_witness + 32 * (size_t)k->v_lo;
     int rc = 0;
     for (int lane = 0; lane < 4 && !rc; lane++) {
         cudaStream_t ls = c->lanes[lane];
         cudaStreamWaitEvent(ls, c->fork_ev, 0);
-        if (lane == 0) rc = msm_g2_run(c, wv, k->tB2 ? k->tB2 : (const void*)k->B2, k->v_cnt, nullptr, p.rB2, ls, 8 + lane, k->tc_v);
-        else if (lane == 1) rc = msm_g1_run(c, wv, k->tA ? k->tA : (const void*)k->A, k->v_cnt, nullptr, p.rA, ls, 8 + lane, k->tc_v);
-        else if (lane == 2) rc = msm_g1_run(c, wv, k->tB1 ? k->tB1 : (const void*)k->B1, k->v_cnt, nullptr, p.rB1, ls, 8 + lane, k->tc_v);
-        else rc = msm_g1_run(c, d_witness + 32 * ((size_t)k->n_public + 1 + k->c_lo), k->tC ? k->tC : (const void*)k->C, k->c_cnt, nullptr, p.rC, ls, 8 + lane, k->tc_c);
+        const int sec = lane == 0 ? SEC_B2 : lane == 1 ? SEC_A : lane == 2 ? SEC_B1 : SEC_C;      // the G2 MSM (the longest) first
+        const uint8_t* sc = d_witness + 32 * ((size_t)k->lo[sec] + (sec == SEC_C ? (size_t)k->n_public + 1 : 0));
+        void* out = sec == SEC_B2 ? (void*)p.rB2 : sec == SEC_A ? (void*)p.rA : sec == SEC_B1 ? (void*)p.rB1 : (void*)p.rC;
+        if (sec == SEC_B2) rc = msm_g2_run(c, sc, k->msm_points(sec), k->cnt[sec], nullptr, out, ls, 8 + lane, k->tc[sec]);
+        else rc = msm_g1_run(c, sc, k->msm_points(sec), k->cnt[sec], nullptr, out, ls, 8 + lane, k->tc[sec]);
         cudaEventRecord(c->lane_done[lane], ls);
     }
     if (rc) return rc;
@@ -598,7 +602,7 @@ static int prove_h_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_witness, Fr
 // MSMs are joined into `st`, after which the 768-byte record is complete in stream order.
 static int prove_h_msm_dev(ws_ctx* c, const ws_pkey* k, const Fr* d_h_shard, uint8_t* d_partials, cudaStream_t st) {
     PartialSlots p(d_partials);
-    int rc = msm_g1_run(c, d_h_shard, k->tH ? k->tH : (const void*)k->H, k->h_cnt, nullptr, p.rH, st, 1, k->tc_h);
+    int rc = msm_g1_run(c, d_h_shard, k->msm_points(SEC_H), k->cnt[SEC_H], nullptr, p.rH, st, 1, k->tc[SEC_H]);
     if (rc) return rc;
     c->timer.mark("msm:H", st);
     for (int lane = 0; lane < 4; lane++) cudaStreamWaitEvent(st, c->lane_done[lane], 0);
@@ -620,7 +624,7 @@ static int prove_partials_dev(ws_ctx* c, const ws_pkey* k, const uint8_t* d_witn
         cudaEventRecord(c->h_done, hs);
         cudaStreamWaitEvent(st, c->h_done, 0);
     }
-    return prove_h_msm_dev(c, k, h + k->h_lo, d_partials, st);
+    return prove_h_msm_dev(c, k, h + k->lo[SEC_H], d_partials, st);
 }
 
 // Starts the (r, s)-only products on a side stream; `st` must have d_rs ready at this point.
@@ -834,7 +838,7 @@ WS_API int ws_bn128_groth16_h_dev(ws_ctx* c, const ws_pkey* k, const void* d_wit
 }
 WS_API int ws_bn128_groth16_h_msm_dev(ws_ctx* c, const ws_pkey* k, const void* d_h_shard, void* d_partials, void* stream) {
     WsLock ws_lock_(c);
-    if (!c || !k || !d_partials || (k->h_cnt && !d_h_shard)) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
+    if (!c || !k || !d_partials || (k->cnt[SEC_H] && !d_h_shard)) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
     if (k->ctx != c) return c->fail(WS_E_ARG, "proving key belongs to another context");
     if (((uintptr_t)d_h_shard | (uintptr_t)d_partials) & 15) return c->fail(WS_E_ARG, "device pointers must be 16-byte aligned");
     if (!c->lanes_ready) return c->fail(WS_E_ARG, "ws_bn128_groth16_witness_msms_dev must be called first");
@@ -846,13 +850,28 @@ WS_API int ws_bn128_groth16_h_msm_dev(ws_ctx* c, const ws_pkey* k, const void* d
 }
 WS_API int ws_bn128_pkey_shard_info(const ws_pkey* k, uint32_t range[6]) {
     if (!k || !range) return WS_E_ARG;
-    range[0] = k->v_lo;
-    range[1] = k->v_cnt;
-    range[2] = k->n_public + 1 + k->c_lo;
-    range[3] = k->c_cnt;
-    range[4] = k->h_lo;
-    range[5] = k->h_cnt;
+    // the hull of the A / B1 / B2 ranges (identical for the uniform shard), the C range, the h range
+    uint32_t vlo = 0xFFFFFFFFu, vhi = 0;
+    for (int sec = SEC_A; sec <= SEC_B2; sec++)
+        if (k->cnt[sec]) {
+            vlo = k->lo[sec] < vlo ? k->lo[sec] : vlo;
+            vhi = k->lo[sec] + k->cnt[sec] > vhi ? k->lo[sec] + k->cnt[sec] : vhi;
+        }
+    range[0] = vhi ? vlo : 0;
+    range[1] = vhi ? vhi - vlo : 0;
+    range[2] = k->n_public + 1 + k->lo[SEC_C];
+    range[3] = k->cnt[SEC_C];
+    range[4] = k->lo[SEC_H];
+    range[5] = k->cnt[SEC_H];
     return WS_OK;
+}
+WS_API int ws_bn128_pkey_load_ranges(ws_ctx* c, const uint8_t* pkey, size_t len, const uint32_t ranges[10], ws_pkey** out) {
+    WsLock ws_lock_(c);
+    if (!c || !pkey || !out || !ranges) return c ? c->fail(WS_E_ARG, "null pointer") : WS_E_ARG;
+    *out = nullptr;
+    int rc = pkey_load(c, pkey, len, out, 0, 1, ranges);
+    if (!rc) (*out)->world = 0;          // a partial key: only the partials / finish entry points accept it
+    return rc;
 }
 WS_API int ws_bn128_groth16_prepare_dev(ws_ctx* c, const ws_pkey* k, const void* d_rs, void* stream) {
     WsLock ws_lock_(c);
