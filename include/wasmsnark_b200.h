@@ -311,8 +311,9 @@ int ws_set_msm_task_cap(ws_ctx* ctx, unsigned cap);
 int ws_set_msm_seg_len(ws_ctx* ctx, unsigned len);
 /* Tuning/test hook: occupancy variant (launch bounds) of the bucket-accumulation kernel; 0 = default. */
 int ws_set_msm_acc_variant(ws_ctx* ctx, int variant);
-/* Tuning/test hook: NTT pass variant -- 0: radix-64, 4 blocks/SM; 1 / 2: 5 / 6 blocks/SM; 3 / 4: warp-local exchange (4 / 5 blocks/SM);
- * 5 / 6: radix-16 passes (6 / 8 blocks/SM).  Same results. */
+/* Tuning/test hook: NTT pass variant -- 0 (default) / 6: radix-16 staged passes, 8 blocks/SM; 5: the same at 6 blocks/SM;
+ * 7: radix-64 passes, 4 blocks/SM (round 1); 1 / 2: radix-64 at 5 / 6 blocks/SM; 3 / 4: radix-64 with a warp-local
+ * exchange (4 / 5 blocks/SM).  Same results. */
 int ws_set_ntt_variant(ws_ctx* ctx, int variant);
 
 /* Elapsed device time (ms, CUDA events on the launch stream) of the kernels enqueued by the last

@@ -269,7 +269,7 @@ def test_fft_in_place_pass_counts_and_variants(bn, logn):
     x = raw.tobytes()
     base = {}
     try:
-        for variant in (0, 1, 2, 3, 4, 5, 6):
+        for variant in (0, 1, 2, 3, 4, 5, 6, 7):
             bn.lib.ws_set_ntt_variant(bn.ctx.h, variant)
             for odd in (0, 1):
                 y = bn.fft(x, odd)
