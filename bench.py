@@ -426,7 +426,9 @@ def section_groth16(env, args):
     pk, wit, gen_s = synth_key(PROVE_LOG2)
     split = os.environ.get("WS_BENCH_SPLIT", "auto")
     if split == "auto":
-        split = "balanced" if world >= 4 else "uniform"
+        # measured (profiles/r2_bench_n*_{balanced,uniform}*.json): balanced 101 vs 91 proofs/s at N = 2, but 145 vs 159 at N = 4
+        # and 210 vs 282 at N = 8 -- with many ranks the cost weights (G2 tails!) decide the balance, 1/N of everything is exact
+        split = "balanced" if world == 2 else "uniform"
     h_w = torch.frombuffer(bytearray(wit), dtype=torch.uint8).pin_memory()
 
     class Lane:

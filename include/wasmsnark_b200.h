@@ -286,7 +286,7 @@ int ws_multi_create(int ngpus, ws_multi** out);
 void ws_multi_destroy(ws_multi* m);
 int ws_multi_gpus(const ws_multi* m);
 /* Point partition for keys loaded afterwards: 0 = uniform (1/N of every section, the reference's worker split,
- * src/bn128.js:353-361), 1 = balanced (see ws_bn128_pkey_load_ranges).  Default: balanced from 4 GPUs.  Same proofs. */
+ * src/bn128.js:353-361; the default), 1 = balanced (see ws_bn128_pkey_load_ranges).  Same proofs. */
 int ws_multi_set_split(ws_multi* m, int mode);
 const char* ws_multi_last_error(const ws_multi* m);
 int ws_multi_bn128_groth16_prove(ws_multi* m, const uint8_t* witness, size_t witness_len, const uint8_t* pkey, size_t pkey_len,

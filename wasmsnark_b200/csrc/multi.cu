@@ -83,7 +83,9 @@ struct ws_multi {
     uint8_t* d_ms[MAXG] = {};
     size_t ms_cap[MAXG] = {};
     unsigned long long proofs = 0;         // rotates the H owner
-    int balanced_from = 4;                 // GPU count from which the balanced split replaces the uniform one (ws_multi_set_split)
+    int balanced_from = 1 << 30;           // GPU count from which the balanced split replaces the uniform one: never by default
+                                           // (ws_multi_set_split(m, 1) turns it on; a single blocking proof measured 9.5 ms uniform
+                                           // vs 11.0 ms balanced on 8 GPUs -- the uniform split balances exactly)
     std::mutex mu;
     std::string err;
     int fail(int code, const std::string& m) {

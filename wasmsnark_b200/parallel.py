@@ -85,11 +85,14 @@ def witness_hull(key_ranges):
 
 
 # ---- balanced split --------------------------------------------------------------------------------------------------
-# The reference gives every worker 1/W of EVERY multiexp (src/bn128.js:353-361).  On GPUs that is wasteful at W = 4 or 8:
-# a rank then runs five small MSMs per proof, each with its own bucket-reduction tail, and small point sets force
-# narrower windows (more additions per point).  The sums are associative, so any partition of the points gives the same
-# proof: here the five point sections are laid end to end, weighted by their cost per point, and cut into `world` equal
-# pieces -- a rank gets one or two LARGE contiguous pieces (e.g. a third of B2, or the tail of A plus the head of B1).
+# The reference gives every worker 1/W of EVERY multiexp (src/bn128.js:353-361).  On GPUs a rank then runs five small
+# MSMs per proof, each with its own bucket-reduction tail, and small point sets force narrower windows (more additions per
+# point).  The sums are associative, so any partition of the points gives the same proof: here the five point sections
+# are laid end to end, weighted by their cost per point, and cut into `world` equal pieces -- a rank gets one or two LARGE
+# contiguous pieces (e.g. a third of B2, or the tail of A plus the head of B1).  Measured on B200s (2^20 constraints,
+# proofs/s, balanced vs uniform): 101 vs 91 on 2 GPUs, 145 vs 159 on 4, 210 vs 282 on 8 -- the static weights do not
+# capture the latency-bound G2 reduction tails, so with many ranks the ones holding B2 pieces lag; "auto" therefore uses
+# the balanced split on 2 ranks only.
 SECTION_ORDER = ("B2", "A", "B1", "C", "H")             # order along the line; index into ranges is A, B1, B2, C, H
 _SEC_INDEX = {"A": 0, "B1": 1, "B2": 2, "C": 3, "H": 4}
 BASE_WEIGHT = {"A": 100, "B1": 100, "B2": 280, "C": 100, "H": 120}    # G2 addition ~2.8 G1 additions; h is full-width
@@ -145,13 +148,16 @@ class ShardedProver:
     proof, bit-identical to the single-GPU one.  All device work of a proof is enqueued on ONE torch.cuda.Stream given
     by the caller (the library launches on it, NCCL orders itself against it): no host synchronisation inside."""
 
-    def __init__(self, bn, pkey_bytes, rank, world, group=None, split="balanced"):
-        """split: "balanced" (default for world > 2: cost-weighted contiguous pieces, see balanced_ranges) or "uniform"
-        (1/world of every section, the reference's worker split)."""
+    def __init__(self, bn, pkey_bytes, rank, world, group=None, split="auto"):
+        """split: "uniform" (1/world of every section, the reference's worker split), "balanced" (cost-weighted contiguous
+        pieces, see balanced_ranges) or "auto" = balanced on 2 ranks, uniform otherwise (what measured fastest: with many
+        ranks the exactness of the uniform split beats the larger pieces of the balanced one)."""
         import torch
         from ._lib import as_ptr
         self.bn, self.rank, self.world, self.group = bn, rank, world, group
         self.key = ctypes.c_void_p()
+        if split == "auto":
+            split = "balanced" if world == 2 else "uniform"
         self.split = split if world > 1 else "uniform"
         if self.split == "balanced":
             weights, sizes = section_weights(pkey_bytes)
