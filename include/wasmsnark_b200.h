@@ -309,7 +309,10 @@ int ws_set_profiling(ws_ctx* ctx, int on);
 int ws_set_msm_task_cap(ws_ctx* ctx, unsigned cap);
 /* Tuning/test hook: buckets per segment in the bucket-reduction step (power of two, default 32). */
 int ws_set_msm_seg_len(ws_ctx* ctx, unsigned len);
-/* Tuning/test hook: occupancy variant (launch bounds) of the bucket-accumulation kernel; 0 = default. */
+/* Tuning/test hook: occupancy variant (launch bounds) of the bucket-accumulation kernel; 0 = default.  Bits 0..3 select the
+ * variant for G1-type curves (1: 128 threads x 5 blocks, 2: 128 x 4, 3: 192 x 3), bits 4..7 for G2-type curves (1: 64
+ * threads x 3 blocks, 2: 128 x 3).  The environment variables WS_MSM_ACC_VARIANT, WS_MSM_SEG_LEN, WS_MSM_TASK_CAP and
+ * WS_NTT_VARIANT preset the corresponding hooks of every context a process creates (A/B runs of whole programs). */
 int ws_set_msm_acc_variant(ws_ctx* ctx, int variant);
 /* Tuning/test hook: NTT pass variant -- 0 (default) / 6: radix-16 staged passes, 8 blocks/SM; 5: the same at 6 blocks/SM;
  * 7: radix-64 passes, 4 blocks/SM (round 1); 1 / 2: radix-64 at 5 / 6 blocks/SM; 3 / 4: radix-64 with a warp-local

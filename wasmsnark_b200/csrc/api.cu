@@ -3,6 +3,7 @@
 // without a device ws_create fails.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -33,6 +34,14 @@ WS_API int ws_create(int device, ws_ctx** out) {
         return WS_E_CUDA;
     }
     for (int i = 0; i < StageTimer::MAX; i++) cudaEventCreate(&c->timer.ev[i]);
+    // tuning overrides for A/B runs of whole programs (bench.py, tools/): same meaning as the ws_set_* hooks
+    if (const char* e = getenv("WS_MSM_SEG_LEN")) {
+        unsigned L = (unsigned)atoi(e);
+        if (L && !(L & (L - 1))) c->seg_len = L;
+    }
+    if (const char* e = getenv("WS_MSM_ACC_VARIANT")) c->acc_variant = atoi(e);
+    if (const char* e = getenv("WS_MSM_TASK_CAP")) c->force_T = (unsigned)atoi(e);
+    if (const char* e = getenv("WS_NTT_VARIANT")) c->ntt_variant = atoi(e);
     *out = c;
     return WS_OK;
 }

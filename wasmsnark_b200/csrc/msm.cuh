@@ -596,6 +596,9 @@ inline cudaError_t msm_launch(const MsmPlan& p, const MsmWorkspace& w, const uin
         kern<<<(p.max_tasks + threads - 1) / threads, threads, 0, st>>>(p, w.bstart, w.tstart, w.task_bucket, w.order, w.entries, d_points, (X*)w.partials);
     };
     bool launched = false;
+    // acc_variant: low 4 bits select the variant of the 8-limb base-field curves, bits 4..7 the one of the Fq2 curves
+    if constexpr (sizeof(typename C::F) == 64) acc_variant = (acc_variant >> 4) & 15;
+    else acc_variant &= 15;
     if constexpr (sizeof(typename C::F) == 32) {
         if (acc_variant == 1) { acc_args(k_msm_accumulate<C, 128, 5>, 128); launched = true; }        // ~100 regs, 20 warps/SM
         else if (acc_variant == 2) { acc_args(k_msm_accumulate<C, 128, 4>, 128); launched = true; }   // 128 regs, smaller blocks
