@@ -278,6 +278,15 @@ int enqueue_proof(ws_multi* m, const uint8_t* witness, const uint8_t* rs) {
     return WS_OK;
 }
 
+// waits for everything enqueued on the handle's streams and clears a pending CUDA error
+void drain(ws_multi* m) {
+    for (int g = 0; g < m->n; g++) {
+        cudaSetDevice(m->dev[g]);
+        cudaStreamSynchronize(m->st[g]);
+    }
+    cudaGetLastError();
+}
+
 int collect_proof(ws_multi* m, uint8_t* pi_a, uint8_t* pi_b, uint8_t* pi_c) {
     cudaSetDevice(m->dev[0]);
     uint8_t outb[384];
@@ -444,7 +453,10 @@ WS_API int ws_multi_bn128_groth16_prove_resident(ws_multi* m, const uint8_t* wit
     if (s) memcpy(rs + 32, s, 32);
     else if (getrandom(rs + 32, 32, 0) != 32) return m->fail(WS_E_ARG, "getrandom failed");
     int rc = enqueue_proof(m, witness, rs);
-    if (rc) return rc;
+    if (rc) {
+        drain(m);             // whatever part of the proof was enqueued must not overlap the next call's buffers
+        return rc;
+    }
     return collect_proof(m, pi_a, pi_b, pi_c);
 }
 
@@ -460,23 +472,19 @@ WS_API int ws_multi_bn128_groth16_prove(ws_multi* m, const uint8_t* witness, siz
     // same-length key cached: start the proof with it and fingerprint the caller's buffer meanwhile (see prover.cu)
     bool optimistic = m->key[0] && m->key_len == plen && wlen >= (size_t)m->n_vars * 32;
     if (optimistic && enqueue_proof(m, witness, rs) != WS_OK) {
-        for (int g = 0; g < m->n; g++) {
-            cudaSetDevice(m->dev[g]);
-            cudaStreamSynchronize(m->st[g]);
-        }
-        cudaGetLastError();
+        drain(m);
         optimistic = false;
     }
     unsigned long long fp = fingerprint(pkey, plen);
     if (optimistic && fp == m->key_fp) return collect_proof(m, pi_a, pi_b, pi_c);
-    for (int g = 0; g < m->n; g++) {
-        cudaSetDevice(m->dev[g]);
-        cudaStreamSynchronize(m->st[g]);
-    }
+    drain(m);
     int rc = load_keys(m, pkey, plen, fp);
     if (rc) return rc;
     if (wlen < (size_t)m->n_vars * 32) return m->fail(WS_E_ARG, "witness shorter than nVars * 32 bytes");
-    if ((rc = enqueue_proof(m, witness, rs))) return rc;
+    if ((rc = enqueue_proof(m, witness, rs))) {
+        drain(m);
+        return rc;
+    }
     return collect_proof(m, pi_a, pi_b, pi_c);
 }
 
