@@ -194,7 +194,10 @@ int ws_bn128_groth16_prove(ws_ctx* ctx, const uint8_t* witness, size_t witness_l
  * a coordinate >= q or a point off its curve also gives *valid = 0 (the reference does not check and computes an
  * unspecified value).
  * ws_bn128_pairing: out = e(P, Q) as 12 plain Fq values in the reference's ftm order (c0.a0, c0.a1, c0.a2, c1.a0,
- * c1.a1, c1.a2, each re|im) -- bit-identical to bn128_pairing + ftm_fromMontgomery.  WS_E_ARG for malformed points. */
+ * c1.a1, c1.a2, each re|im) -- bit-identical to bn128_pairing + ftm_fromMontgomery.  WS_E_ARG for malformed points.
+ * The Miller loop walks the twist point in affine coordinates, which has no formula for a vertical line (T = +-Q in an
+ * addition step): impossible for Q in the order-r subgroup, possible for a twist point outside it.  Such a step is
+ * detected (never fed into the shared batch inversion): ws_bn128_pairing returns WS_E_ARG, the verifier *valid = 0. */
 int ws_bn128_groth16_verify(const uint8_t vk_alfa_1[64], const uint8_t vk_beta_2[128], const uint8_t vk_gamma_2[128],
                             const uint8_t vk_delta_2[128], const uint8_t* ic, size_t n_ic, const uint8_t* inputs, size_t n_inputs,
                             const uint8_t pi_a[64], const uint8_t pi_b[128], const uint8_t pi_c[64], int* valid);
