@@ -33,7 +33,6 @@ import argparse
 import ctypes
 import json
 import os
-import re
 import subprocess
 import sys
 import threading
@@ -248,7 +247,8 @@ def cpu_prover_baseline(cores):
     k = min(CPU_SAMPLE_LOG2, PROVE_LOG2)
     scale = (1 << k) / float(1 << PROVE_LOG2)
     cp = CpuProver(k, cores)
-    cp.prove() if k <= 12 else None                  # tiny samples: touch the pool once
+    if k <= 12:
+        cp.prove()                                   # tiny samples: touch the pool once
     dt, _ = cp.prove()
     cp.close()
     k1 = min(13, k)
@@ -724,9 +724,6 @@ def section_msm(env, args, strong=True):
     for _ in range(W):
         step_dev()
     stage_ms = {}
-
-    def step_prof():
-        step_dev()
     evs = []
     env.barrier()
     for _ in range(K):
