@@ -144,3 +144,23 @@ def test_reference_verifier_on_shipped_proofs():
     pub2 = list(pub)
     pub2[3] = str(int(pub2[3]) + 1)
     assert not ref_wasm.groth16_verify(vk, pub2, json.load(open(os.path.join(EXAMPLE, "proof_good.json"))))
+
+
+@pytest.mark.parametrize("k", [10, 12])
+def test_big_integer_prover_equals_the_reference_on_the_bench_key_family(k):
+    """oracle/bn128.groth16_gen_proof (the big-integer restatement) against the proof the reference's own code computed
+    (tests/golden/make_golden_2p20.py <k>) for the bench's synthetic key family at 2^k constraints with (r, s) != 0 -- the
+    same generator, seed and (r, s) as the 2^20 headline key, whose golden proof pins the GPU prover
+    (tests/golden/synth_2p20.golden.json).  Also pins the key generator itself: its bytes hash to the stored sha256."""
+    import hashlib
+    import json
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import gen_synth_key
+    g = json.load(open(os.path.join(root, "tests", "golden", "synth_2p%d.golden.json" % k)))
+    pk, wit = gen_synth_key.make(1 << k, g["n_public"], 1 << k, seed=g["seed"])
+    assert hashlib.sha256(pk).hexdigest() == g["pkey_sha256"] and hashlib.sha256(wit).hexdigest() == g["witness_sha256"]
+    r, s = (int.from_bytes(bytes.fromhex(g[x]), "little") for x in ("r", "s"))
+    assert O.groth16_gen_proof(wit, pk, r, s) == g["proof"]
