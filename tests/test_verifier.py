@@ -45,6 +45,24 @@ def test_pairing_bilinear_and_degenerate():
     assert e1[:6] == e2[:6] and all((a + b) % Q == 0 for a, b in zip(e1[6:], e2[6:]))
 
 
+def test_pairing_of_twist_points_outside_the_subgroup_equals_the_reference():
+    """The reference never checks that a G2 input lies in the order-r subgroup and runs its projective Miller loop on any
+    point of the twist curve; the affine walk with a shared batch inversion here produces the same bytes for such points
+    (golden values from the reference image, tests/golden/make_pairing_nonsubgroup_golden.py), and a verification whose
+    pi_b is such a point is rejected like any other wrong proof -- the trusted pairs of the product are not disturbed."""
+    vec = json.load(open(os.path.join(GOLD, "pairing_vectors_nonsubgroup.json")))
+    assert len(vec) >= 4
+    for v in vec:
+        assert [str(x) for x in pairing(v["P"], v["Q"])] == v["e"]
+    g = json.load(open(os.path.join(GOLD, "example_bn128.verify.json")))
+    vk, good = g["verification_key"], g["cases"][0]
+    assert groth16Verify(vk, good["public"], good["proof"])
+    bad = copy.deepcopy(good["proof"])
+    bad["pi_b"] = [vec[0]["Q"][0], vec[0]["Q"][1], ["1", "0"]]
+    assert not groth16Verify(vk, good["public"], bad)
+    assert groth16Verify(vk, good["public"], good["proof"])          # and the next good proof still verifies
+
+
 def test_pairing_rejects_points_off_curve():
     vec = json.load(open(os.path.join(GOLD, "pairing_vectors.json")))
     v = vec[1]
