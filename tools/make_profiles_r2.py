@@ -53,7 +53,8 @@ def main():
             "* `r2_bench_n8_only_prove_*.json`, `r2_bench_n2_only_prove_*.json` -- A/B runs (`--only-prove`): proofs in flight, one NCCL communicator vs one per lane, uniform vs balanced split.",
             "* `r2_launches_prove_2p20.csv` -- `ncu --metrics gpu__time_duration.sum --clock-control none` launch list of `tools/run_prove_once.py 20 2` (cold-cache, serialised: compare SHARES).",
             "* `r2_ncu_accumulate_*.txt`, `r2_ncu_ntt_*.txt` -- `ncu --set full --clock-control none` summaries (tools/ncu_summary.py) of the accumulate kernels of one proof and of the NTT passes.",
-            "* `r2_ntt_variants*.txt` -- `tools/run_ntt_once.py` timings of the NTT pass variants (occupancy, warp-local exchange, radix 16).", ""]
+            "* `r2_ntt_variants*.txt` -- `tools/run_ntt_once.py` timings of the NTT pass variants (occupancy, warp-local exchange, radix 16).",
+            "* `r2_ptxas_resources.txt` -- registers / stack / spill bytes of every kernel (`-Xptxas -v`); `r2_tuning_hook_sweep.txt`, `r2_ws_multi_timings.txt` -- see the A/B table at the end.", ""]
     if b1:
         cb = b1.get("cpu_baseline") or {}
         out += ["## Headline: Groth16 proofs/s, BN128, 2^20 constraints (one B200; clocks %s)" % json.dumps(b1.get("clocks")), "",
