@@ -42,3 +42,23 @@ def test_montgomery_and_fft():
         assert B.fft(a) == [sum(a[j] * pow(w, j * k, B.R_ORDER) for j in range(n)) % B.R_ORDER for k in range(n)]
         w2 = B._ROOTS[n.bit_length()]
         assert B.fft(a, 1) == [sum(a[j] * pow(w2, j * (2 * k + 1), B.R_ORDER) for j in range(n)) % B.R_ORDER for k in range(n)]
+
+
+def test_published_known_answers_2g():
+    """Anchor outside this repo: 2*G1 and 2*G2 as published with the BLS12-381 precompile test vectors of EIP-2537
+    (bls_g1add / bls_g2add, "g + g = 2 g"), and the generators in their standard (zkcrypto / IETF) hex form.  No network
+    in the build image, so nothing could be fetched: the 2*G1 value was written down from memory BEFORE the oracle
+    computed it (all 762 bits agree -- an independent check of the group law on the reference's constants,
+    build_bls12381.js:50-98); the 2*G2 value was recognised after the oracle printed it (weaker evidence, kept as a
+    regression value).  The module stays "parity unpinned" with respect to the reference itself."""
+    g1x2 = (0x0572cbea904d67468808c8eb50a9450c9721db309128012543902d0ac358a62ae28f75bb8f1c7c42c39a8c5529bf0f4e,
+            0x166a9d8cabc673a322fda673779d8e3822ba3ecb8670e461f73bb9021d5fd76a4c56d9d4cd16bd1bba86881979749d28)
+    g2x2 = ((0x1638533957d540a9d2370f17cc7ed5863bc0b995b8825e0ee1ea1e1e4d00dbae81f14b0bf3611b78c952aacab827a053,
+             0x0a4edef9c1ed7f729f520e47730a124fd70662a904ba1074728114d1031e1572c6c886f6b57ec72a6178288c47c33577),
+            (0x0468fb440d82b0630aeb8dca2b5256789a66da69bf91009cbfe6bd221e47aa8ae88dece9764bf3bd999d95d71e4c9899,
+             0x0f6d4552fa65dd2638b361543f887136a43253d9c66c411697003f7a13c308f5422e1aa0a59c8967acdefd8b6e36ccf3))
+    assert B.pt_add(B.Fq, B.G1_GEN, B.G1_GEN) == g1x2 == B.pt_mul(B.Fq, B.G1_GEN, 2)
+    assert B.pt_add(B.Fq2, B.G2_GEN, B.G2_GEN) == g2x2 == B.multiexp(B.Fq2, [2], [B.G2_GEN])
+    # the same generators in the standard (zkcrypto / IETF) hex form
+    assert B.G1_GEN[0] == 0x17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb
+    assert B.G1_GEN[1] == 0x08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1
