@@ -56,6 +56,9 @@ enum {
  * each, one CUDA context on `device` with a growable HBM workspace.                           */
 int ws_create(int device, ws_ctx** out);
 void ws_destroy(ws_ctx* ctx);                       /* Bn128.terminate(), src/bn128.js:562-566 */
+/* Text of the CALLING THREAD's last failed call on this context (valid until that thread's next failure); a thread that
+ * never failed on it reads the context's most recent failure.  So several threads sharing a context each see their own
+ * message, whatever the others did in between.  ws_multi_last_error behaves the same way. */
 const char* ws_last_error(const ws_ctx* ctx);
 const char* ws_version(void);
 

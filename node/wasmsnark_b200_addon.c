@@ -2,9 +2,10 @@
  *
  * This is the binding a wasmsnark maintainer adds to make `groth16GenProof(witness, provingKey)`
  * (main_bn128.js:27-41; README name genZKSnarkProof) run on the GPU: no WASM, no workers; the JS side
- * (node/index.js) keeps the reference's surface and result formatting.  It cannot be compiled in the build
+ * (node/index.js) keeps the reference's surface and result formatting.  It cannot be built for Node in the build
  * image (no node_api.h, no node); it is written against the stable N-API (v6) and the C ABI in
- * include/wasmsnark_b200.h only.  Build where Node exists:
+ * include/wasmsnark_b200.h only, and is linked and executed there against a mock N-API runtime
+ * (tests/host/napi_mock, tests/test_node_addon_mock.py).  Build where Node exists (or node-gyp: node/binding.gyp):
  *     cc -shared -fPIC -I$(node -p "require('node:path').dirname(process.execPath)+'/../include/node'") \
  *        -I../include wasmsnark_b200_addon.c -L../wasmsnark_b200 -lwasmsnark_b200 -o wasmsnark_b200.node
  *
@@ -17,6 +18,7 @@
  *   create(device, ngpus) -> external handle                buildBn128()            src/bn128.js:173-265
  *        ngpus > 1 (or 0 = all): proofs and multiexps use every GPU of the box (ws_multi_*, the worker pool = the GPUs)
  *   destroy(handle)                                         Bn128.terminate()       src/bn128.js:562-566
+ *        frees the GPU state at once (after the proofs in flight, if any); later calls on the handle throw
  *   prove(handle, witness, pkey, r|null, s|null, cb)        Bn128.groth16GenProof   src/bn128.js:580-720
  *        cb(err, {pi_a: ArrayBuffer(96), pi_b: ArrayBuffer(192), pi_c: ArrayBuffer(96)})   (async work)
  *   g1Multiexp(handle, scalars, points) -> ArrayBuffer(96)  Bn128.g1_multiexp       src/bn128.js:353-383
@@ -71,18 +73,27 @@ static napi_value throw_ws(napi_env env, ws_ctx* c, int rc) {
     return NULL;
 }
 
-/* one handle = one single-GPU context (always) + optionally the multi-GPU handle the heavy calls go through */
+/* one handle = one single-GPU context (always) + optionally the multi-GPU handle the heavy calls go through.
+ * `inflight` / `closing` are touched on the JS thread only (Prove, prove_complete, Destroy all run there). */
 typedef struct {
     ws_ctx* c;
     ws_multi* m;
+    int inflight; /* proofs queued or running on worker threads */
+    int closing;  /* destroy() was called while proofs were in flight: the last one to complete releases the GPU state */
 } handle_t;
+
+static void release_gpu_state(handle_t* h) {
+    if (h->m) ws_multi_destroy(h->m);
+    if (h->c) ws_destroy(h->c);
+    h->m = NULL;
+    h->c = NULL;
+}
 
 static void finalize_ctx(napi_env env, void* data, void* hint) {
     (void)env;
     (void)hint;
     handle_t* h = (handle_t*)data;
-    if (h->m) ws_multi_destroy(h->m);
-    ws_destroy(h->c);
+    release_gpu_state(h);
     free(h);
 }
 
@@ -111,13 +122,14 @@ static handle_t* handle_arg(napi_env env, napi_value v) {
 }
 static ws_ctx* ctx_arg(napi_env env, napi_value v) {
     handle_t* h = handle_arg(env, v);
-    return h ? h->c : NULL;
+    return h && !h->closing ? h->c : NULL;
 }
 
 /* ---- prove: blocking C call wrapped in napi_async_work (the reference resolves a Promise from its workers) */
 typedef struct {
     napi_async_work work;
-    napi_ref cb, wit_ref, key_ref;
+    napi_ref cb, wit_ref, key_ref, handle_ref;
+    handle_t* handle;
     ws_ctx* ctx;
     ws_multi* multi;
     uint8_t *wit, *key;
@@ -160,10 +172,12 @@ static void prove_complete(napi_env env, napi_status status, void* data) {
         napi_set_named_property(env, obj, "pi_c", make_ab(env, j->pi_c, 96));
         argv[1] = obj;
     }
+    if (--j->handle->inflight == 0 && j->handle->closing) release_gpu_state(j->handle);   /* terminate() during a proof */
     napi_call_function(env, global, cb, 2, argv, &result);
     napi_delete_reference(env, j->cb);
     napi_delete_reference(env, j->wit_ref);
     napi_delete_reference(env, j->key_ref);
+    napi_delete_reference(env, j->handle_ref);
     napi_delete_async_work(env, j->work);
     free(j);
 }
@@ -178,24 +192,41 @@ static napi_value Prove(napi_env env, napi_callback_info info) {
     }
     prove_job* j = (prove_job*)calloc(1, sizeof *j);
     handle_t* hd = handle_arg(env, argv[0]);
-    j->ctx = hd ? hd->c : NULL;
-    j->multi = hd ? hd->m : NULL;
+    if (!j || !hd || !hd->c || hd->closing) {
+        free(j);
+        napi_throw_type_error(env, NULL, "prove: not a live handle (terminated, or not made by create())");
+        return NULL;
+    }
+    j->handle = hd;
+    j->ctx = hd->c;
+    j->multi = hd->m;
     uint8_t* p;
     size_t l;
-    if (!j->ctx || !get_buffer(env, argv[1], &j->wit, &j->wit_len) || !get_buffer(env, argv[2], &j->key, &j->key_len)) {
+    if (!get_buffer(env, argv[1], &j->wit, &j->wit_len) || !get_buffer(env, argv[2], &j->key, &j->key_len)) {
         free(j);
         napi_throw_type_error(env, NULL, "witness and provingKey must be ArrayBuffers");
         return NULL;
     }
     if (get_buffer(env, argv[3], &p, &l) && l >= 32) { memcpy(j->r, p, 32); j->have_r = 1; }
     if (get_buffer(env, argv[4], &p, &l) && l >= 32) { memcpy(j->s, p, 32); j->have_s = 1; }
-    /* keep the input buffers alive until the work completes */
+    /* keep the input buffers (and the handle) alive until the work completes */
+    napi_create_reference(env, argv[0], 1, &j->handle_ref);
     napi_create_reference(env, argv[1], 1, &j->wit_ref);
     napi_create_reference(env, argv[2], 1, &j->key_ref);
     napi_create_reference(env, argv[5], 1, &j->cb);
     napi_create_string_utf8(env, "wasmsnark_b200.prove", NAPI_AUTO_LENGTH, &name);
-    CHECK(napi_create_async_work(env, NULL, name, prove_execute, prove_complete, j, &j->work));
-    CHECK(napi_queue_async_work(env, j->work));
+    napi_status st = napi_create_async_work(env, NULL, name, prove_execute, prove_complete, j, &j->work);
+    if (st == napi_ok && (st = napi_queue_async_work(env, j->work)) != napi_ok) napi_delete_async_work(env, j->work);
+    if (st != napi_ok) {
+        napi_delete_reference(env, j->cb);
+        napi_delete_reference(env, j->wit_ref);
+        napi_delete_reference(env, j->key_ref);
+        napi_delete_reference(env, j->handle_ref);
+        free(j);
+        napi_throw_error(env, NULL, "could not queue the proof (napi_create_async_work / napi_queue_async_work)");
+        return NULL;
+    }
+    hd->inflight++;
     return NULL;
 }
 
@@ -205,7 +236,7 @@ static napi_value Multiexp(napi_env env, napi_callback_info info, int g2) {
     napi_value argv[3];
     CHECK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
     handle_t* hd = handle_arg(env, argv[0]);
-    ws_ctx* c = hd ? hd->c : NULL;
+    ws_ctx* c = hd && !hd->closing ? hd->c : NULL;
     uint8_t *sc, *pt;
     size_t sl, pl;
     if (!c || !get_buffer(env, argv[1], &sc, &sl) || !get_buffer(env, argv[2], &pt, &pl) || sl % 32 || pl < (sl / 32) * (g2 ? 128 : 64)) {
@@ -293,10 +324,20 @@ static napi_value Verify(napi_env env, napi_callback_info info) {
     return res;
 }
 
+/* destroy(handle) = Bn128.terminate(): releases the contexts -- and with them the resident key, its window tables and all
+ * workspaces, several GB of HBM -- NOW rather than at some later garbage collection; with proofs still in flight the last
+ * one to complete does it.  The handle is dead afterwards (every call on it throws). */
 static napi_value Destroy(napi_env env, napi_callback_info info) {
-    /* the external's finalizer destroys the context; nothing to do eagerly */
-    (void)env;
-    (void)info;
+    size_t argc = 1;
+    napi_value argv[1];
+    CHECK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+    handle_t* h = argc >= 1 ? handle_arg(env, argv[0]) : NULL;
+    if (!h) {
+        napi_throw_type_error(env, NULL, "destroy(handle)");
+        return NULL;
+    }
+    if (h->inflight) h->closing = 1;
+    else release_gpu_state(h);
     return NULL;
 }
 

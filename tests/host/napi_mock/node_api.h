@@ -1,6 +1,8 @@
-/* Minimal declaration-only stand-in for Node's <node_api.h> (N-API v6 subset), so that node/wasmsnark_b200_addon.c
- * can be type-checked in an image without Node.js (tests/test_abi.py).  Signatures follow the public N-API
- * documentation; nothing here is linked or executed. */
+/* Stand-in for Node's <node_api.h> (the N-API v6 subset node/wasmsnark_b200_addon.c uses) for an image without Node.js and
+ * without network access to fetch the real header.  Signatures, enum values and the module-initialiser name follow the
+ * public N-API documentation.  tests/test_abi.py type-checks the addon against it; tests/host/napi_mock/napi_mock.c
+ * implements these functions over a toy value model so that the addon can be LINKED AND EXECUTED by
+ * tests/test_node_addon_mock.py (a mock runtime, not Node: it proves the binding's own logic, not V8 behaviour). */
 #ifndef WS_TEST_NODE_API_STUB_H
 #define WS_TEST_NODE_API_STUB_H
 #include <stdbool.h>
@@ -12,7 +14,12 @@ typedef struct napi_value__* napi_value;
 typedef struct napi_ref__* napi_ref;
 typedef struct napi_callback_info__* napi_callback_info;
 typedef struct napi_async_work__* napi_async_work;
-typedef enum { napi_ok, napi_invalid_arg, napi_object_expected, napi_string_expected, napi_generic_failure = 9, napi_cancelled = 11 } napi_status;
+typedef enum {
+    napi_ok, napi_invalid_arg, napi_object_expected, napi_string_expected, napi_name_expected, napi_function_expected, napi_number_expected,
+    napi_boolean_expected, napi_array_expected, napi_generic_failure, napi_pending_exception, napi_cancelled, napi_escape_called_twice,
+    napi_handle_scope_mismatch, napi_callback_scope_mismatch, napi_queue_full, napi_closing, napi_bigint_expected, napi_date_expected,
+    napi_arraybuffer_expected, napi_detachable_arraybuffer_expected, napi_would_deadlock
+} napi_status;
 typedef enum { napi_default = 0, napi_writable = 1, napi_enumerable = 2, napi_configurable = 4, napi_static = 1024 } napi_property_attributes;
 typedef enum {
     napi_int8_array, napi_uint8_array, napi_uint8_clamped_array, napi_int16_array, napi_uint16_array, napi_int32_array, napi_uint32_array,
@@ -32,7 +39,8 @@ typedef struct {
 } napi_property_descriptor;
 
 #define NAPI_AUTO_LENGTH SIZE_MAX
-#define NAPI_MODULE_INIT() napi_value napi_module_init_stub(napi_env env, napi_value exports)
+/* the real macro also registers the module with node; the entry point it defines has this name and signature */
+#define NAPI_MODULE_INIT() __attribute__((visibility("default"))) napi_value napi_register_module_v1(napi_env env, napi_value exports)
 
 napi_status napi_get_cb_info(napi_env env, napi_callback_info cbinfo, size_t* argc, napi_value* argv, napi_value* this_arg, void** data);
 napi_status napi_throw_error(napi_env env, const char* code, const char* msg);

@@ -64,6 +64,6 @@ def test_node_addon_type_checks_against_the_header():
     import subprocess
     cc = shutil.which("gcc") or shutil.which("cc")
     assert cc, "no C compiler"
-    r = subprocess.run([cc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I" + os.path.join(ROOT, "tests", "host", "napi_stub"),
+    r = subprocess.run([cc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I" + os.path.join(ROOT, "tests", "host", "napi_mock"),
                         "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "node", "wasmsnark_b200_addon.c")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr

@@ -430,6 +430,33 @@ def test_context_is_thread_safe(bn):
     assert not errors, errors
 
 
+def test_last_error_text_belongs_to_the_failing_thread(bn):
+    """Two host threads fail differently on ONE context, and only then ask for the text: each reads its own message
+    (ws_last_error keeps a per-thread copy; with a single per-context string the later failure would win for both --
+    the Node addon reads the text on a libuv worker thread right after its blocking call returned)."""
+    import ctypes
+    import threading
+    lib, h = bn.lib, bn.ctx.h
+    both_failed = threading.Barrier(2)
+    got = {}
+
+    def wrong_size():
+        buf = ctypes.create_string_buffer(96)
+        rc = lib.ws_bn128_fr_fft(h, ctypes.cast(buf, ctypes.c_void_p), 3, 0)
+        both_failed.wait(timeout=60)
+        got["size"] = (rc, lib.ws_last_error(h).decode())
+
+    def null_buffer():
+        rc = lib.ws_bn128_fr_ifft(h, None, 4, 0)
+        both_failed.wait(timeout=60)
+        got["null"] = (rc, lib.ws_last_error(h).decode())
+    th = [threading.Thread(target=f) for f in (wrong_size, null_buffer)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert got["size"][0] != 0 and "power of two" in got["size"][1], got
+    assert got["null"][0] != 0 and "null buffer" in got["null"][1], got
+
+
 def test_stateless_call_from_pageable_memory_large_witness(bn):
     """The pinned staging ring (host_io.cuh) is only used above 1 MiB: a 2^15-signal witness from ordinary bytes objects
     through the stateless call, twice (second call: cached key, fingerprint overlapped), equals the resident-key proof."""

@@ -67,10 +67,16 @@ WS_API void ws_destroy(ws_ctx* c) {
         cudaEventDestroy(c->h_done);
     }
     cudaStreamDestroy(c->stream);
+    ws::tls_error_forget(c);
     delete c;
 }
 
-WS_API const char* ws_last_error(const ws_ctx* c) { return c ? c->err.c_str() : "null ctx"; }
+// the calling thread's own last failure on this handle if it had one, else the handle's most recent failure
+WS_API const char* ws_last_error(const ws_ctx* c) {
+    if (!c) return "null ctx";
+    const ws::TlsError& e = ws::tls_error();
+    return e.owner == c ? e.text.c_str() : c->err.c_str();
+}
 
 WS_API unsigned long long ws_kernel_launches(const ws_ctx* c) { return c ? c->launches : 0; }
 

@@ -6,6 +6,7 @@
 
 #include "../../include/wasmsnark_b200.h"
 #include "host_io.cuh"
+#include "tls_error.cuh"
 
 namespace ws {
 
@@ -128,11 +129,13 @@ struct ws_ctx {
     }
     int fail(int code, const char* msg) {
         err = msg;
+        ws::tls_error_set(this, err);
         return code;
     }
     int fail_cuda(const char* where) {
         cudaError_t e = cudaGetLastError();
         err = std::string(where) + ": " + cudaGetErrorString(e);
+        ws::tls_error_set(this, err);
         return WS_E_CUDA;
     }
 };

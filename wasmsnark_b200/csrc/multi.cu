@@ -21,6 +21,7 @@
 
 #include "../../include/wasmsnark_b200.h"
 #include "host_io.cuh"
+#include "tls_error.cuh"
 
 #define WS_API __attribute__((visibility("default")))
 
@@ -90,10 +91,12 @@ struct ws_multi {
     std::string err;
     int fail(int code, const std::string& m) {
         err = m;
+        ws::tls_error_set(this, err);      // see ctx.cuh: the failing thread reads its own message back
         return code;
     }
     int fail_ctx(int g, int code) {
         err = std::string("gpu ") + std::to_string(dev[g]) + ": " + ws_last_error(ctx[g]);
+        ws::tls_error_set(this, err);
         return code;
     }
 };
@@ -183,12 +186,20 @@ int load_keys(ws_multi* m, const uint8_t* pkey, size_t plen, unsigned long long 
         if (wb > m->wit_cap || !m->d_wit[g]) {
             cudaFree(m->d_wit[g]);
             m->d_wit[g] = nullptr;
-            if (cudaMalloc(&m->d_wit[g], wb + 256) != cudaSuccess) return m->fail(WS_E_CUDA, "witness buffer");
+            if (cudaMalloc(&m->d_wit[g], wb + 256) != cudaSuccess) {
+                m->d_wit[g] = nullptr;
+                free_keys(m);          // no resident key without its buffers (prove_resident checks key[0] only)
+                return m->fail(WS_E_CUDA, "witness buffer");
+            }
         }
         if (hb > m->h_cap || !m->d_h[g]) {
             cudaFree(m->d_h[g]);
             m->d_h[g] = nullptr;
-            if (cudaMalloc(&m->d_h[g], hb + 256) != cudaSuccess) return m->fail(WS_E_CUDA, "h buffer");
+            if (cudaMalloc(&m->d_h[g], hb + 256) != cudaSuccess) {
+                m->d_h[g] = nullptr;
+                free_keys(m);
+                return m->fail(WS_E_CUDA, "h buffer");
+            }
         }
     }
     m->wit_cap = std::max(m->wit_cap, wb);
@@ -273,8 +284,8 @@ int enqueue_proof(ws_multi* m, const uint8_t* witness, const uint8_t* rs) {
     for (int g = 1; g < n; g++) cudaStreamWaitEvent(m->st[0], m->ev_part[g], 0);
     rc = ws_bn128_groth16_finish_dev(m->ctx[0], m->key[0], m->d_small[0] + OFF_ALL, n, m->d_small[0] + OFF_RS, m->d_small[0] + OFF_PROOF, m->st[0]);
     if (rc) return m->fail_ctx(0, rc);
-    // the next proof's owner must not overwrite d_h / d_wit before this proof's consumers are done: every GPU's stream
-    // waits for the finish (cheap: one event) -- proofs of one handle are sequential anyway (blocking call)
+    // the next proof's owner must not overwrite d_h / d_wit before this proof's consumers are done: the callers
+    // (collect_proof, or drain after a failed enqueue) synchronise every GPU's stream before the handle is used again
     return WS_OK;
 }
 
@@ -403,6 +414,7 @@ WS_API void ws_multi_destroy(ws_multi* m) {
         if (m->st[g]) cudaStreamDestroy(m->st[g]);
         if (m->ctx[g]) ws_destroy(m->ctx[g]);
     }
+    ws::tls_error_forget(m);
     delete m;
 }
 
@@ -424,7 +436,11 @@ WS_API int ws_multi_set_split(ws_multi* m, int mode) {
     m->balanced_from = mode ? 2 : 1 << 30;
     return WS_OK;
 }
-WS_API const char* ws_multi_last_error(const ws_multi* m) { return m ? m->err.c_str() : "null handle"; }
+WS_API const char* ws_multi_last_error(const ws_multi* m) {
+    if (!m) return "null handle";
+    const ws::TlsError& e = ws::tls_error();
+    return e.owner == m ? e.text.c_str() : m->err.c_str();
+}
 
 WS_API int ws_multi_bn128_g1_multiexp(ws_multi* m, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t out[96]) { return multiexp<1>(m, scalars, points, n, out); }
 WS_API int ws_multi_bn128_g2_multiexp(ws_multi* m, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t out[192]) { return multiexp<2>(m, scalars, points, n, out); }
