@@ -12,6 +12,35 @@ if ROOT not in sys.path:
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     config.addinivalue_line("markers", "slow: takes more than ~30 s on CPU")
+    if os.environ.get("WS_TEST_EMULATED"):
+        # tests/test_emulated_library.py re-runs a selection of the GPU tests in a child pytest with the library's kernels
+        # EXECUTED ON THE CPU (tests/host/cuemu: the same .cu sources compiled by g++ against a kernel emulator).  Test
+        # scaffolding: only this hook ever hands the package that library.
+        sys.path.insert(0, os.path.join(ROOT, "tests", "host", "cuemu"))
+        import build_emu
+        from wasmsnark_b200 import _lib
+        _lib.load_library(path=build_emu.build())
+        _emulated_torch_device()
+
+
+def _emulated_torch_device():
+    """Under emulation "device memory" is host memory: the tests' torch.cuda buffers become CPU tensors (their data_ptr()
+    is what the emulated library dereferences)."""
+    import torch
+
+    def on_cpu(fn):
+        def wrapper(*a, **k):
+            if str(k.get("device", "")).startswith("cuda"):
+                k["device"] = "cpu"
+            return fn(*a, **k)
+        return wrapper
+    for name in ("zeros", "empty", "ones", "full", "tensor", "frombuffer", "arange"):
+        setattr(torch, name, on_cpu(getattr(torch, name)))
+    torch.Tensor.cuda = lambda self, *a, **k: self.clone()
+    torch.cuda.synchronize = lambda *a, **k: None
+    torch.cuda.is_available = lambda: True
+    torch.cuda.device_count = lambda: max(1, int(os.environ.get("CUEMU_DEVICES", "1")))
+    torch.cuda.set_device = lambda *a, **k: None
 
 
 @pytest.fixture(scope="session")

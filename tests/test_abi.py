@@ -57,6 +57,20 @@ def test_product_package_does_not_import_oracle():
                 assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src.replace("the oracle/", ""), f
 
 
+def test_product_never_reaches_for_the_cpu_kernel_emulator():
+    """tests/host/cuemu (the kernels executed on the CPU, for tests) is scaffolding: neither the package, the bench, the
+    driver hooks nor the Node binding may name it or the library built from it -- only tests/ does."""
+    banned = ("cuemu", "libwasmsnark_b200_emu", "WS_TEST_EMULATED")
+    files = [os.path.join(ROOT, f) for f in ("bench.py", "__graft_entry__.py")]
+    for top in ("wasmsnark_b200", "node", "include", "tools", "oracle"):
+        for dirpath, dirs, names in os.walk(os.path.join(ROOT, top)):
+            dirs[:] = [d for d in dirs if d not in ("_obj", "_ref", "__pycache__")]
+            files += [os.path.join(dirpath, f) for f in names if f.endswith((".py", ".cu", ".cuh", ".h", ".c", ".js", ".gyp", ".json"))]
+    for path in files:
+        src = open(path, errors="ignore").read()
+        assert not any(b in src for b in banned), path
+
+
 def test_node_addon_type_checks_against_the_header():
     """node/wasmsnark_b200_addon.c (the N-API binding of INTEGRATION.md) cannot be built here -- no Node.js -- but
     it must at least compile against include/wasmsnark_b200.h and a declaration-only N-API stub."""

@@ -430,6 +430,42 @@ def test_context_is_thread_safe(bn):
     assert not errors, errors
 
 
+@pytest.mark.parametrize("case", ["C empty", "one signal", "domain 1", "domain 2", "nVars < 32", "all infinity", "no infinity", "witness 0",
+                                  "witness 2^256-1", "no coefficients", "dense coefficients"])
+def test_degenerate_keys_and_witnesses(bn, case):
+    """Corners the example key never reaches: an empty C section (nVars = nPublic + 1), one-signal keys, one- and two-point
+    domains (transforms of size 1, 2, 4), sections that are all infinity or never infinity, witnesses of all zeros / all
+    2^256 - 1 (unreduced), polynomial sections without any or with many coefficients -- stateless and resident-key proofs
+    against the big-integer restatement of src/bn128.js:580-720 (oracle/bn128.py, itself pinned on the reference's proofs)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tools"))
+    import gen_synth_key
+    nv, npub, dom, kw, wit_of = {
+        "C empty": (9, 8, 8, {}, None),
+        "one signal": (1, 0, 1, {}, None),
+        "domain 1": (2, 1, 1, {}, None),
+        "domain 2": (5, 1, 2, {}, None),
+        "nVars < 32": (3, 1, 4, {}, None),
+        "all infinity": (200, 5, 128, {"inf_share": 1.0}, None),
+        "no infinity": (200, 5, 128, {"inf_share": 0.0}, None),
+        "witness 0": (200, 5, 128, {}, lambda w: bytes(len(w))),
+        "witness 2^256-1": (200, 5, 128, {}, lambda w: b"\xff" * len(w)),
+        "no coefficients": (100, 5, 64, {"coef_density": (0.0, 0.0)}, None),
+        "dense coefficients": (100, 5, 64, {"coef_density": (6.0, 9.0)}, None),
+    }[case]
+    pk, wit = gen_synth_key.make(nv, npub, dom, seed=3, **kw)
+    if wit_of:
+        wit = wit_of(wit)
+    r, s = bytes(range(7, 39)), bytes(range(100, 132))
+    want = O.groth16_gen_proof(wit, pk, int.from_bytes(r, "little"), int.from_bytes(s, "little"))
+    assert bn.groth16GenProof(wit, pk, r=r, s=s) == want
+    key = bn.load_proving_key(pk)
+    try:
+        assert bn.groth16GenProof(wit, key, r=r, s=s) == want
+    finally:
+        key.free()
+
+
 def test_last_error_text_belongs_to_the_failing_thread(bn):
     """Two host threads fail differently on ONE context, and only then ask for the text: each reads its own message
     (ws_last_error keeps a per-thread copy; with a single per-context string the later failure would win for both --

@@ -34,12 +34,14 @@ def _build():
     _lib.load_library()                     # raises with the build hint when the product library is missing
     srcs = [os.path.join(ROOT, "node", "wasmsnark_b200_addon.c"), os.path.join(MOCK, "napi_mock.c")]
     deps = srcs + [os.path.join(MOCK, "node_api.h"), os.path.join(ROOT, "include", "wasmsnark_b200.h")]
-    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+    so, link = SO, ["-L" + os.path.join(ROOT, "wasmsnark_b200"), "-lwasmsnark_b200", "-Wl,-rpath,$ORIGIN/../../wasmsnark_b200"]
+    if os.environ.get("WS_TEST_EMULATED"):  # tests/test_emulated_library.py: the same addon over the CPU-emulated kernels
+        so, link = SO.replace(".so", "_emu.so"), ["-L" + os.path.join(ROOT, "tests", "host"), "-lwasmsnark_b200_emu", "-Wl,-rpath,$ORIGIN"]
+        deps.append(os.path.join(ROOT, "tests", "host", "libwasmsnark_b200_emu.so"))
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["gcc", "-std=gnu11", "-O1", "-g", "-Wall", "-Wextra", "-Werror", "-fPIC", "-shared", "-fvisibility=hidden",
-                               "-I" + MOCK, "-I" + os.path.join(ROOT, "include")] + srcs +
-                              ["-L" + os.path.join(ROOT, "wasmsnark_b200"), "-lwasmsnark_b200", "-Wl,-rpath,$ORIGIN/../../wasmsnark_b200",
-                               "-lpthread", "-o", SO])
-    return ctypes.CDLL(SO)
+                               "-I" + MOCK, "-I" + os.path.join(ROOT, "include")] + srcs + link + ["-lpthread", "-o", so])
+    return ctypes.CDLL(so)
 
 
 class Js:

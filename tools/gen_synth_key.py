@@ -32,14 +32,14 @@ def _b32(x):
 def make(n_vars, n_public, domain, seed=0xB204, inf_share=0.3, coef_density=(1.5, 2.1)):
     import util
     rnd = random.Random(seed)
-    npts = max(n_vars, domain) + 4
+    npts = max(n_vars, domain, 4) + 4          # the five fixed points take entries 5..7 (tiny keys included)
     aff, P0, D = util.arith_points(O.Fq, O.G1_GEN, npts, seed ^ 0x55)
     g1 = [_b32(O.to_mont(x)) + _b32(O.to_mont(y)) for x, y in aff]
     xi = (rnd.randrange(1, O.Q), rnd.randrange(1, O.Q))
     xi2 = O.Fq2.sqr(xi)
     xi3 = O.Fq2.mul(xi2, xi)
     g2 = []
-    for x, y in aff[:n_vars]:
+    for x, y in aff[:max(n_vars, 7)]:
         X = (xi2[0] * x % O.Q, xi2[1] * x % O.Q)
         Y = (xi3[0] * y % O.Q, xi3[1] * y % O.Q)
         g2.append(b"".join(_b32(O.to_mont(c)) for c in (X[0], X[1], Y[0], Y[1])))
@@ -58,7 +58,7 @@ def make(n_vars, n_public, domain, seed=0xB204, inf_share=0.3, coef_density=(1.5
                 nc = min(domain, heavy)
                 idxs = sorted(rnd.sample(range(domain), nc))
             else:
-                nc = min(domain, max(0, int(rnd.expovariate(1.0 / density)))) if rnd.random() < 0.7 else 0
+                nc = min(domain, max(0, int(rnd.expovariate(1.0 / density)) if density > 0 else 0)) if rnd.random() < 0.7 else 0
                 idxs = sorted(rnd.sample(range(domain), nc))
             out.append(struct.pack("<I", nc))
             for idx in idxs:
