@@ -54,12 +54,13 @@ OTHER_CURVES = [
 MULTI = ["tests/test_gpu_prover.py::test_multi_handle_on_the_visible_gpus"]
 
 
-GROUPS = {"field_msm": (FIELD_MSM, 1), "prover": (PROVER, 1), "other_curves": (OTHER_CURVES, 1), "multi4": (MULTI, 4)}
+MULTI_SPARSE = ["tests/test_gpu_prover.py::test_multi_handle_with_more_gpus_than_points"]
+GROUPS = {"field_msm": (FIELD_MSM, 1), "prover": (PROVER, 1), "other_curves": (OTHER_CURVES, 1), "multi4": (MULTI, 4), "multi8": (MULTI_SPARSE, 8)}
 
 
 @pytest.fixture(scope="module")
 def children():
-    """the four child pytest runs, started together (each is single-threaded; the emulated build is made once, first)"""
+    """the child pytest runs, started together (each is single-threaded; the emulated build is made once, first)"""
     sys.path.insert(0, os.path.join(ROOT, "tests", "host", "cuemu"))
     import build_emu
     build_emu.build()
@@ -97,3 +98,7 @@ def test_multi_gpu_handle_with_four_pretend_devices(children):
     """ws_multi_* (csrc/multi.cu) over four pretend GPUs: key shards per device, the rotating H owner, peer copies of the h
     slices and of the 768-byte records, assembly on device 0 -- bit-identical to the single-context proof."""
     assert "1 passed" in finished(children, "multi4")
+
+
+def test_multi_gpu_handle_with_more_pretend_devices_than_points(children):
+    assert "1 passed" in finished(children, "multi8")

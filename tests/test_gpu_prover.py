@@ -553,6 +553,36 @@ def test_multi_handle_on_the_visible_gpus():
         bn1.terminate()
 
 
+def test_multi_handle_with_more_gpus_than_points():
+    """Keys so small that some GPUs hold EMPTY ranges of every section (nVars 5, domain 2 over up to 8 devices; uniform and
+    balanced split), every device taking its turn as H owner, and multiexps of 0 and 3 pairs: the empty shards contribute
+    the point at infinity.  On a one-GPU box this is the n = 1 path; the CPU suite runs it over eight pretend devices
+    (tests/test_emulated_library.py)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tools"))
+    import gen_synth_key
+    import util
+    from wasmsnark_b200 import build_bn128, build_bn128_multi
+    r, s = bytes(range(7, 39)), bytes(range(100, 132))
+    ri, si = int.from_bytes(r, "little"), int.from_bytes(s, "little")
+    m, bn1 = build_bn128_multi(0), build_bn128(0)
+    try:
+        for mode, (nv, npub, dom, seed) in ((0, (5, 1, 2, 3)), (1, (6, 1, 4, 4))):
+            m.lib.ws_multi_set_split(m.h, mode)
+            pk, wit = gen_synth_key.make(nv, npub, dom, seed=seed)
+            want = O.groth16_gen_proof(wit, pk, ri, si)
+            for _ in range(m.ngpus + 1):
+                assert m.groth16GenProof(wit, pk, r=r, s=s) == want
+        aff, P0, D = util.arith_points(O.Fq, O.G1_GEN, 3, 9)
+        sc = [5, (1 << 255) + 7, 11]
+        got = bn1.g1_affine(m.g1_multiexp(b"".join(util.b32(v) for v in sc), util.g1_points_bytes(aff)))
+        assert util.g1_result_tuple(got) == util.closed_form_sum(sc, P0, D)
+        assert util.g1_result_tuple(bn1.g1_affine(m.g1_multiexp(b"", b"")))[2] == 0
+    finally:
+        m.terminate()
+        bn1.terminate()
+
+
 def test_golden_proof_2p20_constraints(bn):
     """BASELINE's headline config: the 2^20-constraint synthetic key (tools/gen_synth_key.make(2^20, 58, 2^20, seed 0xB204))
     with the bench's (r, s) against the proof the REFERENCE's own code computed for it (tests/golden/make_golden_2p20.py,
