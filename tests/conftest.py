@@ -19,7 +19,8 @@ def pytest_configure(config):
         sys.path.insert(0, os.path.join(ROOT, "tests", "host", "cuemu"))
         import build_emu
         from wasmsnark_b200 import _lib
-        _lib.load_library(path=build_emu.build())
+        # WS_TEST_EMULATED=asan: the AddressSanitizer build (run python under LD_PRELOAD=$(gcc -print-file-name=libasan.so))
+        _lib.load_library(path=build_emu.build(asan=os.environ["WS_TEST_EMULATED"] == "asan"))
         _emulated_torch_device()
 
 

@@ -2,9 +2,10 @@
 compiled by g++ against the CPU kernel emulator in this directory (cuda_runtime.h, cuemu.cpp).
 
 The sources are copied into tests/host/cuemu/_build/pkg/csrc/ with two mechanical rewrites (nothing else is touched):
-  kernel<<<grid, block, smem, stream>>>(args);   ->  cuemu::launch(dim3(grid), dim3(block), smem, [&]() { kernel(args); });
+  kernel<<<grid, block, smem, stream>>>(args);   ->  cuemu::launch(dim3(grid), dim3(block), smem, "kernel", [&]() { kernel(args); });
   extern __shared__ T name[];                    ->  T* name = (T*)cuemu::dyn_smem();
   __noinline__                                   ->  __attribute__((noinline))
+plus one counting line in the host path of fp.cuh's product and squaring (operation census, cuemu.cpp).
 Only tests load the result (tests/test_emulated_library.py); see cuda_runtime.h for what it does and does not cover.
 """
 import os
@@ -18,6 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(HERE)))
 CSRC = os.path.join(ROOT, "wasmsnark_b200", "csrc")
 BUILD = os.path.join(HERE, "_build", "pkg", "csrc")      # so that "../../include/wasmsnark_b200.h" stays inside _build/
 OUT = os.path.join(ROOT, "tests", "host", "libwasmsnark_b200_emu.so")
+OUT_ASAN = os.path.join(ROOT, "tests", "host", "libwasmsnark_b200_emu_asan.so")
 
 
 def _matching(s, i, open_c, close_c, step):
@@ -79,10 +81,27 @@ def rewrite_launches(src):
         assert src[end] == ";", src[i:end + 1]
         smem = cfg[2] if len(cfg) > 2 else "0"
         out.append(src[pos:k + 1])
-        out.append("cuemu::launch(dim3(%s), dim3(%s), %s, [&]() { %s%s; });" % (cfg[0], cfg[1], smem, kern, src[a0:a1 + 1]))
+        name = re.sub(r"\s+", " ", kern).replace('"', "")
+        out.append('cuemu::launch(dim3(%s), dim3(%s), %s, "%s", [&]() { %s%s; });' % (cfg[0], cfg[1], smem, name, kern, src[a0:a1 + 1]))
         pos = end + 1
     out.append(src[pos:])
     return "".join(out)
+
+
+# operation census: one counting line in the portable host path of the COPIED field layer (product and squaring)
+CENSUS = (("    // portable CIOS on 64-bit limbs (host:", "    cuemu::count_op(N, 0);\n"),
+          ("#else\n    return mul(a, a);\n#endif", None))
+
+
+def add_census(name, src):
+    if name != "fp.cuh":
+        return src
+    anchor, line = CENSUS[0]
+    assert src.count(anchor) == 1, "fp.cuh: host path of mul_inline not found"
+    src = src.replace(anchor, line + anchor)
+    anchor = CENSUS[1][0]
+    assert src.count(anchor) == 1, "fp.cuh: host path of sqr not found"
+    return src.replace(anchor, "#else\n    cuemu::count_op(P::N, 1);\n    return mul(a, a);\n#endif")
 
 
 def rewrite(src):
@@ -91,7 +110,14 @@ def rewrite(src):
     return rewrite_launches(src)
 
 
-def build(verbose=False):
+def build(verbose=False, asan=False):
+    """asan=True: the same build with AddressSanitizer (tests/host/libwasmsnark_b200_emu_asan.so; run python with
+    LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0): out-of-bounds accesses of kernels and host
+    code are reported -- the GPU-less counterpart of compute-sanitizer's memcheck."""
+    global BUILD, OUT
+    if asan:
+        BUILD = os.path.join(HERE, "_build", "asan", "csrc")
+        OUT = OUT_ASAN
     os.makedirs(BUILD, exist_ok=True)
     srcs = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")))
     deps = [os.path.join(CSRC, f) for f in srcs] + [os.path.join(HERE, f) for f in ("cuda_runtime.h", "cuemu.cpp", "build_emu.py")] + \
@@ -99,7 +125,7 @@ def build(verbose=False):
     if os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
     for f in srcs:
-        text = rewrite(open(os.path.join(CSRC, f)).read())
+        text = add_census(f, rewrite(open(os.path.join(CSRC, f)).read()))
         assert "<<<" not in text, f
         # the sources include the public header as "../../include/wasmsnark_b200.h": same relative position under _build/
         with open(os.path.join(BUILD, f), "w") as o:
@@ -109,6 +135,8 @@ def build(verbose=False):
     with open(os.path.join(inc, "wasmsnark_b200.h"), "w") as o:
         o.write(open(os.path.join(ROOT, "include", "wasmsnark_b200.h")).read())
     flags = ["-std=c++17", "-O2", "-fno-strict-aliasing", "-fPIC", "-fvisibility=hidden", "-w", "-D__CUDACC__=1", "-I" + HERE, "-include", os.path.join(HERE, "cuda_runtime.h")]
+    if asan:
+        flags = [f for f in flags if f != "-O2"] + ["-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer", "-DCUEMU_ASAN=1"]
     units = [(os.path.join(BUILD, f), os.path.join(BUILD, f[:-3] + ".o")) for f in srcs if f.endswith(".cu")]
     units.append((os.path.join(HERE, "cuemu.cpp"), os.path.join(BUILD, "cuemu.o")))
 
@@ -123,7 +151,7 @@ def build(verbose=False):
             failed |= r.returncode != 0
     if failed:
         raise RuntimeError("emulated build failed")
-    r = subprocess.run(["g++", "-shared", "-o", OUT] + [o for _, o in units] + ["-lpthread"], capture_output=True, text=True)
+    r = subprocess.run(["g++", "-shared", "-o", OUT] + (["-fsanitize=address"] if asan else []) + [o for _, o in units] + ["-lpthread"], capture_output=True, text=True)
     if r.returncode:
         sys.stderr.write(r.stderr)
         raise RuntimeError("emulated link failed")
@@ -131,4 +159,4 @@ def build(verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(verbose="--verbose" in sys.argv))
+    print(build(verbose="--verbose" in sys.argv, asan="--asan" in sys.argv))

@@ -41,7 +41,8 @@ struct dim3 {
 namespace cuemu {
 extern thread_local uint3 tl_threadIdx, tl_blockIdx;
 extern thread_local dim3 tl_blockDim, tl_gridDim;
-void launch(dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()>& body);     // runs the whole grid, returns when done
+void launch(dim3 grid, dim3 block, size_t dyn_smem, const char* kernel, const std::function<void()>& body);     // runs the whole grid, returns when done
+void count_op(int limbs, int squaring);       // operation census (cuemu.cpp)
 void* dyn_smem();                 // the current block's dynamic shared memory
 void sync_block();                // __syncthreads
 void sync_warp();                 // __syncwarp

@@ -14,6 +14,9 @@
 
 #include <atomic>
 #include <cstdio>
+#include <map>
+#include <mutex>
+#include <string>
 #include <vector>
 
 #if !defined(__x86_64__)
@@ -46,6 +49,14 @@ cuemu_switch:
 )");
 extern "C" void cuemu_switch(void** save_sp, void* load_sp);
 
+// AddressSanitizer build (build_emu.py --asan: out-of-bounds accesses of kernels and host code become reports): the
+// sanitizer has to be told about every stack switch
+#ifdef CUEMU_ASAN
+extern "C" void __sanitizer_start_switch_fiber(void** fake_stack_save, const void* bottom, size_t size);
+extern "C" void __sanitizer_finish_switch_fiber(void* fake_stack_save, const void** bottom_old, size_t* size_old);
+extern "C" void __asan_unpoison_memory_region(void const volatile* addr, size_t size);
+#endif
+
 namespace cuemu {
 
 thread_local uint3 tl_threadIdx, tl_blockIdx;
@@ -56,6 +67,7 @@ constexpr size_t STACK_BYTES = 256 << 10;
 
 struct Fiber {
     void* sp = nullptr;
+    void* fake = nullptr;          // ASan fake-stack handle while switched out
     uint3 tid{};
     int lane = 0, warp = 0;
     bool done = false;
@@ -73,6 +85,9 @@ struct Block {
     unsigned long progress = 0;
     int cur = 0;
     void* sched_sp = nullptr;
+    const void* sched_bottom = nullptr;     // ASan: the scheduler's (host thread's) stack
+    size_t sched_size = 0;
+    void* sched_fake = nullptr;
     void* dsm = nullptr;
     const std::function<void()>* body = nullptr;
 };
@@ -87,9 +102,17 @@ struct Sched {
 };
 thread_local Sched tl_sched;
 
-void yield_to_scheduler() {
+void yield_to_scheduler(bool dying = false) {
     Block& b = tl_sched.blk;
+#ifdef CUEMU_ASAN
+    Fiber& f = b.fib[b.cur];
+    __sanitizer_start_switch_fiber(dying ? nullptr : &f.fake, b.sched_bottom, b.sched_size);
+    cuemu_switch(&f.sp, b.sched_sp);
+    __sanitizer_finish_switch_fiber(f.fake, &b.sched_bottom, &b.sched_size);
+#else
+    (void)dying;
     cuemu_switch(&b.fib[b.cur].sp, b.sched_sp);
+#endif
 }
 
 void release_block_barrier_if_complete(Block& b) {
@@ -118,6 +141,9 @@ void warp_barrier() {
 
 void fiber_main() {
     Block& b = tl_sched.blk;
+#ifdef CUEMU_ASAN
+    __sanitizer_finish_switch_fiber(nullptr, &b.sched_bottom, &b.sched_size);
+#endif
     (*b.body)();
     Fiber& f = b.fib[b.cur];
     f.done = true;
@@ -127,11 +153,14 @@ void fiber_main() {
     w.live--;
     release_block_barrier_if_complete(b);       // the others may have been waiting for this thread only
     release_warp_barrier_if_complete(b, w);
-    yield_to_scheduler();
+    yield_to_scheduler(true);
     abort();                                    // a finished fiber is never resumed
 }
 
 void* fresh_context(uint8_t* stack) {
+#ifdef CUEMU_ASAN
+    __asan_unpoison_memory_region(stack, STACK_BYTES);      // the previous fiber on this stack never unwound its frames
+#endif
     uintptr_t top = ((uintptr_t)stack + STACK_BYTES) & ~(uintptr_t)15;
     void** p = (void**)(top - 64);              // 16-byte aligned slot for the entry address: rsp % 16 == 8 at fiber_main's entry
     p[0] = (void*)&fiber_main;
@@ -141,6 +170,34 @@ void* fresh_context(uint8_t* stack) {
     return sp;
 }
 }  // namespace
+
+// ---- operation census: how many Montgomery products / squarings each kernel executes (profiles/: the integer-multiply
+// "roofline" of a proof, counted instead of estimated).  count_op is called from the field layer's host path (a line
+// build_emu.py adds to the COPIED fp.cuh); only work done inside kernels is counted.
+namespace {
+struct OpCounts {
+    unsigned long long launches = 0, threads = 0, mul[3] = {0, 0, 0}, sqr[3] = {0, 0, 0};      // [8, 12, 24 limbs]
+};
+thread_local OpCounts tl_ops;
+std::mutex g_census_mu;
+std::map<std::string, OpCounts> g_census;
+void census_commit(const char* kernel, unsigned long long threads) {
+    std::lock_guard<std::mutex> lk(g_census_mu);
+    OpCounts& c = g_census[kernel];
+    c.launches++;
+    c.threads += threads;
+    for (int i = 0; i < 3; i++) {
+        c.mul[i] += tl_ops.mul[i];
+        c.sqr[i] += tl_ops.sqr[i];
+    }
+    tl_ops = OpCounts();
+}
+}  // namespace
+void count_op(int limbs, int squaring) {
+    if (!tl_sched.running) return;
+    const int k = limbs == 8 ? 0 : limbs == 12 ? 1 : 2;
+    (squaring ? tl_ops.sqr : tl_ops.mul)[k]++;
+}
 
 int lane() { return tl_sched.blk.fib[tl_sched.blk.cur].lane; }
 void* dyn_smem() { return tl_sched.blk.dsm; }
@@ -164,7 +221,7 @@ uint32_t shfl(uint32_t v, int src) {
     return r;
 }
 
-void launch(dim3 grid, dim3 block, size_t dyn_bytes, const std::function<void()>& body) {
+void launch(dim3 grid, dim3 block, size_t dyn_bytes, const char* kernel, const std::function<void()>& body) {
     Sched& s = tl_sched;
     if (s.running) {
         fprintf(stderr, "cuemu: kernel launch from inside a kernel\n");
@@ -188,6 +245,14 @@ void launch(dim3 grid, dim3 block, size_t dyn_bytes, const std::function<void()>
     tl_gridDim = grid;
     tl_blockDim = block;
     const size_t nwarps = (nthreads + 31) / 32;
+    static const int order_mode = [] {
+        const char* e = getenv("CUEMU_ORDER");
+        return !e ? 0 : !strcmp(e, "reverse") ? 1 : !strcmp(e, "shuffle") ? 2 : 0;
+    }();
+    // shuffle: t = (k * mul + add) mod n is a permutation of 0..n-1 whenever gcd(mul, n) = 1; blocks have 32..1024 threads
+    // (powers of two times 1, 3 or 5), so any multiplier coprime to 2, 3 and 5 works
+    const size_t order_mul = 7 * 11 * 13 + 0, order_add = 17;
+    unsigned pass = 0;
     for (unsigned bz = 0; bz < grid.z; bz++)
         for (unsigned by = 0; by < grid.y; by++)
             for (unsigned bx = 0; bx < grid.x; bx++) {
@@ -208,12 +273,23 @@ void launch(dim3 grid, dim3 block, size_t dyn_bytes, const std::function<void()>
                 }
                 while (b.live > 0) {
                     const unsigned long before = b.progress;
-                    for (size_t t = 0; t < nthreads; t++) {
+                    for (size_t k = 0; k < nthreads; k++) {
+                        // CUEMU_ORDER: the order in which the threads of a block get the CPU between rendezvous points.  A kernel
+                        // without shared-memory / global-memory hazards gives the same bytes for any order; running the tests
+                        // with "reverse" and "shuffle" is the emulator's (weak) counterpart of a race check.
+                        const size_t t = order_mode == 0 ? k : order_mode == 1 ? nthreads - 1 - k : (size_t)((k * order_mul + order_add + pass * 7919u) % nthreads);
                         if (b.fib[t].done) continue;
                         b.cur = (int)t;
                         tl_threadIdx = b.fib[t].tid;
+#ifdef CUEMU_ASAN
+                        __sanitizer_start_switch_fiber(&b.sched_fake, s.stacks[t], STACK_BYTES);
                         cuemu_switch(&b.sched_sp, b.fib[t].sp);
+                        __sanitizer_finish_switch_fiber(b.sched_fake, nullptr, nullptr);
+#else
+                        cuemu_switch(&b.sched_sp, b.fib[t].sp);
+#endif
                     }
+                    pass++;
                     if (b.live > 0 && b.progress == before) {
                         fprintf(stderr, "cuemu: deadlock in block (%u,%u,%u): %d threads wait at a rendezvous the others never reach\n", bx, by, bz, b.live);
                         abort();
@@ -221,6 +297,7 @@ void launch(dim3 grid, dim3 block, size_t dyn_bytes, const std::function<void()>
                 }
             }
     s.running = false;
+    census_commit(kernel, (unsigned long long)grid.x * grid.y * grid.z * nthreads);
 }
 
 }  // namespace cuemu
@@ -266,7 +343,29 @@ cudaError_t cudaFree(void* p) {
     free(p);
     return cudaSuccess;
 }
-long cuemu_live_allocations(void) { return g_live_allocs.load(); }
+__attribute__((visibility("default"))) long cuemu_live_allocations(void) { return g_live_allocs.load(); }
+__attribute__((visibility("default"))) void cuemu_census_reset(void) {
+    std::lock_guard<std::mutex> lk(cuemu::g_census_mu);
+    cuemu::g_census.clear();
+}
+// JSON object kernel -> {launches, threads, mul8, sqr8, mul12, sqr12, mul24, sqr24}; "mul" counts every product, the
+// squarings among them are listed again under "sqr".  Returns the length needed (call again with a larger buffer).
+__attribute__((visibility("default"))) size_t cuemu_census_json(char* buf, size_t cap) {
+    std::lock_guard<std::mutex> lk(cuemu::g_census_mu);
+    std::string o = "{";
+    bool first = true;
+    for (auto& kv : cuemu::g_census) {
+        char line[512];
+        const auto& c = kv.second;
+        snprintf(line, sizeof line, "%s\"%s\": {\"launches\": %llu, \"threads\": %llu, \"mul8\": %llu, \"sqr8\": %llu, \"mul12\": %llu, \"sqr12\": %llu, \"mul24\": %llu, \"sqr24\": %llu}",
+                 first ? "" : ", ", kv.first.c_str(), c.launches, c.threads, c.mul[0], c.sqr[0], c.mul[1], c.sqr[1], c.mul[2], c.sqr[2]);
+        o += line;
+        first = false;
+    }
+    o += "}";
+    if (buf && cap > o.size()) memcpy(buf, o.c_str(), o.size() + 1);
+    return o.size() + 1;
+}
 cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) {
     void* m = nullptr;
     if (posix_memalign(&m, 256, n ? n : 256) != 0) return cudaErrorMemoryAllocation;
