@@ -21,27 +21,8 @@ def pytest_configure(config):
         from wasmsnark_b200 import _lib
         # WS_TEST_EMULATED=asan: the AddressSanitizer build (run python under LD_PRELOAD=$(gcc -print-file-name=libasan.so))
         _lib.load_library(path=build_emu.build(asan=os.environ["WS_TEST_EMULATED"] == "asan"))
-        _emulated_torch_device()
-
-
-def _emulated_torch_device():
-    """Under emulation "device memory" is host memory: the tests' torch.cuda buffers become CPU tensors (their data_ptr()
-    is what the emulated library dereferences)."""
-    import torch
-
-    def on_cpu(fn):
-        def wrapper(*a, **k):
-            if str(k.get("device", "")).startswith("cuda"):
-                k["device"] = "cpu"
-            return fn(*a, **k)
-        return wrapper
-    for name in ("zeros", "empty", "ones", "full", "tensor", "frombuffer", "arange"):
-        setattr(torch, name, on_cpu(getattr(torch, name)))
-    torch.Tensor.cuda = lambda self, *a, **k: self.clone()
-    torch.cuda.synchronize = lambda *a, **k: None
-    torch.cuda.is_available = lambda: True
-    torch.cuda.device_count = lambda: max(1, int(os.environ.get("CUEMU_DEVICES", "1")))
-    torch.cuda.set_device = lambda *a, **k: None
+        import emulated_torch
+        emulated_torch.patch()
 
 
 @pytest.fixture(scope="session")

@@ -1,0 +1,42 @@
+"""tests/host/cuemu/emulated_torch.py -- TEST SCAFFOLDING: under the kernel emulator "device memory" is host memory, so the
+tests' torch.cuda buffers become CPU tensors (their data_ptr() is what the emulated library dereferences) and CUDA streams
+become no-ops.  Used by tests/conftest.py (WS_TEST_EMULATED) and by the gloo workers of tests/test_emulated_library.py."""
+import contextlib
+import os
+
+
+class FakeStream:
+    cuda_stream = 0
+
+    def __init__(self, *a, **k):
+        pass
+
+    def synchronize(self):
+        pass
+
+    def wait_stream(self, other):
+        pass
+
+
+def patch():
+    import torch
+
+    def on_cpu(fn):
+        def wrapper(*a, **k):
+            if str(k.get("device", "")).startswith("cuda"):
+                k["device"] = "cpu"
+            return fn(*a, **k)
+        return wrapper
+    if getattr(torch, "_ws_emulated", False):
+        return
+    torch._ws_emulated = True
+    for name in ("zeros", "empty", "ones", "full", "tensor", "frombuffer", "arange"):
+        setattr(torch, name, on_cpu(getattr(torch, name)))
+    torch.Tensor.cuda = lambda self, *a, **k: self.clone()
+    torch.cuda.synchronize = lambda *a, **k: None
+    torch.cuda.is_available = lambda: True
+    torch.cuda.device_count = lambda: max(1, int(os.environ.get("CUEMU_DEVICES", "1")))
+    torch.cuda.set_device = lambda *a, **k: None
+    torch.cuda.Stream = FakeStream
+    torch.cuda.stream = lambda s: contextlib.nullcontext()
+    torch.cuda.current_stream = lambda *a, **k: FakeStream()

@@ -102,3 +102,71 @@ def test_multi_gpu_handle_with_four_pretend_devices(children):
 
 def test_multi_gpu_handle_with_more_pretend_devices_than_points(children):
     assert "1 passed" in finished(children, "multi8")
+
+
+# ---- the torchrun form of the multi-GPU prover (wasmsnark_b200/parallel.py: ShardedProver) on gloo + emulated kernels ------------
+def _sharded_worker(rank, world, port, split, q):
+    """one rank = one process = one emulated GPU: key shard, witness MSMs, H on the rotating owner, send / recv of the h
+    slices, all_gather of the 768-byte records, assembly -- the code path bench.py --gpus N times, with gloo for NCCL"""
+    import json
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), CUEMU_DEVICES="1")
+        sys.path.insert(0, os.path.join(ROOT, "tests", "host", "cuemu"))
+        import build_emu
+        import emulated_torch
+        from wasmsnark_b200 import _lib
+        _lib.load_library(path=build_emu.build())
+        emulated_torch.patch()
+        import torch
+        import torch.distributed as dist
+        from wasmsnark_b200 import build_bn128
+        from wasmsnark_b200.parallel import ShardedProver
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        gold = os.path.join(ROOT, "tests", "golden")
+        pk = open(os.path.join(gold, "synth_small.pkey.bin"), "rb").read()
+        wit = open(os.path.join(gold, "synth_small.witness.bin"), "rb").read()
+        g = json.load(open(os.path.join(gold, "synth_small.golden.json")))
+        bn = build_bn128(0)
+        sp = ShardedProver(bn, pk, rank, world, split=split)
+        h_wit = torch.frombuffer(bytearray(wit), dtype=torch.uint8)
+        d_wit = torch.zeros(len(wit), dtype=torch.uint8, device="cuda")
+        d_rs = torch.frombuffer(bytearray(bytes.fromhex(g["r"]) + bytes.fromhex(g["s"])), dtype=torch.uint8).cuda()
+        d_out = torch.zeros(384, dtype=torch.uint8, device="cuda")
+        stream = torch.cuda.Stream()
+        proofs = []
+        for _ in range(world + 1):                      # every rank takes a turn as H owner
+            owner = sp.next_owner()
+            d_wit.zero_()
+            sp.upload_witness(d_wit, h_wit, owner, stream)          # non-owners get only the ranges they need
+            out = bytes(sp.prove_dev(d_wit, d_rs, d_out, stream, owner=owner).numpy())
+            ints = [str(int.from_bytes(out[32 * i:32 * i + 32], "little")) for i in range(12)]
+            proofs.append({"pi_a": ints[0:3], "pi_b": [ints[3:5], ints[5:7], ints[7:9]], "pi_c": ints[9:12]})
+        sp.free()
+        bn.terminate()
+        dist.destroy_process_group()
+        q.put((rank, all(p == g["proof_rs"] for p in proofs), len(proofs)))
+    except Exception as e:      # noqa: BLE001
+        import traceback
+        q.put((rank, False, traceback.format_exc()[-1500:] + repr(e)))
+
+
+@pytest.mark.parametrize("world,split", [(2, "balanced"), (3, "uniform")])
+def test_sharded_prover_over_gloo_with_emulated_kernels(world, split):
+    """parallel.ShardedProver end to end without a GPU: `world` processes over gloo, each with the emulated library; every
+    rank must end up with the reference's golden proof for every H owner."""
+    import random
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests", "host", "cuemu"))
+    import build_emu
+    build_emu.build()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + random.randrange(2000)
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, split, q)) for r in range(world)]
+    [p.start() for p in procs]
+    try:
+        got = sorted(q.get(timeout=600) for _ in range(world))
+    finally:
+        [p.join(timeout=60) for p in procs]
+        [p.kill() for p in procs if p.is_alive()]
+    assert got == [(r, True, world + 1) for r in range(world)], got
