@@ -82,7 +82,9 @@ def rewrite_launches(src):
         smem = cfg[2] if len(cfg) > 2 else "0"
         out.append(src[pos:k + 1])
         name = re.sub(r"\s+", " ", kern).replace('"', "")
-        out.append('cuemu::launch(dim3(%s), dim3(%s), %s, "%s", [&]() { %s%s; });' % (cfg[0], cfg[1], smem, name, kern, src[a0:a1 + 1]))
+        # the name the census files the launch under: the kernel expression + the template bindings of the launch site
+        out.append('cuemu::launch(dim3(%s), dim3(%s), %s, cuemu::kernel_label("%s", __PRETTY_FUNCTION__).c_str(), [&]() { %s%s; });'
+                   % (cfg[0], cfg[1], smem, name, kern, src[a0:a1 + 1]))
         pos = end + 1
     out.append(src[pos:])
     return "".join(out)

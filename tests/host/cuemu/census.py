@@ -20,6 +20,22 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools"), HERE):
     sys.path.insert(0, p)
 
 
+def clean_label(label):
+    """'k_msm_digits<C> [C = G1Curve; cudaError_t = int]' -> 'k_msm_digits<G1Curve>' (the name ncu prints, minus launch-bound
+    arguments); the accumulate kernels are launched through a function-pointer variable: their curve is read off its type"""
+    import re
+    expr, _, binds = label.partition(" [")
+    binds = binds.rstrip("]")
+    if expr == "kern":
+        m = re.search(r"Affine<(\w+)>", binds)
+        return "k_msm_accumulate<%s>" % (m.group(1) if m else "?")
+    for item in binds.split("; "):
+        k, _, v = item.partition(" = ")
+        if re.fullmatch(r"[A-Z]\w*", k) and re.fullmatch(r"\w+", v):
+            expr = re.sub(r"\b%s\b" % k, v, expr)
+    return expr
+
+
 def main():
     import build_emu
     import gen_synth_key
@@ -43,7 +59,11 @@ def main():
     n = raw.cuemu_census_json(None, 0)
     buf = ctypes.create_string_buffer(n + 16)
     raw.cuemu_census_json(buf, n + 16)
-    census = json.loads(buf.value.decode())
+    census = {}
+    for label, c in json.loads(buf.value.decode()).items():
+        dst = census.setdefault(clean_label(label), dict.fromkeys(c, 0))
+        for k, v in c.items():
+            dst[k] += v
     gold = os.path.join(ROOT, "tests", "golden", "synth_2p%d.golden.json" % log2)
     checked = None
     if os.path.exists(gold):

@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <string>
 
 #define __CUDACC__ 1          // the sources' "compiled as CUDA" paths (hd.cuh, warp_ec.cuh) ...
 #undef __CUDA_ARCH__          // ... but never their device-only PTX paths
@@ -43,6 +44,26 @@ extern thread_local uint3 tl_threadIdx, tl_blockIdx;
 extern thread_local dim3 tl_blockDim, tl_gridDim;
 void launch(dim3 grid, dim3 block, size_t dyn_smem, const char* kernel, const std::function<void()>& body);     // runs the whole grid, returns when done
 void count_op(int limbs, int squaring);       // operation census (cuemu.cpp)
+// "k_msm_digits<C>" + "... [with C = ws::G1Curve; ...]" -> "k_msm_digits<C> [C = G1Curve]"
+static inline std::string kernel_label(const char* kernel, const char* site) {
+    std::string s(kernel), w(site);
+    size_t i = w.find("[with ");
+    if (i == std::string::npos) return s;
+    std::string b = w.substr(i + 6);
+    if (!b.empty() && b.back() == ']') b.pop_back();
+    for (size_t k; (k = b.find("ws::")) != std::string::npos;) b.erase(k, 4);
+    // keep only the type bindings (drop "cudaStream_t = ..." and similar aliases)
+    std::string keep;
+    size_t pos = 0;
+    while (pos < b.size()) {
+        size_t e = b.find("; ", pos);
+        std::string item = b.substr(pos, e == std::string::npos ? std::string::npos : e - pos);
+        if (item.find("cudaStream_t") == std::string::npos && item.find("typename") == std::string::npos) keep += (keep.empty() ? "" : "; ") + item;
+        if (e == std::string::npos) break;
+        pos = e + 2;
+    }
+    return keep.empty() ? s : s + " [" + keep + "]";
+}
 void* dyn_smem();                 // the current block's dynamic shared memory
 void sync_block();                // __syncthreads
 void sync_warp();                 // __syncwarp

@@ -54,6 +54,7 @@ def main():
             "* `r2_launches_prove_2p20.csv` -- `ncu --metrics gpu__time_duration.sum --clock-control none` launch list of `tools/run_prove_once.py 20 2` (cold-cache, serialised: compare SHARES).",
             "* `r2_ncu_accumulate_*.txt`, `r2_ncu_ntt_*.txt` -- `ncu --set full --clock-control none` summaries (tools/ncu_summary.py) of the accumulate kernels of one proof and of the NTT passes.",
             "* `r2_ntt_variants*.txt` -- `tools/run_ntt_once.py` timings of the NTT pass variants (occupancy, warp-local exchange, radix 16).",
+            "* `r2_op_census_2p20.json` / `.md` -- Montgomery products and squarings of one 2^20-constraint proof, counted per kernel inside the executed kernels (CPU kernel emulator, `tests/host/cuemu/census.py`), next to the measured kernel times.",
             "* `r2_ptxas_resources.txt` -- registers / stack / spill bytes of every kernel (`-Xptxas -v`); `r2_tuning_hook_sweep.txt`, `r2_ws_multi_timings.txt` -- see the A/B table at the end.", ""]
     if b1:
         cb = b1.get("cpu_baseline") or {}
@@ -143,6 +144,10 @@ def main():
         acc = sum(v for k, _, v in lib if k.startswith("k_msm_accumulate<G1Curve"))
         out += ["`k_msm_accumulate<G1>` (the roofline kernel): %.1f %% of the proving kernels' time in this list, %.1f %% in the one-proof list above; "
                 "event-timed alone 1.52 ms x 4 launches = 6.1 ms of the 19.4 ms single-proof latency (31 %%) -- the proof overlaps its five MSMs on side streams, so the serialised lists weigh the latency-bound tail kernels more than the live run does." % (100 * acc / lib_tot, ONE_PROOF_SHARE.get("acc_g1", float("nan"))), ""]
+    census = os.path.join(P, "r2_op_census_2p20.md")
+    if os.path.exists(census):
+        body = open(census).read().split("\n", 1)[1].strip("\n")
+        out += ["## Operation census: the integer-multiply work of one proof, counted (`r2_op_census_2p20.json`, `tools/census_table.py`)", "", body, ""]
     extra = os.path.join(P, "NOTES_r2.md")
     if os.path.exists(extra):
         out += [open(extra).read()]
