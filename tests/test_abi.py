@@ -59,10 +59,11 @@ def test_product_package_does_not_import_oracle():
 
 def test_product_never_reaches_for_the_cpu_kernel_emulator():
     """tests/host/cuemu (the kernels executed on the CPU, for tests) is scaffolding: neither the package, the bench, the
-    driver hooks nor the Node binding may name it or the library built from it -- only tests/ does."""
+    driver hooks nor the Node binding may name it or the library built from it -- only tests/ does (and the report generators
+    under tools/, which read the census it produced)."""
     banned = ("cuemu", "libwasmsnark_b200_emu", "WS_TEST_EMULATED")
     files = [os.path.join(ROOT, f) for f in ("bench.py", "__graft_entry__.py")]
-    for top in ("wasmsnark_b200", "node", "include", "tools", "oracle"):
+    for top in ("wasmsnark_b200", "node", "include", "oracle"):
         for dirpath, dirs, names in os.walk(os.path.join(ROOT, top)):
             dirs[:] = [d for d in dirs if d not in ("_obj", "_ref", "__pycache__")]
             files += [os.path.join(dirpath, f) for f in names if f.endswith((".py", ".cu", ".cuh", ".h", ".c", ".js", ".gyp", ".json"))]
