@@ -20,6 +20,9 @@ anything is timed.
             algorithmic bytes per pair / its CUDA-event duration on the launch stream, timed alone on the
             key's A section with the witness scalars, against the measured HBM copy peak (MEASURED_PEAKS.json);
             `traffic` and the pipe utilisation are read from the ncu summary committed under profiles/
+  integer_roofline  (N = 1) the same proof against the bound that actually holds: its Montgomery products, COUNTED inside the
+            executed kernels by the CPU kernel emulator (profiles/r2_op_census_2p20.json), as time on the
+            IMAD.WIDE pipe at the sampled SM clock; `frac` = that time / ms_per_step
   cpu_baseline  the reference's own groth16GenProof (its WASM image compiled natively, oracle/_ref, driven as
             src/bn128.js:580-720 drives it, worker pool = all host cores) on a bounded sample: the same generator's
             2^16-constraint key, scaled by 2^16/2^20 (the reference's cost per constraint does not fall with size --
@@ -148,6 +151,24 @@ def read_ncu_summary(kernel_substr, prefer=("r2", "r1")):
             if out:
                 return out, os.path.join("profiles", fn)
     return {}, None
+
+
+def integer_roofline(log2, ms_per_proof, sm_mhz=None):
+    """The proof against the multiplier pipe instead of HBM: the Montgomery products / squarings of ONE proof
+    were counted inside the executed kernels by the CPU kernel emulator (profiles/r2_op_census_2p<log2>.json); at 137 / 111
+    IMAD.WIDE each and 8 lanes per clock and SM sub-partition they occupy the pipe for `pipe_ms_per_proof`.  None when no
+    census of this key size is committed."""
+    try:
+        path = os.path.join("profiles", "r2_op_census_2p%d.json" % log2)
+        tot = json.load(open(os.path.join(ROOT, path)))["total"]
+        sq = int(tot["sqr8"])
+        mul = int(tot["mul8"]) - sq
+        mhz = float(sm_mhz) if sm_mhz else 1965.0
+        pipe_ms = (mul * 137 + sq * 111) / (148 * 4 * 8 * mhz * 1e6) * 1e3
+        return {"bound": "IMAD.WIDE pipe (8 lanes / clk / SM sub-partition)", "products_per_proof": mul + sq, "squarings_among_them": sq,
+                "pipe_ms_per_proof": pipe_ms, "sm_mhz": mhz, "frac": pipe_ms / ms_per_proof if ms_per_proof else None, "source": path}
+    except Exception:       # noqa: BLE001  -- an explanatory extra must never cost the bench line
+        return None
 
 
 class ClockSampler:
@@ -637,6 +658,8 @@ def section_groth16(env, args):
         "stages_ms": pstages, "dropin_call": dropin, "example_key": example,
         "algorithmic_bytes_per_proof": alg_bytes, "hbm_frac_whole_proof": (alg_bytes / (pms * 1e-3) / 1e9) / peaks()[0],
     }
+    if world == 1:
+        out["line"]["integer_roofline"] = integer_roofline(PROVE_LOG2, pms, (clocks or {}).get("sm_mhz"))
     # ---- roofline of the dominant kernel: k_msm_accumulate<G1>, window-table form, timed alone on the A section
     if rank == 0:
         from oracle import bn128 as O

@@ -17,6 +17,37 @@ class FakeStream:
     def wait_stream(self, other):
         pass
 
+    def wait_event(self, ev):
+        pass
+
+    def record_event(self, ev=None):
+        ev = ev or FakeEvent()
+        ev.record()
+        return ev
+
+
+class FakeEvent:
+    """everything is synchronous under emulation: an event is a host timestamp"""
+
+    def __init__(self, *a, **k):
+        self.t = None
+
+    def record(self, stream=None):
+        import time
+        self.t = time.perf_counter()
+
+    def synchronize(self):
+        pass
+
+    def wait(self, stream=None):
+        pass
+
+    def query(self):
+        return True
+
+    def elapsed_time(self, other):
+        return (other.t - self.t) * 1000.0
+
 
 def patch():
     import torch
@@ -30,13 +61,16 @@ def patch():
     if getattr(torch, "_ws_emulated", False):
         return
     torch._ws_emulated = True
-    for name in ("zeros", "empty", "ones", "full", "tensor", "frombuffer", "arange"):
+    for name in ("zeros", "empty", "ones", "full", "tensor", "frombuffer", "arange", "randint"):
         setattr(torch, name, on_cpu(getattr(torch, name)))
     torch.Tensor.cuda = lambda self, *a, **k: self.clone()
     torch.cuda.synchronize = lambda *a, **k: None
     torch.cuda.is_available = lambda: True
     torch.cuda.device_count = lambda: max(1, int(os.environ.get("CUEMU_DEVICES", "1")))
     torch.cuda.set_device = lambda *a, **k: None
+    torch.Tensor.pin_memory = lambda self, *a, **k: self
     torch.cuda.Stream = FakeStream
+    torch.cuda.Event = FakeEvent
+    torch.cuda.set_stream = lambda *a, **k: None
     torch.cuda.stream = lambda s: contextlib.nullcontext()
     torch.cuda.current_stream = lambda *a, **k: FakeStream()

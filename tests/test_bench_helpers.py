@@ -63,3 +63,18 @@ def test_reference_worker_pool_replay_equals_the_serial_replay():
         assert serial.groth16GenProof(wit, pk, r=r, s=s) == g["proof_rs"]
     finally:
         serial.close()
+
+
+def test_integer_roofline_reads_the_committed_census():
+    """bench.py's `integer_roofline` object: the products of one 2^20-constraint proof as COUNTED by the kernel emulator
+    (profiles/r2_op_census_2p20.json), turned into multiplier-pipe time; absent census -> None, never an error."""
+    r = bench.integer_roofline(20, 17.41, 1965.0)
+    census = json.load(open(os.path.join(ROOT, "profiles", "r2_op_census_2p20.json")))
+    assert census["equals_reference_golden_proof"] is True and census["log2_constraints"] == 20
+    assert r["products_per_proof"] == census["total"]["mul8"] and r["source"] == "profiles/r2_op_census_2p20.json"
+    assert 7e8 < r["products_per_proof"] < 9e8 and 10.0 < r["pipe_ms_per_proof"] < 13.0 and 0.5 < r["frac"] < 0.8
+    assert abs(bench.integer_roofline(20, 17.41, 982.5)["pipe_ms_per_proof"] - 2 * r["pipe_ms_per_proof"]) < 1e-9     # scales with the sampled clock
+    assert bench.integer_roofline(7, 1.0) is None and bench.integer_roofline(20, 0.0)["frac"] is None
+    # per-kernel: the accumulate kernels carry most of the products, one mixed addition = 8 products + 2 squarings on G1
+    acc = census["kernels"]["k_msm_accumulate<G1Curve>"]
+    assert acc["launches"] == 4 and acc["sqr8"] * 5 == acc["mul8"]
