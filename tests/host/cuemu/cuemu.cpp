@@ -333,7 +333,14 @@ cudaError_t cudaMalloc(void** p, size_t n) {
         *p = nullptr;
         return cudaErrorMemoryAllocation;
     }
-    memset(m, 0xA5, n < 4096 ? n : 4096);          // device memory is not zeroed: make accidental reliance on zeros visible
+    // device memory is not zeroed: make accidental reliance on its contents visible.  CUEMU_FILL=<byte> fills every allocation
+    // completely with that byte (run the tests with 0, 255, ...: results must not depend on it -- a weak initcheck)
+    static const int fill = [] {
+        const char* e = getenv("CUEMU_FILL");
+        return e ? atoi(e) & 255 : -1;
+    }();
+    if (fill >= 0) memset(m, fill, n);
+    else memset(m, 0xA5, n < 4096 ? n : 4096);
     g_live_allocs++;
     *p = m;
     return cudaSuccess;
