@@ -170,3 +170,11 @@ def test_sharded_prover_over_gloo_with_emulated_kernels(world, split):
         [p.join(timeout=60) for p in procs]
         [p.kill() for p in procs if p.is_alive()]
     assert got == [(r, True, world + 1) for r in range(world)], got
+
+
+def test_driver_smoke_hook_on_the_cpu_emulator():
+    """__graft_entry__.smoke() (what the driver runs on cuda:0 before the bench) through tests/host/cuemu/run_emulated.py: its own
+    logic is checked here; on the B200 box it runs against the real library."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "host", "cuemu", "run_emulated.py"), os.path.join(ROOT, "__graft_entry__.py"), "smoke"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0 and "smoke ok" in r.stdout, (r.stdout + r.stderr)[-2000:]
