@@ -1,6 +1,7 @@
 """The C-ABI library loads and exports every symbol include/wasmsnark_b200.h declares
 (no compute calls: this runs on the CPU-only box)."""
 import os
+import sys
 import re
 
 import pytest
@@ -70,6 +71,20 @@ def test_product_never_reaches_for_the_cpu_kernel_emulator():
     for path in files:
         src = open(path, errors="ignore").read()
         assert not any(b in src for b in banned), path
+
+
+def test_device_code_is_the_gpu_verified_one():
+    """The SASS of every kernel in the built library hashes to the value recorded after the last GPU run of the round
+    (profiles/r2_device_sass.sha256, tools/sass_hash.py): later commits changed host code, tests and documents only.  A change
+    that touches device code must be re-verified on a GPU and the hash re-recorded (python tools/sass_hash.py --write)."""
+    import shutil
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_hash
+    if not (os.path.exists(os.environ.get("CUOBJDUMP", "/usr/local/cuda/bin/cuobjdump")) or shutil.which("cuobjdump")):
+        pytest.skip("cuobjdump not installed")
+    want = open(os.path.join(ROOT, "profiles", "r2_device_sass.sha256")).read().split()[0]
+    got, kernels = sass_hash.sass_hash()
+    assert kernels > 100 and got == want, "device code differs from the GPU-verified build"
 
 
 def test_node_addon_type_checks_against_the_header():
