@@ -20,7 +20,8 @@ def pytest_configure(config):
         import build_emu
         from wasmsnark_b200 import _lib
         # WS_TEST_EMULATED=asan: the AddressSanitizer build (run python under LD_PRELOAD=$(gcc -print-file-name=libasan.so))
-        _lib.load_library(path=build_emu.build(asan=os.environ["WS_TEST_EMULATED"] == "asan"))
+        # WS_TEST_EMULATED=ubsan: the UndefinedBehaviorSanitizer build
+        _lib.load_library(path=build_emu.build(asan=os.environ["WS_TEST_EMULATED"] == "asan", ubsan=os.environ["WS_TEST_EMULATED"] == "ubsan"))
         import emulated_torch
         emulated_torch.patch()
 

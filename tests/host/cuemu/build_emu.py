@@ -112,14 +112,18 @@ def rewrite(src):
     return rewrite_launches(src)
 
 
-def build(verbose=False, asan=False):
+def build(verbose=False, asan=False, ubsan=False):
     """asan=True: the same build with AddressSanitizer (tests/host/libwasmsnark_b200_emu_asan.so; run python with
     LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0): out-of-bounds accesses of kernels and host
-    code are reported -- the GPU-less counterpart of compute-sanitizer's memcheck."""
+    code are reported -- the GPU-less counterpart of compute-sanitizer's memcheck -- and so are misaligned accesses (a 16-byte
+    vector load from an address that is not 16-byte aligned faults on the GPU)."""
     global BUILD, OUT
     if asan:
         BUILD = os.path.join(HERE, "_build", "asan", "csrc")
         OUT = OUT_ASAN
+    elif ubsan:        # UndefinedBehaviorSanitizer alone (no LD_PRELOAD needed): shifts by >= the width, misaligned accesses, ...
+        BUILD = os.path.join(HERE, "_build", "ubsan", "csrc")
+        OUT = OUT_ASAN.replace("_asan", "_ubsan")
     os.makedirs(BUILD, exist_ok=True)
     srcs = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")))
     deps = [os.path.join(CSRC, f) for f in srcs] + [os.path.join(HERE, f) for f in ("cuda_runtime.h", "cuemu.cpp", "build_emu.py")] + \
@@ -138,7 +142,9 @@ def build(verbose=False, asan=False):
         o.write(open(os.path.join(ROOT, "include", "wasmsnark_b200.h")).read())
     flags = ["-std=c++17", "-O2", "-fno-strict-aliasing", "-fPIC", "-fvisibility=hidden", "-w", "-D__CUDACC__=1", "-I" + HERE, "-include", os.path.join(HERE, "cuda_runtime.h")]
     if asan:
-        flags = [f for f in flags if f != "-O2"] + ["-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer", "-DCUEMU_ASAN=1"]
+        flags = [f for f in flags if f != "-O2"] + ["-O1", "-g", "-fsanitize=address,alignment", "-fno-sanitize-recover=alignment", "-fno-omit-frame-pointer", "-DCUEMU_ASAN=1"]
+    if ubsan and not asan:
+        flags = [f for f in flags if f != "-O2"] + ["-O1", "-g", "-fsanitize=undefined", "-fno-sanitize=vptr", "-fno-sanitize-recover=undefined"]
     units = [(os.path.join(BUILD, f), os.path.join(BUILD, f[:-3] + ".o")) for f in srcs if f.endswith(".cu")]
     units.append((os.path.join(HERE, "cuemu.cpp"), os.path.join(BUILD, "cuemu.o")))
 
@@ -153,7 +159,7 @@ def build(verbose=False, asan=False):
             failed |= r.returncode != 0
     if failed:
         raise RuntimeError("emulated build failed")
-    r = subprocess.run(["g++", "-shared", "-o", OUT] + (["-fsanitize=address"] if asan else []) + [o for _, o in units] + ["-lpthread"], capture_output=True, text=True)
+    r = subprocess.run(["g++", "-shared", "-o", OUT] + (["-fsanitize=address,alignment"] if asan else ["-fsanitize=undefined"] if ubsan else []) + [o for _, o in units] + ["-lpthread"], capture_output=True, text=True)
     if r.returncode:
         sys.stderr.write(r.stderr)
         raise RuntimeError("emulated link failed")
@@ -161,4 +167,4 @@ def build(verbose=False, asan=False):
 
 
 if __name__ == "__main__":
-    print(build(verbose="--verbose" in sys.argv, asan="--asan" in sys.argv))
+    print(build(verbose="--verbose" in sys.argv, asan="--asan" in sys.argv, ubsan="--ubsan" in sys.argv))

@@ -59,6 +59,7 @@ extern "C" void __asan_unpoison_memory_region(void const volatile* addr, size_t 
 
 namespace cuemu {
 
+thread_local int tl_last_error = 0;      // sticky until read, like the runtime's
 thread_local uint3 tl_threadIdx, tl_blockIdx;
 thread_local dim3 tl_blockDim, tl_gridDim;
 
@@ -228,7 +229,13 @@ void launch(dim3 grid, dim3 block, size_t dyn_bytes, const char* kernel, const s
         abort();
     }
     const size_t nthreads = (size_t)block.x * block.y * block.z;
-    if (nthreads == 0 || nthreads > 1024 || (size_t)grid.x * grid.y * grid.z == 0) return;       // a real launch would fail; the library never does this
+    if (nthreads == 0 || nthreads > 1024 || block.z > 64 || (size_t)grid.x * grid.y * grid.z == 0 || grid.y > 65535 || grid.z > 65535 || dyn_bytes > (227u << 10)) {
+        // what the hardware refuses (an empty grid or block, more than 1024 threads, too much shared memory): the launch does
+        // not happen and cudaGetLastError() reports it, exactly as on the GPU
+        tl_last_error = 9;       // cudaErrorInvalidConfiguration
+        if (getenv("CUEMU_VERBOSE")) fprintf(stderr, "cuemu: invalid launch configuration for %s: grid (%u,%u,%u) block (%u,%u,%u) smem %zu\n", kernel, grid.x, grid.y, grid.z, block.x, block.y, block.z, dyn_bytes);
+        return;
+    }
     s.running = true;
     while (s.stacks.size() < nthreads) {
         void* m = mmap(nullptr, STACK_BYTES, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
@@ -329,7 +336,11 @@ cudaError_t cudaGetDevice(int* d) {
 }
 cudaError_t cudaMalloc(void** p, size_t n) {
     void* m = nullptr;
-    if (posix_memalign(&m, 256, n ? n : 256) != 0) {
+    if (n == 0) {                 // the runtime hands back a null pointer for an empty allocation
+        *p = nullptr;
+        return cudaSuccess;
+    }
+    if (posix_memalign(&m, 256, n) != 0) {
         *p = nullptr;
         return cudaErrorMemoryAllocation;
     }
@@ -447,9 +458,13 @@ cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) {
     *ms = 0.f;
     return cudaSuccess;
 }
-cudaError_t cudaGetLastError(void) { return cudaSuccess; }
-cudaError_t cudaPeekAtLastError(void) { return cudaSuccess; }
-const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
+cudaError_t cudaGetLastError(void) {
+    cudaError_t e = cuemu::tl_last_error;
+    cuemu::tl_last_error = 0;
+    return e;
+}
+cudaError_t cudaPeekAtLastError(void) { return cuemu::tl_last_error; }
+const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : e == 9 ? "invalid configuration argument" : "emulated CUDA error"; }
 cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {
     a->type = cudaMemoryTypeUnregistered;          // every host buffer is "pageable": the library's staging ring gets exercised
     a->device = 0;
