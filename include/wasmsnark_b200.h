@@ -69,7 +69,9 @@ const char* ws_version(void);
  *          f1m_square               src/build_f1m.js:439-737      (y ignored)
  *          f1m_toMontgomery / fromMontgomery  src/build_f1m.js:749-770   (y ignored)
  *          f1m_inverse              src/build_f1m.js:772-783      (y ignored)
- * and the batch forms fft_toMontgomeryN / fromMontgomeryN / mulN  src/build_fft.js:418-547.  */
+ * and the batch forms fft_toMontgomeryN / fromMontgomeryN / mulN  src/build_fft.js:418-547.
+ * Operands are field elements (< p) -- except for WS_OP_TOMONT, which like f1m_toMontgomery takes ANY number that fits
+ * the element's bytes and returns the canonical x R mod p (the witness enters the prover that way, src/bn128.js:134). */
 enum { WS_OP_MUL = 0, WS_OP_ADD = 1, WS_OP_SUB = 2, WS_OP_SQUARE = 3, WS_OP_TOMONT = 4, WS_OP_FROMMONT = 5, WS_OP_INVERSE = 6 };
 int ws_fp_batch(ws_ctx* ctx, int field, int op, const uint8_t* x, const uint8_t* y, uint8_t* out, size_t n);
 

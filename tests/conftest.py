@@ -26,6 +26,38 @@ def pytest_configure(config):
         emulated_torch.patch()
 
 
+# GPU tests written after the round's last B200 run (GPU budget spent): so far they have passed only on the kernel
+# emulator (tests/host/cuemu), not on the hardware.  They run LAST, each under a hard time limit, so that under `pytest -x`
+# a surprise in one of them cannot keep the hardware-verified tests (golden proofs, MSM / NTT parity) from running, and a
+# hung kernel ends as a test failure instead of a hung box.  Nothing is skipped.
+_EMULATOR_ONLY_SO_FAR = (
+    "test_gpu_field.py::test_to_montgomery_takes_raw_values",
+    "test_gpu_prover.py::test_degenerate_keys_and_witnesses",
+    "test_gpu_prover.py::test_last_error_text_belongs_to_the_failing_thread",
+    "test_gpu_prover.py::test_multi_handle_with_more_gpus_than_points",
+    "test_node_addon_mock.py::test_prove_through_the_addon_equals_the_reference_proof",
+    "test_node_addon_mock.py::test_overlapping_proofs_on_one_handle",
+    "test_node_addon_mock.py::test_terminate_semantics",
+    "test_node_addon_mock.py::test_multiexp_affine_calch_through_the_addon",
+)
+
+
+def _emulator_only_so_far(item):
+    return any(key in item.nodeid for key in _EMULATOR_ONLY_SO_FAR)
+
+
+def pytest_collection_modifyitems(config, items):
+    if os.environ.get("WS_TEST_EMULATED"):
+        return
+    late = [it for it in items if _emulator_only_so_far(it)]
+    if not late:
+        return
+    if config.pluginmanager.hasplugin("timeout"):
+        for it in late:
+            it.add_marker(pytest.mark.timeout(300, method="thread"))
+    items[:] = [it for it in items if not _emulator_only_so_far(it)] + late
+
+
 @pytest.fixture(scope="session")
 def host_math():
     """ctypes handle on the HOST build of the arithmetic headers (tests/host/host_math.cpp)."""

@@ -77,6 +77,7 @@ struct Warp {
     int live = 0, count = 0;
     unsigned gen = 0;
     uint32_t slot[32];
+    uint32_t fresh = 0;            // lanes that wrote their slot in the running shuffle
 };
 struct Block {
     std::vector<Fiber> fib;
@@ -102,6 +103,7 @@ struct Sched {
     }
 };
 thread_local Sched tl_sched;
+thread_local const char* tl_kernel = "";
 
 void yield_to_scheduler(bool dying = false) {
     Block& b = tl_sched.blk;
@@ -216,9 +218,23 @@ uint32_t shfl(uint32_t v, int src) {
     Fiber& f = b.fib[b.cur];
     Warp& w = b.warps[f.warp];
     w.slot[f.lane] = v;
+    w.fresh |= 1u << f.lane;
     warp_barrier();
-    const uint32_t r = w.slot[src & 31];
+    // a source lane that takes no part in this shuffle (it returned earlier, or lies beyond the block's last thread) gives
+    // UNDEFINED data on the hardware: poison instead of the stale slot, so a kernel that consumes such a value cannot pass here
+    const bool taking_part = (w.fresh >> (src & 31)) & 1;
+    const uint32_t r = taking_part ? w.slot[src & 31] : 0xBAADF00Du ^ (uint32_t)(b.progress * 2654435761u);
+    if (!taking_part) {
+        static const bool verbose = getenv("CUEMU_VERBOSE") != nullptr;
+        static std::mutex mu;
+        static std::map<std::string, int> seen;
+        if (verbose) {
+            std::lock_guard<std::mutex> lk(mu);
+            if (seen[tl_kernel]++ == 0) fprintf(stderr, "cuemu: %s reads a shuffle value from a lane that takes no part (poisoned)\n", tl_kernel);
+        }
+    }
     warp_barrier();                             // nobody overwrites a slot before everybody has read
+    w.fresh &= ~(1u << f.lane);
     return r;
 }
 
@@ -237,6 +253,7 @@ void launch(dim3 grid, dim3 block, size_t dyn_bytes, const char* kernel, const s
         return;
     }
     s.running = true;
+    tl_kernel = kernel;
     while (s.stacks.size() < nthreads) {
         void* m = mmap(nullptr, STACK_BYTES, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
         if (m == MAP_FAILED) {

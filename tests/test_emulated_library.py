@@ -178,3 +178,24 @@ def test_driver_smoke_hook_on_the_cpu_emulator():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "host", "cuemu", "run_emulated.py"), os.path.join(ROOT, "__graft_entry__.py"), "smoke"],
                        cwd=ROOT, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0 and "smoke ok" in r.stdout, (r.stdout + r.stderr)[-2000:]
+
+
+@pytest.mark.parametrize("order", ["", "reverse", "shuffle"])
+def test_emulator_self_test(order):
+    """The emulator itself on kernels with known answers (tests/host/cuemu/selftest.cpp), so that a pass of the suites above
+    means something: a shuffle hands over the value of a lane that takes part and POISON for a lane that does not (one that
+    returned earlier, or beyond the last thread of a partial warp -- undefined data on the GPU, where the emulator used to
+    return the lane's stale slot); barriers order a shared-memory exchange for every thread order; launch configurations the
+    hardware refuses are refused with cudaErrorInvalidConfiguration."""
+    here = os.path.join(ROOT, "tests", "host", "cuemu")
+    exe = os.path.join(here, "_build", "selftest")
+    deps = [os.path.join(here, f) for f in ("selftest.cpp", "cuemu.cpp", "cuda_runtime.h")]
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-w", "-D__CUDACC__=1", "-I" + here, "-include", os.path.join(here, "cuda_runtime.h"),
+                               deps[0], deps[1], "-lpthread", "-o", exe])
+    r = subprocess.run([exe], env=dict(os.environ, CUEMU_ORDER=order), capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = dict((k, int(v)) for k, v in (line.split() for line in r.stdout.splitlines()))
+    assert got == {"shuffle_good": 24, "shuffle_poisoned": 16, "shuffle_stale": 0, "exchange_good": 576, "empty_grid_error": 9,
+                   "too_many_threads_error": 9, "error_cleared": 0}, got

@@ -150,3 +150,61 @@ def test_255_bit_modulus_would_overflow_so_it_is_not_enabled():
     assert any(sqr_model(a, p) != a * a * rinv % p for a in [rnd.randrange(p >> 1, p) for _ in range(200)])
     src = open(os.path.join(ROOT, "wasmsnark_b200", "csrc", "fp.cuh")).read()
     assert "P::BITS <= 254) return sqr_inline8(a)" in src
+
+
+def mul_model(a_int, b_int, p):
+    """mirror of the DEVICE path of fp.cuh::mul_inline (N = 8): WS_ROW0, seven WS_ROWs with the accumulators swapping roles,
+    merge_n8, sub_n8 + select on the borrow -- 256-bit truncation included, exactly what the registers hold"""
+    np0 = (-pow(p, -1, 1 << 32)) & M32
+    a, b, pl = limbs(a_int) + [0], limbs(b_int), limbs(p) + [0]
+    e, o = mul_n(a, b[0]), mul_n(a[1:], b[0])
+    m = (e[0] * np0) & M32
+    cmad_from(0, o, pl[1:], m)
+    o[N - 1] = (o[N - 1] + cmad_from(0, e, pl, m)) & M32
+    for i in range(1, N):
+        E, O = (o, e) if i & 1 else (e, o)
+        shift_mad_from(0, E, O, a[1:], b[i])
+        O[N - 1] = (O[N - 1] + cmad_from(0, E, a, b[i])) & M32
+        m = (E[0] * np0) & M32
+        cmad_from(0, O, pl[1:], m)
+        O[N - 1] = (O[N - 1] + cmad_from(0, E, pl, m)) & M32
+    merge(e, o)
+    r = value(e)
+    return r - p if r >= p else r
+
+
+def test_product_model_matches_definition_for_reduced_operands():
+    rnd = random.Random(4)
+    for p in (Q, RR):
+        rinv = pow(1 << 256, -1, p)
+        edge = [0, 1, 2, p - 1, p - 2, (1 << 253), 0xFFFFFFFF, 1 << 32, (1 << 224) - 1]
+        for a, b in [(x, y) for x in edge for y in edge] + [(rnd.randrange(p), rnd.randrange(p)) for _ in range(400)]:
+            assert mul_model(a, b, p) == a * b * rinv % p, (hex(a), hex(b))
+
+
+def test_product_model_with_a_raw_operand_it_must_be_the_second_one():
+    """to_mont(a) is how the witness enters the H pipeline (prover.cu::k_fr_to_mont), and the reference feeds
+    frm_toMontgomery RAW 256-bit signals (src/bn128.js:134; a witness value need not be < r).  In the device product the
+    running value of the row loop stays below A + p and must fit the nine limbs the two staggered accumulators span:
+      mul(R^2, a)  -- raw value second: canonical a R mod p for EVERY 256-bit a (what fp.cuh::to_mont does);
+      mul(a, R^2)  -- raw value first: right below 2^256 - p, loses a carry now and then above (what to_mont did until the
+                      model found it: wrong for about 1 % of the witness values above 0.85 * 2^256 -- none occur in real
+                      witnesses, all are legal inputs of the reference).
+    The emulator cannot show this (it runs the portable host path); tests/test_ptx_kernels.py executes the compiled kernel."""
+    rnd = random.Random(5)
+    for p in (Q, RR):
+        r2 = (1 << 512) % p
+        rinv = pow(1 << 256, -1, p)
+        top = (1 << 256) - 1
+        cases = [top, top - 1, p, p + 1, 2 * p, 2 * p + 1, 5 * p + 3, top - p, top - p + 1, (1 << 255), (1 << 255) + 1, top ^ 0xFFFFFFFF, top ^ (0xFFFFFFFF << 224)]
+        cases += [rnd.randrange(4 * p, 1 << 256) for _ in range(1500)] + [rnd.randrange(1 << 256) for _ in range(500)]
+        for a in cases:
+            assert mul_model(r2, a, p) == (a << 256) % p, hex(a)
+        for _ in range(500):                      # any reduced first operand, any raw second operand
+            a, b = rnd.choice([p - 1, p - 2, rnd.randrange(p)]), rnd.choice([top, rnd.randrange(1 << 256)])
+            assert mul_model(a, b, p) == a * b * rinv % p, (hex(a), hex(b))
+        # the other order: exact while A + p < 2^256 ...
+        for a in [p, 2 * p + 1, top - p - 1] + [rnd.randrange(p, (1 << 256) - p) for _ in range(500)]:
+            assert mul_model(a, r2, p) == (a << 256) % p, hex(a)
+        # ... and not above (the limit is real, not an artefact of a cautious bound)
+        assert any(mul_model(a, r2, p) != (a << 256) % p for a in [top - 1, top ^ 0xFFFFFFFF] + [rnd.randrange(4 * p, 1 << 256) for _ in range(400)])

@@ -59,6 +59,36 @@ def test_field_ops_bit_exact(bn, field, p, esz):
     assert got == [(pow(x * Rinv % p, -1, p) * R % p if x else 0) for x in xs[:m]]
 
 
+def raw_values(p, esz, seed):
+    """numbers that fit the element's bytes but need not be below p, dense at the top of the range"""
+    rnd = random.Random(seed)
+    top = (1 << (8 * esz)) - 1
+    lim = top - 2 * p if top > 4 * p else p
+    return [0, 1, p - 1, p, p + 1, top, top - 1, top ^ 0xFFFFFFFF, top ^ (0xFFFFFFFF << (8 * esz - 32)), top - p, top - p + 1, 1 << (8 * esz - 1)] + \
+           [rnd.randrange(lim, top + 1) for _ in range(700)] + [rnd.randrange(top + 1) for _ in range(300)]
+
+
+@pytest.mark.parametrize("field,p,esz", [(_lib.FIELD_BN128_FQ, Q, 32), (_lib.FIELD_BN128_FR, RR, 32), (_lib.FIELD_MNT6753_FQ, MNT_Q, 96)])
+def test_to_montgomery_takes_raw_values(bn, field, p, esz):
+    """f1m_toMontgomery / frm_toMontgomery accept ANY number that fits the element (the witness enters the prover that way,
+    src/bn128.js:134) and return the canonical x R mod p -- checked against the definition and, for BN128, against the
+    reference's own functions on the same bytes.  (The device product needs the raw value as its SECOND operand:
+    tests/test_fp_asm_model.py, tests/test_ptx_kernels.py.)"""
+    xs = raw_values(p, esz, 21)
+    X = b"".join(v.to_bytes(esz, "little") for v in xs)
+    got = bn.fp_batch(field, _lib.OP_TOMONT, X)
+    assert [int.from_bytes(got[i * esz:(i + 1) * esz], "little") for i in range(len(xs))] == [(x << (8 * esz)) % p for x in xs]
+    if esz == 32 and ref_wasm.available():
+        inst = ref_wasm.RefInstance(pages=100)
+        px, pr = inst.alloc(32), inst.alloc(32)
+        fn = "f1m_toMontgomery" if field == _lib.FIELD_BN128_FQ else "frm_toMontgomery"
+        for i in range(len(xs)):
+            inst.put(px, X[32 * i:32 * i + 32])
+            inst.call(fn, px, pr)
+            assert inst.get(pr, 32) == got[32 * i:32 * i + 32], (fn, hex(xs[i]))
+        inst.close()
+
+
 @pytest.mark.skipif(not ref_wasm.available(), reason="oracle/_ref not built")
 def test_mul_against_reference_image(bn):
     """config C1: 1k random pairs vs the reference's f1m_mul / frm_mul, byte for byte."""

@@ -430,8 +430,20 @@ def test_context_is_thread_safe(bn):
     assert not errors, errors
 
 
+def _witness_near_2p256(w):
+    """raw signals in the top 1/8 of the 256-bit range (legal for the reference: frm_toMontgomeryN takes them as they come,
+    src/bn128.js:134), among them values for which a device product with the raw operand FIRST drops a carry
+    (tests/test_fp_asm_model.py): 2^256 - 2, 2^256 - 2^32, ..."""
+    rnd = random.Random(9)
+    top = (1 << 256) - 1
+    vals = [top - 1, top ^ 0xFFFFFFFF, top ^ (0xFFFFFFFF << 224), top - O.R_ORDER + 1]
+    n = len(w) // 32
+    vals = (vals + [rnd.randrange(7 << 253, 1 << 256) for _ in range(n)])[:n]
+    return b"".join(v.to_bytes(32, "little") for v in vals)
+
+
 @pytest.mark.parametrize("case", ["C empty", "one signal", "domain 1", "domain 2", "nVars < 32", "all infinity", "no infinity", "witness 0",
-                                  "witness 2^256-1", "no coefficients", "dense coefficients"])
+                                  "witness 2^256-1", "witness near 2^256", "no coefficients", "dense coefficients"])
 def test_degenerate_keys_and_witnesses(bn, case):
     """Corners the example key never reaches: an empty C section (nVars = nPublic + 1), one-signal keys, one- and two-point
     domains (transforms of size 1, 2, 4), sections that are all infinity or never infinity, witnesses of all zeros / all
@@ -450,6 +462,7 @@ def test_degenerate_keys_and_witnesses(bn, case):
         "no infinity": (200, 5, 128, {"inf_share": 0.0}, None),
         "witness 0": (200, 5, 128, {}, lambda w: bytes(len(w))),
         "witness 2^256-1": (200, 5, 128, {}, lambda w: b"\xff" * len(w)),
+        "witness near 2^256": (200, 5, 128, {}, _witness_near_2p256),
         "no coefficients": (100, 5, 64, {"coef_density": (0.0, 0.0)}, None),
         "dense coefficients": (100, 5, 64, {"coef_density": (6.0, 9.0)}, None),
     }[case]

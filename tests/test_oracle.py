@@ -48,6 +48,35 @@ def test_montgomery_limb_restatement():
     assert O.to_mont(11, O.R_ORDER) == 11 * (1 << 256) % O.R_ORDER
 
 
+@pytest.mark.skipif(not ref_wasm.available(), reason="oracle/_ref not built")
+def test_raw_witness_values_reference_vs_oracle():
+    """A witness value need not be below r: frm_toMontgomeryN takes the signals as they come (src/bn128.js:134) and the
+    multiexps take them as raw 256-bit scalars.  (1) the reference's f1m_toMontgomery / frm_toMontgomery return the canonical
+    a R mod p for raw a, the top of the range included; (2) the reference's whole prover on a witness of such values equals the
+    big-integer restatement -- which is what the GPU proof of that witness is compared with (test_gpu_prover.py, case
+    "witness near 2^256")."""
+    rnd = random.Random(3)
+    top = (1 << 256) - 1
+    inst = ref_wasm.RefInstance(pages=100)
+    px, pr = inst.alloc(32), inst.alloc(32)
+    for fn, p in (("f1m_toMontgomery", O.Q), ("frm_toMontgomery", O.R_ORDER)):
+        for v in [top, top - 1, top ^ 0xFFFFFFFF, top ^ (0xFFFFFFFF << 224), p, p + 1, 5 * p + 1, top - p + 1] + [rnd.randrange(4 * p, 1 << 256) for _ in range(300)]:
+            inst.put(px, v.to_bytes(32, "little"))
+            inst.call(fn, px, pr)
+            assert int.from_bytes(inst.get(pr, 32), "little") == (v << 256) % p == O.to_mont(v, p), (fn, hex(v))
+    inst.close()
+    pk = open(os.path.join(GOLD, "synth_small.pkey.bin"), "rb").read()
+    n = len(open(os.path.join(GOLD, "synth_small.witness.bin"), "rb").read()) // 32
+    vals = ([top - 1, top ^ 0xFFFFFFFF, top ^ (0xFFFFFFFF << 224), top - O.R_ORDER + 1] + [rnd.randrange(7 << 253, 1 << 256) for _ in range(n)])[:n]
+    wit = b"".join(v.to_bytes(32, "little") for v in vals)
+    r, s = bytes(range(7, 39)), bytes(range(100, 132))
+    ref = ref_wasm.RefBn128(concurrency=2, pages=400)
+    try:
+        assert ref.groth16GenProof(wit, pk, r=r, s=s) == O.groth16_gen_proof(wit, pk, int.from_bytes(r, "little"), int.from_bytes(s, "little"))
+    finally:
+        ref.close()
+
+
 def test_synth_small_calch_and_proofs():
     pk = open(os.path.join(GOLD, "synth_small.pkey.bin"), "rb").read()
     wit = open(os.path.join(GOLD, "synth_small.witness.bin"), "rb").read()

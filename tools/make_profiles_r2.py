@@ -55,7 +55,7 @@ def main():
             "* `r2_ncu_accumulate_*.txt`, `r2_ncu_ntt_*.txt` -- `ncu --set full --clock-control none` summaries (tools/ncu_summary.py) of the accumulate kernels of one proof and of the NTT passes.",
             "* `r2_ntt_variants*.txt` -- `tools/run_ntt_once.py` timings of the NTT pass variants (occupancy, warp-local exchange, radix 16).",
             "* `r2_op_census_2p20.json` / `.md` -- Montgomery products and squarings of one 2^20-constraint proof, counted per kernel inside the executed kernels (CPU kernel emulator, `tests/host/cuemu/census.py`), next to the measured kernel times.",
-            "* `r2_device_sass.sha256` -- hash of the SASS of all 177 kernels (`tools/sass_hash.py`): the device code the last GPU session ran is the device code of HEAD (later commits: host code, tests, documents); `tests/test_abi.py` checks the built library against it.",
+            "* `r2_device_sass.sha256` -- hash of the SASS of all 177 kernels of the build the last GPU session ran; `r2_device_sass_per_kernel.txt` -- the same per kernel for the CURRENT build, each kernel marked `gpu-verified` (byte-identical to that build: 171 kernels) or `changed-after-last-gpu-run` (6 kernels, see the note at the end); `tools/sass_hash.py` writes both, `tests/test_abi.py` checks the built library against them.",
             "* `r2_ptxas_resources.txt` -- registers / stack / spill bytes of every kernel (`-Xptxas -v`); `r2_tuning_hook_sweep.txt`, `r2_ws_multi_timings.txt` -- see the A/B table at the end.", ""]
     if b1:
         cb = b1.get("cpu_baseline") or {}

@@ -378,8 +378,14 @@ HD Fp<P> sqr(const Fp<P>& a) {
 #endif
 }
 
+// f1m_toMontgomery (build_f1m.js:118-125) takes RAW N-limb numbers -- a witness value need not be below the modulus
+// (src/bn128.js:134 hands frm_toMontgomeryN the signals as they come) -- and returns the canonical a R mod p.  The raw
+// value must be the SECOND operand of the device product: the row loop's running value stays below A + p, which has to fit
+// the N + 1 limbs the two staggered accumulators span (A + p < 2^(32 N)); B only ever enters limb by limb.  With the raw
+// value first, a >= 2^256 - p loses a carry now and then (tests/test_fp_asm_model.py::test_product_model_with_an_unreduced_
+// first_operand shows both orders on the generated PTX).
 template <class P>
-HD Fp<P> to_mont(const Fp<P>& a) { return mul(a, Fp<P>::r2()); }
+HD Fp<P> to_mont(const Fp<P>& a) { return mul(Fp<P>::r2(), a); }
 
 template <class P>
 HD Fp<P> from_mont(const Fp<P>& a) {
