@@ -382,8 +382,8 @@ HD Fp<P> sqr(const Fp<P>& a) {
 // (src/bn128.js:134 hands frm_toMontgomeryN the signals as they come) -- and returns the canonical a R mod p.  The raw
 // value must be the SECOND operand of the device product: the row loop's running value stays below A + p, which has to fit
 // the N + 1 limbs the two staggered accumulators span (A + p < 2^(32 N)); B only ever enters limb by limb.  With the raw
-// value first, a >= 2^256 - p loses a carry now and then (tests/test_fp_asm_model.py::test_product_model_with_an_unreduced_
-// first_operand shows both orders on the generated PTX).
+// value first, a >= 2^256 - p loses a carry now and then (tests/test_fp_asm_model.py shows both orders on the generated
+// PTX, tests/test_ptx_kernels.py executes the compiled kernels).
 template <class P>
 HD Fp<P> to_mont(const Fp<P>& a) { return mul(Fp<P>::r2(), a); }
 
