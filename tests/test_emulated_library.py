@@ -41,6 +41,7 @@ PROVER = [
     "tests/test_gpu_prover.py::test_balanced_split_emulated_on_one_gpu[3]",
     "tests/test_gpu_prover.py::test_last_error_text_belongs_to_the_failing_thread",
     "tests/test_gpu_prover.py::test_degenerate_keys_and_witnesses",
+    "tests/test_gpu_prover.py::test_int_mul_edge_grid_as_r_times_s",
     "tests/test_node_addon_mock.py",
 ]
 OTHER_CURVES = [

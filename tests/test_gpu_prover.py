@@ -479,6 +479,40 @@ def test_degenerate_keys_and_witnesses(bn, case):
         key.free()
 
 
+def int_edge_values(n=8, bits=32):
+    """helpers.genValues(n, false) of the reference's tests (test/helpers/helpers.js:3-23): 0, 2^(32 i) - 1, 2^(32 i), 2^(32 i) + 1"""
+    res = [0]
+    for i in range(n):
+        if i > 0:
+            res.append((1 << (bits * i)) - 1)
+        if i < n - 1:
+            res += [1 << (bits * i), (1 << (bits * i)) + 1]
+    return res
+
+
+def test_int_mul_edge_grid_as_r_times_s(bn):
+    """test/int.js:22-47 multiplies every pair of its edge patterns with int_mul and compares the 512-bit products.  On this
+    path int_mul has one job: r * s, exact, as the 512-bit scalar of (r s) delta1 in pi_c (src/bn128.js:701) -- so every pair
+    of the grid, plus 2^256 - 1, goes in as (r, s) of a proof (tiny resident key), against the big-integer prover; r and s
+    alone also drive the fixed-base products r delta1, s delta1, s delta2 and the windowed s pi_a, r pib1."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tools"))
+    import gen_synth_key
+    pk, wit = gen_synth_key.make(6, 1, 4, seed=4)
+    vals = int_edge_values() + [(1 << 256) - 1]
+    if os.environ.get("WS_TEST_EMULATED"):          # the CPU emulator takes a second per proof: a diagonal band of the grid
+        pairs = [(a, vals[(i + d) % len(vals)]) for i, a in enumerate(vals) for d in (0, 1, 11)]
+    else:
+        pairs = [(a, b) for a in vals for b in vals]
+    key = bn.load_proving_key(pk)
+    try:
+        for a, b in pairs:
+            got = bn.groth16GenProof(wit, key, r=a.to_bytes(32, "little"), s=b.to_bytes(32, "little"))
+            assert got == O.groth16_gen_proof(wit, pk, a, b), (hex(a), hex(b))
+    finally:
+        key.free()
+
+
 def test_last_error_text_belongs_to_the_failing_thread(bn):
     """Two host threads fail differently on ONE context, and only then ask for the text: each reads its own message
     (ws_last_error keeps a per-thread copy; with a single per-context string the later failure would win for both --
