@@ -31,6 +31,7 @@ PROVER = [
     "tests/test_gpu_prover.py::test_fft_golden_vectors",
     "tests/test_gpu_prover.py::test_fft_vs_oracle_all_radix_mixes",
     "tests/test_gpu_prover.py::test_fft_rejects_bad_sizes",
+    "tests/test_gpu_prover.py::test_fft_reference_zeros_pattern",
     "tests/test_gpu_prover.py::test_fft_interleave_identity[16]",
     "tests/test_gpu_prover.py::test_fft_in_place_pass_counts_and_variants[13]",
     "tests/test_gpu_prover.py::test_synth_small_calch_and_proofs",

@@ -55,6 +55,20 @@ def test_fft_vs_oracle_all_radix_mixes(bn, logn):
         assert from_mont_list(bn.ifft(xb, odd)) == O.ifft(x, odd)
 
 
+def test_fft_reference_zeros_pattern(bn):
+    """test/fft.js:53-70 ("test with zeros"), step for step: 0 / 1 alternating, N = 1024, fft_toMontgomeryN -> fft_ifft ->
+    fft_fft -> fft_fromMontgomeryN gives the input back; the transform of the pattern itself also equals the oracle's."""
+    from wasmsnark_b200 import _lib
+    n = 1024
+    vals = [i & 1 for i in range(n)]
+    x = b"".join(v.to_bytes(32, "little") for v in vals)
+    xm = bn.fp_batch(_lib.FIELD_BN128_FR, _lib.OP_TOMONT, x)
+    mid = bn.ifft(xm, 0)
+    assert from_mont_list(mid) == O.ifft(vals, 0)
+    back = bn.fp_batch(_lib.FIELD_BN128_FR, _lib.OP_FROMMONT, bn.fft(mid, 0))
+    assert back == x
+
+
 def test_fft_rejects_bad_sizes(bn):
     from wasmsnark_b200._lib import WsError
     for n in (3, 12, 1000):
