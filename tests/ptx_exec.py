@@ -8,7 +8,8 @@ file runs what the COMPILER composed: `nvcc -ptx` of the real translation unit, 
 constant folding, the optimiser's register renaming and all).  What is left to the hardware run is ptxas (PTX -> SASS).
 
 Supported: the integer subset these kernels use (mov, add/sub/mul/mad with .cc / addc / subc / madc carry forms, mul.wide,
-shifts, logic, setp / selp, predicated execution and branches, ld.param, ld/st.global scalar and .v2/.v4 vectors, cvta).
+shifts, logic, setp / selp, predicated execution and branches, ld.param, ld/st scalar and .v2/.v4 vectors on global, local
+and generic addresses, cvta, per-frame local memory, calls of .func device functions with .param passing).
 Anything else raises -- a kernel outside the subset fails loudly instead of being half-executed."""
 import os
 import re
@@ -34,29 +35,74 @@ def ptx_of(cu_name):
     return open(out).read()
 
 
+def ptx_of_many(cu_names):
+    """the same for several translation units at once (nvcc runs side by side: a cold cache costs the slowest, not the sum)"""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(cu_names)) as ex:
+        return dict(zip(cu_names, ex.map(ptx_of, cu_names)))
+
+
+class Code(list):
+    """statements of one entry / function + what they need around them"""
+    funcs = None          # {name: (parameter names, Code)} of the whole translation unit
+    local_bytes = 0       # size of the frame's local depot
+    depot = None          # its symbol
+
+
+def _parse_body(body):
+    body = re.sub(r"//[^\n]*", "", body)
+    code = Code()
+    m = re.search(r"\.local\s+\.align\s+\d+\s+\.b8\s+(\w+)\[(\d+)\]", body)
+    if m:
+        code.depot, code.local_bytes = m.group(1), int(m.group(2))
+    for raw in body.replace("\n", " ").split(";"):
+        s = raw.strip()
+        while s[:1] in ("{", "}"):                         # call sequences sit in their own { } scope
+            s = s[1:].strip()
+        while True:                                        # labels in front of a statement
+            m = re.match(r"(\$?[\w$]+):\s*", s)
+            if not m or s.startswith("@"):
+                break
+            code.append(("label", m.group(1)))
+            s = s[m.end():]
+        if s and not s.startswith((".reg", ".local", ".shared", ".maxntid", ".reqntid", ".pragma", ".param")):
+            code.append(("ins", s))
+    return code
+
+
+def _split_unit(ptx, start):
+    """(parameter names, Code) of the .entry / .func whose parameter list opens at ptx[start - 1] == '('"""
+    j = ptx.index(")", start)
+    params = re.findall(r"\.param\s+\.\w+(?:\s+\.ptr)?(?:\s+\.align\s+\d+)?\s+(\w+)", ptx[start:j])
+    b0 = ptx.index("{", j)
+    b1 = ptx.index("\n}", b0)
+    return params, _parse_body(ptx[b0 + 1:b1])
+
+
+def functions(ptx):
+    """{name: (parameter names, Code)} of every .func DEFINED in the translation unit (no return values: the library's
+    out-of-line helpers return through pointers)"""
+    funcs = {}
+    for m in re.finditer(r"\.func\s+(\w+)\s*\(", ptx):
+        end = ptx.index(")", m.end())
+        k = end + 1
+        while ptx[k].isspace():
+            k += 1
+        if ptx[k] == "{":                                   # a definition, not a forward declaration
+            funcs[m.group(1)] = _split_unit(ptx, m.end())
+    for _, code in funcs.values():
+        code.funcs = funcs
+    return funcs
+
+
 def entry(ptx, name_part):
     """(parameter names, statements) of the one .entry whose mangled name contains every string of name_part"""
     parts = [name_part] if isinstance(name_part, str) else list(name_part)
     hits = [m for m in re.finditer(r"\.entry\s+(\w+)\s*\(", ptx) if all(p in m.group(1) for p in parts)]
     assert len(hits) == 1, "%d entries match %r" % (len(hits), parts)
-    i = hits[0].end()
-    j = ptx.index(")", i)
-    params = re.findall(r"\.param\s+\.\w+(?:\s+\.ptr)?(?:\s+\.align\s+\d+)?\s+(\w+)", ptx[i:j])
-    b0 = ptx.index("{", j)
-    b1 = ptx.index("\n}", b0)
-    body = re.sub(r"//[^\n]*", "", ptx[b0 + 1:b1])
-    stmts = []
-    for raw in body.replace("\n", " ").split(";"):
-        s = raw.strip()
-        while True:                                        # labels in front of a statement
-            m = re.match(r"(\$?[\w$]+):\s*", s)
-            if not m or s.startswith("@"):
-                break
-            stmts.append(("label", m.group(1)))
-            s = s[m.end():]
-        if s and not s.startswith((".reg", ".local", ".shared", ".maxntid", ".reqntid", ".pragma")):
-            stmts.append(("ins", s))
-    return params, stmts
+    params, code = _split_unit(ptx, hits[0].end())
+    code.funcs = functions(ptx) if "call" in ptx[hits[0].end():ptx.index("\n}", hits[0].end())] else {}
+    return params, code
 
 
 class Memory:
@@ -71,6 +117,9 @@ class Memory:
         self.bufs.append((base, buf))
         self.next += (len(buf) + 0xFFFF) & ~0xFFFF
         return base
+
+    def free(self, base):
+        self.bufs = [(b, buf) for b, buf in self.bufs if b != base]
 
     def _find(self, addr, size):
         for base, buf in self.bufs:
@@ -101,11 +150,27 @@ def _signed(v, bits):
 
 def run_thread(params, stmts, args, mem, tid, ntid, ctaid, nctaid=(1, 1, 1), max_steps=5_000_000):
     """one CUDA thread from entry to ret"""
-    reg, cc = {}, 0
+    budget = [max_steps]
     special = {"%tid": tid, "%ntid": ntid, "%ctaid": ctaid, "%nctaid": nctaid}
+    _run_frame(params, stmts, args, mem, special, budget)
+
+
+def _run_frame(params, stmts, args, mem, special, budget):
+    """one activation of an entry or a device function: its own registers, carry flag and local depot"""
+    reg, cc = {}, 0
     pvals = dict(zip(params, args))
     labels = {s[1]: i for i, s in enumerate(stmts) if s[0] == "label"}
+    depot = getattr(stmts, "depot", None)
+    local_base = mem.alloc(bytes(stmts.local_bytes)) if depot else None
+    outgoing = {}                                  # .param values of the call being set up
+    try:
+        return _run_body(stmts, reg, cc, pvals, labels, depot, local_base, outgoing, mem, special, budget)
+    finally:
+        if local_base is not None:
+            mem.free(local_base)
 
+
+def _run_body(stmts, reg, cc, pvals, labels, depot, local_base, outgoing, mem, special, budget):
     def val(tok, bits=32):
         tok = tok.strip()
         if tok.startswith("%"):
@@ -113,6 +178,8 @@ def run_thread(params, stmts, args, mem, tid, ntid, ctaid, nctaid=(1, 1, 1), max
             if m:
                 return special[m.group(1)]["xyz".index(m.group(2))]
             return reg[tok]
+        if depot and tok == depot:
+            return local_base
         return int(tok, 0) & ((1 << bits) - 1)
 
     def addr_of(tok):
@@ -122,10 +189,10 @@ def run_thread(params, stmts, args, mem, tid, ntid, ctaid, nctaid=(1, 1, 1), max
         off = int(m.group(2), 0) if m.group(2) else 0
         return base, off
 
-    pc, steps = 0, 0
+    pc = 0
     while pc < len(stmts):
-        steps += 1
-        assert steps < max_steps, "runaway kernel"
+        budget[0] -= 1
+        assert budget[0] > 0, "runaway kernel"
         kind, s = stmts[pc]
         pc += 1
         if kind == "label":
@@ -148,9 +215,9 @@ def run_thread(params, stmts, args, mem, tid, ntid, ctaid, nctaid=(1, 1, 1), max
         # operands: split on commas outside braces / brackets
         ops, depth, cur = [], 0, ""
         for ch in rest:
-            if ch in "{[":
+            if ch in "{[(":
                 depth += 1
-            elif ch in "}]":
+            elif ch in "}])":
                 depth -= 1
             if ch == "," and depth == 0:
                 ops.append(cur.strip())
@@ -165,10 +232,20 @@ def run_thread(params, stmts, args, mem, tid, ntid, ctaid, nctaid=(1, 1, 1), max
             name, off = addr_of(ops[1])
             assert off == 0
             reg[ops[0]] = pvals[name] & ((1 << bits) - 1)
+        elif base == "st" and f[1] == "param":
+            name, off = addr_of(ops[0])
+            assert off == 0
+            outgoing[name] = val(ops[1], bits)
+        elif base == "call":
+            assert len(ops) == 2 and ops[1].startswith("("), "ptx_exec: calls with return values are not modelled: " + s
+            fparams, fcode = stmts.funcs[ops[0]]
+            names = [x.strip() for x in ops[1].strip("() ").split(",")]
+            _run_frame(fparams, fcode, [outgoing[x] for x in names], mem, special, budget)
+            outgoing.clear()
         elif base == "cvta":
-            reg[ops[0]] = reg[ops[1]]
+            reg[ops[0]] = val(ops[1], 64)
         elif base in ("ld", "st"):
-            assert "global" in f, op
+            assert not ({"shared", "const", "param"} & set(f)), op        # global, local or generic: one flat address space here
             vec = 4 if "v4" in f else 2 if "v2" in f else 1
             size = bits // 8
             if base == "ld":
@@ -223,10 +300,12 @@ def run_thread(params, stmts, args, mem, tid, ntid, ctaid, nctaid=(1, 1, 1), max
                 if "cc" in f:
                     cc = t >> bits
         elif base in ("and", "or", "xor"):
-            a, b = val(ops[1], bits or 1), val(ops[2], bits or 1)
+            a, b = int(val(ops[1], bits or 1)), int(val(ops[2], bits or 1))           # .pred operands are Python bools
             reg[ops[0]] = (a & b) if base == "and" else (a | b) if base == "or" else (a ^ b)
+        elif base == "neg":
+            reg[ops[0]] = (-val(ops[1], bits)) & ((1 << bits) - 1)
         elif base == "not":
-            reg[ops[0]] = ~val(ops[1], bits or 1) & ((1 << (bits or 1)) - 1)
+            reg[ops[0]] = ~int(val(ops[1], bits or 1)) & ((1 << (bits or 1)) - 1)
         elif base in ("shl", "shr"):
             a, n = val(ops[1], bits), val(ops[2], 32)
             if base == "shl":

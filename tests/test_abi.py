@@ -79,7 +79,7 @@ def test_device_code_is_the_gpu_verified_one():
     B200 run executed (whole-library hash profiles/r2_device_sass.sha256), or "changed-after-last-gpu-run".  Exactly six kernels
     are in the second state: the witness conversion k_fr_to_mont and the five toMontgomery instantiations of k_fp_batch, which
     differ by the operand order of ONE Montgomery product (fp.cuh::to_mont, a raw value must be the second operand:
-    tests/test_fp_asm_model.py) and whose compiled PTX is executed on the CPU by tests/test_ptx_kernels.py.  A change that touches
+    tests/test_fp_asm_model.py) and whose compiled PTX -- all six -- is executed on the CPU by tests/test_ptx_kernels.py.  A change that touches
     any other kernel must be verified on a GPU and re-recorded (python tools/sass_hash.py --write)."""
     import shutil
     sys.path.insert(0, os.path.join(ROOT, "tools"))
