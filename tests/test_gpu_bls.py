@@ -46,6 +46,20 @@ def test_field_ops(bls, which):
     assert ints(bls.fp_batch(fid, _lib.OP_INVERSE, X), esz) == [pow(a * rinv % p, -1, p) * Rm % p if a else 0 for a in xs]
 
 
+@pytest.mark.parametrize("which", ["fq", "fr"])
+def test_to_montgomery_takes_raw_values(bls, which):
+    """f1m_toMontgomery on ANY number that fits the element (as for BN128, tests/test_gpu_field.py): the canonical x R mod p,
+    the top of the range included -- the device product takes the raw value as its second operand (fp.cuh::to_mont)"""
+    from wasmsnark_b200 import _lib
+    p, fid, esz = (B.Q, _lib.FIELD_BLS12381_FQ, 48) if which == "fq" else (B.R_ORDER, _lib.FIELD_BLS12381_FR, 32)
+    Rm = 1 << (8 * esz)
+    top = Rm - 1
+    rnd = random.Random(5)
+    xs = [top, top - 1, top ^ 0xFFFFFFFF, top ^ (0xFFFFFFFF << (8 * esz - 32)), top - p, top - p + 1, p, p + 1, 2 * p + 1] + \
+         [rnd.randrange(top - 2 * p if top > 4 * p else p, Rm) for _ in range(600)] + [rnd.randrange(Rm) for _ in range(200)]
+    assert ints(bls.fp_batch(fid, _lib.OP_TOMONT, b"".join(le(v, esz) for v in xs)), esz) == [a * Rm % p for a in xs]
+
+
 def test_fq2_mul(bls):
     rnd = random.Random(4)
     xs = [(rnd.randrange(B.Q), rnd.randrange(B.Q)) for _ in range(300)] + [(0, 0), (1, 0), (0, 1), (B.Q - 1, B.Q - 1)]
