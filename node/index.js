@@ -32,6 +32,21 @@ const cat = (parts) => { const o = new Uint8Array(parts.reduce((n, p) => n + p.l
 const g1bin = (e) => cat([int2bin(e[0]), int2bin(e[1])]);                                                // setG1Affine :503-507
 const g2bin = (e) => cat([int2bin(e[0][0]), int2bin(e[0][1]), int2bin(e[1][0]), int2bin(e[1][1])]);      // setG2Affine :509-513
 
+// g?m_fromMontgomery (src/build_curve_jacobian_a0.js:258-277): every 32-byte Fq coordinate x -> x R^-1 mod q, nothing else
+const BN128_Q = 21888242871839275222246405745257275088696311157297823662689037894645226208583n;
+const BN128_RINV = 20988524275117001072002809824448087578619730785600314334253784976379291040311n;      // (2^256)^-1 mod q
+function fromMontgomery(p, size) {
+    const b = p instanceof ArrayBuffer ? new Uint8Array(p) : new Uint8Array(p.buffer, p.byteOffset, p.byteLength);
+    if (b.length === 0 || b.length % size) throw new RangeError("whole " + size + "-byte points expected");
+    const out = new Uint8Array(b.length);
+    for (let o = 0; o < b.length; o += 32) {
+        let x = 0n;
+        for (let i = 31; i >= 0; i--) x = (x << 8n) | BigInt(b[o + i]);
+        out.set(int2bin((x * BN128_RINV) % BN128_Q), o);
+    }
+    return out.buffer;
+}
+
 class Bn128 {
     // opts: a device index, or { device, gpus } -- gpus > 1 (0 = all) spreads every proof / multiexp over that many GPUs
     constructor(opts) {
@@ -50,6 +65,8 @@ class Bn128 {
     async g2_multiexp(scalars, points) { return native.g2Multiexp(this.h, scalars, points); }
     g1_affine(p) { return native.g1Affine(this.h, p); }
     g2_affine(p) { return native.g2Affine(this.h, p); }
+    g1_fromMontgomery(p) { return fromMontgomery(p, 96); }             // src/bn128.js:429-433
+    g2_fromMontgomery(p) { return fromMontgomery(p, 192); }            // :435-439
     async calcH(signals, polsA, polsB, nSignals, domainSize) { return native.calcH(this.h, signals, polsA, polsB, nSignals, domainSize); }
     async groth16Verify(verificationKey, input, proof) {                // src/bn128.js:722-786
         if (input === undefined || input === null) input = [];

@@ -120,6 +120,28 @@ def test_group_identities_from_reference_suite(bn):
 
 
 @pytest.mark.skipif(not ref_wasm.available(), reason="oracle/_ref not built")
+def test_from_montgomery_methods_equal_the_reference_functions(bn):
+    """Bn128.g1_fromMontgomery / g2_fromMontgomery (src/bn128.js:429-439): un-normalised multiexp results (Z != 1) and the
+    point at infinity through the mirror's methods and through the reference image's g1m_ / g2m_fromMontgomery, byte for byte;
+    g?_affine followed by g?_fromMontgomery equals the combined g?_affine_std the prover's output path uses."""
+    rnd = random.Random(31)
+    inst = ref_wasm.RefInstance(pages=100)
+    for g, gen, enc, fn, size, ref_fn, mexp, aff, aff_std in ((1, O.G1_GEN, util.g1_affine_m, bn.g1_fromMontgomery, 96, "g1m_fromMontgomery", bn.g1_multiexp, bn.g1_affine, bn.g1_affine_std),
+                                                               (2, O.G2_GEN, util.g2_affine_m, bn.g2_fromMontgomery, 192, "g2m_fromMontgomery", bn.g2_multiexp, bn.g2_affine, bn.g2_affine_std)):
+        F = O.Fq if g == 1 else O.Fq2
+        G_ = (gen[0], gen[1], F.one)
+        pts = [mexp(b32(rnd.getrandbits(256)) + b32(rnd.getrandbits(200)), enc(G_) * 2) for _ in range(4)] + [mexp(b32(RR), enc(G_))]
+        px = inst.alloc(size)
+        for P in pts:
+            inst.put(px, P)
+            inst.call(ref_fn, px, px)
+            assert fn(P) == inst.get(px, size)
+            assert fn(aff(P)) == aff_std(P)
+        assert fn(b"".join(pts)) == b"".join(fn(P) for P in pts)
+    inst.close()
+
+
+@pytest.mark.skipif(not ref_wasm.available(), reason="oracle/_ref not built")
 def test_2p14_vs_reference_multiexp2(bn):
     n = 1 << 14
     aff, P0, D = util.arith_points(O.Fq, O.G1_GEN, n, 0xB202)

@@ -195,6 +195,21 @@ def proof_json(p):
 
 
 # ------------------------------------------------------------------------------------------------ CPU
+def test_js_wrapper_constants_and_reference_method_names():
+    """node/index.js cannot be executed here (no Node.js); what can be checked from its text: the two BigInt constants of its
+    g?_fromMontgomery (q, and R^-1 mod q with R = 2^256) and that the class offers the reference's proving-path methods under
+    the reference's names (src/bn128.js:353-439, 562-786)."""
+    import re
+    src = open(os.path.join(ROOT, "node", "index.js")).read()
+    q = int(re.search(r"BN128_Q = (\d+)n", src).group(1))
+    rinv = int(re.search(r"BN128_RINV = (\d+)n", src).group(1))
+    assert q == 21888242871839275222246405745257275088696311157297823662689037894645226208583
+    assert (rinv << 256) % q == 1
+    for name in ("groth16GenProof", "groth16Verify", "g1_multiexp", "g2_multiexp", "g1_affine", "g2_affine", "g1_fromMontgomery", "g2_fromMontgomery",
+                 "calcH", "bin2g1", "bin2g2", "terminate"):
+        assert re.search(r"^\s+(async )?%s\(" % name, src, re.M), name
+
+
 def test_module_registers_the_documented_exports(js):
     for name in EXPORTS:
         assert js.lib.mock_kind(js.get(js.exports, name)) == K_FUNCTION, name

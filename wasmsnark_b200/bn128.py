@@ -62,6 +62,19 @@ class Bn128:
         """src/bn128.js:423-427."""
         return self._affine(self.lib.ws_bn128_g2_affine, p, 192, 0)
 
+    def g1_fromMontgomery(self, p):
+        """src/bn128.js:429-433 -> g1m_fromMontgomery (build_curve_jacobian_a0.js:258-277): every coordinate of the 96-byte
+        triple(s) out of Montgomery form, nothing else (no normalisation)."""
+        if len(p) % 96:
+            raise ValueError("whole 96-byte G1 triples expected")
+        return self.fp_batch(_lib.FIELD_BN128_FQ, _lib.OP_FROMMONT, bytes(p))
+
+    def g2_fromMontgomery(self, p):
+        """src/bn128.js:435-439 -> g2m_fromMontgomery: the six Fq components of each 192-byte triple."""
+        if len(p) % 192:
+            raise ValueError("whole 192-byte G2 triples expected")
+        return self.fp_batch(_lib.FIELD_BN128_FQ, _lib.OP_FROMMONT, bytes(p))
+
     def g1_affine_std(self, p):
         """g1_affine followed by g1_fromMontgomery (src/bn128.js:706-712)."""
         return self._affine(self.lib.ws_bn128_g1_affine, p, 96, 1)
