@@ -2,7 +2,7 @@
 compiled by g++ against the CPU kernel emulator in this directory (cuda_runtime.h, cuemu.cpp).
 
 The sources are copied into tests/host/cuemu/_build/pkg/csrc/ with two mechanical rewrites (nothing else is touched):
-  kernel<<<grid, block, smem, stream>>>(args);   ->  cuemu::launch(dim3(grid), dim3(block), smem, "kernel", [&]() { kernel(args); });
+  kernel<<<grid, block, smem, stream>>>(args);   ->  { auto a = std::make_tuple(args); cuemu::launch_on(stream, dim3(grid), dim3(block), smem, "kernel", [a]() { std::apply(kernel, a); }); }
   extern __shared__ T name[];                    ->  T* name = (T*)cuemu::dyn_smem();
   __noinline__                                   ->  __attribute__((noinline))
 plus one counting line in the host path of fp.cuh's product and squaring (operation census, cuemu.cpp).
@@ -83,8 +83,12 @@ def rewrite_launches(src):
         out.append(src[pos:k + 1])
         name = re.sub(r"\s+", " ", kern).replace('"', "")
         # the name the census files the launch under: the kernel expression + the template bindings of the launch site
-        out.append('cuemu::launch(dim3(%s), dim3(%s), %s, cuemu::kernel_label("%s", __PRETTY_FUNCTION__).c_str(), [&]() { %s%s; });'
-                   % (cfg[0], cfg[1], smem, name, kern, src[a0:a1 + 1]))
+        # the arguments are evaluated HERE, at the launch, and copied into the closure -- as the hardware launch does; the
+        # closure may run much later (CUEMU_ASYNC: deferred execution of the streams, cuemu.cpp)
+        stream = cfg[3] if len(cfg) > 3 else "nullptr"
+        out.append('{ auto cuemu_args = std::make_tuple%s; cuemu::launch_on((cudaStream_t)(%s), dim3(%s), dim3(%s), %s, '
+                   'cuemu::kernel_label("%s", __PRETTY_FUNCTION__), [=]() { std::apply([=](auto&... cuemu_a) { %s(cuemu_a...); }, cuemu_args); }); }'
+                   % (src[a0:a1 + 1], stream, cfg[0], cfg[1], smem, name, kern))
         pos = end + 1
     out.append(src[pos:])
     return "".join(out)

@@ -17,6 +17,7 @@
 #include <cstring>
 #include <functional>
 #include <string>
+#include <tuple>
 
 #define __CUDACC__ 1          // the sources' "compiled as CUDA" paths (hd.cuh, warp_ec.cuh) ...
 #undef __CUDA_ARCH__          // ... but never their device-only PTX paths
@@ -168,3 +169,9 @@ cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p);
 }
 template <class T>
 static inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
+
+namespace cuemu {
+// a launch on a stream: `body` owns copies of the kernel's arguments, evaluated at the launch (build_emu.py).  Runs at once
+// in the synchronous mode, is queued on `st` under CUEMU_ASYNC (cuemu.cpp)
+void launch_on(cudaStream_t st, dim3 grid, dim3 block, size_t dyn_smem, const std::string& kernel, std::function<void()> body);
+}  // namespace cuemu

@@ -12,9 +12,13 @@
 
 #include <sys/mman.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstring>
+#include <deque>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -238,6 +242,11 @@ uint32_t shfl(uint32_t v, int src) {
     return r;
 }
 
+bool bad_launch_configuration(dim3 grid, dim3 block, size_t dyn_bytes) {
+    const size_t nthreads = (size_t)block.x * block.y * block.z;
+    return nthreads == 0 || nthreads > 1024 || block.z > 64 || (size_t)grid.x * grid.y * grid.z == 0 || grid.y > 65535 || grid.z > 65535 || dyn_bytes > (227u << 10);
+}
+
 void launch(dim3 grid, dim3 block, size_t dyn_bytes, const char* kernel, const std::function<void()>& body) {
     Sched& s = tl_sched;
     if (s.running) {
@@ -245,7 +254,7 @@ void launch(dim3 grid, dim3 block, size_t dyn_bytes, const char* kernel, const s
         abort();
     }
     const size_t nthreads = (size_t)block.x * block.y * block.z;
-    if (nthreads == 0 || nthreads > 1024 || block.z > 64 || (size_t)grid.x * grid.y * grid.z == 0 || grid.y > 65535 || grid.z > 65535 || dyn_bytes > (227u << 10)) {
+    if (bad_launch_configuration(grid, block, dyn_bytes)) {
         // what the hardware refuses (an empty grid or block, more than 1024 threads, too much shared memory): the launch does
         // not happen and cudaGetLastError() reports it, exactly as on the GPU
         tl_last_error = 9;       // cudaErrorInvalidConfiguration
@@ -327,6 +336,15 @@ void launch(dim3 grid, dim3 block, size_t dyn_bytes, const char* kernel, const s
 }  // namespace cuemu
 
 // ------------------------------------------------------------------------------------------------- runtime API
+// Two modes.  Default: synchronous -- every launch and copy happens inside the call that asks for it.
+// CUEMU_ASYNC=lazy|eager: DEFERRED -- launches and asynchronous copies are queued on their stream and run only when
+// something forces them: a synchronize, a blocking copy, an event another forced stream waits for.  `lazy` then runs the
+// bare minimum (the forced stream, and of other streams only what its event waits name); `eager` runs every OTHER stream to
+// the end first.  Both are legal schedules of the same program; a program whose streams are ordered by stream order and
+// events alone gives the same bytes under all three.  One that relies on timing -- a consumer without a wait on its
+// producer's event, a buffer reused before its last reader was ordered behind the writer -- gives different bytes under
+// lazy (consumers run before unordered producers) or eager (unordered later writers run before earlier readers).  That is
+// the class of defect a GPU run hides by luck and the synchronous emulator hides by construction.
 namespace {
 thread_local int tl_device = 0;
 int device_count() {
@@ -335,7 +353,183 @@ int device_count() {
     return n < 1 ? 1 : n > 16 ? 16 : n;
 }
 std::atomic<long> g_live_allocs{0};
+
+int async_mode() {
+    static const int m = [] {
+        const char* e = getenv("CUEMU_ASYNC");
+        return !e ? 0 : !strcmp(e, "lazy") ? 1 : !strcmp(e, "eager") ? 2 : 0;
+    }();
+    return m;
+}
+std::recursive_mutex g_rt_mu;
+struct Ev {
+    unsigned long long enqueued = 0, done = 0;      // record calls issued / executed
+};
+struct Op {
+    int kind;                                       // 0 work, 1 record, 2 wait
+    std::function<void()> fn;
+    std::shared_ptr<Ev> ev;
+    unsigned long long gen;
+};
+struct Stream {
+    std::deque<Op> q;
+    bool nonblocking = true, running = false;
+    unsigned long long id = 0;
+};
+unsigned long long g_next_stream_id = 1;
+std::map<cudaStream_t, std::shared_ptr<Stream>> g_streams;          // live handles
+std::vector<std::shared_ptr<Stream>> g_zombies;                     // destroyed with work pending: it still completes
+std::map<cudaEvent_t, std::shared_ptr<Ev>> g_events;
+std::map<uintptr_t, size_t> g_device_ranges, g_pinned_ranges;
+unsigned long long g_deferred_ops = 0, g_forced_drains = 0;
+
+bool in_ranges(const std::map<uintptr_t, size_t>& m, const void* p) {
+    auto it = m.upper_bound((uintptr_t)p);
+    if (it == m.begin()) return false;
+    --it;
+    return (uintptr_t)p < it->first + it->second;
+}
+std::shared_ptr<Stream> stream_of(cudaStream_t h) {                  // h != nullptr
+    auto it = g_streams.find(h);
+    if (it != g_streams.end()) return it->second;
+    auto s = std::make_shared<Stream>();                             // a handle the runtime did not hand out (tests): its own queue
+    s->id = g_next_stream_id++;
+    return g_streams[h] = s;
+}
+std::vector<std::shared_ptr<Stream>> all_streams() {
+    std::vector<std::shared_ptr<Stream>> v;
+    for (auto& kv : g_streams) v.push_back(kv.second);
+    for (auto& z : g_zombies) v.push_back(z);
+    std::sort(v.begin(), v.end(), [](const std::shared_ptr<Stream>& a, const std::shared_ptr<Stream>& b) { return a->id < b->id; });
+    return v;
+}
+void run_stream(Stream& s, const Ev* until_ev, unsigned long long until_gen);
+
+// make `ev` reach generation `gen`: run the stream that holds that record, up to it
+void advance_event(const std::shared_ptr<Ev>& ev, unsigned long long gen) {
+    while (ev->done < gen) {
+        bool found = false;
+        for (auto& sp : all_streams()) {
+            for (auto& op : sp->q)
+                if (op.kind == 1 && op.ev == ev && op.gen >= gen) {
+                    found = true;
+                    break;
+                }
+            if (found) {
+                if (sp->running) {
+                    fprintf(stderr, "cuemu: circular wait between streams (an event is awaited by work queued in front of its own record)\n");
+                    abort();
+                }
+                run_stream(*sp, ev.get(), gen);
+                break;
+            }
+        }
+        if (!found) {
+            fprintf(stderr, "cuemu: wait for an event record that is in no queue\n");
+            abort();
+        }
+    }
+}
+// execute the head of `s` until its queue is empty, or (until_ev) until that event has reached until_gen
+void run_stream(Stream& s, const Ev* until_ev, unsigned long long until_gen) {
+    s.running = true;
+    while (!s.q.empty() && !(until_ev && until_ev->done >= until_gen)) {
+        Op op = std::move(s.q.front());
+        s.q.pop_front();
+        if (op.kind == 0) op.fn();
+        else if (op.kind == 1) op.ev->done = std::max(op.ev->done, op.gen);
+        else advance_event(op.ev, op.gen);
+    }
+    s.running = false;
+}
+void reap_zombies() {
+    g_zombies.erase(std::remove_if(g_zombies.begin(), g_zombies.end(), [](const std::shared_ptr<Stream>& z) { return z->q.empty(); }), g_zombies.end());
+}
+void drain_everything(const Stream* last = nullptr) {
+    for (auto& sp : all_streams())
+        if (sp.get() != last && !sp->running) run_stream(*sp, nullptr, 0);
+    reap_zombies();
+}
+// a forcing point on one stream
+void force_stream(const std::shared_ptr<Stream>& s) {
+    g_forced_drains++;
+    if (async_mode() == 2) drain_everything(s.get());              // eager: everybody else first, to the end
+    if (!s->running) run_stream(*s, nullptr, 0);
+    reap_zombies();
+}
+// the legacy default stream orders itself against the BLOCKING streams only
+void force_blocking_streams() {
+    g_forced_drains++;
+    if (async_mode() == 2) {
+        drain_everything();
+        return;
+    }
+    for (auto& sp : all_streams())
+        if (!sp->nonblocking && !sp->running) run_stream(*sp, nullptr, 0);
+}
+void enqueue(cudaStream_t h, std::function<void()> fn) {
+    if (!h) {                                                       // legacy default stream: after the blocking streams, now
+        force_blocking_streams();
+        fn();
+        return;
+    }
+    g_deferred_ops++;
+    stream_of(h)->q.push_back(Op{0, std::move(fn), nullptr, 0});
+}
+cudaStream_t new_stream(unsigned flags) {
+    cudaStream_t h = (cudaStream_t)malloc(8);
+    if (async_mode()) {
+        std::lock_guard<std::recursive_mutex> lk(g_rt_mu);
+        auto s = std::make_shared<Stream>();
+        s->nonblocking = (flags & cudaStreamNonBlocking) != 0;
+        s->id = g_next_stream_id++;
+        g_streams[h] = s;
+    }
+    return h;
+}
+cudaError_t copy_async(void* d, const void* s, size_t n, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    if (!async_mode()) {
+        memmove(d, s, n);
+        return cudaSuccess;
+    }
+    std::lock_guard<std::recursive_mutex> lk(g_rt_mu);
+    const bool src_dev = in_ranges(g_device_ranges, s), dst_dev = in_ranges(g_device_ranges, d);
+    const bool src_pin = in_ranges(g_pinned_ranges, s), dst_pin = in_ranges(g_pinned_ranges, d);
+    if (!src_dev && !dst_dev) {                                     // host to host: done by the call
+        memmove(d, s, n);
+        return cudaSuccess;
+    }
+    if (!src_dev && !src_pin) {                                     // from pageable memory: staged before the call returns
+        auto snap = std::make_shared<std::vector<uint8_t>>((const uint8_t*)s, (const uint8_t*)s + n);
+        enqueue(st, [d, snap] { memcpy(d, snap->data(), snap->size()); });
+        return cudaSuccess;
+    }
+    if (!dst_dev && !dst_pin) {                                     // into pageable memory: the call returns when the copy is done
+        if (st) force_stream(stream_of(st));
+        else force_blocking_streams();
+        memmove(d, s, n);
+        return cudaSuccess;
+    }
+    enqueue(st, [d, s, n] { memmove(d, s, n); });                   // device / pinned on both sides: truly asynchronous
+    return cudaSuccess;
+}
 }  // namespace
+
+namespace cuemu {
+void launch_on(cudaStream_t st, dim3 grid, dim3 block, size_t dyn_bytes, const std::string& kernel, std::function<void()> body) {
+    if (!async_mode()) {
+        launch(grid, block, dyn_bytes, kernel.c_str(), body);
+        return;
+    }
+    if (bad_launch_configuration(grid, block, dyn_bytes)) {         // refused at the launch, as on the GPU
+        tl_last_error = 9;
+        return;
+    }
+    std::lock_guard<std::recursive_mutex> lk(g_rt_mu);
+    enqueue(st, [grid, block, dyn_bytes, kernel, body] { launch(grid, block, dyn_bytes, kernel.c_str(), body); });
+}
+}  // namespace cuemu
 
 extern "C" {
 cudaError_t cudaGetDeviceCount(int* n) {
@@ -371,13 +565,30 @@ cudaError_t cudaMalloc(void** p, size_t n) {
     else memset(m, 0xA5, n < 4096 ? n : 4096);
     g_live_allocs++;
     *p = m;
+    if (async_mode()) {
+        std::lock_guard<std::recursive_mutex> lk(g_rt_mu);
+        g_device_ranges[(uintptr_t)m] = n;
+    }
     return cudaSuccess;
 }
 cudaError_t cudaFree(void* p) {
+    if (p && async_mode()) {                      // cudaFree synchronises the device before it releases anything
+        std::lock_guard<std::recursive_mutex> lk(g_rt_mu);
+        drain_everything();
+        g_device_ranges.erase((uintptr_t)p);
+    }
     if (p) g_live_allocs--;
     free(p);
     return cudaSuccess;
 }
+__attribute__((visibility("default"))) int cuemu_async_mode(void) { return async_mode(); }
+// everything queued anywhere runs now (the tests' torch stand-ins: torch.cuda.synchronize(), tensor.cpu(), a collective)
+__attribute__((visibility("default"))) void cuemu_sync_all(void) {
+    if (!async_mode()) return;
+    std::lock_guard<std::recursive_mutex> lk(g_rt_mu);
+    drain_everything();
+}
+__attribute__((visibility("default"))) unsigned long long cuemu_deferred_ops(void) { return g_deferred_ops; }
 __attribute__((visibility("default"))) long cuemu_live_allocations(void) { return g_live_allocs.load(); }
 __attribute__((visibility("default"))) void cuemu_census_reset(void) {
     std::lock_guard<std::mutex> lk(cuemu::g_census_mu);
@@ -405,48 +616,103 @@ cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) {
     void* m = nullptr;
     if (posix_memalign(&m, 256, n ? n : 256) != 0) return cudaErrorMemoryAllocation;
     *p = m;
+    if (async_mode()) {
+        std::lock_guard<std::recursive_mutex> lk(g_rt_mu);
+        g_pinned_ranges[(uintptr_t)m] = n ? n : 256;
+    }
     return cudaSuccess;
 }
 cudaError_t cudaFreeHost(void* p) {
+    if (p && async_mode()) {
+        std::lock_guard<std::recursive_mutex> lk(g_rt_mu);
+        drain_everything();
+        g_pinned_ranges.erase((uintptr_t)p);
+    }
     free(p);
     return cudaSuccess;
 }
-cudaError_t cudaHostRegister(void*, size_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaHostRegister(void* p, size_t n, unsigned) {
+    if (async_mode()) {
+        std::lock_guard<std::recursive_mutex> lk(g_rt_mu);
+        g_pinned_ranges[(uintptr_t)p] = n;
+    }
+    return cudaSuccess;
+}
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) {
+    if (async_mode()) {                           // a blocking copy: the legacy default stream's ordering, then the copy itself
+        std::lock_guard<std::recursive_mutex> lk(g_rt_mu);
+        force_blocking_streams();
+    }
     if (n) memmove(d, s, n);
     return cudaSuccess;
 }
-cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) {
-    if (n) memmove(d, s, n);
-    return cudaSuccess;
-}
-cudaError_t cudaMemcpyPeerAsync(void* d, int, const void* s, int, size_t n, cudaStream_t) {
-    if (n) memmove(d, s, n);
-    return cudaSuccess;
-}
-cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) {
-    if (n) memset(d, v, n);
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t st) { return copy_async(d, s, n, st); }
+cudaError_t cudaMemcpyPeerAsync(void* d, int, const void* s, int, size_t n, cudaStream_t st) { return copy_async(d, s, n, st); }
+cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    if (!async_mode()) {
+        memset(d, v, n);
+        return cudaSuccess;
+    }
+    std::lock_guard<std::recursive_mutex> lk(g_rt_mu);
+    enqueue(st, [d, v, n] { memset(d, v, n); });
     return cudaSuccess;
 }
 cudaError_t cudaMemset(void* d, int v, size_t n) {
+    if (async_mode()) {
+        std::lock_guard<std::recursive_mutex> lk(g_rt_mu);
+        force_blocking_streams();
+    }
     if (n) memset(d, v, n);
     return cudaSuccess;
 }
-cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
-    *s = (cudaStream_t)malloc(8);
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned flags) {
+    *s = new_stream(flags);
     return cudaSuccess;
 }
-cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) {
-    *s = (cudaStream_t)malloc(8);
+cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned flags, int) {
+    *s = new_stream(flags);
     return cudaSuccess;
 }
 cudaError_t cudaStreamDestroy(cudaStream_t s) {
+    if (async_mode()) {                           // returns at once; the work queued on the stream still completes
+        std::lock_guard<std::recursive_mutex> lk(g_rt_mu);
+        auto it = g_streams.find(s);
+        if (it != g_streams.end()) {
+            if (!it->second->q.empty()) g_zombies.push_back(it->second);
+            g_streams.erase(it);
+        }
+    }
     free(s);
     return cudaSuccess;
 }
-cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
-cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t s) {
+    if (!async_mode()) return cudaSuccess;
+    std::lock_guard<std::recursive_mutex> lk(g_rt_mu);
+    if (s) force_stream(stream_of(s));
+    else force_blocking_streams();
+    return cudaSuccess;
+}
+cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned) {
+    if (!async_mode()) return cudaSuccess;
+    std::lock_guard<std::recursive_mutex> lk(g_rt_mu);
+    auto it = g_events.find(e);
+    if (it == g_events.end() || it->second->enqueued == 0) return cudaSuccess;         // never recorded: nothing to wait for
+    if (!s) {
+        force_blocking_streams();
+        advance_event(it->second, it->second->enqueued);
+        return cudaSuccess;
+    }
+    stream_of(s)->q.push_back(Op{2, nullptr, it->second, it->second->enqueued});       // the most recent record at THIS moment
+    return cudaSuccess;
+}
+cudaError_t cudaDeviceSynchronize(void) {
+    if (!async_mode()) return cudaSuccess;
+    std::lock_guard<std::recursive_mutex> lk(g_rt_mu);
+    g_forced_drains++;
+    drain_everything();
+    return cudaSuccess;
+}
 cudaError_t cudaDeviceGetStreamPriorityRange(int* least, int* greatest) {
     if (least) *least = 0;
     if (greatest) *greatest = -1;
@@ -457,20 +723,47 @@ cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) {
     return cudaSuccess;
 }
 cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
-cudaError_t cudaEventCreate(cudaEvent_t* e) {
-    *e = (cudaEvent_t)malloc(8);
-    return cudaSuccess;
-}
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) {
     *e = (cudaEvent_t)malloc(8);
+    if (async_mode()) {
+        std::lock_guard<std::recursive_mutex> lk(g_rt_mu);
+        g_events[*e] = std::make_shared<Ev>();
+    }
     return cudaSuccess;
 }
+cudaError_t cudaEventCreate(cudaEvent_t* e) { return cudaEventCreateWithFlags(e, 0); }
 cudaError_t cudaEventDestroy(cudaEvent_t e) {
+    if (async_mode()) {                           // queued records / waits keep the state alive
+        std::lock_guard<std::recursive_mutex> lk(g_rt_mu);
+        g_events.erase(e);
+    }
     free(e);
     return cudaSuccess;
 }
-cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
-cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) {
+    if (!async_mode()) return cudaSuccess;
+    std::lock_guard<std::recursive_mutex> lk(g_rt_mu);
+    auto it = g_events.find(e);
+    if (it == g_events.end()) return cudaErrorInvalidValue;
+    const unsigned long long gen = ++it->second->enqueued;
+    if (!s) {
+        force_blocking_streams();
+        it->second->done = gen;
+        return cudaSuccess;
+    }
+    stream_of(s)->q.push_back(Op{1, nullptr, it->second, gen});
+    return cudaSuccess;
+}
+cudaError_t cudaEventSynchronize(cudaEvent_t e) {
+    if (!async_mode()) return cudaSuccess;
+    std::lock_guard<std::recursive_mutex> lk(g_rt_mu);
+    auto it = g_events.find(e);
+    if (it == g_events.end()) return cudaErrorInvalidValue;
+    g_forced_drains++;
+    if (async_mode() == 2) drain_everything();
+    advance_event(it->second, it->second->enqueued);
+    return cudaSuccess;
+}
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) {
     *ms = 0.f;
     return cudaSuccess;

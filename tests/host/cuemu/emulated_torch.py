@@ -5,6 +5,16 @@ import contextlib
 import os
 
 
+def drain():
+    """CUEMU_ASYNC (deferred execution, cuemu.cpp): everything queued on any stream runs now.  Called where the real torch
+    would order itself behind the library's work -- torch.cuda.synchronize(), stream / event .synchronize(), tensor.cpu(), a
+    collective on the stream the work was queued on.  A no-op in the synchronous mode."""
+    from wasmsnark_b200 import _lib
+    lib = _lib.load_library()
+    if hasattr(lib, "cuemu_sync_all"):
+        lib.cuemu_sync_all()
+
+
 class FakeStream:
     cuda_stream = 0
 
@@ -12,7 +22,7 @@ class FakeStream:
         pass
 
     def synchronize(self):
-        pass
+        drain()
 
     def wait_stream(self, other):
         pass
@@ -37,7 +47,7 @@ class FakeEvent:
         self.t = time.perf_counter()
 
     def synchronize(self):
-        pass
+        drain()
 
     def wait(self, stream=None):
         pass
@@ -64,7 +74,25 @@ def patch():
     for name in ("zeros", "empty", "ones", "full", "tensor", "frombuffer", "arange", "randint"):
         setattr(torch, name, on_cpu(getattr(torch, name)))
     torch.Tensor.cuda = lambda self, *a, **k: self.clone()
-    torch.cuda.synchronize = lambda *a, **k: None
+    if os.environ.get("CUEMU_ASYNC"):
+        # a device-to-host read is ordered behind the stream's work; so is a collective enqueued on that stream
+        cpu = torch.Tensor.cpu
+
+        def cpu_after_the_streams(self, *a, **k):
+            drain()
+            return cpu(self, *a, **k)
+        torch.Tensor.cpu = cpu_after_the_streams
+        import torch.distributed as dist
+
+        def after_the_streams(fn):
+            def wrapper(*a, **k):
+                drain()
+                return fn(*a, **k)
+            return wrapper
+        for name in ("all_gather_into_tensor", "all_gather", "all_reduce", "broadcast", "send", "recv", "batch_isend_irecv", "barrier"):
+            if hasattr(dist, name):
+                setattr(dist, name, after_the_streams(getattr(dist, name)))
+    torch.cuda.synchronize = lambda *a, **k: drain()
     torch.cuda.is_available = lambda: True
     torch.cuda.device_count = lambda: max(1, int(os.environ.get("CUEMU_DEVICES", "1")))
     torch.cuda.set_device = lambda *a, **k: None

@@ -3,6 +3,7 @@
 #include "cuda_runtime.h"
 
 #include <cstdio>
+#include <tuple>
 #include <vector>
 
 // every lane asks for the value of lane (l + 8) % 32; lanes 24..31 returned before the shuffle, the block has 40 threads
@@ -60,6 +61,72 @@ int main() {
         for (unsigned r = 0; r < 3; r++)
             for (unsigned t = 0; t < 96; t++) ok += e[(b * 3 + r) * 96 + t] == 100 * r + (95 - t) + b;
     printf("exchange_good %d\n", ok);
+
+    // ---- streams.  Two mis-ordered programs and their repaired versions; what each prints depends on CUEMU_ASYNC:
+    //   missing wait   the consumer (stream B) copies a buffer the producer (stream A) fills, with no event between them:
+    //                  right in the synchronous mode and under `eager`, STALE under `lazy` (B runs before A)
+    //   early reuse    A refills the buffer without waiting for B's read of the first contents:
+    //                  right in the synchronous mode and under `lazy`, OVERWRITTEN under `eager` (A runs to its end before B)
+    // the repaired versions (event record + wait) give the right bytes in every mode
+    for (int repaired = 0; repaired < 2; repaired++) {
+        uint8_t *a, *b;
+        cudaMalloc((void**)&a, 64);
+        cudaMalloc((void**)&b, 64);
+        cudaStream_t A, B;
+        cudaStreamCreateWithFlags(&A, cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&B, cudaStreamNonBlocking);
+        cudaEvent_t filled, read;
+        cudaEventCreate(&filled);
+        cudaEventCreate(&read);
+        cudaMemsetAsync(a, 0, 64, A);
+        cudaMemsetAsync(b, 0, 64, B);
+        cudaStreamSynchronize(A);
+        cudaStreamSynchronize(B);
+        // missing wait
+        cudaMemsetAsync(a, 1, 64, A);
+        if (repaired) {
+            cudaEventRecord(filled, A);
+            cudaStreamWaitEvent(B, filled, 0);
+        }
+        cudaMemcpyAsync(b, a, 64, cudaMemcpyDeviceToDevice, B);
+        cudaStreamSynchronize(B);
+        const int got1 = b[0];
+        cudaStreamSynchronize(A);
+        // early reuse
+        cudaMemsetAsync(a, 5, 64, A);
+        cudaEventRecord(filled, A);
+        cudaStreamWaitEvent(B, filled, 0);
+        cudaMemcpyAsync(b, a, 64, cudaMemcpyDeviceToDevice, B);
+        if (repaired) {
+            cudaEventRecord(read, B);
+            cudaStreamWaitEvent(A, read, 0);
+        }
+        cudaMemsetAsync(a, 9, 64, A);
+        cudaStreamSynchronize(B);
+        const int got2 = b[0];
+        cudaDeviceSynchronize();
+        printf("%s_consumer_sees %d\n%s_reader_sees %d\n", repaired ? "ordered" : "unordered", got1, repaired ? "ordered" : "unordered", got2);
+        cudaStreamDestroy(A);
+        cudaStreamDestroy(B);
+        cudaEventDestroy(filled);
+        cudaEventDestroy(read);
+        cudaFree(a);
+        cudaFree(b);
+    }
+    // a launch's arguments are evaluated at the launch, not when the kernel runs
+    {
+        uint32_t* d;
+        cudaMalloc((void**)&d, 4 * 40);
+        cudaStream_t S;
+        cudaStreamCreateWithFlags(&S, cudaStreamNonBlocking);
+        uint32_t* target = d;
+        { auto args = std::make_tuple(target); cuemu::launch_on(S, dim3(1), dim3(40), 0, "k_shuffle", [=]() { std::apply([=](auto&... x) { k_shuffle(x...); }, args); }); }
+        target = nullptr;                      // must not matter any more
+        cudaStreamSynchronize(S);
+        printf("launch_arguments_kept %d\n", d[0] == 2008 ? 1 : 0);
+        cudaStreamDestroy(S);
+        cudaFree(d);
+    }
 
     // what the hardware refuses: an empty grid, 1025 threads
     cuemu::launch(dim3(0), dim3(32), 0, "none", [&]() {});

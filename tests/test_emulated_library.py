@@ -182,22 +182,28 @@ def test_driver_smoke_hook_on_the_cpu_emulator():
     assert r.returncode == 0 and "smoke ok" in r.stdout, (r.stdout + r.stderr)[-2000:]
 
 
-@pytest.mark.parametrize("order", ["", "reverse", "shuffle"])
-def test_emulator_self_test(order):
+@pytest.mark.parametrize("order,streams", [("", ""), ("reverse", ""), ("shuffle", ""), ("", "lazy"), ("", "eager")])
+def test_emulator_self_test(order, streams):
     """The emulator itself on kernels with known answers (tests/host/cuemu/selftest.cpp), so that a pass of the suites above
     means something: a shuffle hands over the value of a lane that takes part and POISON for a lane that does not (one that
     returned earlier, or beyond the last thread of a partial warp -- undefined data on the GPU, where the emulator used to
     return the lane's stale slot); barriers order a shared-memory exchange for every thread order; launch configurations the
-    hardware refuses are refused with cudaErrorInvalidConfiguration."""
+    hardware refuses are refused with cudaErrorInvalidConfiguration.  Streams (CUEMU_ASYNC, deferred execution): two programs
+    whose streams are NOT ordered by events -- a consumer without a wait on its producer, a buffer refilled before its reader
+    was ordered -- give the right bytes synchronously, stale bytes under `lazy` resp. overwritten bytes under `eager`; their
+    repaired versions give the right bytes in every mode; a launch's arguments are those of the moment of the launch."""
     here = os.path.join(ROOT, "tests", "host", "cuemu")
     exe = os.path.join(here, "_build", "selftest")
     deps = [os.path.join(here, f) for f in ("selftest.cpp", "cuemu.cpp", "cuda_runtime.h")]
     os.makedirs(os.path.dirname(exe), exist_ok=True)
     if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-w", "-D__CUDACC__=1", "-I" + here, "-include", os.path.join(here, "cuda_runtime.h"),
-                               deps[0], deps[1], "-lpthread", "-o", exe])
-    r = subprocess.run([exe], env=dict(os.environ, CUEMU_ORDER=order), capture_output=True, text=True, timeout=120)
+                               deps[0], deps[1], "-lpthread", "-o", exe + ".tmp"])
+        os.replace(exe + ".tmp", exe)
+    r = subprocess.run([exe], env=dict(os.environ, CUEMU_ORDER=order, CUEMU_ASYNC=streams), capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr[-2000:]
     got = dict((k, int(v)) for k, v in (line.split() for line in r.stdout.splitlines()))
     assert got == {"shuffle_good": 24, "shuffle_poisoned": 16, "shuffle_stale": 0, "exchange_good": 576, "empty_grid_error": 9,
-                   "too_many_threads_error": 9, "error_cleared": 0}, got
+                   "too_many_threads_error": 9, "error_cleared": 0, "launch_arguments_kept": 1,
+                   "unordered_consumer_sees": 0 if streams == "lazy" else 1, "unordered_reader_sees": 9 if streams == "eager" else 5,
+                   "ordered_consumer_sees": 1, "ordered_reader_sees": 5}, got
