@@ -57,7 +57,12 @@ MULTI = ["tests/test_gpu_prover.py::test_multi_handle_on_the_visible_gpus"]
 
 
 MULTI_SPARSE = ["tests/test_gpu_prover.py::test_multi_handle_with_more_gpus_than_points"]
-GROUPS = {"field_msm": (FIELD_MSM, 1), "prover": (PROVER, 1), "other_curves": (OTHER_CURVES, 1), "multi4": (MULTI, 4), "multi8": (MULTI_SPARSE, 8)}
+# the prover's stream choreography and the multi-GPU handle once more with the streams executed DEFERRED (cuemu.cpp, CUEMU_ASYNC):
+# lazily (a consumer without a wait on its producer's event reads stale bytes) and eagerly (a buffer reused before its reader was
+# ordered is read overwritten) -- proofs must not change
+PROVER_STREAMS = [t for t in PROVER if "test_fft" not in t and "degenerate" not in t and "int_mul" not in t] + ["tests/test_gpu_prover.py::test_context_is_thread_safe"]
+GROUPS = {"field_msm": (FIELD_MSM, 1, ""), "prover": (PROVER, 1, ""), "other_curves": (OTHER_CURVES, 1, ""), "multi4": (MULTI, 4, ""), "multi8": (MULTI_SPARSE, 8, ""),
+          "prover_lazy": (PROVER_STREAMS, 1, "lazy"), "prover_eager": (PROVER_STREAMS, 1, "eager"), "multi4_lazy": (MULTI, 4, "lazy"), "multi4_eager": (MULTI, 4, "eager")}
 
 
 @pytest.fixture(scope="module")
@@ -67,8 +72,8 @@ def children():
     import build_emu
     build_emu.build()
     procs = {}
-    for name, (selection, devices) in GROUPS.items():
-        env = dict(os.environ, WS_TEST_EMULATED="1", CUEMU_DEVICES=str(devices))
+    for name, (selection, devices, streams) in GROUPS.items():
+        env = dict(os.environ, WS_TEST_EMULATED="1", CUEMU_DEVICES=str(devices), CUEMU_ASYNC=streams)
         procs[name] = subprocess.Popen([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider"] + selection, cwd=ROOT, env=env,
                                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     yield procs
@@ -104,6 +109,16 @@ def test_multi_gpu_handle_with_four_pretend_devices(children):
 
 def test_multi_gpu_handle_with_more_pretend_devices_than_points(children):
     assert "1 passed" in finished(children, "multi8")
+
+
+@pytest.mark.parametrize("group", ["prover_lazy", "prover_eager", "multi4_lazy", "multi4_eager"])
+def test_stream_choreography_under_deferred_execution(children, group):
+    """The prover (side streams for the witness MSMs and the (r, s) products, the H chain on the caller's stream, the joins in
+    front of the assembly, the stateless call's key cache and staging ring, four host threads on one context) and the
+    multi-GPU handle (peer copies of the h slices and records, cross-device events, the rotating H owner) with every stream
+    executed deferred: lazily and eagerly.  Same proofs as always -- the streams are ordered by stream order and events, not
+    by timing."""
+    assert " passed" in finished(children, group)
 
 
 # ---- the torchrun form of the multi-GPU prover (wasmsnark_b200/parallel.py: ShardedProver) on gloo + emulated kernels ------------
