@@ -357,9 +357,22 @@ std::atomic<long> g_live_allocs{0};
 int async_mode() {
     static const int m = [] {
         const char* e = getenv("CUEMU_ASYNC");
-        return !e ? 0 : !strcmp(e, "lazy") ? 1 : !strcmp(e, "eager") ? 2 : 0;
+        return !e ? 0 : !strcmp(e, "lazy") ? 1 : !strcmp(e, "eager") ? 2 : !strcmp(e, "random") ? 3 : 0;
     }();
     return m;
+}
+// CUEMU_ASYNC=random (CUEMU_SEED=<n>): at every forcing point ONE operation at a time, from a randomly chosen stream whose head
+// can run (a wait whose event is not there yet blocks its stream), until what was forced is done -- interleavings between
+// the two extremes, at the granularity of single launches and copies
+unsigned long long g_rng = [] {
+    const char* e = getenv("CUEMU_SEED");
+    return 0x9E3779B97F4A7C15ull * (unsigned long long)(e ? atoll(e) + 1 : 1) | 1;
+}();
+unsigned next_random() {
+    g_rng ^= g_rng << 13;
+    g_rng ^= g_rng >> 7;
+    g_rng ^= g_rng << 17;
+    return (unsigned)(g_rng >> 24);
 }
 std::recursive_mutex g_rt_mu;
 struct Ev {
@@ -404,9 +417,31 @@ std::vector<std::shared_ptr<Stream>> all_streams() {
     return v;
 }
 void run_stream(Stream& s, const Ev* until_ev, unsigned long long until_gen);
+// random mode: single steps of randomly chosen runnable streams until `done()` holds
+template <class Done>
+void random_steps(Done done) {
+    while (!done()) {
+        std::vector<std::shared_ptr<Stream>> can;
+        for (auto& sp : all_streams())
+            if (!sp->q.empty() && (sp->q.front().kind != 2 || sp->q.front().ev->done >= sp->q.front().gen)) can.push_back(sp);
+        if (can.empty()) {
+            fprintf(stderr, "cuemu: nothing can run but something is waited for (a wait on an event whose record is stuck behind it)\n");
+            abort();
+        }
+        Stream& s = *can[next_random() % can.size()];
+        Op op = std::move(s.q.front());
+        s.q.pop_front();
+        if (op.kind == 0) op.fn();
+        else if (op.kind == 1) op.ev->done = std::max(op.ev->done, op.gen);
+    }
+}
 
 // make `ev` reach generation `gen`: run the stream that holds that record, up to it
 void advance_event(const std::shared_ptr<Ev>& ev, unsigned long long gen) {
+    if (async_mode() == 3) {
+        random_steps([&] { return ev->done >= gen; });
+        return;
+    }
     while (ev->done < gen) {
         bool found = false;
         for (auto& sp : all_streams()) {
@@ -446,6 +481,15 @@ void reap_zombies() {
     g_zombies.erase(std::remove_if(g_zombies.begin(), g_zombies.end(), [](const std::shared_ptr<Stream>& z) { return z->q.empty(); }), g_zombies.end());
 }
 void drain_everything(const Stream* last = nullptr) {
+    if (async_mode() == 3) {
+        random_steps([&] {
+            for (auto& sp : all_streams())
+                if (sp.get() != last && !sp->q.empty()) return false;
+            return true;
+        });
+        reap_zombies();
+        return;
+    }
     for (auto& sp : all_streams())
         if (sp.get() != last && !sp->running) run_stream(*sp, nullptr, 0);
     reap_zombies();
@@ -453,6 +497,11 @@ void drain_everything(const Stream* last = nullptr) {
 // a forcing point on one stream
 void force_stream(const std::shared_ptr<Stream>& s) {
     g_forced_drains++;
+    if (async_mode() == 3) {
+        random_steps([&] { return s->q.empty(); });
+        reap_zombies();
+        return;
+    }
     if (async_mode() == 2) drain_everything(s.get());              // eager: everybody else first, to the end
     if (!s->running) run_stream(*s, nullptr, 0);
     reap_zombies();
@@ -462,6 +511,14 @@ void force_blocking_streams() {
     g_forced_drains++;
     if (async_mode() == 2) {
         drain_everything();
+        return;
+    }
+    if (async_mode() == 3) {
+        random_steps([&] {
+            for (auto& sp : all_streams())
+                if (!sp->nonblocking && !sp->q.empty()) return false;
+            return true;
+        });
         return;
     }
     for (auto& sp : all_streams())
