@@ -36,6 +36,7 @@ _EMULATOR_ONLY_SO_FAR = (
     "test_gpu_msm.py::test_from_montgomery_methods_equal_the_reference_functions",
     "test_gpu_prover.py::test_degenerate_keys_and_witnesses",
     "test_gpu_prover.py::test_fft_reference_zeros_pattern",
+    "test_gpu_prover.py::test_back_to_back_async_proofs_without_a_sync_between_them",
     "test_gpu_prover.py::test_int_mul_edge_grid_as_r_times_s",
     "test_gpu_prover.py::test_last_error_text_belongs_to_the_failing_thread",
     "test_gpu_prover.py::test_multi_handle_with_more_gpus_than_points",

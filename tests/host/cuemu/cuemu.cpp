@@ -646,6 +646,13 @@ __attribute__((visibility("default"))) void cuemu_sync_all(void) {
     drain_everything();
 }
 __attribute__((visibility("default"))) unsigned long long cuemu_deferred_ops(void) { return g_deferred_ops; }
+// launches / copies / event records and waits sitting in the queues right now
+__attribute__((visibility("default"))) unsigned long long cuemu_pending_ops(void) {
+    std::lock_guard<std::recursive_mutex> lk(g_rt_mu);
+    unsigned long long n = 0;
+    for (auto& sp : all_streams()) n += sp->q.size();
+    return n;
+}
 __attribute__((visibility("default"))) long cuemu_live_allocations(void) { return g_live_allocs.load(); }
 __attribute__((visibility("default"))) void cuemu_census_reset(void) {
     std::lock_guard<std::mutex> lk(cuemu::g_census_mu);

@@ -40,6 +40,7 @@ PROVER = [
     "tests/test_gpu_prover.py::test_sharded_partials_emulated_on_one_gpu",
     "tests/test_gpu_prover.py::test_split_prover_entry_points_equal_the_single_call",
     "tests/test_gpu_prover.py::test_balanced_split_emulated_on_one_gpu[3]",
+    "tests/test_gpu_prover.py::test_back_to_back_async_proofs_without_a_sync_between_them",
     "tests/test_gpu_prover.py::test_last_error_text_belongs_to_the_failing_thread",
     "tests/test_gpu_prover.py::test_degenerate_keys_and_witnesses",
     "tests/test_gpu_prover.py::test_int_mul_edge_grid_as_r_times_s",

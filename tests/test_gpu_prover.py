@@ -406,6 +406,48 @@ def test_balanced_split_emulated_on_one_gpu(bn, world):
         bn.lib.ws_bn128_pkey_free(k_)
 
 
+def test_back_to_back_async_proofs_without_a_sync_between_them(bn):
+    """The pipelined form bench.py times: several ws_bn128_groth16_prove_dev calls queued on ONE context and ONE stream with no
+    synchronisation between them -- different witnesses, different (r, s), one output buffer each -- and only then a sync.
+    Every call shares the context's workspace (MSM arenas, the H buffers, the side streams), so the library has to order proof
+    i + 1 behind proof i ON THE DEVICE; every one of the proofs must be the right one (the bench itself only sees the last).
+    Under the emulator's deferred modes (CUEMU_ASYNC) this is where a missing dependency between consecutive proofs shows."""
+    import ctypes
+    import torch
+    pk, wit, g = _synth_small()
+    n = len(wit) // 32
+    rnd = random.Random(17)
+    cases = []
+    for i in range(5):
+        w = bytearray(wit)
+        for k in rnd.sample(range(1, n), 40):
+            w[32 * k:32 * k + 32] = rnd.randrange(O.R_ORDER).to_bytes(32, "little")
+        cases.append((bytes(w), rnd.getrandbits(256).to_bytes(32, "little"), rnd.getrandbits(256).to_bytes(32, "little")))
+    cases[0] = (wit, bytes.fromhex(g["r"]), bytes.fromhex(g["s"]))             # the golden one among them
+    key = bn.load_proving_key(pk)
+    try:
+        d_w = [torch.frombuffer(bytearray(w), dtype=torch.uint8).cuda() for w, _, _ in cases]
+        d_rs = [torch.frombuffer(bytearray(r + s), dtype=torch.uint8).cuda() for _, r, s in cases]
+        d_out = [torch.zeros(384, dtype=torch.uint8, device="cuda") for _ in cases]
+        st = torch.cuda.Stream()
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            for i in range(len(cases)):
+                bn.ctx.check(bn.lib.ws_bn128_groth16_prove_dev(bn.ctx.h, key.h, d_w[i].data_ptr(), d_rs[i].data_ptr(), d_out[i].data_ptr(),
+                                                               ctypes.c_void_p(st.cuda_stream)))
+        if os.environ.get("CUEMU_ASYNC") and hasattr(bn.lib, "cuemu_pending_ops"):        # emulator, deferred: nothing has run yet
+            bn.lib.cuemu_pending_ops.restype = ctypes.c_ulonglong
+            assert bn.lib.cuemu_pending_ops() > 100 * len(cases), bn.lib.cuemu_pending_ops()
+        st.synchronize()
+        for i, (w, r, s) in enumerate(cases):
+            out = bytes(d_out[i].cpu().numpy())
+            got = {"pi_a": bn.bin2g1(out[:96]), "pi_b": bn.bin2g2(out[96:288]), "pi_c": bn.bin2g1(out[288:])}
+            assert got == O.groth16_gen_proof(w, pk, int.from_bytes(r, "little"), int.from_bytes(s, "little")), i
+        assert O.groth16_gen_proof(*cases[0][:1], pk, int.from_bytes(cases[0][1], "little"), int.from_bytes(cases[0][2], "little")) == g["proof_rs"]
+    finally:
+        key.free()
+
+
 def test_context_is_thread_safe(bn):
     """Several host threads proving / multiplying on ONE context (the reference queues any number of commands,
     src/bn128.js:282-300; the Node addon runs proofs on libuv worker threads): every result is the right one."""
