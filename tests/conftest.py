@@ -34,6 +34,7 @@ _EMULATOR_ONLY_SO_FAR = (
     "test_gpu_field.py::test_to_montgomery_takes_raw_values",
     "test_gpu_bls.py::test_to_montgomery_takes_raw_values",
     "test_gpu_msm.py::test_from_montgomery_methods_equal_the_reference_functions",
+    "test_gpu_msm.py::test_back_to_back_async_multiexps_without_a_sync_between_them",
     "test_gpu_prover.py::test_degenerate_keys_and_witnesses",
     "test_gpu_prover.py::test_fft_reference_zeros_pattern",
     "test_gpu_prover.py::test_back_to_back_async_proofs_without_a_sync_between_them",

@@ -61,7 +61,8 @@ MULTI_SPARSE = ["tests/test_gpu_prover.py::test_multi_handle_with_more_gpus_than
 # the prover's stream choreography and the multi-GPU handle once more with the streams executed DEFERRED (cuemu.cpp, CUEMU_ASYNC):
 # lazily (a consumer without a wait on its producer's event reads stale bytes) and eagerly (a buffer reused before its reader was
 # ordered is read overwritten) -- proofs must not change
-PROVER_STREAMS = [t for t in PROVER if "test_fft" not in t and "degenerate" not in t and "int_mul" not in t] + ["tests/test_gpu_prover.py::test_context_is_thread_safe"]
+PROVER_STREAMS = [t for t in PROVER if "test_fft" not in t and "degenerate" not in t and "int_mul" not in t] + \
+    ["tests/test_gpu_prover.py::test_context_is_thread_safe", "tests/test_gpu_msm.py::test_back_to_back_async_multiexps_without_a_sync_between_them"]
 GROUPS = {"field_msm": (FIELD_MSM, 1, ""), "prover": (PROVER, 1, ""), "other_curves": (OTHER_CURVES, 1, ""), "multi4": (MULTI, 4, ""), "multi8": (MULTI_SPARSE, 8, ""),
           "prover_lazy": (PROVER_STREAMS, 1, "lazy"), "prover_eager": (PROVER_STREAMS, 1, "eager"), "multi4_lazy": (MULTI, 4, "lazy"), "multi4_eager": (MULTI, 4, "eager")}
 

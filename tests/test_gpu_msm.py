@@ -119,6 +119,34 @@ def test_group_identities_from_reference_suite(bn):
         assert dec(aff(fn(b32(RR - 1), enc(G_)))) == O.pt_affine(F, O.pt_neg(F, G_))
 
 
+def test_back_to_back_async_multiexps_without_a_sync_between_them(bn):
+    """Six ws_bn128_g?_multiexp_dev calls (G1 and G2 alternating, different sizes, scalars and output buffers) queued on ONE
+    context with no synchronisation between them: they share the context's MSM workspace (digits, bucket tables, partial
+    sums), so each must be ordered behind its predecessor on the device -- every result against the oracle's sum.  Under the
+    emulator's deferred modes (CUEMU_ASYNC) a missing dependency between consecutive calls shows here."""
+    import torch
+    from test_host_math import gen_points
+    rnd = random.Random(23)
+    jobs = []
+    for i, n in enumerate((300, 48, 700, 17, 512, 96)):
+        g = 1 + (i & 1)
+        F, gen, enc = (O.Fq, O.G1_GEN, util.g1_affine_m) if g == 1 else (O.Fq2, O.G2_GEN, util.g2_affine_m)
+        ps = gen_points(F, gen, rnd, n)
+        sc = [rnd.getrandbits(256) for _ in range(n)]
+        jobs.append((g, n, torch.frombuffer(bytearray(b"".join(b32(v) for v in sc)), dtype=torch.uint8).cuda(),
+                     torch.frombuffer(bytearray(b"".join(enc(P) for P in ps)), dtype=torch.uint8).cuda(), torch.zeros(256, dtype=torch.uint8, device="cuda"),
+                     O.pt_affine(F, O.multiexp(F, sc, ps))))
+    torch.cuda.synchronize()
+    for g, n, ds, dp, dout, _ in jobs:
+        fn = bn.lib.ws_bn128_g1_multiexp_dev if g == 1 else bn.lib.ws_bn128_g2_multiexp_dev
+        bn.ctx.check(fn(bn.ctx.h, ds.data_ptr(), dp.data_ptr(), n, dout.data_ptr(), 0, None))
+    torch.cuda.synchronize()
+    for g, n, ds, dp, dout, want in jobs:
+        out = bytes(dout[:96 if g == 1 else 192].cpu().numpy())
+        got = (util.g1_result_tuple(bn.g1_affine(out)) if g == 1 else util.g2_result_tuple(bn.g2_affine(out)))
+        assert got == want, (g, n)
+
+
 @pytest.mark.skipif(not ref_wasm.available(), reason="oracle/_ref not built")
 def test_from_montgomery_methods_equal_the_reference_functions(bn):
     """Bn128.g1_fromMontgomery / g2_fromMontgomery (src/bn128.js:429-439): un-normalised multiexp results (Z != 1) and the
