@@ -52,9 +52,18 @@ def _emulator_only_so_far(item):
     return any(key in item.nodeid for key in _EMULATOR_ONLY_SO_FAR)
 
 
+def _collects_emulated_children(item):
+    return "test_emulated_library.py" in item.nodeid and "children" in getattr(item, "fixturenames", ())
+
+
 def pytest_collection_modifyitems(config, items):
     if os.environ.get("WS_TEST_EMULATED"):
         return
+    # CPU suite: the emulated child runs (tests/test_emulated_library.py) are subprocesses -- started when the session starts
+    # (fixture below), their results collected LAST, so they run beside the serial tests instead of in front of them
+    waiting = [it for it in items if _collects_emulated_children(it)]
+    if waiting:
+        items[:] = [it for it in items if not _collects_emulated_children(it)] + waiting
     late = [it for it in items if _emulator_only_so_far(it)]
     if not late:
         return
@@ -62,6 +71,19 @@ def pytest_collection_modifyitems(config, items):
         for it in late:
             it.add_marker(pytest.mark.timeout(300, method="thread"))
     items[:] = [it for it in items if not _emulator_only_so_far(it)] + late
+
+
+@pytest.fixture(scope="session", autouse=True)
+def emulated_children_started_early(request):
+    started = False
+    if not os.environ.get("WS_TEST_EMULATED") and sum(_collects_emulated_children(it) for it in request.session.items) > 1:
+        import test_emulated_library
+        test_emulated_library.start_children()
+        started = True
+    yield
+    if started:
+        import test_emulated_library
+        test_emulated_library.stop_children()
 
 
 @pytest.fixture(scope="session")

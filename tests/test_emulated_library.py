@@ -67,21 +67,36 @@ GROUPS = {"field_msm": (FIELD_MSM, 1, ""), "prover": (PROVER, 1, ""), "other_cur
           "prover_lazy": (PROVER_STREAMS, 1, "lazy"), "prover_eager": (PROVER_STREAMS, 1, "eager"), "multi4_lazy": (MULTI, 4, "lazy"), "multi4_eager": (MULTI, 4, "eager")}
 
 
-@pytest.fixture(scope="module")
-def children():
-    """the child pytest runs, started together (each is single-threaded; the emulated build is made once, first)"""
+_PROCS = {}
+
+
+def start_children():
+    """the child pytest runs, started together (each is single-threaded; the emulated build is made once, first).  Called at
+    the START of the session (tests/conftest.py) so that they run beside the serial tests of the CPU suite; the tests below
+    only collect the results"""
+    if _PROCS:
+        return _PROCS
     sys.path.insert(0, os.path.join(ROOT, "tests", "host", "cuemu"))
     import build_emu
     build_emu.build()
-    procs = {}
     for name, (selection, devices, streams) in GROUPS.items():
         env = dict(os.environ, WS_TEST_EMULATED="1", CUEMU_DEVICES=str(devices), CUEMU_ASYNC=streams)
-        procs[name] = subprocess.Popen([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider"] + selection, cwd=ROOT, env=env,
-                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    yield procs
-    for p in procs.values():
+        _PROCS[name] = subprocess.Popen([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider"] + selection, cwd=ROOT, env=env,
+                                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    return _PROCS
+
+
+def stop_children():
+    for p in _PROCS.values():
         if p.poll() is None:
             p.kill()
+    _PROCS.clear()
+
+
+@pytest.fixture(scope="module")
+def children():
+    yield start_children()
+    stop_children()
 
 
 def finished(children, name, timeout=1500):
