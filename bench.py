@@ -655,7 +655,11 @@ def section_groth16(env, args):
                              "balanced split: the five point sections laid end to end, cost-weighted, cut into equal contiguous pieces" if split == "balanced" else "uniform split: 1/N of every point section (src/bn128.js:353-361)", world)) if world > 1 else "single GPU",
                          "l2": "key sections + window tables (5.5 GB) and MSM workspaces are far larger than the 126 MB L2; the latency run also flushes L2 between proofs",
                          "bit_exact_vs_reference_golden": golden_ok, "key_load_s": L0.load_s, "keygen_s": gen_s},
-        "stages_ms": pstages, "dropin_call": dropin, "example_key": example,
+        "stages_ms": pstages,
+        "stages_note": ("stamps on the H stream only: the four witness MSMs are forked onto side streams BEFORE the H chain is enqueued and fill the "
+                        "SMs first, so 'h:ntt' is the wall time of the H chain (6 transforms, about 2.3 ms when run alone) time-sliced with "
+                        "about 11 ms of witness-MSM kernels, not NTT kernel time; the sum of the stamps is the proof's latency"),
+        "dropin_call": dropin, "example_key": example,
         "algorithmic_bytes_per_proof": alg_bytes, "hbm_frac_whole_proof": (alg_bytes / (pms * 1e-3) / 1e9) / peaks()[0],
     }
     if world == 1:

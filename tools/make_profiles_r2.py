@@ -72,7 +72,8 @@ def main():
         if rf:
             out += ["| dominant kernel %s | %.3f ms per launch; %d algorithmic B => %.1f GB/s = %.2f %% of the measured %.1f GB/s; ncu: fmaheavy pipe %s %%, DRAM traffic %s B per launch (%s) |"
                     % (rf["kernel"], rf["kernel_ms"], rf["algorithmic_bytes_per_launch"], rf["achieved"], 100 * rf["frac"], rf["peak"], (rf.get("ncu") or {}).get("fmaheavy_pipe_busy_pct"), rf.get("traffic"), rf.get("traffic_source"))]
-        out += ["", "Stage stamps of one proof (CUDA events, ms): " + ", ".join("%s %.3f" % kv for kv in (b1.get("stages_ms") or {}).items()), ""]
+        out += ["", "Stage stamps of one proof (CUDA events, ms): " + ", ".join("%s %.3f" % kv for kv in (b1.get("stages_ms") or {}).items()),
+                "(" + (b1.get("stages_note") or "stamps on the H stream only: the witness MSMs are forked onto side streams before the H chain and fill the SMs first, so 'h:ntt' is the H chain's wall time while time-sliced with the witness MSMs (about 2.3 ms alone), not NTT kernel time") + ")", ""]
         m = b1.get("msm") or {}
         if m:
             out += ["## G1 MSM 2^20 (BASELINE configs[1])", "", "| quantity | value |", "|---|---|",
